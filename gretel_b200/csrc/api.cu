@@ -1,0 +1,385 @@
+// C-ABI plumbing of libhanselx.so: lifetime, ingestion entry points, the scalar Hansel
+// surface and bulk matrix I/O.  See include/hanselx.h for the reference interface each
+// function replaces.
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "hx_internal.cuh"
+
+static thread_local char g_err[512] = "";
+
+void hx_set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+namespace {
+
+__global__ void k_fold_counts(const uint32_t *__restrict__ cnt, float *__restrict__ band, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const uint32_t c = cnt[i];
+        if (c) band[i] += (float)c;
+    }
+}
+
+__global__ void k_add_one(float *p, float amount) { *p += amount; }
+
+__global__ void k_reweight_one(float *p, double ratio, double *removed) {
+    const double old = (double)*p;
+    const double nw = old - (ratio * old);
+    *p = (float)nw;
+    *removed = old - nw;
+}
+
+int in_band(const hx_matrix *h, int a, int b, int64_t i, int64_t j) {
+    if (a < 0 || a >= HX_NSYM || b < 0 || b >= HX_NSYM) return HX_E_ARG;
+    if (i < 0 || j < 0 || i > (int64_t)h->N + 1 || j > (int64_t)h->N + 1) return HX_E_ARG;
+    if (j - i < 1 || j - i > h->W) return HX_E_BAND;
+    return HX_OK;
+}
+
+void free_all(hx_matrix *h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->band) cudaFree(h->band);
+    if (h->cnt) cudaFree(h->cnt);
+    if (h->d_totals) cudaFree(h->d_totals);
+    if (h->d_err) cudaFree(h->d_err);
+    if (h->s_rank) cudaFree(h->s_rank);
+    if (h->s_off) cudaFree(h->s_off);
+    if (h->s_codes) cudaFree(h->s_codes);
+    if (h->scnt) cudaFree(h->scnt);
+    if (h->vseen) cudaFree(h->vseen);
+    if (h->d_path) cudaFree(h->d_path);
+    if (h->d_stats) cudaFree(h->d_stats);
+    if (h->d_site) cudaFree(h->d_site);
+    if (h->d_partials) cudaFree(h->d_partials);
+    if (h->d_flags) cudaFree(h->d_flags);
+    if (h->d_misc) cudaFree(h->d_misc);
+    if (h->h_pinned) cudaFreeHost(h->h_pinned);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+    free(h);
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *hx_last_error(void) { return g_err; }
+int hx_version(void) { return 100; }
+
+int hx_device_count(int *n) {
+    HX_CHECK_ARG(n);
+    HX_CUDA(cudaGetDeviceCount(n));
+    return HX_OK;
+}
+
+int hx_create(int32_t n_snps, int32_t band_w, int32_t device, hx_matrix **out) {
+    HX_CHECK_ARG(out && n_snps >= 0 && band_w >= 1);
+    *out = nullptr;
+    HX_CUDA(cudaSetDevice(device));
+    hx_matrix *h = (hx_matrix *)calloc(1, sizeof(hx_matrix));
+    if (!h) return HX_E_NOMEM;
+    h->N = n_snps;
+    h->W = band_w;
+    h->device = device;
+    h->band_elems = ((int64_t)n_snps + 2) * band_w * HX_CELL;
+    h->counts_dirty = true;
+#define HX_TRY(call)                                                                     \
+    do {                                                                                 \
+        cudaError_t e__ = (call);                                                        \
+        if (e__ != cudaSuccess) {                                                        \
+            hx_set_error("hx_create: %s -> %s", #call, cudaGetErrorString(e__));         \
+            free_all(h);                                                                 \
+            return e__ == cudaErrorMemoryAllocation ? HX_E_NOMEM : HX_E_CUDA;            \
+        }                                                                                \
+    } while (0)
+    HX_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    h->own_stream = true;
+    HX_TRY(cudaEventCreate(&h->ev0));
+    HX_TRY(cudaEventCreate(&h->ev1));
+    HX_TRY(cudaMalloc(&h->band, sizeof(float) * (size_t)h->band_elems));
+    HX_TRY(cudaMemsetAsync(h->band, 0, sizeof(float) * (size_t)h->band_elems, h->stream));
+    HX_TRY(cudaMalloc(&h->d_totals, 8 * sizeof(unsigned long long)));
+    HX_TRY(cudaMemsetAsync(h->d_totals, 0, 8 * sizeof(unsigned long long), h->stream));
+    HX_TRY(cudaMalloc(&h->d_err, sizeof(int)));
+    HX_TRY(cudaMemsetAsync(h->d_err, 0, sizeof(int), h->stream));
+    HX_TRY(cudaMalloc(&h->scnt, sizeof(double) * 8 * ((size_t)n_snps + 2)));
+    HX_TRY(cudaMalloc(&h->vseen, sizeof(int32_t) * ((size_t)n_snps + 2)));
+    HX_TRY(cudaMalloc(&h->d_site, sizeof(double) * 3 * ((size_t)n_snps + 2)));
+    HX_TRY(cudaMalloc(&h->d_flags, 8 * sizeof(int)));
+    HX_TRY(cudaMemsetAsync(h->d_flags, 0, 8 * sizeof(int), h->stream));
+    HX_TRY(cudaMalloc(&h->d_misc, 32 * sizeof(double)));
+    HX_TRY(cudaMallocHost(&h->h_pinned, 256));
+    HX_TRY(cudaStreamSynchronize(h->stream));
+#undef HX_TRY
+    *out = h;
+    return HX_OK;
+}
+
+int hx_destroy(hx_matrix *h) {
+    free_all(h);
+    return HX_OK;
+}
+
+int hx_copy(const hx_matrix *src, hx_matrix **out) {
+    HX_CHECK_ARG(src && out);
+    if (src->cnt) {
+        hx_set_error("hx_copy: integer counts pending; call hx_finalize_counts first");
+        return HX_E_STATE;
+    }
+    int rc = hx_create(src->N, src->W, src->device, out);
+    if (rc) return rc;
+    hx_matrix *h = *out;
+    HX_CUDA(cudaStreamSynchronize(src->stream));
+    HX_CUDA(cudaMemcpyAsync(h->band, src->band, sizeof(float) * (size_t)src->band_elems,
+                            cudaMemcpyDeviceToDevice, h->stream));
+    HX_CUDA(cudaMemcpyAsync(h->d_totals, src->d_totals, 8 * sizeof(unsigned long long),
+                            cudaMemcpyDeviceToDevice, h->stream));
+    HX_CUDA(cudaStreamSynchronize(h->stream));
+    h->ingest_kernel = src->ingest_kernel;
+    return HX_OK;
+}
+
+int hx_info(const hx_matrix *h, int32_t *n_snps, int32_t *band_w, int32_t *device) {
+    HX_CHECK_ARG(h);
+    if (n_snps) *n_snps = h->N;
+    if (band_w) *band_w = h->W;
+    if (device) *device = h->device;
+    return HX_OK;
+}
+
+int hx_stream(const hx_matrix *h, void **stream) {
+    HX_CHECK_ARG(h && stream);
+    *stream = (void *)h->stream;
+    return HX_OK;
+}
+
+int hx_set_stream(hx_matrix *h, void *stream) {
+    HX_CHECK_ARG(h);
+    HX_CUDA(cudaSetDevice(h->device));
+    HX_CUDA(cudaStreamSynchronize(h->stream));
+    if (h->own_stream) cudaStreamDestroy(h->stream);
+    h->stream = (cudaStream_t)stream;
+    h->own_stream = false;
+    return HX_OK;
+}
+
+int hx_sync(hx_matrix *h) {
+    HX_CHECK_ARG(h);
+    HX_CUDA(cudaSetDevice(h->device));
+    HX_CUDA(cudaStreamSynchronize(h->stream));
+    return HX_OK;
+}
+
+// ------------------------------------------------------------------------------ ingestion
+static int ensure_counts_buffer(hx_matrix *h) {
+    if (h->cnt) return HX_OK;
+    HX_CUDA(cudaMalloc(&h->cnt, sizeof(uint32_t) * (size_t)h->band_elems));
+    HX_CUDA(cudaMemsetAsync(h->cnt, 0, sizeof(uint32_t) * (size_t)h->band_elems, h->stream));
+    return HX_OK;
+}
+
+int hx_set_ingest_kernel(hx_matrix *h, int which) {
+    HX_CHECK_ARG(h && which >= 0 && which <= 2);
+    h->ingest_kernel = which;
+    return HX_OK;
+}
+
+int hx_ingest_device(hx_matrix *h, const int32_t *d_rank, const int64_t *d_off,
+                     const uint8_t *d_codes, int64_t n_reads) {
+    HX_CHECK_ARG(h && n_reads >= 0);
+    if (n_reads == 0) return HX_OK;
+    HX_CHECK_ARG(d_rank && d_off && d_codes);
+    HX_CUDA(cudaSetDevice(h->device));
+    int rc = ensure_counts_buffer(h);
+    if (rc) return rc;
+    return hx_launch_ingest(h, d_rank, d_off, d_codes, n_reads);
+}
+
+int hx_ingest_totals(hx_matrix *h, int64_t totals[4]) {
+    HX_CHECK_ARG(h && totals);
+    HX_CUDA(cudaSetDevice(h->device));
+    unsigned long long *hp = (unsigned long long *)h->h_pinned;
+    int *he = (int *)(hp + 8);
+    HX_CUDA(cudaMemcpyAsync(hp, h->d_totals, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+    HX_CUDA(cudaMemcpyAsync(he, h->d_err, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    HX_CUDA(cudaStreamSynchronize(h->stream));
+    if (h->ev_rec) cudaEventElapsedTime(&h->last_ms[0], h->ev0, h->ev1);
+    for (int i = 0; i < 4; ++i) totals[i] = (int64_t)hp[i];
+    if (*he) {
+        hx_set_error("ingest: invalid packed read(s): %s%s",
+                     (*he & 1) ? "[read leaves [0,N] or has more SNPs than band_w+1] " : "",
+                     (*he & 2) ? "[allele code > 6]" : "");
+        return HX_E_READ;
+    }
+    return HX_OK;
+}
+
+int hx_ingest_host(hx_matrix *h, const int32_t *rank, const int64_t *off, const uint8_t *codes,
+                   int64_t n_reads, int64_t totals[4]) {
+    HX_CHECK_ARG(h && totals && n_reads >= 0);
+    HX_CUDA(cudaSetDevice(h->device));
+    if (n_reads > 0) {
+        HX_CHECK_ARG(rank && off && codes);
+        const int64_t n_codes = off[n_reads] - off[0];
+        HX_CHECK_ARG(n_codes >= 0);
+        if (n_reads > h->cap_reads) {
+            if (h->s_rank) cudaFree(h->s_rank);
+            if (h->s_off) cudaFree(h->s_off);
+            h->s_rank = nullptr; h->s_off = nullptr; h->cap_reads = 0;
+            HX_CUDA(cudaMalloc(&h->s_rank, sizeof(int32_t) * (size_t)n_reads));
+            HX_CUDA(cudaMalloc(&h->s_off, sizeof(int64_t) * ((size_t)n_reads + 1)));
+            h->cap_reads = n_reads;
+        }
+        if (n_codes > h->cap_codes) {
+            if (h->s_codes) cudaFree(h->s_codes);
+            h->s_codes = nullptr; h->cap_codes = 0;
+            HX_CUDA(cudaMalloc(&h->s_codes, (size_t)n_codes + 16));
+            h->cap_codes = n_codes;
+        }
+        HX_CUDA(cudaMemcpyAsync(h->s_rank, rank, sizeof(int32_t) * (size_t)n_reads, cudaMemcpyHostToDevice, h->stream));
+        HX_CUDA(cudaMemcpyAsync(h->s_off, off, sizeof(int64_t) * ((size_t)n_reads + 1), cudaMemcpyHostToDevice, h->stream));
+        HX_CUDA(cudaMemcpyAsync(h->s_codes, codes + off[0], (size_t)n_codes, cudaMemcpyHostToDevice, h->stream));
+        int rc = ensure_counts_buffer(h);
+        if (rc) return rc;
+        // kernels index codes by absolute offsets: bias the base pointer by off[0]
+        rc = hx_launch_ingest(h, h->s_rank, h->s_off, h->s_codes - off[0], n_reads);
+        if (rc) return rc;
+    }
+    return hx_ingest_totals(h, totals);
+}
+
+int hx_counts_buffer(hx_matrix *h, void **d_counts, int64_t *n_u32, void **d_totals, int64_t *n_i64) {
+    HX_CHECK_ARG(h && d_counts && n_u32 && d_totals && n_i64);
+    HX_CUDA(cudaSetDevice(h->device));
+    int rc = ensure_counts_buffer(h);
+    if (rc) return rc;
+    *d_counts = h->cnt;
+    *n_u32 = h->band_elems;
+    *d_totals = h->d_totals;
+    *n_i64 = 4;
+    return HX_OK;
+}
+
+int hx_finalize_counts(hx_matrix *h) {
+    HX_CHECK_ARG(h);
+    if (!h->cnt) return HX_OK;
+    HX_CUDA(cudaSetDevice(h->device));
+    const int64_t n = h->band_elems;
+    k_fold_counts<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->cnt, h->band, n);
+    h->launches++;
+    HX_CUDA(cudaGetLastError());
+    HX_CUDA(cudaStreamSynchronize(h->stream));
+    HX_CUDA(cudaFree(h->cnt));
+    h->cnt = nullptr;
+    h->counts_dirty = true;
+    return HX_OK;
+}
+
+// ------------------------------------------------------------------------------ scalar surface
+int hx_add_observation(hx_matrix *h, int a, int b, int32_t i, int32_t j, float amount) {
+    HX_CHECK_ARG(h);
+    int rc = in_band(h, a, b, i, j);
+    if (rc) { hx_set_error("add_observation(%d,%d,%d,%d): outside band/arguments", a, b, i, j); return rc; }
+    HX_CUDA(cudaSetDevice(h->device));
+    k_add_one<<<1, 1, 0, h->stream>>>(h->band + hx_cell_off(h->W, i, j) + a * HX_NSYM + b, amount);
+    h->launches++;
+    h->counts_dirty = true;
+    HX_CUDA(cudaGetLastError());
+    return HX_OK;
+}
+
+int hx_get_observation(hx_matrix *h, int a, int b, int32_t i, int32_t j, float *out) {
+    HX_CHECK_ARG(h && out);
+    int rc = in_band(h, a, b, i, j);
+    if (rc == HX_E_BAND) { *out = 0.0f; return HX_E_BAND; }
+    if (rc) { hx_set_error("get_observation(%d,%d,%d,%d): bad arguments", a, b, i, j); return rc; }
+    HX_CUDA(cudaSetDevice(h->device));
+    const int64_t o = hx_cell_off(h->W, i, j) + a * HX_NSYM + b;
+    float v = 0.0f;
+    HX_CUDA(cudaMemcpyAsync(&v, h->band + o, sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    HX_CUDA(cudaStreamSynchronize(h->stream));
+    if (h->cnt) {       // counts not folded yet: report the sum
+        uint32_t c = 0;
+        HX_CUDA(cudaMemcpyAsync(&c, h->cnt + o, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+        HX_CUDA(cudaStreamSynchronize(h->stream));
+        v += (float)c;
+    }
+    *out = v;
+    return HX_OK;
+}
+
+int hx_reweight_observation(hx_matrix *h, int a, int b, int32_t i, int32_t j, double ratio,
+                            double *removed) {
+    HX_CHECK_ARG(h && removed);
+    int rc = in_band(h, a, b, i, j);
+    if (rc == HX_E_BAND) { *removed = 0.0; return HX_E_BAND; }
+    if (rc) { hx_set_error("reweight_observation(%d,%d,%d,%d): bad arguments", a, b, i, j); return rc; }
+    if (h->cnt) { hx_set_error("reweight_observation: call hx_finalize_counts first"); return HX_E_STATE; }
+    HX_CUDA(cudaSetDevice(h->device));
+    k_reweight_one<<<1, 1, 0, h->stream>>>(h->band + hx_cell_off(h->W, i, j) + a * HX_NSYM + b, ratio, h->d_misc + 16);
+    h->launches++;
+    h->counts_dirty = true;
+    HX_CUDA(cudaGetLastError());
+    HX_CUDA(cudaMemcpyAsync(removed, h->d_misc + 16, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    HX_CUDA(cudaStreamSynchronize(h->stream));
+    return HX_OK;
+}
+
+// ------------------------------------------------------------------------------ bulk I/O
+int hx_band_to_host(hx_matrix *h, float *out) {
+    HX_CHECK_ARG(h && out);
+    if (h->cnt) { hx_set_error("band_to_host: call hx_finalize_counts first"); return HX_E_STATE; }
+    HX_CUDA(cudaSetDevice(h->device));
+    HX_CUDA(cudaMemcpyAsync(out, h->band, sizeof(float) * (size_t)h->band_elems, cudaMemcpyDeviceToHost, h->stream));
+    HX_CUDA(cudaStreamSynchronize(h->stream));
+    return HX_OK;
+}
+
+int hx_band_from_host(hx_matrix *h, const float *in) {
+    HX_CHECK_ARG(h && in);
+    if (h->cnt) { hx_set_error("band_from_host: call hx_finalize_counts first"); return HX_E_STATE; }
+    HX_CUDA(cudaSetDevice(h->device));
+    HX_CUDA(cudaMemcpyAsync(h->band, in, sizeof(float) * (size_t)h->band_elems, cudaMemcpyHostToDevice, h->stream));
+    HX_CUDA(cudaStreamSynchronize(h->stream));
+    h->counts_dirty = true;
+    return HX_OK;
+}
+
+int hx_to_dense(hx_matrix *h, float *out) {
+    HX_CHECK_ARG(h && out);
+    const int64_t P = (int64_t)h->N + 2;
+    float *tmp = (float *)malloc(sizeof(float) * (size_t)h->band_elems);
+    if (!tmp) return HX_E_NOMEM;
+    int rc = hx_band_to_host(h, tmp);
+    if (rc) { free(tmp); return rc; }
+    memset(out, 0, sizeof(float) * (size_t)(HX_CELL * P * P));
+    for (int64_t pj = 1; pj < P; ++pj)
+        for (int64_t d = 1; d <= h->W && pj - d >= 0; ++d) {
+            const float *cell = tmp + hx_cell_off(h->W, pj - d, pj);
+            for (int ab = 0; ab < HX_CELL; ++ab) out[(ab * P + (pj - d)) * P + pj] = cell[ab];
+        }
+    free(tmp);
+    return HX_OK;
+}
+
+int hx_last_kernel_ms(hx_matrix *h, int which, float *ms) {
+    HX_CHECK_ARG(h && ms && which >= 0 && which < 3);
+    *ms = h->last_ms[which];
+    return HX_OK;
+}
+
+int hx_launch_count(const hx_matrix *h, int64_t *n) {
+    HX_CHECK_ARG(h && n);
+    *n = h->launches;
+    return HX_OK;
+}
+
+}  // extern "C"

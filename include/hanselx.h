@@ -1,0 +1,138 @@
+/* hanselx.h - C ABI of the B200-native Hansel matrix + Gretel recovery hot path.
+ *
+ * This is the drop-in boundary.  The reference has no FFI layer of its own: Gretel
+ * is pure Python and reaches the matrix through the Python class ``hansel.Hansel``
+ * (pip hanselx==0.0.92, /root/reference/setup.py:8) and three Python functions.
+ * Each entry point below names the reference interface it stands behind
+ * (paths relative to /root/reference).  INTEGRATION.md shows the ctypes binding a
+ * Gretel maintainer would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types cross this boundary
+ *   - every function returns an hx_status; HX_OK == 0, errors < 0, HX_HOLE > 0
+ *   - hx_last_error() returns a thread-local message for the last failing call
+ *   - host buffers are borrowed for the duration of the call only
+ *   - symbols are codes 0..6 = A C G T N - _   (order fixed by gretel/util.py:83);
+ *     unsymbols are N(4) and _(6)
+ *   - positions: 0 = start sentinel, 1..N = SNP sites, N+1 = end sentinel
+ *   - a read is (rank r >= 0, codes c[0..k-1]); c[t] is the allele at site r+t+1
+ *
+ * Storage: counts live in a diagonal band, cell (pi,pj) with 1 <= pj-pi <= W at
+ * band[(pj*W + (pj-pi-1))*49 + a*7 + b].  Cells outside the band are structurally
+ * zero for ingested reads as long as W >= (longest read's SNP count - 1).
+ */
+#ifndef HANSELX_H
+#define HANSELX_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct hx_matrix hx_matrix;
+
+typedef enum {
+    HX_OK = 0,
+    HX_HOLE = 1,        /* generate_path found no branch (gretel/gretel.py:176-180); not an error */
+    HX_E_CUDA = -1,
+    HX_E_ARG = -2,
+    HX_E_BAND = -3,     /* cell outside the band */
+    HX_E_READ = -4,     /* a packed read leaves [0,N], is wider than the band, or has a code > 6 */
+    HX_E_NOMEM = -5,
+    HX_E_STATE = -6
+} hx_status;
+
+/* flags for the recovery arithmetic (the switchable, unpinned choices; see oracle/) */
+#define HX_F_VSITE_TO        1   /* Laplace denominator counts valid symbols at the *to* site */
+#define HX_F_KEEP_UNSYMBOLS  2   /* offer N and _ as candidate branches */
+
+const char *hx_last_error(void);
+int hx_version(void);
+int hx_device_count(int *n);
+
+/* ---- lifetime ------------------------------------------------------------------- */
+/* Hansel.init_matrix(symbols, unsymbols, N)            gretel/util.py:83 */
+int hx_create(int32_t n_snps, int32_t band_w, int32_t device, hx_matrix **out);
+int hx_destroy(hx_matrix *h);
+/* Hansel.copy()                                        gretel/cmd.py:79 */
+int hx_copy(const hx_matrix *src, hx_matrix **out);
+int hx_info(const hx_matrix *h, int32_t *n_snps, int32_t *band_w, int32_t *device);
+/* the CUDA stream all work of this matrix is ordered on (cudaStream_t as void*) */
+int hx_stream(const hx_matrix *h, void **stream);
+int hx_set_stream(hx_matrix *h, void *stream);
+int hx_sync(hx_matrix *h);
+
+/* ---- ingestion: replaces the pair-expansion loop gretel/util.py:226-286 --------- */
+/* Host-buffer entry point (H2D + kernel + D2H of the totals), synchronous.
+ * totals[4] = { n_slices (util.py:233), n_crumbs (util.py:268,276,281),
+ *               covered_snps (util.py:239), sentinel increments }.
+ * Counts accumulate over calls until hx_finalize_counts(). */
+int hx_ingest_host(hx_matrix *h, const int32_t *rank, const int64_t *off, const uint8_t *codes,
+                   int64_t n_reads, int64_t totals[4]);
+/* Device-buffer entry point, asynchronous on the matrix's stream. */
+int hx_ingest_device(hx_matrix *h, const int32_t *d_rank, const int64_t *d_off,
+                     const uint8_t *d_codes, int64_t n_reads);
+/* Select the ingestion kernel: 0 = auto, 1 = per-pair global reductions (generic),
+ * 2 = bit-sliced shared-memory tiles (rank-sorted short reads). */
+int hx_set_ingest_kernel(hx_matrix *h, int which);
+int hx_ingest_totals(hx_matrix *h, int64_t totals[4]);               /* synchronises */
+/* Partial-matrix exchange across GPUs (the reference's fork-shared matrix,
+ * util.py:303-326): device pointer + length of the uint32 counts and of the int64
+ * totals, for an integer sum-allreduce by the caller (NCCL). */
+int hx_counts_buffer(hx_matrix *h, void **d_counts, int64_t *n_u32, void **d_totals, int64_t *n_i64);
+/* Fold the integer counts into the float32 working matrix used by everything below
+ * (util.py:329-333 happens in the caller from the totals). */
+int hx_finalize_counts(hx_matrix *h);
+
+/* ---- scalar Hansel surface ------------------------------------------------------- */
+/* Hansel.add_observation(a,b,i,j)                      gretel/util.py:266-286 */
+int hx_add_observation(hx_matrix *h, int a, int b, int32_t i, int32_t j, float amount);
+/* Hansel.get_observation(a,b,i,j)                      tests/test_test.py:41-52 */
+int hx_get_observation(hx_matrix *h, int a, int b, int32_t i, int32_t j, float *out);
+/* Hansel.reweight_observation(a,b,i,j,ratio)->removed  gretel/gretel.py:84,96 */
+int hx_reweight_observation(hx_matrix *h, int a, int b, int32_t i, int32_t j, double ratio,
+                            double *removed);
+/* Hansel.reweight_matrix(ratio)                        gretel/gretel.py:72 (dead code upstream) */
+int hx_reweight_matrix(hx_matrix *h, double ratio);
+/* Hansel.get_counts_at(i) for every i in 0..N          gretel/cmd.py:85-92,123-145
+ * out[(N+1)*8]: 7 symbol counts (0 where absent) then the total. */
+int hx_counts_all(hx_matrix *h, double *out);
+/* Hansel.get_marginal_of_at(sym, pos)                  gretel/gretel.py:182,186 */
+int hx_marginal_of_at(hx_matrix *h, int sym, int32_t pos, double *out);
+/* Hansel.get_edge_weights_at(snp, path)                gretel/gretel.py:155
+ * path[0..snp-1] are the symbols chosen so far (path[0] = '_').  weights[7] are the
+ * normalised branch weights (0 where not a candidate), *mask the candidate set,
+ * *total the "total" entry. */
+int hx_edge_weights_at(hx_matrix *h, int32_t snp, const uint8_t *path, int32_t L, int flags,
+                       double weights[7], double *total, int *mask);
+
+/* ---- bulk recovery --------------------------------------------------------------- */
+/* gretel.generate_path(n_snps, hansel, original_hansel) gretel/gretel.py:102-189
+ * out_path[N+1]; out[3] = { hp_current, hp_original, min_marginal }.
+ * Returns HX_HOLE with *hole_site = snp when no branch exists. */
+int hx_generate_path(hx_matrix *cur, hx_matrix *orig, int32_t L, int flags, uint8_t *out_path,
+                     double out[3], int32_t *hole_site);
+/* gretel.reweight_hansel_from_path(hansel, path, ratio) gretel/gretel.py:13-98 */
+int hx_reweight_path(hx_matrix *h, const uint8_t *path, double ratio, double *removed);
+/* The recovery driver loop gretel/cmd.py:148-161 kept resident on the device:
+ * up to max_paths x (generate_path; ratio = max(min_marginal, min_remove);
+ * reweight).  paths[max_paths*(N+1)], stats[max_paths*5] = { hp_current,
+ * hp_original, min_marginal, ratio, removed }.  *n_found = iterations completed. */
+int hx_recover(hx_matrix *cur, hx_matrix *orig, int32_t L, int flags, int32_t max_paths,
+               double min_remove, uint8_t *paths, double *stats, int32_t *n_found);
+
+/* ---- bulk matrix I/O (tests, --dumpmatrix gretel/cmd.py:81-82) ------------------- */
+int hx_band_to_host(hx_matrix *h, float *out /* (N+2)*W*49 */);
+int hx_band_from_host(hx_matrix *h, const float *in);
+int hx_to_dense(hx_matrix *h, float *out /* 7*7*(N+2)*(N+2) */);
+/* last kernel timings in ms measured with CUDA events on the matrix's stream:
+ * which = 0 ingest, 1 generate_path walk, 2 reweight */
+int hx_last_kernel_ms(hx_matrix *h, int which, float *ms);
+/* number of kernel launches issued by this matrix so far */
+int hx_launch_count(const hx_matrix *h, int64_t *n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HANSELX_H */

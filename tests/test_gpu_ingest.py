@@ -1,0 +1,151 @@
+"""Parity of the CUDA ingestion path (through the C ABI) against the oracle."""
+import os
+
+import numpy as np
+import pytest
+
+from gretel_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _gpu_band(rank, off, codes, N, W, kernel=0):
+    from gretel_b200.hansel import Hansel, REF_SYMBOLS, REF_UNSYMBOLS
+    h = Hansel.init_matrix(REF_SYMBOLS, REF_UNSYMBOLS, N, band_w=W)
+    h.set_ingest_kernel(kernel)
+    totals = h.ingest_packed(rank, off, codes)
+    band = h.band()
+    h.close()
+    return band, totals
+
+
+def test_reference_golden_through_gpu(golden_dir):
+    """tests/test_test.py:33-52 of the reference, through load_from_bam on the GPU."""
+    from gretel_b200 import util
+    for threads in (1, 2):
+        v = util.process_vcf(os.path.join(golden_dir, "ref_test.vcf.gz"), "hoot", 1, 20)
+        h = util.load_from_bam(os.path.join(golden_dir, "ref_test.bam"), "hoot", 1, 20, v, n_threads=threads)
+        assert h.n_slices == 5
+        assert h.n_crumbs == 9
+        assert h.L > 0
+        g = h.get_observation
+        assert g('_', 'A', 0, 1) == 1
+        assert g('A', 'A', 1, 2) == 1
+        assert g('A', 'A', 1, 3) == 1
+        assert g('A', 'A', 1, 4) == 0
+        assert g('C', 'C', 1, 2) == 1
+        assert g('C', 'C', 1, 3) == 1
+        assert g('C', 'C', 1, 4) == 0
+        assert g('T', 'T', 1, 2) == 2
+        assert g('G', 'G', 1, 2) == 0
+        assert g('G', 'G', 2, 3) == 0
+        assert g('G', 'G', 3, 4) == 1
+        assert g('G', '_', 4, 5) == 1
+        assert h.to_dense().sum() == 14
+        assert h.L == 3
+
+
+@pytest.mark.parametrize("kernel", [1, 2])
+@pytest.mark.parametrize("seed", range(8))
+def test_random_packed_bit_exact(c_oracle, seed, kernel):
+    rng = np.random.default_rng(500 + seed)
+    N = int(rng.integers(2, 200))
+    R = int(rng.integers(1, 3000))
+    mk = int(rng.integers(2, 40))
+    rank, off, codes = synth.random_packed(rng, N, R, mk, p_special=0.2, sort=bool(seed % 2))
+    W = max(1, min(mk, N) - 1) if seed % 3 else min(N + 1, 64)
+    ref, rt = c_oracle.ingest(rank, off, codes, N, W)
+    band, totals = _gpu_band(rank, off, codes, N, W, kernel)
+    assert totals == tuple(int(x) for x in rt)
+    assert np.array_equal(band, ref.astype(np.float32))
+
+
+@pytest.mark.parametrize("kernel", [1, 2])
+def test_edge_cases(c_oracle, kernel):
+    # empty input, reads with k<2, N=2 (start rule beats end rule), reads ending on the last SNP
+    cases = []
+    cases.append((np.zeros(0, np.int32), np.zeros(1, np.int64), np.zeros(0, np.uint8), 5, 3))
+    cases.append((np.array([0, 1, 2], np.int32), np.array([0, 1, 1, 2], np.int64), np.array([0, 1], np.uint8), 5, 3))
+    cases.append((np.array([0, 0], np.int32), np.array([0, 2, 4], np.int64), np.array([0, 1, 4, 2], np.uint8), 2, 1))
+    cases.append((np.array([0, 2, 3], np.int32), np.array([0, 5, 8, 10], np.int64),
+                  np.array([0, 1, 2, 3, 5, 6, 0, 4, 4, 1], np.uint8), 5, 4))
+    for rank, off, codes, N, W in cases:
+        ref, rt = c_oracle.ingest(rank, off, codes, N, W)
+        band, totals = _gpu_band(rank, off, codes, N, W, kernel)
+        assert totals == tuple(int(x) for x in rt)
+        assert np.array_equal(band, ref.astype(np.float32))
+
+
+def test_bad_reads_raise():
+    from gretel_b200 import _lib
+    from gretel_b200.hansel import Hansel, REF_SYMBOLS, REF_UNSYMBOLS
+    h = Hansel.init_matrix(REF_SYMBOLS, REF_UNSYMBOLS, 5, band_w=2)
+    with pytest.raises(_lib.HanselxError):
+        h.ingest_packed(np.array([4], np.int32), np.array([0, 3], np.int64), np.array([0, 1, 2], np.uint8))
+    h2 = Hansel.init_matrix(REF_SYMBOLS, REF_UNSYMBOLS, 5, band_w=1)
+    with pytest.raises(_lib.HanselxError):
+        h2.ingest_packed(np.array([0], np.int32), np.array([0, 3], np.int64), np.array([0, 1, 2], np.uint8))
+    h3 = Hansel.init_matrix(REF_SYMBOLS, REF_UNSYMBOLS, 5, band_w=4)
+    with pytest.raises(_lib.HanselxError):
+        h3.ingest_packed(np.array([0], np.int32), np.array([0, 3], np.int64), np.array([0, 9, 2], np.uint8))
+
+
+@pytest.mark.parametrize("name,n_reads", [("hiv", 200_000), ("metagenome", 300_000), ("ont", 600)])
+@pytest.mark.parametrize("kernel", [0, 1])
+def test_workloads_bit_exact(c_oracle, name, n_reads, kernel):
+    """Config 2 at full size, configs 3/4 at sizes the C oracle finishes in seconds."""
+    w = synth.scaled(synth.WORKLOADS[name], n_reads)
+    d = synth.generate(w)
+    W = d["max_k"] - 1
+    ref, rt = c_oracle.ingest(d["rank"], d["off"], d["codes"], w.n_snps, W)
+    band, totals = _gpu_band(d["rank"], d["off"], d["codes"], w.n_snps, W, kernel)
+    assert totals == tuple(int(x) for x in rt)
+    assert np.array_equal(band, ref.astype(np.float32))
+
+
+def test_scalar_surface_and_spill():
+    from gretel_b200.hansel import Hansel, REF_SYMBOLS, REF_UNSYMBOLS
+    h = Hansel.init_matrix(REF_SYMBOLS, REF_UNSYMBOLS, 6, band_w=2)
+    h.add_observation('A', 'C', 1, 2)
+    h.add_observation('A', 'C', 1, 2)
+    h.add_observation('A', 'C', 1, 5)           # outside the band -> host spill
+    h.add_observation('G', 'G', 3, 3)           # diagonal -> spill
+    assert h.get_observation('A', 'C', 1, 2) == 2
+    assert h.get_observation('A', 'C', 1, 5) == 1
+    assert h.get_observation('G', 'G', 3, 3) == 1
+    assert h.get_observation('T', 'T', 2, 3) == 0
+    assert h.reweight_observation('A', 'C', 1, 2, 0.25) == 0.5
+    assert h.get_observation('A', 'C', 1, 2) == 1.5
+    c = h.copy()
+    c.add_observation('A', 'C', 1, 2)
+    assert h.get_observation('A', 'C', 1, 2) == 1.5 and c.get_observation('A', 'C', 1, 2) == 2.5
+    d = h.to_dense()
+    assert d.shape == (7, 7, 8, 8) and d[0, 1, 1, 2] == 1.5 and d[0, 1, 1, 5] == 1
+
+
+def test_linearity_and_order_independence():
+    """Size-independent properties at a size the oracle is not asked to match:
+    ingest(A)+ingest(B) == ingest(A||B) == ingest(shuffled A||B); sum == crumbs+sentinels."""
+    from gretel_b200.hansel import Hansel, REF_SYMBOLS, REF_UNSYMBOLS
+    w = synth.scaled(synth.WORKLOADS["metagenome"], 2_000_000)
+    d = synth.generate(w)
+    W = d["max_k"] - 1
+    R = len(d["rank"])
+    whole, t_whole = _gpu_band(d["rank"], d["off"], d["codes"], w.n_snps, W)
+    h = Hansel.init_matrix(REF_SYMBOLS, REF_UNSYMBOLS, w.n_snps, band_w=W)
+    half = R // 2
+    off = d["off"]
+    h.ingest_packed(d["rank"][:half], off[:half + 1], d["codes"])
+    t2 = h.ingest_packed(d["rank"][half:], off[half:], d["codes"])
+    assert t2 == t_whole
+    assert np.array_equal(h.band(), whole)
+    assert float(whole.astype(np.float64).sum()) == t_whole[1] + t_whole[3]
+    # generic kernel on a permutation of the reads
+    rng = np.random.default_rng(3)
+    perm = rng.permutation(R)
+    k = np.diff(off)
+    poff = np.zeros(R + 1, np.int64)
+    np.cumsum(k[perm], out=poff[1:])
+    idx = np.repeat(off[:-1][perm], k[perm]) + (np.arange(poff[-1]) - np.repeat(poff[:-1], k[perm]))
+    pb, pt = _gpu_band(d["rank"][perm], poff, d["codes"][idx], w.n_snps, W)
+    assert pt == t_whole and np.array_equal(pb, whole)
