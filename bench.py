@@ -1,0 +1,380 @@
+#!/usr/bin/env python
+"""bench.py - SNP-pair observations/s into the Hansel matrix (+ haplotype recovery seconds).
+
+  python bench.py --gpus N --steps K --warmup W            (N>1: launched under torchrun)
+  python bench.py --impl reference ...                      (the reference's CPU way, timed on host cores)
+
+Workload = BASELINE.json configs[2]: synthetic metagenomic gene region, 10k SNPs,
+10M x 150 bp reads (the configuration the 1/2/4/8-GPU metric is quoted on; it fits one
+GPU).  A "step" is one complete ingestion of the batch: zero the counts, pair-expand
+every read into the banded matrix, and (N>1) sum the partial matrices with an NCCL
+integer all-reduce.  Weak scaling: every rank ingests its own 10M-read shard of the
+same metagenome (different reads, same strains/sites).
+
+`value`  : observations/s with the packed reads already resident in HBM.
+`e2e`    : the same metric through the public API (util.load_from_packed ->
+           hx_ingest_host) from pinned HOST buffers: H2D of the packed reads, kernel,
+           fold to the working matrix, D2H of the totals, every step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+from gretel_b200 import synth  # noqa: E402
+
+METRIC = "snp_pair_observations_per_sec"
+UNIT = "obs/s"
+
+
+def b_obs(k_mean):
+    """Algorithmic bytes per observation, SURVEY.md section 8(d): one uint32 counter
+    read-modify-write plus the read's amortised input."""
+    return 8.0 + (k_mean + 12.0) / (k_mean * (k_mean - 1.0) / 2.0)
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def workload_config(args, k_mean=None, n_reads=None):
+    w = synth.WORKLOADS[args.workload]
+    cfg = {"workload": "BASELINE.json configs[%d] %s: %d SNPs, %d x %s reads per GPU%s" % (
+        w.config, w.name, w.n_snps, args.reads or w.n_reads,
+        ("~%d bp ONT-like" % w.read_len) if w.long_reads else ("%d bp" % w.read_len),
+        "" if not args.reads or args.reads == w.n_reads else " (reduced by --reads)"),
+        "n_snps": w.n_snps, "reads_per_gpu": args.reads or w.n_reads, "seed": 20260000 + w.config + 1,
+        "l2_policy": "inputs larger than L2 (packed reads are streamed once per step)"}
+    if k_mean is not None:
+        cfg["mean_snps_per_read"] = round(k_mean, 3)
+    if n_reads is not None:
+        cfg["reads_with_2plus_snps"] = int(n_reads)
+    return cfg
+
+
+# ----------------------------------------------------------------------------------- reference arm
+def run_reference(args):
+    """The reference's own CPU implementation of the path (per-pair Python calls into a NumPy
+    array, forked workers over read chunks: gretel/util.py:242-286, 294-326), restated in
+    oracle/py_baseline.py because hanselx/pysam are not installable here."""
+    rank_env = int(os.environ.get("RANK", "0"))
+    if rank_env != 0:
+        return 0
+    from oracle import py_baseline as pb
+    cores = os.cpu_count() or 1
+    w = synth.WORKLOADS[args.workload]
+    # bounded sample: about 3 s of work per step on all cores (~1 M obs/s/core)
+    sample_reads = args.ref_sample or int(min(w.n_reads, 2_000_000, max(2000, 30_000 * cores)))
+    d = synth.generate(synth.scaled(w, sample_reads))
+    k = np.diff(d["off"])
+    W = d["max_k"] - 1
+    times, crumbs = [], 0
+    for it in range(args.warmup + args.steps):
+        crumbs, dt = pb.timed_ingest(d["rank"], d["off"], d["codes"], w.n_snps, W, n_procs=cores)
+        if it >= args.warmup:
+            times.append(dt)
+    total_t = float(sum(times))
+    value = crumbs * len(times) / total_t
+    sample = "%d of %d reads (%d observations) of the same workload, %d forked workers" % (
+        len(k), w.n_reads, crumbs, cores)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_t / len(times),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
+            "data": "synthetic", "config": workload_config(args, float(k.mean()), len(k)),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+# ----------------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import torch
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus %d needs torchrun (one process per GPU)" % args.gpus)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device; there is no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from gretel_b200 import dist as gdist, util
+    from gretel_b200.hansel import Hansel, REF_SYMBOLS, REF_UNSYMBOLS
+
+    w = synth.WORKLOADS[args.workload]
+    if args.reads:
+        w = synth.scaled(w, args.reads)
+    t0 = time.time()
+    d = synth.generate(w, shard=rank)
+    gen_s = time.time() - t0
+    N = w.n_snps
+    k = np.diff(d["off"])
+    R = len(k)
+    # band width must agree on every rank
+    W = d["max_k"] - 1
+    if world > 1:
+        tw = torch.tensor([W], device="cuda")
+        dist.all_reduce(tw, op=dist.ReduceOp.MAX)
+        W = int(tw.item())
+    n_obs_local = None
+
+    # device-resident inputs for `value`
+    dev = torch.device("cuda", local_rank)
+    t_rank = torch.from_numpy(d["rank"]).to(dev)
+    t_off = torch.from_numpy(d["off"]).to(dev)
+    t_codes = torch.from_numpy(d["codes"]).to(dev)
+    # pinned host inputs for `e2e`
+    p_rank = torch.from_numpy(d["rank"]).pin_memory()
+    p_off = torch.from_numpy(d["off"]).pin_memory()
+    p_codes = torch.from_numpy(d["codes"]).pin_memory()
+    h2d_bytes = p_rank.numel() * 4 + p_off.numel() * 8 + p_codes.numel()
+
+    h = Hansel.init_matrix(REF_SYMBOLS, REF_UNSYMBOLS, N, band_w=W, device=local_rank)
+    h.set_ingest_kernel(args.kernel)
+    h.counts_buffer()                      # allocate the pending counts outside the timed region
+    stream = torch.cuda.ExternalStream(h.stream, device=dev)
+
+    def step():
+        h.reset_counts()
+        h.ingest_device(t_rank.data_ptr(), t_off.data_ptr(), t_codes.data_ptr(), R)
+        if world > 1:
+            gdist.allreduce_counts(h)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    totals = h.ingest_totals()
+    n_obs_global = totals[1]               # crumbs of ALL ranks (totals are all-reduced too)
+    kernel_ms = []
+    launches0 = h.launch_count()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    t_wall0 = time.perf_counter()
+    with torch.cuda.stream(stream):
+        for i in range(args.steps):
+            ev[i][0].record(stream)
+            step()
+            ev[i][1].record(stream)
+    barrier()
+    wall_s = time.perf_counter() - t_wall0
+    clocks = sampler.stop() if rank == 0 else None
+    launches = h.launch_count() - launches0
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = float(sum(step_ms))
+    # kernel-only duration (events inside the library, on the launching stream) for the roofline
+    for _ in range(3):
+        h.reset_counts()
+        h.ingest_device(t_rank.data_ptr(), t_off.data_ptr(), t_codes.data_ptr(), R)
+        h.ingest_totals()
+        kernel_ms.append(h.kernel_ms("ingest"))
+    if world > 1:
+        tt = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        total_ms = float(tt.item())
+    value = n_obs_global * args.steps / (total_ms * 1e-3)
+
+    # ---- e2e through the public API with host buffers
+    def e2e_step():
+        hh = Hansel.init_matrix(REF_SYMBOLS, REF_UNSYMBOLS, N, band_w=W, device=local_rank)
+        hh.set_ingest_kernel(args.kernel)
+        hh.ingest_packed(p_rank.numpy(), p_off.numpy(), p_codes.numpy())
+        if world > 1:
+            gdist.allreduce_counts(hh)
+        s, c, v, _ = hh.ingest_totals()
+        hh.finalize()
+        util.set_totals(hh, s, c, v)
+        return hh
+
+    for _ in range(2):
+        e2e_step().close()
+    barrier()
+    e2e_steps = max(3, min(args.steps, 10))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        hh = e2e_step()
+        crumbs_e2e = hh.n_crumbs
+        hh.close()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        tt = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_s = float(tt.item())
+    e2e_value = crumbs_e2e * e2e_steps / e2e_s
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel (this rank's launch)
+    k_mean = float(k.mean())
+    local_obs = n_obs_global / world
+    kms = float(np.mean(kernel_ms))
+    bytes_per_launch = local_obs * b_obs(k_mean)
+    peak, peak_src = measured_peak_gbs()
+    achieved = bytes_per_launch / (kms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            tj = json.load(open(tpath))
+            key = "%s:%d:k%d" % (args.workload, R, args.kernel)
+            traffic = tj.get(key, tj.get(args.workload))
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": "ingestion (pair expansion)", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "kernel_ms": kms, "algorithmic_bytes_per_obs": b_obs(k_mean),
+                "obs_per_launch": local_obs}
+
+    # ---- CPU baseline: the reference's per-pair Python loop on a bounded sample, all cores
+    cpu = None
+    if not args.no_cpu_baseline:
+        from oracle import py_baseline as pb
+        cores = os.cpu_count() or 1
+        sample_reads = int(min(R, 1_000_000, max(2000, 15_000 * cores)))
+        lo = (R - sample_reads) // 2
+        sr, so = d["rank"][lo:lo + sample_reads], d["off"][lo:lo + sample_reads + 1]
+        c_cr, c_t = pb.timed_ingest(sr, so - so[0], d["codes"][so[0]:so[-1]], N, W, n_procs=cores)
+        cpu = {"value": c_cr / c_t, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": "%d consecutive reads (%d observations) from the middle of rank 0's shard, %d forked "
+                         "workers, oracle/py_baseline.py (per-pair Python calls as gretel/util.py:242-286)" % (
+                             sample_reads, c_cr, cores)}
+
+    # ---- secondary metric: haplotype recovery seconds on this matrix (rank 0, one GPU)
+    recovery = None
+    if args.recover_paths > 0:
+        s, c, v, _ = h.ingest_totals()
+        h.finalize()
+        util.set_totals(h, s, c, v)
+        orig = h.copy()
+        t0 = time.perf_counter()
+        paths, stats = h.recover_codes(orig, args.recover_paths, 0.01)
+        rec_s = time.perf_counter() - t0
+        recovery = {"haplotypes": int(len(paths)), "seconds": rec_s, "L": h.L, "n_snps": N,
+                    "us_per_site": (1e6 * rec_s / max(1, len(paths)) / N) if len(paths) else None}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "config": workload_config(args, k_mean, R),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes),
+                    "d2h_bytes_per_step": 32 + 4, "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps,
+                    "api": "gretel_b200.util.load_from_packed equivalent: Hansel.init_matrix + ingest_packed(host) "
+                           "[+ all-reduce] + finalize + totals"},
+            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+            "observations_per_step": int(n_obs_global), "wall_s_timed_region": wall_s,
+            "recovery": recovery, "synth_seconds": gen_s, "band_w": W,
+            "ingest_kernel": args.kernel}
+    print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="metagenome", choices=sorted(synth.WORKLOADS))
+    ap.add_argument("--reads", type=int, default=0, help="reads per GPU (default: the workload's full size)")
+    ap.add_argument("--kernel", type=int, default=0, help="ingestion kernel: 0 auto, 1 generic, 2 bit-sliced")
+    ap.add_argument("--recover-paths", type=int, default=5)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-sample", type=int, default=0)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -33,6 +33,7 @@ SIGNATURES = {
     "hx_ingest_totals": (_int, [_p, _p]),
     "hx_counts_buffer": (_int, [_p, _pp, C.POINTER(_i64), _pp, C.POINTER(_i64)]),
     "hx_finalize_counts": (_int, [_p]),
+    "hx_reset_counts": (_int, [_p]),
     "hx_add_observation": (_int, [_p, _int, _int, _i32, _i32, _flt]),
     "hx_get_observation": (_int, [_p, _int, _int, _i32, _i32, C.POINTER(_flt)]),
     "hx_reweight_observation": (_int, [_p, _int, _int, _i32, _i32, _dbl, C.POINTER(_dbl)]),

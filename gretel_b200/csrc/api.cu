@@ -268,6 +268,15 @@ int hx_counts_buffer(hx_matrix *h, void **d_counts, int64_t *n_u32, void **d_tot
     return HX_OK;
 }
 
+int hx_reset_counts(hx_matrix *h) {
+    HX_CHECK_ARG(h);
+    HX_CUDA(cudaSetDevice(h->device));
+    if (h->cnt) HX_CUDA(cudaMemsetAsync(h->cnt, 0, sizeof(uint32_t) * (size_t)h->band_elems, h->stream));
+    HX_CUDA(cudaMemsetAsync(h->d_totals, 0, 8 * sizeof(unsigned long long), h->stream));
+    HX_CUDA(cudaMemsetAsync(h->d_err, 0, sizeof(int), h->stream));
+    return HX_OK;
+}
+
 int hx_finalize_counts(hx_matrix *h) {
     HX_CHECK_ARG(h);
     if (!h->cnt) return HX_OK;

@@ -1,17 +1,29 @@
 // K1: pair-expansion ingestion of packed reads into the banded Hansel counts.
 // Replaces gretel/util.py:226-286 (+ Hansel.add_observation) of the reference.
 //
-// Two kernels:
-//   k1_pairs_red    generic: one warp per read, lanes over the linearised (i,j)
-//                   triangle, one fire-and-forget integer reduction (RED) per pair
-//                   into the L2-resident band.  Any read order, any k.
-//   k1_bitsliced    (see below) rank-sorted short reads: 32 reads per warp are
-//                   transposed into per-site allele bit-planes with warp ballots; a
-//                   pair of sites then costs AND+POPC per (a,b) instead of one atomic
-//                   per read, accumulated in registers and flushed once per tile.
+// Two kernels (chosen per launch, see hx_launch_ingest):
+//
+//   k1_pairs_red   generic: one warp per read, lanes over the linearised (i,j) triangle,
+//                  one fire-and-forget integer reduction (RED) per pair into the band.
+//                  Any read order, any k.  Bound by the chip-wide RED rate
+//                  (measured 187 G/s on B200, tools/microbench.cu).
+//
+//   k1_bitsliced   rank-sorted reads with at most BS_KMAX SNPs.  Reads that share a rank
+//                  (same first SNP) cover the same site pairs, so 32 of them are
+//                  transposed with warp ballots into per-site allele bit-planes
+//                  (A,C,G,T masks over the 32 reads); a site pair (t1,t2) then costs
+//                  16 x (AND, POPC, ADD) for 32 reads instead of 32 atomics, accumulated
+//                  in registers by the thread that owns the pair (warp-aggregation by
+//                  construction).  Per-CTA the counts are privatised in a sliding
+//                  shared-memory tile (ring of band rows); a row is flushed to HBM with
+//                  REDs once no later read of the CTA can touch it.  Rare alleles
+//                  (N, -, _), sentinels and totals are handled per read on the side.
 #include "hx_internal.cuh"
 
 namespace {
+
+constexpr int BS_KMAX = 56;      // widest read (in SNPs) the bit-sliced kernel takes
+constexpr int BS_GB = 32;        // groups (of 32 reads) per build/accumulate batch
 
 __device__ __forceinline__ unsigned long long warp_sum_ull(unsigned long long v) {
 #pragma unroll
@@ -20,7 +32,6 @@ __device__ __forceinline__ unsigned long long warp_sum_ull(unsigned long long v)
 }
 
 // Block-level accumulation of the four ingestion totals into global memory.
-template <int BLOCK>
 __device__ __forceinline__ void flush_totals(unsigned long long t0, unsigned long long t1,
                                              unsigned long long t2, unsigned long long t3,
                                              unsigned long long *totals) {
@@ -38,7 +49,11 @@ __device__ __forceinline__ void flush_totals(unsigned long long t0, unsigned lon
     if (threadIdx.x < 4 && sh[threadIdx.x]) atomicAdd(&totals[threadIdx.x], sh[threadIdx.x]);
 }
 
-// The per-pair rules of util.py:254-281 for one (i,j) of one read.
+__device__ __forceinline__ bool sym_valid_from(unsigned a) {   // util.py:258
+    return a != HX_SYM_N && a != HX_SYM_GAP && a <= 6;
+}
+
+// The per-pair rules of util.py:254-281 for one (i,j) of one read (sentinels included).
 __device__ __forceinline__ void add_pair(uint32_t *__restrict__ cnt, int N, int64_t W, int rk, int i,
                                          int j, unsigned a, unsigned b, unsigned long long &sent) {
     const int pi = rk + i + 1, pj = rk + j + 1;
@@ -52,12 +67,44 @@ __device__ __forceinline__ void add_pair(uint32_t *__restrict__ cnt, int N, int6
     }
 }
 
+// One whole read, cooperatively by the calling warp (all 32 lanes converged).
+__device__ __forceinline__ void warp_read_generic(const uint8_t *__restrict__ c, int k, int rk, int N,
+                                                  int64_t W, uint32_t *__restrict__ cnt,
+                                                  unsigned long long &t_crumbs, unsigned long long &t_cov,
+                                                  unsigned long long &t_sent, int *err) {
+    const int lane = threadIdx.x & 31;
+    for (int t = lane; t < k; t += 32) {
+        const unsigned a = c[t];
+        if (a > 6) atomicOr(err, 2);
+        const bool v = sym_valid_from(a);
+        t_cov += v;                                                             // util.py:239
+        t_crumbs += v ? (unsigned)(k - 1 - t) : 0u;                             // pairs with a valid first allele
+    }
+    const int64_t npairs = (int64_t)k * (k - 1) / 2;
+    const int m = 2 * k - 1;
+    for (int64_t q = lane; q < npairs; q += 32) {
+        // row-major upper triangle: row i starts at i*(m-i)/2
+        const float disc = (float)((int64_t)m * m - 8 * q);
+        int i = (int)(((float)m - sqrtf(disc)) * 0.5f);
+        i = max(0, min(i, k - 2));
+        while ((int64_t)(i + 1) * (m - (i + 1)) / 2 <= q) ++i;
+        while ((int64_t)i * (m - i) / 2 > q) --i;
+        const int j = i + 1 + (int)(q - (int64_t)i * (m - i) / 2);
+        const unsigned a = c[i], b = c[j];
+        if (!sym_valid_from(a) || b > 6) continue;
+        add_pair(cnt, N, W, rk, i, j, a, b, t_sent);
+    }
+}
+
 template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK)
 k1_pairs_red(const int32_t *__restrict__ rank, const int64_t *__restrict__ off,
              const uint8_t *__restrict__ codes, int64_t n_reads, int N, int W,
              uint32_t *__restrict__ cnt, unsigned long long *__restrict__ totals,
-             int *__restrict__ err) {
+             int *__restrict__ err, const int *__restrict__ sorted_flag, int run_if_sorted) {
+    // sorted_flag: 1 when the reads are rank-sorted.  run_if_sorted = 0 makes this launch the
+    // fallback that only runs when the bit-sliced kernel declined the input.
+    if (!run_if_sorted && *sorted_flag) return;
     const int lane = threadIdx.x & 31;
     const int64_t nwarps = (int64_t)gridDim.x * (BLOCK / 32);
     unsigned long long t_slices = 0, t_crumbs = 0, t_cov = 0, t_sent = 0;
@@ -70,32 +117,239 @@ k1_pairs_red(const int32_t *__restrict__ rank, const int64_t *__restrict__ off,
             if (lane == 0) atomicOr(err, 1);
             continue;
         }
-        const int k = (int)k64;
-        const uint8_t *__restrict__ c = codes + o;
         if (lane == 0) t_slices++;
-        for (int t = lane; t < k; t += 32) {
-            const unsigned a = c[t];
-            if (a > 6) atomicOr(err, 2);
-            const bool v = (a != HX_SYM_N && a != HX_SYM_GAP && a <= 6);
-            t_cov += v;                                                         // util.py:239
-            t_crumbs += v ? (unsigned)(k - 1 - t) : 0u;                         // pairs with valid a
-        }
-        const int64_t npairs = (int64_t)k * (k - 1) / 2;
-        const int m = 2 * k - 1;
-        for (int64_t q = lane; q < npairs; q += 32) {
-            // row-major upper triangle: row i starts at i*(m-i)/2
-            const float disc = (float)((int64_t)m * m - 8 * q);
-            int i = (int)(((float)m - sqrtf(disc)) * 0.5f);
-            i = max(0, min(i, k - 2));
-            while ((int64_t)(i + 1) * (m - (i + 1)) / 2 <= q) ++i;
-            while ((int64_t)i * (m - i) / 2 > q) --i;
-            const int j = i + 1 + (int)(q - (int64_t)i * (m - i) / 2);
-            const unsigned a = c[i], b = c[j];
-            if (a == HX_SYM_N || a == HX_SYM_GAP || a > 6 || b > 6) continue;   // util.py:258
-            add_pair(cnt, N, W, rk, i, j, a, b, t_sent);
+        warp_read_generic(codes + o, (int)k64, rk, N, W, cnt, t_crumbs, t_cov, t_sent, err);
+    }
+    flush_totals(t_slices, t_crumbs, t_cov, t_sent, totals);
+}
+
+__global__ void k_check_sorted(const int32_t *__restrict__ rank, int64_t n_reads, int *__restrict__ flag) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i + 1 < n_reads && rank[i] > rank[i + 1]) *flag = 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Bit-sliced kernel.
+//
+// Shared memory (dynamic):
+//   tile   [(kmax+1) rows][(kmax-1) cells][16 u32]   ring of band rows; row = pj % (kmax+1),
+//          cell = d-1 (d = pj-pi), 16 = (a,b) in ACGT x ACGT.
+//   planes [BS_GB groups][kmax sites] uint4           A,C,G,T masks over the group's 32 reads
+//   gk     [BS_GB] int                                 widest read of each group
+//
+// Thread p owns site pair (t1,t2), t2-major (p = t2(t2-1)/2 + t1), relative to the rank
+// of the current run of reads, so the pairs covered by reads of k SNPs are the prefix
+// p < k(k-1)/2 and warps stay converged.
+struct BsLayout {
+    int rows, cells;           // kmax+1, kmax-1
+    __host__ __device__ size_t tile_u4() const { return (size_t)rows * cells * 4; }
+    __host__ __device__ size_t bytes(int kmax) const {
+        return tile_u4() * 16 + (size_t)BS_GB * kmax * 16 + BS_GB * sizeof(int) + 64;
+    }
+};
+
+__device__ __forceinline__ void bs_flush_rows(uint32_t *tile32, int rows, int cells, int64_t pj_lo,
+                                              int64_t pj_hi, int64_t W, uint32_t *__restrict__ cnt) {
+    // rows pj in [pj_lo, pj_hi]: add every non-zero counter to HBM, then clear it.
+    const int per_row = cells * 16;
+    const int64_t total = (pj_hi - pj_lo + 1) * per_row;
+    for (int64_t w = threadIdx.x; w < total; w += blockDim.x) {
+        const int64_t pj = pj_lo + w / per_row;
+        const int rem = (int)(w % per_row);
+        const int d = rem / 16 + 1, ab = rem % 16;
+        uint32_t *p = tile32 + ((size_t)(pj % rows) * cells + (d - 1)) * 16 + ab;
+        const uint32_t v = *p;
+        if (v) {
+            atomicAdd(cnt + hx_cell_off(W, pj - d, pj) + (ab >> 2) * HX_NSYM + (ab & 3), v);
+            *p = 0;
         }
     }
-    flush_totals<BLOCK>(t_slices, t_crumbs, t_cov, t_sent, totals);
+}
+
+template <int NP, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB)
+k1_bitsliced(const int32_t *__restrict__ rank, const int64_t *__restrict__ off,
+             const uint8_t *__restrict__ codes, int64_t n_reads, int N, int W, int kmax,
+             uint32_t *__restrict__ cnt, unsigned long long *__restrict__ totals,
+             int *__restrict__ err, const int *__restrict__ sorted_flag) {
+    extern __shared__ uint4 smem4[];
+    if (!*sorted_flag) return;                       // the generic fallback launch takes over
+    const int rows = kmax + 1, cells = kmax - 1;
+    uint4 *tile = smem4;
+    uint32_t *tile32 = reinterpret_cast<uint32_t *>(tile);
+    uint4 *planes = tile + (size_t)rows * cells * 4;
+    int *gk = reinterpret_cast<int *>(planes + (size_t)BS_GB * kmax);
+    __shared__ int64_t s_run_hi;
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int64_t per = (n_reads + gridDim.x - 1) / gridDim.x;
+    const int64_t lo = (int64_t)blockIdx.x * per;
+    const int64_t hi = lo + per < n_reads ? lo + per : n_reads;
+    if (lo >= hi) return;
+
+    for (size_t w = threadIdx.x; w < (size_t)rows * cells * 4; w += blockDim.x) tile[w] = make_uint4(0, 0, 0, 0);
+
+    // this thread's site pair(s)
+    int t1[NP], t2[NP];
+#pragma unroll
+    for (int q = 0; q < NP; ++q) {
+        const int p = threadIdx.x + q * blockDim.x;
+        int b = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)p)) * 0.5f);
+        while (b * (b - 1) / 2 > p) --b;
+        while ((b + 1) * b / 2 <= p) ++b;
+        t2[q] = b;
+        t1[q] = p - b * (b - 1) / 2;
+    }
+    unsigned long long t_slices = 0, t_crumbs = 0, t_cov = 0, t_sent = 0;
+    int64_t flushed_upto = (int64_t)rank[lo] + 1;    // rows pj <= flushed_upto hold nothing
+    int64_t cur = lo;
+    __syncthreads();
+
+    while (cur < hi) {
+        const int r = rank[cur];
+        // rows pj <= r+1 can no longer be touched by this CTA (reads of rank >= r start at pj = r+2)
+        if ((int64_t)r + 1 > flushed_upto) {
+            const int64_t last = min((int64_t)r + 1, flushed_upto + rows - 2);
+            bs_flush_rows(tile32, rows, cells, flushed_upto + 1, last, W, cnt);
+            flushed_upto = (int64_t)r + 1;
+        }
+        if (threadIdx.x == 0) {                      // end of the run of reads with rank r
+            int64_t a = cur, b = hi;
+            while (a < b) {
+                const int64_t m = (a + b) >> 1;
+                if (rank[m] <= r) a = m + 1; else b = m;
+            }
+            s_run_hi = a;
+        }
+        __syncthreads();
+        const int64_t run_hi = s_run_hi;
+        const int64_t ngroups = (run_hi - cur + 31) / 32;
+        const bool run_ok = r >= 0 && r < N;
+
+        uint32_t acc[NP][16];
+#pragma unroll
+        for (int q = 0; q < NP; ++q)
+#pragma unroll
+            for (int x = 0; x < 16; ++x) acc[q][x] = 0;
+
+        for (int64_t g0 = 0; g0 < ngroups; g0 += BS_GB) {
+            const int nb = (int)min((int64_t)BS_GB, ngroups - g0);
+            // ---- build: one warp per group of 32 reads -------------------------------------
+            for (int g = warp; g < nb; g += nwarps) {
+                const int64_t idx = cur + (g0 + g) * 32 + lane;
+                int64_t o = 0;
+                int k = 0;
+                if (idx < run_hi) {
+                    o = off[idx];
+                    const int64_t k64 = off[idx + 1] - o;
+                    if (k64 >= 2) {
+                        if (!run_ok || (int64_t)r + k64 > N || k64 - 1 > W) atomicOr(err, 1);
+                        else k = (int)k64;
+                    }
+                }
+                const bool wide = k > kmax;          // too wide for the tile: generic path below
+                const int kb = wide ? 0 : k;
+                t_slices += k >= 2;
+                int kg = kb;
+#pragma unroll
+                for (int s = 16; s > 0; s >>= 1) kg = max(kg, __shfl_xor_sync(0xffffffffu, kg, s));
+                if (lane == 0) gk[g] = kg;
+                const uint8_t *__restrict__ c = codes + o;
+                bool has_rare = false;
+                for (int t = 0; t < kg; ++t) {
+                    unsigned a = 255;
+                    if (t < kb) a = c[t];
+                    if (t < kb && a > 6) { atomicOr(err, 2); a = 255; }
+                    const bool pv = a < 4;
+                    const unsigned v = __ballot_sync(0xffffffffu, pv);
+                    const unsigned b0 = __ballot_sync(0xffffffffu, pv && (a & 1));
+                    const unsigned b1 = __ballot_sync(0xffffffffu, pv && (a & 2));
+                    if (lane == 0)
+                        planes[(size_t)g * kmax + t] = make_uint4(v & ~b1 & ~b0, v & ~b1 & b0, v & b1 & ~b0, v & b1 & b0);
+                    if (t < kb) {
+                        const bool vf = sym_valid_from(a);
+                        t_cov += vf;
+                        t_crumbs += vf ? (unsigned)(kb - 1 - t) : 0u;
+                        has_rare |= (a >= 4 && a <= 6);
+                    }
+                }
+                if (kb >= 2) {
+                    // start sentinel (util.py:262-266) / end sentinel (:271-275); the start rule wins
+                    const unsigned a0 = c[0], ap = c[kb - 2], bl = c[kb - 1];
+                    if (r == 0 && sym_valid_from(a0)) {
+                        atomicAdd(cnt + hx_cell_off(W, 0, 1) + HX_SYM_GAP * HX_NSYM + a0, 1u);
+                        t_sent++;
+                    }
+                    if (r + kb == N && sym_valid_from(ap) && bl <= 6 && !(kb == 2 && r == 0)) {
+                        atomicAdd(cnt + hx_cell_off(W, N, N + 1) + bl * HX_NSYM + HX_SYM_GAP, 1u);
+                        t_sent++;
+                    }
+                    if (has_rare) {
+                        // pairs with a rare allele (N, -, _) on either side are not in the planes
+                        for (int i = 0; i < kb; ++i) {
+                            const unsigned a = c[i];
+                            if (a < 4 || a > 6) continue;
+                            if (a == HX_SYM_DEL)                 // '-' is a valid first allele
+                                for (int j = i + 1; j < kb; ++j)
+                                    if (c[j] <= 6)
+                                        atomicAdd(cnt + hx_cell_off(W, r + i + 1, r + j + 1) + a * HX_NSYM + c[j], 1u);
+                            for (int i2 = 0; i2 < i; ++i2)       // common first allele, rare second
+                                if (c[i2] < 4)
+                                    atomicAdd(cnt + hx_cell_off(W, r + i2 + 1, r + i + 1) + c[i2] * HX_NSYM + a, 1u);
+                        }
+                    }
+                }
+                // reads wider than the tile: whole warp, one read at a time
+                unsigned wmask = __ballot_sync(0xffffffffu, wide);
+                while (wmask) {
+                    const int src = __ffs(wmask) - 1;
+                    wmask &= wmask - 1;
+                    const int64_t o2 = __shfl_sync(0xffffffffu, o, src);
+                    const int k2 = __shfl_sync(0xffffffffu, k, src);
+                    warp_read_generic(codes + o2, k2, r, N, W, cnt, t_crumbs, t_cov, t_sent, err);
+                }
+            }
+            __syncthreads();
+            // ---- accumulate: each thread its own site pair over the batch's groups --------
+#pragma unroll
+            for (int q = 0; q < NP; ++q) {
+                const int a1 = t1[q], a2 = t2[q];
+                for (int g = 0; g < nb; ++g) {
+                    if (a2 < gk[g]) {
+                        const uint4 m1 = planes[(size_t)g * kmax + a1];
+                        const uint4 m2 = planes[(size_t)g * kmax + a2];
+                        const unsigned x1[4] = {m1.x, m1.y, m1.z, m1.w};
+                        const unsigned x2[4] = {m2.x, m2.y, m2.z, m2.w};
+#pragma unroll
+                        for (int a = 0; a < 4; ++a)
+#pragma unroll
+                            for (int b = 0; b < 4; ++b) acc[q][a * 4 + b] += __popc(x1[a] & x2[b]);
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        // ---- add this run's counts into the sliding tile (each cell has one owner thread) ----
+#pragma unroll
+        for (int q = 0; q < NP; ++q) {
+            if (t2[q] < kmax) {
+                const int64_t pj = (int64_t)r + t2[q] + 1;
+                const int d = t2[q] - t1[q];
+                uint4 *cell = tile + ((size_t)(pj % rows) * cells + (d - 1)) * 4;
+#pragma unroll
+                for (int x = 0; x < 4; ++x) {
+                    uint4 v = cell[x];
+                    v.x += acc[q][4 * x + 0]; v.y += acc[q][4 * x + 1];
+                    v.z += acc[q][4 * x + 2]; v.w += acc[q][4 * x + 3];
+                    cell[x] = v;
+                }
+            }
+        }
+        cur = run_hi;
+        __syncthreads();
+    }
+    bs_flush_rows(tile32, rows, cells, flushed_upto + 1, flushed_upto + rows - 1, W, cnt);
+    flush_totals(t_slices, t_crumbs, t_cov, t_sent, totals);
 }
 
 }  // namespace
@@ -105,13 +359,53 @@ int hx_launch_ingest(hx_matrix *h, const int32_t *d_rank, const int64_t *d_off,
     if (n_reads <= 0) return HX_OK;
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
-    constexpr int BLOCK = 256;
-    int64_t want = (n_reads + (BLOCK / 32) - 1) / (BLOCK / 32);
-    int grid = (int)(want < (int64_t)sms * 8 ? want : (int64_t)sms * 8);
+    int *sorted_flag = h->d_flags + 4;
+    constexpr int GBLOCK = 256;
+    const int64_t gwant = (n_reads + (GBLOCK / 32) - 1) / (GBLOCK / 32);
+    const int ggrid = (int)(gwant < (int64_t)sms * 8 ? gwant : (int64_t)sms * 8);
+
+    // crumbs in a read are all distinct cells, so W+1 bounds the SNPs per read
+    const int kmax = h->W + 1;
+    const bool bs_possible = kmax >= 2 && kmax <= BS_KMAX;
+    const bool use_bs = h->ingest_kernel == 2 ? bs_possible : (h->ingest_kernel == 0 && bs_possible);
+
     HX_CUDA(cudaEventRecord(h->ev0, h->stream));
-    k1_pairs_red<BLOCK><<<grid, BLOCK, 0, h->stream>>>(d_rank, d_off, d_codes, n_reads, h->N, h->W,
-                                                       h->cnt, h->d_totals, h->d_err);
-    h->launches++;
+    if (!use_bs) {
+        k1_pairs_red<GBLOCK><<<ggrid, GBLOCK, 0, h->stream>>>(d_rank, d_off, d_codes, n_reads, h->N, h->W, h->cnt,
+                                                              h->d_totals, h->d_err, sorted_flag, 1);
+        h->launches++;
+    } else {
+        HX_CUDA(cudaMemsetAsync(sorted_flag, 1, sizeof(int), h->stream));     // non-zero = sorted
+        k_check_sorted<<<(unsigned)((n_reads + 255) / 256), 256, 0, h->stream>>>(d_rank, n_reads, sorted_flag);
+        BsLayout lay{kmax + 1, kmax - 1};
+        const size_t smem = lay.bytes(kmax);
+        const int npairs = kmax * (kmax - 1) / 2;
+        const int np = npairs > 1024 ? 2 : 1;
+        int block = ((npairs + np - 1) / np + 31) / 32 * 32;
+        if (block < 64) block = 64;
+        if (block > 1024) block = 1024;
+#define HX_BS_LAUNCH(NP_, MAXT_, MINB_)                                                                       \
+    do {                                                                                                       \
+        auto kern = k1_bitsliced<NP_, MAXT_, MINB_>;                                                           \
+        HX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));           \
+        int occ = 1;                                                                                           \
+        HX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, block, smem));                       \
+        if (occ < 1) occ = 1;                                                                                  \
+        int64_t grid = (int64_t)sms * occ;                                                                     \
+        const int64_t max_useful = (n_reads + 255) / 256;   /* no thinner than 256 reads per CTA */            \
+        if (grid > max_useful) grid = max_useful;                                                              \
+        kern<<<(unsigned)grid, block, smem, h->stream>>>(d_rank, d_off, d_codes, n_reads, h->N, h->W, kmax,    \
+                                                         h->cnt, h->d_totals, h->d_err, sorted_flag);          \
+    } while (0)
+        if (np == 2) HX_BS_LAUNCH(2, 1024, 1);
+        else if (block > 512) HX_BS_LAUNCH(1, 1024, 1);
+        else HX_BS_LAUNCH(1, 512, 2);
+#undef HX_BS_LAUNCH
+        // fallback for unsorted input: runs only when the flag says the bit-sliced kernel declined
+        k1_pairs_red<GBLOCK><<<ggrid, GBLOCK, 0, h->stream>>>(d_rank, d_off, d_codes, n_reads, h->N, h->W, h->cnt,
+                                                              h->d_totals, h->d_err, sorted_flag, 0);
+        h->launches += 3;
+    }
     HX_CUDA(cudaGetLastError());
     HX_CUDA(cudaEventRecord(h->ev1, h->stream));
     h->ev_rec = true;

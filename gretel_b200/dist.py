@@ -1,0 +1,71 @@
+"""Multi-GPU ingestion: reads shard naturally (the matrix is a sum over reads), so each
+GPU builds a partial integer band from its slice of the rank-sorted reads and the
+partials are summed with one integer all-reduce (NCCL over NVLink; gloo in CPU tests).
+This replaces the reference's fork-shared matrix written by ``n_threads`` window workers
+(gretel/util.py:294-326).  Recovery is sequential across haplotypes and runs on one GPU
+(every rank holds the full matrix after the all-reduce; rank 0 recovers).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def shard_bounds(off, world_size):
+    """Split reads into ``world_size`` contiguous chunks balanced by pair count
+    sum k(k-1)/2 (not by read count).  Returns int64[world_size+1] read indices."""
+    off = np.asarray(off, dtype=np.int64)
+    k = np.diff(off)
+    work = np.concatenate([[0], np.cumsum(k * (k - 1) // 2)])
+    total = work[-1]
+    targets = (total * np.arange(1, world_size)) // world_size
+    cuts = np.searchsorted(work, targets, side="left")
+    return np.concatenate([[0], cuts, [len(k)]]).astype(np.int64)
+
+
+def take_shard(rank, off, codes, lo, hi):
+    """Slice reads [lo,hi) without copying codes (offsets stay absolute)."""
+    return rank[lo:hi], off[lo:hi + 1], codes
+
+
+class _DevBuf:
+    """Expose a raw device pointer to torch through __cuda_array_interface__."""
+
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+
+
+def allreduce_counts(hansel, group=None):
+    """Sum the pending integer counts and totals of ``hansel`` across ranks, in place."""
+    import torch
+    import torch.distributed as dist
+    cptr, cn, tptr, tn = hansel.counts_buffer()
+    dev = torch.device("cuda", hansel.device)
+    with torch.cuda.device(dev):
+        s = torch.cuda.ExternalStream(hansel.stream, device=dev)
+        with torch.cuda.stream(s):
+            counts = torch.as_tensor(_DevBuf(cptr, cn, "<i4"), device=dev)      # uint32 sums are exact mod 2^32
+            totals = torch.as_tensor(_DevBuf(tptr, tn, "<i8"), device=dev)
+            dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=group)
+            dist.all_reduce(totals, op=dist.ReduceOp.SUM, group=group)
+
+
+def load_from_packed_sharded(rank, off, codes, n_snps, band_w, world_size=None, my_rank=None, device=None,
+                             presharded=False, group=None):
+    """Every rank calls this with the same packed reads (or, with ``presharded``, its own
+    slice); returns the full Hansel on every rank."""
+    import torch.distributed as dist
+    from . import util
+    from .hansel import Hansel, REF_SYMBOLS, REF_UNSYMBOLS
+    world_size = dist.get_world_size(group) if world_size is None else world_size
+    my_rank = dist.get_rank(group) if my_rank is None else my_rank
+    if not presharded:
+        b = shard_bounds(off, world_size)
+        rank, off, codes = take_shard(rank, off, codes, int(b[my_rank]), int(b[my_rank + 1]))
+    h = Hansel.init_matrix(REF_SYMBOLS, REF_UNSYMBOLS, n_snps, band_w=band_w, device=device)
+    h.ingest_packed(rank, off, codes)
+    if world_size > 1:
+        allreduce_counts(h, group=group)
+    slices, crumbs, covered, _ = h.ingest_totals()
+    h.finalize()
+    return util.set_totals(h, slices, crumbs, covered)

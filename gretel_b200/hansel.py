@@ -147,6 +147,15 @@ class Hansel:
         _lib.check(self._lib.hx_counts_buffer(self._h, C.byref(a), C.byref(na), C.byref(b), C.byref(nb)))
         return a.value, na.value, b.value, nb.value
 
+    def ingest_device(self, d_rank_ptr, d_off_ptr, d_codes_ptr, n_reads):
+        """Asynchronous ingestion of packed reads already resident on this GPU (raw device pointers)."""
+        _lib.check(self._lib.hx_ingest_device(self._h, d_rank_ptr, d_off_ptr, d_codes_ptr, int(n_reads)))
+        self._touch()
+
+    def reset_counts(self):
+        _lib.check(self._lib.hx_reset_counts(self._h))
+        self._touch()
+
     def finalize(self):
         _lib.check(self._lib.hx_finalize_counts(self._h))
         self._touch()

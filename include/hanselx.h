@@ -84,6 +84,8 @@ int hx_counts_buffer(hx_matrix *h, void **d_counts, int64_t *n_u32, void **d_tot
 /* Fold the integer counts into the float32 working matrix used by everything below
  * (util.py:329-333 happens in the caller from the totals). */
 int hx_finalize_counts(hx_matrix *h);
+/* Zero the pending integer counts and the totals (start a new ingestion job). */
+int hx_reset_counts(hx_matrix *h);
 
 /* ---- scalar Hansel surface ------------------------------------------------------- */
 /* Hansel.add_observation(a,b,i,j)                      gretel/util.py:266-286 */

@@ -117,7 +117,7 @@ def test_hole_reported():
     off = np.array([0, 2, 4], np.int64)
     codes = np.array([0, 1, 2, 3], np.uint8)          # sites 1,2 and 4,5 bridged; site 3 is not
     h = _mk(rank, off, codes, 5, 6)
-    assert gretel.gap_check(h, 5) == [2, 3, 5]
+    assert gretel.gap_check(h, 5) == [2, 3]      # site 5 carries the end sentinel (util.py:271-275)
     assert gretel.generate_path(5, h, h.copy()) == (None, None, None)
     its, paths = gretel.recover(h, 5, max_paths=3)
     assert its == [] and paths == {}
