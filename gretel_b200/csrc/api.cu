@@ -59,6 +59,7 @@ void free_all(hx_matrix *h) {
     if (h->d_site) cudaFree(h->d_site);
     if (h->d_partials) cudaFree(h->d_partials);
     if (h->d_flags) cudaFree(h->d_flags);
+    if (h->d_run_end) cudaFree(h->d_run_end);
     if (h->d_misc) cudaFree(h->d_misc);
     if (h->h_pinned) cudaFreeHost(h->h_pinned);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -116,6 +117,7 @@ int hx_create(int32_t n_snps, int32_t band_w, int32_t device, hx_matrix **out) {
     HX_TRY(cudaMalloc(&h->d_flags, 8 * sizeof(int)));
     HX_TRY(cudaMemsetAsync(h->d_flags, 0, 8 * sizeof(int), h->stream));
     HX_TRY(cudaMalloc(&h->d_misc, 32 * sizeof(double)));
+    HX_TRY(cudaMalloc(&h->d_run_end, sizeof(int64_t) * ((size_t)n_snps + 2)));
     HX_TRY(cudaMallocHost(&h->h_pinned, 256));
     HX_TRY(cudaStreamSynchronize(h->stream));
 #undef HX_TRY

@@ -38,6 +38,7 @@ struct hx_matrix {
     double *d_partials;              // block partials of the reweight reduction
     int64_t cap_partials;
     int *d_flags;                    // [0] hole site / abort flag, [1..] misc
+    int64_t *d_run_end;              // (N+1) end (exclusive) of the run of reads with each rank
     double *d_misc;                  // small outputs (weights etc.)
     void *h_pinned;                  // small pinned host buffer for D2H of scalars
     int ingest_kernel;

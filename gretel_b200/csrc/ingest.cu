@@ -123,9 +123,20 @@ k1_pairs_red(const int32_t *__restrict__ rank, const int64_t *__restrict__ off,
     flush_totals(t_slices, t_crumbs, t_cov, t_sent, totals);
 }
 
-__global__ void k_check_sorted(const int32_t *__restrict__ rank, int64_t n_reads, int *__restrict__ flag) {
+// Pre-pass over the rank array: clears *flag when the reads are not rank-sorted and records
+// where the run of reads of each rank ends (exclusive), so the main kernel never searches.
+__global__ void k_prepass(const int32_t *__restrict__ rank, int64_t n_reads, int N, int *__restrict__ flag,
+                          int64_t *__restrict__ run_end) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i + 1 < n_reads && rank[i] > rank[i + 1]) *flag = 0;
+    if (i >= n_reads) return;
+    const int r = rank[i];
+    if (i + 1 < n_reads) {
+        const int r2 = rank[i + 1];
+        if (r > r2) *flag = 0;
+        if (r != r2 && r >= 0 && r <= N) run_end[r] = i + 1;
+    } else if (r >= 0 && r <= N) {
+        run_end[r] = n_reads;
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -136,50 +147,98 @@ __global__ void k_check_sorted(const int32_t *__restrict__ rank, int64_t n_reads
 //          cell = d-1 (d = pj-pi), 16 = (a,b) in ACGT x ACGT.
 //   planes [BS_GB groups][kmax sites] uint4           A,C,G,T masks over the group's 32 reads
 //   gk     [BS_GB] int                                 widest read of each group
+//   rareq  [BS_GB*32] int                              reads of the batch holding N, - or _
 //
 // Thread p owns site pair (t1,t2), t2-major (p = t2(t2-1)/2 + t1), relative to the rank
 // of the current run of reads, so the pairs covered by reads of k SNPs are the prefix
 // p < k(k-1)/2 and warps stay converged.
 struct BsLayout {
-    int rows, cells;           // kmax+1, kmax-1
-    __host__ __device__ size_t tile_u4() const { return (size_t)rows * cells * 4; }
-    __host__ __device__ size_t bytes(int kmax) const {
-        return tile_u4() * 16 + (size_t)BS_GB * kmax * 16 + BS_GB * sizeof(int) + 64;
+    int kmax;
+    __host__ __device__ int rows() const { return kmax + 1; }
+    __host__ __device__ int cells() const { return kmax - 1; }
+    __host__ __device__ size_t tile_u4() const { return (size_t)rows() * cells() * 4; }
+    __host__ __device__ size_t bytes() const {
+        return tile_u4() * 16 + (size_t)BS_GB * kmax * 16 + BS_GB * sizeof(int) + BS_GB * 32 * sizeof(int);
     }
 };
 
-__device__ __forceinline__ void bs_flush_rows(uint32_t *tile32, int rows, int cells, int64_t pj_lo,
-                                              int64_t pj_hi, int64_t W, uint32_t *__restrict__ cnt) {
-    // rows pj in [pj_lo, pj_hi]: add every non-zero counter to HBM, then clear it.
+// rows [pj_lo, pj_hi] of the tile: add every non-zero counter to HBM, clear it; returns the sum
+// flushed by this thread (every regular-cell increment is one crumb, util.py:268,276,281).
+__device__ __forceinline__ unsigned long long bs_flush_rows(uint32_t *tile32, int rows, int cells,
+                                                            int64_t pj_lo, int64_t pj_hi, int64_t W,
+                                                            uint32_t *__restrict__ cnt) {
+    unsigned long long sum = 0;
     const int per_row = cells * 16;
-    const int64_t total = (pj_hi - pj_lo + 1) * per_row;
-    for (int64_t w = threadIdx.x; w < total; w += blockDim.x) {
-        const int64_t pj = pj_lo + w / per_row;
-        const int rem = (int)(w % per_row);
-        const int d = rem / 16 + 1, ab = rem % 16;
-        uint32_t *p = tile32 + ((size_t)(pj % rows) * cells + (d - 1)) * 16 + ab;
-        const uint32_t v = *p;
-        if (v) {
-            atomicAdd(cnt + hx_cell_off(W, pj - d, pj) + (ab >> 2) * HX_NSYM + (ab & 3), v);
-            *p = 0;
+    int row = (int)(pj_lo % rows);
+    for (int64_t pj = pj_lo; pj <= pj_hi; ++pj) {
+        uint32_t *base = tile32 + (size_t)row * per_row;
+        for (int w = threadIdx.x; w < per_row; w += blockDim.x) {
+            const uint32_t v = base[w];
+            if (v) {
+                const int d = (w >> 4) + 1, ab = w & 15;
+                atomicAdd(cnt + hx_cell_off(W, pj - d, pj) + (ab >> 2) * HX_NSYM + (ab & 3), v);
+                base[w] = 0;
+                sum += v;
+            }
+        }
+        if (++row == rows) row = 0;
+    }
+    return sum;
+}
+
+// A read that holds N, - or _ : the pairs with such an allele on either side are not in the
+// bit-planes; the whole warp adds them with REDs (lanes over the read's positions).
+__device__ __forceinline__ void bs_rare_read(const uint8_t *__restrict__ c, int kb, int r, int64_t W,
+                                             uint32_t *__restrict__ cnt, unsigned &crumbs, unsigned &notcov,
+                                             unsigned &errbits) {
+    const int lane = threadIdx.x & 31;
+    const unsigned a_lo = lane < kb ? c[lane] : 0xffu;
+    const unsigned a_hi = lane + 32 < kb ? c[lane + 32] : 0xffu;
+    const unsigned m_lo = __ballot_sync(0xffffffffu, a_lo >= 4 && a_lo != 0xffu);
+    const unsigned m_hi = __ballot_sync(0xffffffffu, a_hi >= 4 && a_hi != 0xffu);
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        unsigned m = half ? m_hi : m_lo;
+        while (m) {
+            const int src = __ffs(m) - 1;
+            m &= m - 1;
+            const unsigned ai = __shfl_sync(0xffffffffu, half ? a_hi : a_lo, src);
+            const int i = src + 32 * half;
+            if (ai > 6) { errbits |= 2; continue; }
+            if (lane == 0 && (ai == HX_SYM_N || ai == HX_SYM_GAP)) notcov++;
+#pragma unroll
+            for (int h2 = 0; h2 < 2; ++h2) {
+                const int j = lane + 32 * h2;
+                const unsigned aj = h2 ? a_hi : a_lo;
+                if (j >= kb || aj > 6) continue;
+                if (j > i && ai == HX_SYM_DEL) {                 // '-' is a valid first allele
+                    atomicAdd(cnt + hx_cell_off(W, r + i + 1, r + j + 1) + ai * HX_NSYM + aj, 1u);
+                    crumbs++;
+                } else if (j < i && aj < 4) {                    // common first allele, rare second
+                    atomicAdd(cnt + hx_cell_off(W, r + j + 1, r + i + 1) + aj * HX_NSYM + ai, 1u);
+                    crumbs++;
+                }
+            }
         }
     }
 }
 
-template <int NP, int MAXT, int MINB>
+template <int KW, int NP, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB)
 k1_bitsliced(const int32_t *__restrict__ rank, const int64_t *__restrict__ off,
              const uint8_t *__restrict__ codes, int64_t n_reads, int N, int W, int kmax,
              uint32_t *__restrict__ cnt, unsigned long long *__restrict__ totals,
-             int *__restrict__ err, const int *__restrict__ sorted_flag) {
+             int *__restrict__ err, const int *__restrict__ sorted_flag,
+             const int64_t *__restrict__ run_end) {
     extern __shared__ uint4 smem4[];
     if (!*sorted_flag) return;                       // the generic fallback launch takes over
     const int rows = kmax + 1, cells = kmax - 1;
-    uint4 *tile = smem4;
-    uint32_t *tile32 = reinterpret_cast<uint32_t *>(tile);
-    uint4 *planes = tile + (size_t)rows * cells * 4;
-    int *gk = reinterpret_cast<int *>(planes + (size_t)BS_GB * kmax);
-    __shared__ int64_t s_run_hi;
+    uint4 *const tile = smem4;
+    uint32_t *const tile32 = reinterpret_cast<uint32_t *>(tile);
+    uint4 *const planes = tile + (size_t)rows * cells * 4;
+    int *const gk = reinterpret_cast<int *>(planes + (size_t)BS_GB * kmax);
+    int *const rareq = gk + BS_GB;
+    __shared__ int s_rare_n[2];                      // per batch parity (reset one batch ahead)
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int64_t per = (n_reads + gridDim.x - 1) / gridDim.x;
@@ -188,6 +247,8 @@ k1_bitsliced(const int32_t *__restrict__ rank, const int64_t *__restrict__ off,
     if (lo >= hi) return;
 
     for (size_t w = threadIdx.x; w < (size_t)rows * cells * 4; w += blockDim.x) tile[w] = make_uint4(0, 0, 0, 0);
+    if (threadIdx.x == 0) s_rare_n[0] = s_rare_n[1] = 0;
+    unsigned batch_no = 0;
 
     // this thread's site pair(s)
     int t1[NP], t2[NP];
@@ -200,37 +261,35 @@ k1_bitsliced(const int32_t *__restrict__ rank, const int64_t *__restrict__ off,
         t2[q] = b;
         t1[q] = p - b * (b - 1) / 2;
     }
-    unsigned long long t_slices = 0, t_crumbs = 0, t_cov = 0, t_sent = 0;
+    unsigned long long t_crumbs = 0;
+    unsigned n_slices = 0, n_codes = 0, n_notcov = 0, n_sent = 0, n_rcrumbs = 0, errbits = 0;
     int64_t flushed_upto = (int64_t)rank[lo] + 1;    // rows pj <= flushed_upto hold nothing
     int64_t cur = lo;
     __syncthreads();
 
     while (cur < hi) {
         const int r = rank[cur];
+        const bool run_ok = r >= 0 && r <= N;        // ranks the pre-pass indexed; reads are checked one by one
+        int64_t run_hi = cur + 1;
+        if (run_ok) {
+            run_hi = run_end[r];
+            if (run_hi > hi) run_hi = hi;
+        }
         // rows pj <= r+1 can no longer be touched by this CTA (reads of rank >= r start at pj = r+2)
         if ((int64_t)r + 1 > flushed_upto) {
             const int64_t last = min((int64_t)r + 1, flushed_upto + rows - 2);
-            bs_flush_rows(tile32, rows, cells, flushed_upto + 1, last, W, cnt);
+            t_crumbs += bs_flush_rows(tile32, rows, cells, flushed_upto + 1, last, W, cnt);
             flushed_upto = (int64_t)r + 1;
         }
-        if (threadIdx.x == 0) {                      // end of the run of reads with rank r
-            int64_t a = cur, b = hi;
-            while (a < b) {
-                const int64_t m = (a + b) >> 1;
-                if (rank[m] <= r) a = m + 1; else b = m;
-            }
-            s_run_hi = a;
-        }
-        __syncthreads();
-        const int64_t run_hi = s_run_hi;
         const int64_t ngroups = (run_hi - cur + 31) / 32;
-        const bool run_ok = r >= 0 && r < N;
+        int rbase = (int)(((int64_t)r + 1) % rows);  // ring row of pj = r+1+t2 is rbase+t2 (mod rows)
 
         uint32_t acc[NP][16];
 #pragma unroll
         for (int q = 0; q < NP; ++q)
 #pragma unroll
             for (int x = 0; x < 16; ++x) acc[q][x] = 0;
+        int run_kmax = 0;
 
         for (int64_t g0 = 0; g0 < ngroups; g0 += BS_GB) {
             const int nb = (int)min((int64_t)BS_GB, ngroups - g0);
@@ -238,104 +297,108 @@ k1_bitsliced(const int32_t *__restrict__ rank, const int64_t *__restrict__ off,
             for (int g = warp; g < nb; g += nwarps) {
                 const int64_t idx = cur + (g0 + g) * 32 + lane;
                 int64_t o = 0;
-                int k = 0;
+                int kb = 0;
                 if (idx < run_hi) {
                     o = off[idx];
                     const int64_t k64 = off[idx + 1] - o;
                     if (k64 >= 2) {
-                        if (!run_ok || (int64_t)r + k64 > N || k64 - 1 > W) atomicOr(err, 1);
-                        else k = (int)k64;
+                        if (!run_ok || (int64_t)r + k64 > N || k64 - 1 > W) errbits |= 1;
+                        else kb = (int)k64;
                     }
                 }
-                const bool wide = k > kmax;          // too wide for the tile: generic path below
-                const int kb = wide ? 0 : k;
-                t_slices += k >= 2;
-                int kg = kb;
-#pragma unroll
-                for (int s = 16; s > 0; s >>= 1) kg = max(kg, __shfl_xor_sync(0xffffffffu, kg, s));
+                n_slices += kb >= 2;
+                n_codes += kb;
+                const int kg = __reduce_max_sync(0xffffffffu, kb);
                 if (lane == 0) gk[g] = kg;
                 const uint8_t *__restrict__ c = codes + o;
-                bool has_rare = false;
-                for (int t = 0; t < kg; ++t) {
-                    unsigned a = 255;
-                    if (t < kb) a = c[t];
-                    if (t < kb && a > 6) { atomicOr(err, 2); a = 255; }
-                    const bool pv = a < 4;
-                    const unsigned v = __ballot_sync(0xffffffffu, pv);
-                    const unsigned b0 = __ballot_sync(0xffffffffu, pv && (a & 1));
-                    const unsigned b1 = __ballot_sync(0xffffffffu, pv && (a & 2));
-                    if (lane == 0)
-                        planes[(size_t)g * kmax + t] = make_uint4(v & ~b1 & ~b0, v & ~b1 & b0, v & b1 & ~b0, v & b1 & b0);
-                    if (t < kb) {
-                        const bool vf = sym_valid_from(a);
-                        t_cov += vf;
-                        t_crumbs += vf ? (unsigned)(kb - 1 - t) : 0u;
-                        has_rare |= (a >= 4 && a <= 6);
+                const unsigned mis = (unsigned)(reinterpret_cast<uintptr_t>(c) & 3u);
+                const uint32_t *__restrict__ cw = reinterpret_cast<const uint32_t *>(c - mis);
+                const int nw = kb ? (int)((mis + kb + 3) >> 2) : 0;
+                uint32_t wd[KW + 1];
+#pragma unroll
+                for (int w = 0; w <= KW; ++w) wd[w] = w < nw ? __ldg(cw + w) : 0u;
+                const unsigned sh = 8u * mis;
+                uint4 *const pg = planes + (size_t)g * kmax;
+                uint32_t rare_or = 0, x0 = 0xffffffffu;
+#pragma unroll
+                for (int w = 0; w < KW; ++w) {
+                    if (4 * w >= kg) break;                        // warp-uniform
+                    uint32_t x = __funnelshift_r(wd[w], wd[w + 1], sh);
+                    const int nv = kb - 4 * w;                    // valid bytes in this word
+                    const uint32_t vmask = nv >= 4 ? 0xffffffffu : (nv <= 0 ? 0u : ((1u << (8 * nv)) - 1u));
+                    rare_or |= x & 0xfcfcfcfcu & vmask;
+                    x |= ~vmask;                                  // bytes past the read's end -> 0xff
+                    if (w == 0) x0 = x;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        if (4 * w + u >= kg) break;                // warp-uniform
+                        const bool pv = (x & (0xfcu << (8 * u))) == 0;
+                        const unsigned v = __ballot_sync(0xffffffffu, pv);
+                        const unsigned b0 = __ballot_sync(0xffffffffu, pv && (x & (1u << (8 * u))));
+                        const unsigned b1 = __ballot_sync(0xffffffffu, pv && (x & (2u << (8 * u))));
+                        if (lane == 0)
+                            pg[4 * w + u] = make_uint4(v & ~b1 & ~b0, v & ~b1 & b0, v & b1 & ~b0, v & b1 & b0);
                     }
                 }
                 if (kb >= 2) {
                     // start sentinel (util.py:262-266) / end sentinel (:271-275); the start rule wins
-                    const unsigned a0 = c[0], ap = c[kb - 2], bl = c[kb - 1];
+                    const unsigned a0 = x0 & 0xffu;
                     if (r == 0 && sym_valid_from(a0)) {
                         atomicAdd(cnt + hx_cell_off(W, 0, 1) + HX_SYM_GAP * HX_NSYM + a0, 1u);
-                        t_sent++;
+                        n_sent++;
                     }
-                    if (r + kb == N && sym_valid_from(ap) && bl <= 6 && !(kb == 2 && r == 0)) {
-                        atomicAdd(cnt + hx_cell_off(W, N, N + 1) + bl * HX_NSYM + HX_SYM_GAP, 1u);
-                        t_sent++;
-                    }
-                    if (has_rare) {
-                        // pairs with a rare allele (N, -, _) on either side are not in the planes
-                        for (int i = 0; i < kb; ++i) {
-                            const unsigned a = c[i];
-                            if (a < 4 || a > 6) continue;
-                            if (a == HX_SYM_DEL)                 // '-' is a valid first allele
-                                for (int j = i + 1; j < kb; ++j)
-                                    if (c[j] <= 6)
-                                        atomicAdd(cnt + hx_cell_off(W, r + i + 1, r + j + 1) + a * HX_NSYM + c[j], 1u);
-                            for (int i2 = 0; i2 < i; ++i2)       // common first allele, rare second
-                                if (c[i2] < 4)
-                                    atomicAdd(cnt + hx_cell_off(W, r + i2 + 1, r + i + 1) + c[i2] * HX_NSYM + a, 1u);
+                    if (r + kb == N && !(kb == 2 && r == 0)) {
+                        const unsigned ap = c[kb - 2], bl = c[kb - 1];
+                        if (sym_valid_from(ap) && bl <= 6) {
+                            atomicAdd(cnt + hx_cell_off(W, N, N + 1) + bl * HX_NSYM + HX_SYM_GAP, 1u);
+                            n_sent++;
                         }
                     }
-                }
-                // reads wider than the tile: whole warp, one read at a time
-                unsigned wmask = __ballot_sync(0xffffffffu, wide);
-                while (wmask) {
-                    const int src = __ffs(wmask) - 1;
-                    wmask &= wmask - 1;
-                    const int64_t o2 = __shfl_sync(0xffffffffu, o, src);
-                    const int k2 = __shfl_sync(0xffffffffu, k, src);
-                    warp_read_generic(codes + o2, k2, r, N, W, cnt, t_crumbs, t_cov, t_sent, err);
+                    if (rare_or) rareq[atomicAdd(&s_rare_n[batch_no & 1], 1)] = g * 32 + lane;
                 }
             }
             __syncthreads();
             // ---- accumulate: each thread its own site pair over the batch's groups --------
+            const int bkm = __reduce_max_sync(0xffffffffu, lane < nb ? gk[lane] : 0);
+            run_kmax = max(run_kmax, bkm);
 #pragma unroll
             for (int q = 0; q < NP; ++q) {
                 const int a1 = t1[q], a2 = t2[q];
-                for (int g = 0; g < nb; ++g) {
-                    if (a2 < gk[g]) {
-                        const uint4 m1 = planes[(size_t)g * kmax + a1];
-                        const uint4 m2 = planes[(size_t)g * kmax + a2];
-                        const unsigned x1[4] = {m1.x, m1.y, m1.z, m1.w};
-                        const unsigned x2[4] = {m2.x, m2.y, m2.z, m2.w};
+                if (a2 < bkm) {
+                    for (int g = 0; g < nb; ++g) {
+                        if (a2 < gk[g]) {
+                            const uint4 m1 = planes[(size_t)g * kmax + a1];
+                            const uint4 m2 = planes[(size_t)g * kmax + a2];
+                            const unsigned x1[4] = {m1.x, m1.y, m1.z, m1.w};
+                            const unsigned x2[4] = {m2.x, m2.y, m2.z, m2.w};
 #pragma unroll
-                        for (int a = 0; a < 4; ++a)
+                            for (int a = 0; a < 4; ++a)
 #pragma unroll
-                            for (int b = 0; b < 4; ++b) acc[q][a * 4 + b] += __popc(x1[a] & x2[b]);
+                                for (int b = 0; b < 4; ++b) acc[q][a * 4 + b] += __popc(x1[a] & x2[b]);
+                        }
                     }
                 }
             }
+            // ---- reads with rare alleles, one warp per read -----------------------------------
+            const int nrare = s_rare_n[batch_no & 1];
+            if (threadIdx.x == 0) s_rare_n[(batch_no + 1) & 1] = 0;     // nobody touches it until the next build
+            for (int qi = warp; qi < nrare; qi += nwarps) {
+                const int64_t idx = cur + g0 * 32 + rareq[qi];
+                const int64_t o = off[idx];
+                const int kb = (int)(off[idx + 1] - o);
+                bs_rare_read(codes + o, kb, r, W, cnt, n_rcrumbs, n_notcov, errbits);
+            }
             __syncthreads();
+            ++batch_no;
         }
         // ---- add this run's counts into the sliding tile (each cell has one owner thread) ----
 #pragma unroll
         for (int q = 0; q < NP; ++q) {
-            if (t2[q] < kmax) {
-                const int64_t pj = (int64_t)r + t2[q] + 1;
+            if (t2[q] < run_kmax) {
+                int row = rbase + t2[q];
+                if (row >= rows) row -= rows;
                 const int d = t2[q] - t1[q];
-                uint4 *cell = tile + ((size_t)(pj % rows) * cells + (d - 1)) * 4;
+                uint4 *cell = tile + ((size_t)row * cells + (d - 1)) * 4;
 #pragma unroll
                 for (int x = 0; x < 4; ++x) {
                     uint4 v = cell[x];
@@ -348,8 +411,10 @@ k1_bitsliced(const int32_t *__restrict__ rank, const int64_t *__restrict__ off,
         cur = run_hi;
         __syncthreads();
     }
-    bs_flush_rows(tile32, rows, cells, flushed_upto + 1, flushed_upto + rows - 1, W, cnt);
-    flush_totals(t_slices, t_crumbs, t_cov, t_sent, totals);
+    t_crumbs += bs_flush_rows(tile32, rows, cells, flushed_upto + 1, flushed_upto + rows - 1, W, cnt);
+    if (errbits) atomicOr(err, (int)errbits);
+    // covered SNPs (util.py:239) = all codes of the kept reads minus the N and _ among them
+    flush_totals(n_slices, t_crumbs + n_rcrumbs, (unsigned long long)n_codes - n_notcov, n_sent, totals);
 }
 
 }  // namespace
@@ -376,17 +441,18 @@ int hx_launch_ingest(hx_matrix *h, const int32_t *d_rank, const int64_t *d_off,
         h->launches++;
     } else {
         HX_CUDA(cudaMemsetAsync(sorted_flag, 1, sizeof(int), h->stream));     // non-zero = sorted
-        k_check_sorted<<<(unsigned)((n_reads + 255) / 256), 256, 0, h->stream>>>(d_rank, n_reads, sorted_flag);
-        BsLayout lay{kmax + 1, kmax - 1};
-        const size_t smem = lay.bytes(kmax);
+        k_prepass<<<(unsigned)((n_reads + 255) / 256), 256, 0, h->stream>>>(d_rank, n_reads, h->N, sorted_flag,
+                                                                            h->d_run_end);
+        BsLayout lay{kmax};
+        const size_t smem = lay.bytes();
         const int npairs = kmax * (kmax - 1) / 2;
         const int np = npairs > 1024 ? 2 : 1;
         int block = ((npairs + np - 1) / np + 31) / 32 * 32;
-        if (block < 64) block = 64;
+        if (block < 128) block = 128;
         if (block > 1024) block = 1024;
-#define HX_BS_LAUNCH(NP_, MAXT_, MINB_)                                                                       \
+#define HX_BS_LAUNCH(KW_, NP_, MAXT_, MINB_)                                                                  \
     do {                                                                                                       \
-        auto kern = k1_bitsliced<NP_, MAXT_, MINB_>;                                                           \
+        auto kern = k1_bitsliced<KW_, NP_, MAXT_, MINB_>;                                                      \
         HX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));           \
         int occ = 1;                                                                                           \
         HX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, block, smem));                       \
@@ -395,11 +461,12 @@ int hx_launch_ingest(hx_matrix *h, const int32_t *d_rank, const int64_t *d_off,
         const int64_t max_useful = (n_reads + 255) / 256;   /* no thinner than 256 reads per CTA */            \
         if (grid > max_useful) grid = max_useful;                                                              \
         kern<<<(unsigned)grid, block, smem, h->stream>>>(d_rank, d_off, d_codes, n_reads, h->N, h->W, kmax,    \
-                                                         h->cnt, h->d_totals, h->d_err, sorted_flag);          \
+                                                         h->cnt, h->d_totals, h->d_err, sorted_flag,           \
+                                                         h->d_run_end);                                        \
     } while (0)
-        if (np == 2) HX_BS_LAUNCH(2, 1024, 1);
-        else if (block > 512) HX_BS_LAUNCH(1, 1024, 1);
-        else HX_BS_LAUNCH(1, 512, 2);
+        if (np == 2) HX_BS_LAUNCH(14, 2, 1024, 1);
+        else if (kmax > 32) HX_BS_LAUNCH(14, 1, 1024, 1);
+        else HX_BS_LAUNCH(8, 1, 512, 2);
 #undef HX_BS_LAUNCH
         // fallback for unsorted input: runs only when the flag says the bit-sliced kernel declined
         k1_pairs_red<GBLOCK><<<ggrid, GBLOCK, 0, h->stream>>>(d_rank, d_off, d_codes, n_reads, h->N, h->W, h->cnt,
