@@ -22,8 +22,8 @@
 
 namespace {
 
-constexpr int BS_KMAX = 56;      // widest read (in SNPs) the bit-sliced kernel takes
-constexpr int BS_GB = 32;        // groups (of 32 reads) per build/accumulate batch
+constexpr int BS_KMAX = 52;      // widest read (in SNPs) the bit-sliced kernel takes
+constexpr int BS_GB = 32;        // most groups (of 32 reads) per build/accumulate batch
 
 __device__ __forceinline__ unsigned long long warp_sum_ull(unsigned long long v) {
 #pragma unroll
@@ -153,12 +153,10 @@ __global__ void k_prepass(const int32_t *__restrict__ rank, int64_t n_reads, int
 // of the current run of reads, so the pairs covered by reads of k SNPs are the prefix
 // p < k(k-1)/2 and warps stay converged.
 struct BsLayout {
-    int kmax;
-    __host__ __device__ int rows() const { return kmax + 1; }
-    __host__ __device__ int cells() const { return kmax - 1; }
-    __host__ __device__ size_t tile_u4() const { return (size_t)rows() * cells() * 4; }
+    int kmax, gb;
+    __host__ __device__ size_t tile_u4() const { return (size_t)(kmax + 1) * (kmax - 1) * 4; }
     __host__ __device__ size_t bytes() const {
-        return tile_u4() * 16 + (size_t)BS_GB * kmax * 16 + BS_GB * sizeof(int) + BS_GB * 32 * sizeof(int);
+        return tile_u4() * 16 + (size_t)2 * gb * kmax * 16 + 64 * sizeof(int) + (size_t)2 * gb * 32 * sizeof(int);
     }
 };
 
@@ -223,10 +221,18 @@ __device__ __forceinline__ void bs_rare_read(const uint8_t *__restrict__ c, int 
     }
 }
 
+// One batch of up to `gb` groups (32 reads each) out of a run of reads that share rank r.
+struct BsBatch {
+    int64_t start;      // first read
+    int n;              // reads in the batch (0 = no batch)
+    int r;              // rank of the run
+    bool first, last;   // first / last batch of its run (within this CTA's slice)
+};
+
 template <int KW, int NP, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB)
 k1_bitsliced(const int32_t *__restrict__ rank, const int64_t *__restrict__ off,
-             const uint8_t *__restrict__ codes, int64_t n_reads, int N, int W, int kmax,
+             const uint8_t *__restrict__ codes, int64_t n_reads, int N, int W, int kmax, int gb,
              uint32_t *__restrict__ cnt, unsigned long long *__restrict__ totals,
              int *__restrict__ err, const int *__restrict__ sorted_flag,
              const int64_t *__restrict__ run_end) {
@@ -235,10 +241,11 @@ k1_bitsliced(const int32_t *__restrict__ rank, const int64_t *__restrict__ off,
     const int rows = kmax + 1, cells = kmax - 1;
     uint4 *const tile = smem4;
     uint32_t *const tile32 = reinterpret_cast<uint32_t *>(tile);
-    uint4 *const planes = tile + (size_t)rows * cells * 4;
-    int *const gk = reinterpret_cast<int *>(planes + (size_t)BS_GB * kmax);
-    int *const rareq = gk + BS_GB;
-    __shared__ int s_rare_n[2];                      // per batch parity (reset one batch ahead)
+    uint4 *const planes0 = tile + (size_t)rows * cells * 4;          // two buffers of gb*kmax uint4
+    int *const gk0 = reinterpret_cast<int *>(planes0 + (size_t)2 * gb * kmax);   // two buffers of 32 ints
+    int *const rareq0 = gk0 + 64;                                     // two buffers of gb*32 ints
+    const uint32_t planes_saddr = (uint32_t)__cvta_generic_to_shared(planes0);
+    __shared__ int s_rare_n[3];                      // rotating: built / consumed / being cleared
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int64_t per = (n_reads + gridDim.x - 1) / gridDim.x;
@@ -247,8 +254,8 @@ k1_bitsliced(const int32_t *__restrict__ rank, const int64_t *__restrict__ off,
     if (lo >= hi) return;
 
     for (size_t w = threadIdx.x; w < (size_t)rows * cells * 4; w += blockDim.x) tile[w] = make_uint4(0, 0, 0, 0);
-    if (threadIdx.x == 0) s_rare_n[0] = s_rare_n[1] = 0;
-    unsigned batch_no = 0;
+    if (threadIdx.x == 0) s_rare_n[0] = s_rare_n[1] = s_rare_n[2] = 0;
+    int rc_build = 1, rc_cons = 0, rc_clear = 2;      // indices into s_rare_n, rotated every phase
 
     // this thread's site pair(s)
     int t1[NP], t2[NP];
@@ -264,103 +271,63 @@ k1_bitsliced(const int32_t *__restrict__ rank, const int64_t *__restrict__ off,
     unsigned long long t_crumbs = 0;
     unsigned n_slices = 0, n_codes = 0, n_notcov = 0, n_sent = 0, n_rcrumbs = 0, errbits = 0;
     int64_t flushed_upto = (int64_t)rank[lo] + 1;    // rows pj <= flushed_upto hold nothing
-    int64_t cur = lo;
+    uint32_t acc[NP][16];
+    int run_kmax = 0, rbase = 0;
+
+    // batch scheduler state (identical in every thread)
+    int64_t cur = lo, run_hi = lo;
+    int run_r = 0;
+    BsBatch prev{0, 0, 0, false, false};
+    int buf = 0;
+    int prev_aw = 0;                                 // warps that own active pairs in `prev`
     __syncthreads();
 
-    while (cur < hi) {
-        const int r = rank[cur];
-        const bool run_ok = r >= 0 && r <= N;        // ranks the pre-pass indexed; reads are checked one by one
-        int64_t run_hi = cur + 1;
-        if (run_ok) {
-            run_hi = run_end[r];
-            if (run_hi > hi) run_hi = hi;
-        }
-        // rows pj <= r+1 can no longer be touched by this CTA (reads of rank >= r start at pj = r+2)
-        if ((int64_t)r + 1 > flushed_upto) {
-            const int64_t last = min((int64_t)r + 1, flushed_upto + rows - 2);
-            t_crumbs += bs_flush_rows(tile32, rows, cells, flushed_upto + 1, last, W, cnt);
-            flushed_upto = (int64_t)r + 1;
-        }
-        const int64_t ngroups = (run_hi - cur + 31) / 32;
-        int rbase = (int)(((int64_t)r + 1) % rows);  // ring row of pj = r+1+t2 is rbase+t2 (mod rows)
-
-        uint32_t acc[NP][16];
-#pragma unroll
-        for (int q = 0; q < NP; ++q)
-#pragma unroll
-            for (int x = 0; x < 16; ++x) acc[q][x] = 0;
-        int run_kmax = 0;
-
-        for (int64_t g0 = 0; g0 < ngroups; g0 += BS_GB) {
-            const int nb = (int)min((int64_t)BS_GB, ngroups - g0);
-            // ---- build: one warp per group of 32 reads -------------------------------------
-            for (int g = warp; g < nb; g += nwarps) {
-                const int64_t idx = cur + (g0 + g) * 32 + lane;
-                int64_t o = 0;
-                int kb = 0;
-                if (idx < run_hi) {
-                    o = off[idx];
-                    const int64_t k64 = off[idx + 1] - o;
-                    if (k64 >= 2) {
-                        if (!run_ok || (int64_t)r + k64 > N || k64 - 1 > W) errbits |= 1;
-                        else kb = (int)k64;
-                    }
-                }
-                n_slices += kb >= 2;
-                n_codes += kb;
-                const int kg = __reduce_max_sync(0xffffffffu, kb);
-                if (lane == 0) gk[g] = kg;
-                const uint8_t *__restrict__ c = codes + o;
-                const unsigned mis = (unsigned)(reinterpret_cast<uintptr_t>(c) & 3u);
-                const uint32_t *__restrict__ cw = reinterpret_cast<const uint32_t *>(c - mis);
-                const int nw = kb ? (int)((mis + kb + 3) >> 2) : 0;
-                uint32_t wd[KW + 1];
-#pragma unroll
-                for (int w = 0; w <= KW; ++w) wd[w] = w < nw ? __ldg(cw + w) : 0u;
-                const unsigned sh = 8u * mis;
-                uint4 *const pg = planes + (size_t)g * kmax;
-                uint32_t rare_or = 0, x0 = 0xffffffffu;
-#pragma unroll
-                for (int w = 0; w < KW; ++w) {
-                    if (4 * w >= kg) break;                        // warp-uniform
-                    uint32_t x = __funnelshift_r(wd[w], wd[w + 1], sh);
-                    const int nv = kb - 4 * w;                    // valid bytes in this word
-                    const uint32_t vmask = nv >= 4 ? 0xffffffffu : (nv <= 0 ? 0u : ((1u << (8 * nv)) - 1u));
-                    rare_or |= x & 0xfcfcfcfcu & vmask;
-                    x |= ~vmask;                                  // bytes past the read's end -> 0xff
-                    if (w == 0) x0 = x;
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        if (4 * w + u >= kg) break;                // warp-uniform
-                        const bool pv = (x & (0xfcu << (8 * u))) == 0;
-                        const unsigned v = __ballot_sync(0xffffffffu, pv);
-                        const unsigned b0 = __ballot_sync(0xffffffffu, pv && (x & (1u << (8 * u))));
-                        const unsigned b1 = __ballot_sync(0xffffffffu, pv && (x & (2u << (8 * u))));
-                        if (lane == 0)
-                            pg[4 * w + u] = make_uint4(v & ~b1 & ~b0, v & ~b1 & b0, v & b1 & ~b0, v & b1 & b0);
-                    }
-                }
-                if (kb >= 2) {
-                    // start sentinel (util.py:262-266) / end sentinel (:271-275); the start rule wins
-                    const unsigned a0 = x0 & 0xffu;
-                    if (r == 0 && sym_valid_from(a0)) {
-                        atomicAdd(cnt + hx_cell_off(W, 0, 1) + HX_SYM_GAP * HX_NSYM + a0, 1u);
-                        n_sent++;
-                    }
-                    if (r + kb == N && !(kb == 2 && r == 0)) {
-                        const unsigned ap = c[kb - 2], bl = c[kb - 1];
-                        if (sym_valid_from(ap) && bl <= 6) {
-                            atomicAdd(cnt + hx_cell_off(W, N, N + 1) + bl * HX_NSYM + HX_SYM_GAP, 1u);
-                            n_sent++;
-                        }
-                    }
-                    if (rare_or) rareq[atomicAdd(&s_rare_n[batch_no & 1], 1)] = g * 32 + lane;
+    for (;;) {
+        // ---- next batch -----------------------------------------------------------------------
+        BsBatch next{0, 0, 0, false, false};
+        if (cur < hi) {
+            next.first = cur >= run_hi;
+            if (next.first) {
+                run_r = rank[cur];
+                run_hi = cur + 1;
+                if (run_r >= 0 && run_r <= N) {      // ranks the pre-pass indexed
+                    run_hi = run_end[run_r];
+                    if (run_hi > hi) run_hi = hi;
                 }
             }
-            __syncthreads();
-            // ---- accumulate: each thread its own site pair over the batch's groups --------
+            next.start = cur;
+            next.r = run_r;
+            next.n = (int)min((int64_t)gb * 32, run_hi - cur);
+            cur += next.n;
+            next.last = cur >= run_hi;
+        }
+        if (!prev.n && !next.n) break;
+
+        // ---- consume `prev` (planes buffer buf^1) ---------------------------------------------
+        if (prev.n) {
+            const int pb = buf ^ 1;
+            const uint4 *planes = planes0 + (size_t)pb * gb * kmax;
+            const int *gk = gk0 + pb * 32;
+            const int nb = (prev.n + 31) >> 5;
+            const int r = prev.r;
+            if (prev.first) {
+                // rows pj <= r+1 can no longer be touched by this CTA (reads of rank >= r start at pj = r+2)
+                if ((int64_t)r + 1 > flushed_upto) {
+                    const int64_t last = min((int64_t)r + 1, flushed_upto + rows - 2);
+                    t_crumbs += bs_flush_rows(tile32, rows, cells, flushed_upto + 1, last, W, cnt);
+                    flushed_upto = (int64_t)r + 1;
+                    __syncthreads();                 // the retired ring slots may be reused by this run's tile add
+                }
+                rbase = (int)(((int64_t)r + 1) % rows);   // ring row of pj = r+1+t2 is rbase+t2 (mod rows)
+                run_kmax = 0;
+#pragma unroll
+                for (int q = 0; q < NP; ++q)
+#pragma unroll
+                    for (int x = 0; x < 16; ++x) acc[q][x] = 0;
+            }
             const int bkm = __reduce_max_sync(0xffffffffu, lane < nb ? gk[lane] : 0);
             run_kmax = max(run_kmax, bkm);
+            prev_aw = (bkm * (bkm - 1) / 2 + 31) >> 5;
 #pragma unroll
             for (int q = 0; q < NP; ++q) {
                 const int a1 = t1[q], a2 = t2[q];
@@ -379,38 +346,125 @@ k1_bitsliced(const int32_t *__restrict__ rank, const int64_t *__restrict__ off,
                     }
                 }
             }
-            // ---- reads with rare alleles, one warp per read -----------------------------------
-            const int nrare = s_rare_n[batch_no & 1];
-            if (threadIdx.x == 0) s_rare_n[(batch_no + 1) & 1] = 0;     // nobody touches it until the next build
-            for (int qi = warp; qi < nrare; qi += nwarps) {
-                const int64_t idx = cur + g0 * 32 + rareq[qi];
+            if (prev.last) {
+                // add this run's counts into the sliding tile (each cell has one owner thread)
+#pragma unroll
+                for (int q = 0; q < NP; ++q) {
+                    if (t2[q] < run_kmax) {
+                        int row = rbase + t2[q];
+                        if (row >= rows) row -= rows;
+                        const int d = t2[q] - t1[q];
+                        uint4 *cell = tile + ((size_t)row * cells + (d - 1)) * 4;
+#pragma unroll
+                        for (int x = 0; x < 4; ++x) {
+                            uint4 v = cell[x];
+                            v.x += acc[q][4 * x + 0]; v.y += acc[q][4 * x + 1];
+                            v.z += acc[q][4 * x + 2]; v.w += acc[q][4 * x + 3];
+                            cell[x] = v;
+                        }
+                    }
+                }
+            }
+            // reads with rare alleles, one warp per read (warps without active pairs get here first)
+            const int nrare = s_rare_n[rc_cons];
+            const int *rareq = rareq0 + (size_t)pb * gb * 32;
+            for (int qi = nwarps - 1 - warp; qi < nrare; qi += nwarps) {
+                const int64_t idx = prev.start + rareq[qi];
                 const int64_t o = off[idx];
                 const int kb = (int)(off[idx + 1] - o);
                 bs_rare_read(codes + o, kb, r, W, cnt, n_rcrumbs, n_notcov, errbits);
             }
-            __syncthreads();
-            ++batch_no;
+        } else {
+            prev_aw = 0;
         }
-        // ---- add this run's counts into the sliding tile (each cell has one owner thread) ----
+
+        // ---- produce `next` (planes buffer buf): one warp per group, pair-less warps first -----
+        if (next.n) {
+            int *gk = gk0 + buf * 32;
+            int *rareq = rareq0 + (size_t)buf * gb * 32;
+            const int nb = (next.n + 31) >> 5;
+            const int r = next.r;
+            const int64_t run_stop = next.start + next.n;
+            // builders: the warps that own no active pair of `prev`, unless that leaves too few
+            int nbuild = nwarps - prev_aw, wfirst = prev_aw;
+            if (nbuild < (nwarps + 1) / 2) { nbuild = nwarps; wfirst = 0; }
+            for (int g = warp - wfirst; g >= 0 && g < nb; g += nbuild) {
+                const int64_t idx = next.start + (int64_t)g * 32 + lane;
+                int64_t o = 0;
+                int kb = 0;
+                if (idx < run_stop) {
+                    o = off[idx];
+                    const int64_t k64 = off[idx + 1] - o;
+                    if (k64 >= 2) {
+                        if (r < 0 || (int64_t)r + k64 > N || k64 - 1 > W) errbits |= 1;
+                        else kb = (int)k64;
+                    }
+                }
+                n_slices += kb >= 2;
+                n_codes += kb;
+                const int kg = __reduce_max_sync(0xffffffffu, kb);
+                if (lane == 0) gk[g] = kg;
+                const uint8_t *__restrict__ c = codes + o;
+                const unsigned mis = (unsigned)(reinterpret_cast<uintptr_t>(c) & 3u);
+                const uint32_t *__restrict__ cw = reinterpret_cast<const uint32_t *>(c - mis);
+                const int nw = kb ? (int)((mis + kb + 3) >> 2) : 0;
+                uint32_t wd[KW + 1];
 #pragma unroll
-        for (int q = 0; q < NP; ++q) {
-            if (t2[q] < run_kmax) {
-                int row = rbase + t2[q];
-                if (row >= rows) row -= rows;
-                const int d = t2[q] - t1[q];
-                uint4 *cell = tile + ((size_t)row * cells + (d - 1)) * 4;
+                for (int w = 0; w <= KW; ++w) wd[w] = w < nw ? __ldg(cw + w) : 0u;
+                const unsigned sh = 8u * mis;
+                // shared-window byte address of this group's planes (keeps the per-site store to one STS)
+                uint32_t pg_addr = planes_saddr + (uint32_t)((buf * gb + g) * kmax) * 16u;
+                asm volatile("" : "+r"(pg_addr));              // keep it in a register (no rematerialisation per site)
+                const unsigned lane_nz = lane;                 // predicate source for the lane-0 store
+                uint32_t rare_or = 0, x0 = 0xffffffffu;
 #pragma unroll
-                for (int x = 0; x < 4; ++x) {
-                    uint4 v = cell[x];
-                    v.x += acc[q][4 * x + 0]; v.y += acc[q][4 * x + 1];
-                    v.z += acc[q][4 * x + 2]; v.w += acc[q][4 * x + 3];
-                    cell[x] = v;
+                for (int w = 0; w < KW; ++w) {
+                    if (4 * w >= kg) break;                        // warp-uniform
+                    uint32_t x = __funnelshift_r(wd[w], wd[w + 1], sh);
+                    const int nv = kb - 4 * w;                    // valid bytes in this word
+                    const uint32_t vmask = nv >= 4 ? 0xffffffffu : (nv <= 0 ? 0u : ((1u << (8 * nv)) - 1u));
+                    rare_or |= x & 0xfcfcfcfcu & vmask;
+                    x |= ~vmask;                                  // bytes past the read's end -> 0xff
+                    if (w == 0) x0 = x;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        if (4 * w + u >= kg) break;                // warp-uniform
+                        const bool pv = (x & (0xfcu << (8 * u))) == 0;
+                        const unsigned v = __ballot_sync(0xffffffffu, pv);
+                        const unsigned b0 = __ballot_sync(0xffffffffu, pv && (x & (1u << (8 * u))));
+                        const unsigned b1 = __ballot_sync(0xffffffffu, pv && (x & (2u << (8 * u))));
+                        asm volatile(
+                            "{ .reg .pred p; setp.eq.u32 p, %5, 0;\n\t"
+                            "@p st.shared.v4.u32 [%0], {%1, %2, %3, %4}; }" ::"r"(pg_addr + (4 * w + u) * 16),
+                            "r"(v & ~b1 & ~b0), "r"(v & ~b1 & b0), "r"(v & b1 & ~b0), "r"(v & b1 & b0), "r"(lane_nz)
+                            : "memory");
+                    }
+                }
+                if (kb >= 2) {
+                    // start sentinel (util.py:262-266) / end sentinel (:271-275); the start rule wins
+                    const unsigned a0 = x0 & 0xffu;
+                    if (r == 0 && sym_valid_from(a0)) {
+                        atomicAdd(cnt + hx_cell_off(W, 0, 1) + HX_SYM_GAP * HX_NSYM + a0, 1u);
+                        n_sent++;
+                    }
+                    if (r + kb == N && !(kb == 2 && r == 0)) {
+                        const unsigned ap = c[kb - 2], bl = c[kb - 1];
+                        if (sym_valid_from(ap) && bl <= 6) {
+                            atomicAdd(cnt + hx_cell_off(W, N, N + 1) + bl * HX_NSYM + HX_SYM_GAP, 1u);
+                            n_sent++;
+                        }
+                    }
+                    if (rare_or) rareq[atomicAdd(&s_rare_n[rc_build], 1)] = g * 32 + lane;
                 }
             }
         }
-        cur = run_hi;
+        if (threadIdx.x == 0) s_rare_n[rc_clear] = 0;  // consumed one phase ago, refilled one phase ahead
         __syncthreads();
+        prev = next;
+        buf ^= 1;
+        { const int t = rc_clear; rc_clear = rc_cons; rc_cons = rc_build; rc_build = t; }
     }
+    __syncthreads();
     t_crumbs += bs_flush_rows(tile32, rows, cells, flushed_upto + 1, flushed_upto + rows - 1, W, cnt);
     if (errbits) atomicOr(err, (int)errbits);
     // covered SNPs (util.py:239) = all codes of the kept reads minus the N and _ among them
@@ -443,8 +497,9 @@ int hx_launch_ingest(hx_matrix *h, const int32_t *d_rank, const int64_t *d_off,
         HX_CUDA(cudaMemsetAsync(sorted_flag, 1, sizeof(int), h->stream));     // non-zero = sorted
         k_prepass<<<(unsigned)((n_reads + 255) / 256), 256, 0, h->stream>>>(d_rank, n_reads, h->N, sorted_flag,
                                                                             h->d_run_end);
-        BsLayout lay{kmax};
-        const size_t smem = lay.bytes();
+        int gb = BS_GB;
+        while (gb > 4 && BsLayout{kmax, gb}.bytes() > (size_t)200 * 1024) gb >>= 1;
+        const size_t smem = BsLayout{kmax, gb}.bytes();
         const int npairs = kmax * (kmax - 1) / 2;
         const int np = npairs > 1024 ? 2 : 1;
         int block = ((npairs + np - 1) / np + 31) / 32 * 32;
@@ -461,7 +516,7 @@ int hx_launch_ingest(hx_matrix *h, const int32_t *d_rank, const int64_t *d_off,
         const int64_t max_useful = (n_reads + 255) / 256;   /* no thinner than 256 reads per CTA */            \
         if (grid > max_useful) grid = max_useful;                                                              \
         kern<<<(unsigned)grid, block, smem, h->stream>>>(d_rank, d_off, d_codes, n_reads, h->N, h->W, kmax,    \
-                                                         h->cnt, h->d_totals, h->d_err, sorted_flag,           \
+                                                         gb, h->cnt, h->d_totals, h->d_err, sorted_flag,       \
                                                          h->d_run_end);                                        \
     } while (0)
         if (np == 2) HX_BS_LAUNCH(14, 2, 1024, 1);
