@@ -58,6 +58,7 @@ void free_all(hx_matrix *h) {
     if (h->d_stats) cudaFree(h->d_stats);
     if (h->d_site) cudaFree(h->d_site);
     if (h->d_partials) cudaFree(h->d_partials);
+    if (h->d_terms) cudaFree(h->d_terms);
     if (h->d_flags) cudaFree(h->d_flags);
     if (h->d_run_end) cudaFree(h->d_run_end);
     if (h->d_misc) cudaFree(h->d_misc);

@@ -35,6 +35,8 @@ struct hx_matrix {
     double *d_stats;                 // per-iteration stats
     int64_t cap_stats;
     double *d_site;                  // 3*(N+2) per-site log10 marginal (cur), (orig), marginal
+    double *d_terms;                 // walk tables: (N+2)*Lw*49 log10 lookback terms + (N+2)*8 log10 marginals
+    int64_t cap_terms;
     double *d_partials;              // block partials of the reweight reduction
     int64_t cap_partials;
     int *d_flags;                    // [0] hole site / abort flag, [1..] misc

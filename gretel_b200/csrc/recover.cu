@@ -3,7 +3,7 @@
 //
 // Replaces, for the reference (paths under /root/reference):
 //   k_site_counts      Hansel.get_counts_at for every site   (cmd.py:85-92,123-145)
-//   k_walk             gretel.py:143-187 + Hansel.get_edge_weights_at (call gretel.py:155)
+//   k_walk_terms/_logm/_tables   gretel.py:143-187 + Hansel.get_edge_weights_at (call gretel.py:155)
 //   k_path_stats/_sum  gretel.py:182-189 + Hansel.get_marginal_of_at  (calls :182,186)
 //   k_reweight_path    gretel.py:79-98 + Hansel.reweight_observation  (calls :84,96)
 //
@@ -102,31 +102,6 @@ __device__ __forceinline__ int normalise_and_pick(double ws, unsigned cmask, dou
     return next;
 }
 
-// ---- the walk: one warp, strictly sequential over sites -------------------------------
-__global__ void __launch_bounds__(32)
-k_walk(const float *__restrict__ band, const double *__restrict__ scnt,
-       const int32_t *__restrict__ vseen, int N, int W, int L, int flags,
-       uint8_t *__restrict__ path, int *__restrict__ flagsd /* [0] hole site, [1] abort */) {
-    __shared__ uint8_t ring[HX_RING];
-    const int lane = threadIdx.x;
-    if (flagsd[1]) return;                       // an earlier iteration of hx_recover hit a hole
-    if (lane == 0) { ring[0] = HX_SYM_GAP; path[0] = HX_SYM_GAP; }
-    __syncwarp();
-    for (int snp = 1; snp <= N; ++snp) {
-        unsigned cmask;
-        const double ws = edge_weight_lane(band, scnt, vseen, W, L, flags, snp, ring, HX_RING - 1, &cmask);
-        double wn, tw;
-        const int next = normalise_and_pick(ws, cmask, &wn, &tw);
-        if (next < 0) {                          // gretel.py:176-180
-            if (lane == 0) { flagsd[0] = snp; flagsd[1] = 1; }
-            return;
-        }
-        if (lane == 0) { ring[snp & (HX_RING - 1)] = (uint8_t)next; path[snp] = (uint8_t)next; }
-        __syncwarp();
-    }
-    if (lane == 0) flagsd[0] = 0;
-}
-
 __global__ void __launch_bounds__(32)
 k_edge_one(const float *__restrict__ band, const double *__restrict__ scnt,
            const int32_t *__restrict__ vseen, int W, int L, int flags, int snp,
@@ -138,6 +113,256 @@ k_edge_one(const float *__restrict__ band, const double *__restrict__ scnt,
     const int lane = threadIdx.x;
     if (lane < HX_NSYM) out[lane] = ((cmask >> lane) & 1u) ? wn : 0.0;
     if (lane == 0) { out[7] = tw; out[8] = (double)cmask; }
+}
+
+// ---- walk tables: everything that does not depend on the path, computed in parallel ----
+// terms[((snp*Lw + (l-1))*7 + a)*7 + s] = log10((1 + H[a,s,snp-l,snp]) / (V + sum_a' H[a',s,snp-l,snp]))
+// (0.0 where the Laplace denominator is 0, i.e. the term is dropped), for every symbol a
+// the path could hold at snp-l.  logm[snp*8+s] = log10(count_s / total); logm[snp*8+7] holds
+// the candidate mask as a double.
+__global__ void k_walk_terms(const float *__restrict__ band, const int32_t *__restrict__ vseen, int N, int W,
+                             int Lw, int flags, double *__restrict__ terms) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t total = (int64_t)(N + 1) * Lw * 8;
+    if (idx >= total) return;
+    const int s = (int)(idx & 7);
+    const int l = (int)((idx >> 3) % Lw) + 1;
+    const int snp = (int)((idx >> 3) / Lw);
+    double *out = terms + (((int64_t)snp * Lw + (l - 1)) * HX_NSYM) * 8 + s;   // [snp][l][a][8]: 448-byte blocks
+    const int pf = snp - l;
+    if (s >= HX_NSYM || snp < 1 || pf < 0) {
+#pragma unroll
+        for (int a = 0; a < HX_NSYM; ++a) out[a * 8] = 0.0;
+        return;
+    }
+    const float *cell = band + hx_cell_off(W, pf, snp);
+    double obs[HX_NSYM], sup = 0.0;
+#pragma unroll
+    for (int a = 0; a < HX_NSYM; ++a) {
+        obs[a] = (double)cell[a * HX_NSYM + s];
+        sup += obs[a];
+    }
+    const int v = (flags & HX_F_VSITE_TO) ? vseen[snp] : vseen[pf];
+    const double den = (double)v + sup;
+#pragma unroll
+    for (int a = 0; a < HX_NSYM; ++a) out[a * 8] = den != 0 ? log10((1.0 + obs[a]) / den) : 0.0;
+}
+
+__global__ void k_walk_logm(const double *__restrict__ scnt, int N, int flags, double *__restrict__ logm) {
+    const int snp = blockIdx.x * blockDim.x + threadIdx.x;
+    if (snp > N) return;
+    const double total = scnt[(int64_t)snp * 8 + 7];
+    const bool skip_unsym = !(flags & HX_F_KEEP_UNSYMBOLS);
+    unsigned mask = 0;
+    for (int s = 0; s < HX_NSYM; ++s) {
+        const double c = scnt[(int64_t)snp * 8 + s];
+        const bool cand = c > 0 && !(skip_unsym && (s == HX_SYM_N || s == HX_SYM_GAP));
+        logm[(int64_t)snp * 8 + s] = cand ? log10(c / total) : 0.0;
+        if (cand) mask |= 1u << s;
+    }
+    logm[(int64_t)snp * 8 + 7] = (double)mask;
+}
+
+// ---- TMA / mbarrier helpers (1-D bulk copies of the walk tables into shared memory) -------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+
+// The walk over the precomputed tables: one warp, lanes 0..6 = candidate symbols, strictly
+// sequential over sites.  The tables of the next sites are staged into shared memory by TMA
+// bulk copies (three chunks of C sites in flight, one mbarrier each), so the dependent chain
+// per site is: previous choice -> one shared-memory load -> one add -> 7-way argmax.
+// The reference's ordered sum, 10**x and normalisation (Hansel.get_edge_weights_at) only
+// matter for the argmax when two candidates are within rounding of each other, so they are
+// evaluated only then (and whenever 10**x could under/overflow); otherwise the largest
+// log-weight wins outright.
+__global__ void __launch_bounds__(32)
+k_walk_tables(const double *__restrict__ terms, const double *__restrict__ logm,
+              const int32_t *__restrict__ vseen, int N, int L, int Lw, int flags, int C,
+              uint8_t *__restrict__ path, int *__restrict__ flagsd) {
+    extern __shared__ __align__(128) unsigned char smraw[];
+    __shared__ __align__(8) unsigned long long bars[3];
+    __shared__ uint8_t ring[HX_RING];
+    const int lane = threadIdx.x;
+    const int s = lane < HX_NSYM ? lane : 0;
+    if (flagsd[1]) return;
+    const uint32_t site_t_bytes = (uint32_t)Lw * 448u;                 // terms of one site
+    const uint32_t chunk_t_bytes = (uint32_t)C * site_t_bytes;
+    double *const sm_terms = reinterpret_cast<double *>(smraw);                        // [3][C][Lw][7][8]
+    double *const sm_logm = reinterpret_cast<double *>(smraw + 3 * (size_t)chunk_t_bytes);   // [3][C][8]
+    const int nchunks = (N + C - 1) / C;
+    if (lane == 0) {
+        ring[0] = HX_SYM_GAP;
+        path[0] = HX_SYM_GAP;
+        for (int b = 0; b < 3; ++b) mbar_init(smem_u32(&bars[b]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    auto issue = [&](int k) {        // lane 0: stage chunk k (sites 1+kC ..) into buffer k%3
+        if (k >= nchunks) return;
+        const int b = k % 3;
+        const int first = 1 + k * C;
+        const int ns = min(C, N - first + 1);
+        const uint32_t bar = smem_u32(&bars[b]);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier reads of this buffer are done
+        mbar_expect_tx(bar, (uint32_t)ns * (site_t_bytes + 64u));
+        bulk_g2s(smem_u32(sm_terms) + (uint32_t)b * chunk_t_bytes, terms + (int64_t)first * Lw * 56,
+                 (uint32_t)ns * site_t_bytes, bar);
+        bulk_g2s(smem_u32(sm_logm) + (uint32_t)b * C * 64u, logm + (int64_t)first * 8, (uint32_t)ns * 64u, bar);
+    };
+    if (lane == 0) { issue(0); issue(1); }
+    unsigned last = HX_SYM_GAP;
+    unsigned long long hist = HX_SYM_GAP;               // 4 bits per chosen symbol, newest in bits 0..3
+    for (int k = 0; k < nchunks; ++k) {
+        __syncwarp();
+        if (lane == 0) issue(k + 2);
+        mbar_wait(smem_u32(&bars[k % 3]), (uint32_t)((k / 3) & 1));
+        const int first = 1 + k * C;
+        const int ns = min(C, N - first + 1);
+        const double *ct = sm_terms + (size_t)(k % 3) * (chunk_t_bytes / 8);
+        const double *cl = sm_logm + (size_t)(k % 3) * C * 8;
+        for (int j = 0; j < ns; ++j) {
+            const int snp = first + j;
+            const double *base = ct + (size_t)j * Lw * 56 + s;
+            const double lm = cl[j * 8 + s];
+            const unsigned cmask = (unsigned)cl[j * 8 + 7];
+            const bool cand = lane < HX_NSYM && ((cmask >> lane) & 1u);
+            const int lmax = L < snp ? L : snp;
+            const int lt = lmax < Lw ? lmax : Lw;
+            // the only load that depends on the previous choice
+            const double v1 = lt >= 1 ? base[last * 8] : 0.0;
+            // everything else, in any order (two accumulators); exactness is restored below if needed
+            double p0 = lm, p1 = 0.0;
+            {
+                const int n16 = lt < 16 ? lt : 16;
+#pragma unroll
+                for (int l = 2; l <= 16; ++l) {
+                    if (l <= n16) {
+                        const unsigned a = (unsigned)(hist >> (4 * (l - 1))) & 7u;
+                        const double v = base[((l - 1) * HX_NSYM + a) * 8];
+                        if (l & 1) p1 += v; else p0 += v;
+                    }
+                }
+                for (int l = 17; l <= lt; ++l) {
+                    const unsigned a = ring[(snp - l) & (HX_RING - 1)];
+                    const double v = base[((l - 1) * HX_NSYM + a) * 8];
+                    if (l & 1) p1 += v; else p0 += v;
+                }
+            }
+            double tail = 0.0;                           // lookback beyond the band: cells are zero
+            for (int l = lt + 1; l <= lmax; ++l) {
+                const int v = (flags & HX_F_VSITE_TO) ? vseen[snp] : vseen[snp - l];
+                if (v != 0) tail += log10(1.0 / (double)v);
+            }
+            const double lwf = (p0 + p1) + tail + v1;
+            const double key = cand ? lwf : -INFINITY;
+            double best = -INFINITY, second = -INFINITY;
+            int bi = -1;
+#pragma unroll
+            for (int q = 0; q < HX_NSYM; ++q) {
+                const double v = __shfl_sync(0xffffffffu, key, q);
+                if ((cmask >> q) & 1u) {
+                    if (bi < 0) { best = v; bi = q; }
+                    else if (v > best) { second = best; best = v; bi = q; }
+                    else if (v > second) second = v;
+                }
+            }
+            int next = bi;
+            if (bi >= 0 && !(best - second > 1e-6 && best > -300.0 && best < 300.0)) {
+                // exact evaluation in the reference's order: ((log10 P(s) + t1) + t2) + ...
+                double lw = lm;
+                for (int l = 1; l <= lt; ++l) {
+                    const unsigned a = l == 1 ? last : (unsigned)ring[(snp - l) & (HX_RING - 1)];
+                    lw += base[((l - 1) * HX_NSYM + a) * 8];
+                }
+                for (int l = lt + 1; l <= lmax; ++l) {
+                    const int v = (flags & HX_F_VSITE_TO) ? vseen[snp] : vseen[snp - l];
+                    if (v != 0) lw += log10(1.0 / (double)v);
+                }
+                const double ws = cand ? pow(10.0, lw) : 0.0;
+                double wn, tw;
+                next = normalise_and_pick(ws, cmask, &wn, &tw);
+            }
+            if (next < 0) {                              // gretel.py:176-180
+                if (lane == 0) { flagsd[0] = snp; flagsd[1] = 1; }
+                // let the bulk copies already in flight land before this CTA's shared memory is released
+                for (int k2 = k + 1; k2 <= k + 2 && k2 < nchunks; ++k2)
+                    mbar_wait(smem_u32(&bars[k2 % 3]), (uint32_t)((k2 / 3) & 1));
+                return;
+            }
+            last = (unsigned)next;
+            hist = (hist << 4) | (unsigned long long)next;
+            if (lane == 0) { ring[snp & (HX_RING - 1)] = (uint8_t)next; path[snp] = (uint8_t)next; }
+            __syncwarp();
+        }
+    }
+    if (lane == 0) flagsd[0] = 0;
+}
+
+// Same walk straight from global memory, for lookbacks too long to stage (L*448 B per site
+// exceeds shared memory): ordered sums as in the reference, no fast path.
+__global__ void __launch_bounds__(32)
+k_walk_global(const double *__restrict__ terms, const double *__restrict__ logm,
+              const int32_t *__restrict__ vseen, int N, int L, int Lw, int flags,
+              uint8_t *__restrict__ path, int *__restrict__ flagsd) {
+    __shared__ uint8_t ring[HX_RING];
+    const int lane = threadIdx.x;
+    const int s = lane < HX_NSYM ? lane : 0;
+    if (flagsd[1]) return;
+    if (lane == 0) { ring[0] = HX_SYM_GAP; path[0] = HX_SYM_GAP; }
+    __syncwarp();
+    for (int snp = 1; snp <= N; ++snp) {
+        const double *lmrow = logm + (int64_t)snp * 8;
+        const unsigned cmask = (unsigned)lmrow[7];
+        const bool cand = lane < HX_NSYM && ((cmask >> lane) & 1u);
+        double lw = lmrow[s];
+        const int lmax = L < snp ? L : snp;
+        const int lt = lmax < Lw ? lmax : Lw;
+        const double *base = terms + ((int64_t)snp * Lw) * 56 + s;
+        int l = 1;
+        for (; l + 7 <= lt; l += 8) {
+            double v[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v[q] = base[((l + q - 1) * HX_NSYM + ring[(snp - (l + q)) & (HX_RING - 1)]) * 8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) lw += v[q];
+        }
+        for (; l <= lt; ++l) lw += base[((l - 1) * HX_NSYM + ring[(snp - l) & (HX_RING - 1)]) * 8];
+        for (; l <= lmax; ++l) {
+            const int v = (flags & HX_F_VSITE_TO) ? vseen[snp] : vseen[snp - l];
+            if (v != 0) lw += log10(1.0 / (double)v);
+        }
+        const double ws = cand ? pow(10.0, lw) : 0.0;
+        double wn, tw;
+        const int next = normalise_and_pick(ws, cmask, &wn, &tw);
+        if (next < 0) {
+            if (lane == 0) { flagsd[0] = snp; flagsd[1] = 1; }
+            return;
+        }
+        if (lane == 0) { ring[snp & (HX_RING - 1)] = (uint8_t)next; path[snp] = (uint8_t)next; }
+        __syncwarp();
+    }
+    if (lane == 0) flagsd[0] = 0;
 }
 
 // ---- per-site marginals of the chosen path, then ordered sums -------------------------
@@ -282,8 +507,28 @@ int launch_generate(hx_matrix *cur, hx_matrix *orig, int L, int flags, uint8_t *
     rc = hx_ensure_counts(orig);
     if (rc) return rc;
     const int N = cur->N;
-    k_walk<<<1, 32, 0, cur->stream>>>(cur->band, cur->scnt, cur->vseen, N, cur->W, L, flags, d_path,
-                                      cur->d_flags);
+    const int Lw = L < cur->W ? (L < 1 ? 1 : L) : cur->W;          // lookbacks that stay inside the band
+    const int64_t n_terms = ((int64_t)N + 2) * Lw * HX_NSYM * 8;
+    rc = ensure_buf((void **)&cur->d_terms, &cur->cap_terms, (n_terms + ((int64_t)N + 2) * 8) * (int64_t)sizeof(double));
+    if (rc) return rc;
+    double *logm = cur->d_terms + n_terms;
+    const int64_t tthreads = (int64_t)(N + 1) * Lw * 8;
+    k_walk_terms<<<(unsigned)((tthreads + 255) / 256), 256, 0, cur->stream>>>(cur->band, cur->vseen, N, cur->W, Lw,
+                                                                              flags, cur->d_terms);
+    k_walk_logm<<<(N + 1 + 127) / 128, 128, 0, cur->stream>>>(cur->scnt, N, flags, logm);
+    // sites per staged chunk: three chunks (terms + log-marginals) must fit in shared memory
+    const int64_t site_bytes = (int64_t)Lw * 448 + 64;
+    int C = (int)((200 * 1024) / (3 * site_bytes));
+    if (C > 64) C = 64;
+    if (C < 1) {
+        k_walk_global<<<1, 32, 0, cur->stream>>>(cur->d_terms, logm, cur->vseen, N, L, Lw, flags, d_path, cur->d_flags);
+    } else {
+        const size_t wsmem = (size_t)3 * C * site_bytes;
+        HX_CUDA(cudaFuncSetAttribute(k_walk_tables, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem));
+        k_walk_tables<<<1, 32, wsmem, cur->stream>>>(cur->d_terms, logm, cur->vseen, N, L, Lw, flags, C, d_path,
+                                                     cur->d_flags);
+    }
+    cur->launches += 2;
     k_path_stats<<<(N + 255) / 256, 256, 0, cur->stream>>>(cur->scnt, orig->scnt, N, d_path, cur->d_site,
                                                            cur->d_flags);
     k_path_sum<<<1, 32, 0, cur->stream>>>(cur->d_site, N, min_remove, d_stats, cur->d_flags);
