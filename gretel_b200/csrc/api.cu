@@ -45,23 +45,24 @@ int in_band(const hx_matrix *h, int a, int b, int64_t i, int64_t j) {
 void free_all(hx_matrix *h) {
     if (!h) return;
     cudaSetDevice(h->device);
-    if (h->band) cudaFree(h->band);
-    if (h->cnt) cudaFree(h->cnt);
-    if (h->d_totals) cudaFree(h->d_totals);
-    if (h->d_err) cudaFree(h->d_err);
-    if (h->s_rank) cudaFree(h->s_rank);
-    if (h->s_off) cudaFree(h->s_off);
-    if (h->s_codes) cudaFree(h->s_codes);
-    if (h->scnt) cudaFree(h->scnt);
-    if (h->vseen) cudaFree(h->vseen);
-    if (h->d_path) cudaFree(h->d_path);
-    if (h->d_stats) cudaFree(h->d_stats);
-    if (h->d_site) cudaFree(h->d_site);
-    if (h->d_partials) cudaFree(h->d_partials);
-    if (h->d_terms) cudaFree(h->d_terms);
-    if (h->d_flags) cudaFree(h->d_flags);
-    if (h->d_run_end) cudaFree(h->d_run_end);
-    if (h->d_misc) cudaFree(h->d_misc);
+    if (h->band) cudaFreeAsync(h->band, h->stream);
+    if (h->cnt) cudaFreeAsync(h->cnt, h->stream);
+    if (h->d_totals) cudaFreeAsync(h->d_totals, h->stream);
+    if (h->d_err) cudaFreeAsync(h->d_err, h->stream);
+    if (h->s_rank) cudaFreeAsync(h->s_rank, h->stream);
+    if (h->s_off) cudaFreeAsync(h->s_off, h->stream);
+    if (h->s_codes) cudaFreeAsync(h->s_codes, h->stream);
+    if (h->scnt) cudaFreeAsync(h->scnt, h->stream);
+    if (h->vseen) cudaFreeAsync(h->vseen, h->stream);
+    if (h->d_path) cudaFreeAsync(h->d_path, h->stream);
+    if (h->d_stats) cudaFreeAsync(h->d_stats, h->stream);
+    if (h->d_site) cudaFreeAsync(h->d_site, h->stream);
+    if (h->d_partials) cudaFreeAsync(h->d_partials, h->stream);
+    if (h->d_terms) cudaFreeAsync(h->d_terms, h->stream);
+    if (h->d_flags) cudaFreeAsync(h->d_flags, h->stream);
+    if (h->d_run_end) cudaFreeAsync(h->d_run_end, h->stream);
+    if (h->d_misc) cudaFreeAsync(h->d_misc, h->stream);
+    if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->h_pinned) cudaFreeHost(h->h_pinned);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -102,23 +103,30 @@ int hx_create(int32_t n_snps, int32_t band_w, int32_t device, hx_matrix **out) {
             return e__ == cudaErrorMemoryAllocation ? HX_E_NOMEM : HX_E_CUDA;            \
         }                                                                                \
     } while (0)
+    {   // keep freed blocks cached in the device's default pool (a new matrix per BAM must not pay cudaMalloc again)
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            unsigned long long thr = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        }
+    }
     HX_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     h->own_stream = true;
     HX_TRY(cudaEventCreate(&h->ev0));
     HX_TRY(cudaEventCreate(&h->ev1));
-    HX_TRY(cudaMalloc(&h->band, sizeof(float) * (size_t)h->band_elems));
+    HX_TRY(cudaMallocAsync((void **)&h->band, sizeof(float) * (size_t)h->band_elems, h->stream));
     HX_TRY(cudaMemsetAsync(h->band, 0, sizeof(float) * (size_t)h->band_elems, h->stream));
-    HX_TRY(cudaMalloc(&h->d_totals, 8 * sizeof(unsigned long long)));
+    HX_TRY(cudaMallocAsync((void **)&h->d_totals, 8 * sizeof(unsigned long long), h->stream));
     HX_TRY(cudaMemsetAsync(h->d_totals, 0, 8 * sizeof(unsigned long long), h->stream));
-    HX_TRY(cudaMalloc(&h->d_err, sizeof(int)));
+    HX_TRY(cudaMallocAsync((void **)&h->d_err, sizeof(int), h->stream));
     HX_TRY(cudaMemsetAsync(h->d_err, 0, sizeof(int), h->stream));
-    HX_TRY(cudaMalloc(&h->scnt, sizeof(double) * 8 * ((size_t)n_snps + 2)));
-    HX_TRY(cudaMalloc(&h->vseen, sizeof(int32_t) * ((size_t)n_snps + 2)));
-    HX_TRY(cudaMalloc(&h->d_site, sizeof(double) * 3 * ((size_t)n_snps + 2)));
-    HX_TRY(cudaMalloc(&h->d_flags, 8 * sizeof(int)));
+    HX_TRY(cudaMallocAsync((void **)&h->scnt, sizeof(double) * 8 * ((size_t)n_snps + 2), h->stream));
+    HX_TRY(cudaMallocAsync((void **)&h->vseen, sizeof(int32_t) * ((size_t)n_snps + 2), h->stream));
+    HX_TRY(cudaMallocAsync((void **)&h->d_site, sizeof(double) * 3 * ((size_t)n_snps + 2), h->stream));
+    HX_TRY(cudaMallocAsync((void **)&h->d_flags, 8 * sizeof(int), h->stream));
     HX_TRY(cudaMemsetAsync(h->d_flags, 0, 8 * sizeof(int), h->stream));
-    HX_TRY(cudaMalloc(&h->d_misc, 32 * sizeof(double)));
-    HX_TRY(cudaMalloc(&h->d_run_end, sizeof(int64_t) * ((size_t)n_snps + 2)));
+    HX_TRY(cudaMallocAsync((void **)&h->d_misc, 32 * sizeof(double), h->stream));
+    HX_TRY(cudaMallocAsync((void **)&h->d_run_end, sizeof(int64_t) * ((size_t)n_snps + 2), h->stream));
     HX_TRY(cudaMallocHost(&h->h_pinned, 256));
     HX_TRY(cudaStreamSynchronize(h->stream));
 #undef HX_TRY
@@ -184,7 +192,7 @@ int hx_sync(hx_matrix *h) {
 // ------------------------------------------------------------------------------ ingestion
 static int ensure_counts_buffer(hx_matrix *h) {
     if (h->cnt) return HX_OK;
-    HX_CUDA(cudaMalloc(&h->cnt, sizeof(uint32_t) * (size_t)h->band_elems));
+    HX_CUDA(cudaMallocAsync((void **)&h->cnt, sizeof(uint32_t) * (size_t)h->band_elems, h->stream));
     HX_CUDA(cudaMemsetAsync(h->cnt, 0, sizeof(uint32_t) * (size_t)h->band_elems, h->stream));
     return HX_OK;
 }
@@ -234,17 +242,17 @@ int hx_ingest_host(hx_matrix *h, const int32_t *rank, const int64_t *off, const 
         const int64_t n_codes = off[n_reads] - off[0];
         HX_CHECK_ARG(n_codes >= 0);
         if (n_reads > h->cap_reads) {
-            if (h->s_rank) cudaFree(h->s_rank);
-            if (h->s_off) cudaFree(h->s_off);
+            if (h->s_rank) cudaFreeAsync(h->s_rank, h->stream);
+            if (h->s_off) cudaFreeAsync(h->s_off, h->stream);
             h->s_rank = nullptr; h->s_off = nullptr; h->cap_reads = 0;
-            HX_CUDA(cudaMalloc(&h->s_rank, sizeof(int32_t) * (size_t)n_reads));
-            HX_CUDA(cudaMalloc(&h->s_off, sizeof(int64_t) * ((size_t)n_reads + 1)));
+            HX_CUDA(cudaMallocAsync((void **)&h->s_rank, sizeof(int32_t) * (size_t)n_reads, h->stream));
+            HX_CUDA(cudaMallocAsync((void **)&h->s_off, sizeof(int64_t) * ((size_t)n_reads + 1), h->stream));
             h->cap_reads = n_reads;
         }
         if (n_codes > h->cap_codes) {
-            if (h->s_codes) cudaFree(h->s_codes);
+            if (h->s_codes) cudaFreeAsync(h->s_codes, h->stream);
             h->s_codes = nullptr; h->cap_codes = 0;
-            HX_CUDA(cudaMalloc(&h->s_codes, (size_t)n_codes + 16));
+            HX_CUDA(cudaMallocAsync((void **)&h->s_codes, (size_t)n_codes + 16, h->stream));
             h->cap_codes = n_codes;
         }
         HX_CUDA(cudaMemcpyAsync(h->s_rank, rank, sizeof(int32_t) * (size_t)n_reads, cudaMemcpyHostToDevice, h->stream));
@@ -289,7 +297,7 @@ int hx_finalize_counts(hx_matrix *h) {
     h->launches++;
     HX_CUDA(cudaGetLastError());
     HX_CUDA(cudaStreamSynchronize(h->stream));
-    HX_CUDA(cudaFree(h->cnt));
+    HX_CUDA(cudaFreeAsync(h->cnt, h->stream));
     h->cnt = nullptr;
     h->counts_dirty = true;
     return HX_OK;

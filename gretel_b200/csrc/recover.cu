@@ -474,12 +474,12 @@ __global__ void k_reweight_matrix(float *__restrict__ band, int64_t n, double ra
     }
 }
 
-int ensure_buf(void **p, int64_t *cap, int64_t need_bytes) {
+int ensure_buf(void **p, int64_t *cap, int64_t need_bytes, cudaStream_t st) {
     if (*cap >= need_bytes) return HX_OK;
-    if (*p) cudaFree(*p);
+    if (*p) cudaFreeAsync(*p, st);
     *p = nullptr;
     *cap = 0;
-    HX_CUDA(cudaMalloc(p, (size_t)need_bytes));
+    HX_CUDA(cudaMallocAsync(p, (size_t)need_bytes, st));
     *cap = need_bytes;
     return HX_OK;
 }
@@ -489,7 +489,7 @@ int launch_reweight(hx_matrix *h, const uint8_t *d_path, const double *d_ratio, 
     constexpr int BLOCK = 256;
     const int64_t cells = ((int64_t)h->N + 1) * h->W;
     const int64_t grid = (cells + BLOCK - 1) / BLOCK;
-    int rc = ensure_buf((void **)&h->d_partials, &h->cap_partials, grid * (int64_t)sizeof(double));
+    int rc = ensure_buf((void **)&h->d_partials, &h->cap_partials, grid * (int64_t)sizeof(double), h->stream);
     if (rc) return rc;
     k_reweight_path<BLOCK><<<(unsigned)grid, BLOCK, 0, h->stream>>>(h->band, h->N, h->W, d_path, d_ratio,
                                                                     ratio, h->d_partials, h->d_flags);
@@ -509,7 +509,7 @@ int launch_generate(hx_matrix *cur, hx_matrix *orig, int L, int flags, uint8_t *
     const int N = cur->N;
     const int Lw = L < cur->W ? (L < 1 ? 1 : L) : cur->W;          // lookbacks that stay inside the band
     const int64_t n_terms = ((int64_t)N + 2) * Lw * HX_NSYM * 8;
-    rc = ensure_buf((void **)&cur->d_terms, &cur->cap_terms, (n_terms + ((int64_t)N + 2) * 8) * (int64_t)sizeof(double));
+    rc = ensure_buf((void **)&cur->d_terms, &cur->cap_terms, (n_terms + ((int64_t)N + 2) * 8) * (int64_t)sizeof(double), cur->stream);
     if (rc) return rc;
     double *logm = cur->d_terms + n_terms;
     const int64_t tthreads = (int64_t)(N + 1) * Lw * 8;
@@ -580,7 +580,7 @@ int hx_edge_weights_at(hx_matrix *h, int32_t snp, const uint8_t *path, int32_t L
     HX_CUDA(cudaSetDevice(h->device));
     int rc = hx_ensure_counts(h);
     if (rc) return rc;
-    rc = ensure_buf((void **)&h->d_path, &h->cap_path, (int64_t)h->N + 2);
+    rc = ensure_buf((void **)&h->d_path, &h->cap_path, (int64_t)h->N + 2, h->stream);
     if (rc) return rc;
     HX_CUDA(cudaMemcpyAsync(h->d_path, path, (size_t)snp, cudaMemcpyHostToDevice, h->stream));
     k_edge_one<<<1, 32, 0, h->stream>>>(h->band, h->scnt, h->vseen, h->W, L, flags, snp, h->d_path, h->d_misc);
@@ -601,9 +601,9 @@ int hx_generate_path(hx_matrix *cur, hx_matrix *orig, int32_t L, int flags, uint
     HX_CHECK_ARG(cur->N == orig->N && cur->device == orig->device && L >= 0 && L <= HX_MAX_L);
     HX_CUDA(cudaSetDevice(cur->device));
     const int N = cur->N;
-    int rc = ensure_buf((void **)&cur->d_path, &cur->cap_path, (int64_t)N + 2);
+    int rc = ensure_buf((void **)&cur->d_path, &cur->cap_path, (int64_t)N + 2, cur->stream);
     if (rc) return rc;
-    rc = ensure_buf((void **)&cur->d_stats, &cur->cap_stats, 8 * (int64_t)sizeof(double));
+    rc = ensure_buf((void **)&cur->d_stats, &cur->cap_stats, 8 * (int64_t)sizeof(double), cur->stream);
     if (rc) return rc;
     // orig's counts are produced on orig's stream; order them before our walk
     if (orig->stream != cur->stream && orig->counts_dirty) {
@@ -636,7 +636,7 @@ int hx_generate_path(hx_matrix *cur, hx_matrix *orig, int32_t L, int flags, uint
 int hx_reweight_path(hx_matrix *h, const uint8_t *path, double ratio, double *removed) {
     HX_CHECK_ARG(h && path && removed);
     HX_CUDA(cudaSetDevice(h->device));
-    int rc = ensure_buf((void **)&h->d_path, &h->cap_path, (int64_t)h->N + 2);
+    int rc = ensure_buf((void **)&h->d_path, &h->cap_path, (int64_t)h->N + 2, h->stream);
     if (rc) return rc;
     HX_CUDA(cudaMemsetAsync(h->d_flags, 0, 2 * sizeof(int), h->stream));
     HX_CUDA(cudaMemcpyAsync(h->d_path, path, (size_t)h->N + 1, cudaMemcpyHostToDevice, h->stream));
@@ -659,9 +659,9 @@ int hx_recover(hx_matrix *cur, hx_matrix *orig, int32_t L, int flags, int32_t ma
     const int64_t N = cur->N;
     *n_found = 0;
     if (max_paths == 0) return HX_OK;
-    int rc = ensure_buf((void **)&cur->d_path, &cur->cap_path, (N + 1) * (int64_t)max_paths);
+    int rc = ensure_buf((void **)&cur->d_path, &cur->cap_path, (N + 1) * (int64_t)max_paths, cur->stream);
     if (rc) return rc;
-    rc = ensure_buf((void **)&cur->d_stats, &cur->cap_stats, 8 * (int64_t)sizeof(double) * max_paths);
+    rc = ensure_buf((void **)&cur->d_stats, &cur->cap_stats, 8 * (int64_t)sizeof(double) * max_paths, cur->stream);
     if (rc) return rc;
     if (orig->stream != cur->stream && orig->counts_dirty) {
         rc = hx_ensure_counts(orig);
