@@ -275,20 +275,18 @@ k_walk_tables(const double *__restrict__ terms, const double *__restrict__ logm,
                 if (v != 0) tail += log10(1.0 / (double)v);
             }
             const double lwf = (p0 + p1) + tail + v1;
+            // best log-weight over the 7 candidate lanes (butterfly), then who is within 1e-6 of it
             const double key = cand ? lwf : -INFINITY;
-            double best = -INFINITY, second = -INFINITY;
-            int bi = -1;
+            double best = key;
 #pragma unroll
-            for (int q = 0; q < HX_NSYM; ++q) {
-                const double v = __shfl_sync(0xffffffffu, key, q);
-                if ((cmask >> q) & 1u) {
-                    if (bi < 0) { best = v; bi = q; }
-                    else if (v > best) { second = best; best = v; bi = q; }
-                    else if (v > second) second = v;
-                }
-            }
-            int next = bi;
-            if (bi >= 0 && !(best - second > 1e-6 && best > -300.0 && best < 300.0)) {
+            for (int o = 4; o > 0; o >>= 1) best = fmax(best, __shfl_xor_sync(0xffffffffu, best, o));
+            const unsigned near = __ballot_sync(0xffffffffu, cand && key >= best - 1e-6);
+            int next;
+            if (cmask == 0) {
+                next = -1;
+            } else if (__popc(near) == 1 && best > -300.0 && best < 300.0) {
+                next = __ffs(near) - 1;                  // a clear winner: no other candidate within rounding
+            } else {
                 // exact evaluation in the reference's order: ((log10 P(s) + t1) + t2) + ...
                 double lw = lm;
                 for (int l = 1; l <= lt; ++l) {
@@ -391,12 +389,28 @@ k_path_sum(const double *__restrict__ site, int N, double min_remove, double *__
     if (lane < 2) {
         double acc = 0.0;
         const double *p = site + lane * stride;
-        for (int snp = 1; snp <= N; ++snp) acc += p[snp];
+        int snp = 1;
+        for (; snp + 7 <= N; snp += 8) {                   // loads first, then the ordered adds
+            double v[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v[q] = p[snp + q];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) acc += v[q];
+        }
+        for (; snp <= N; ++snp) acc += p[snp];
         stats[lane] = acc;                                 // hp_current, hp_original
     } else if (lane == 2) {
         double mn = INFINITY;
         const double *p = site + 2 * stride;
-        for (int snp = 1; snp <= N; ++snp) mn = p[snp] < mn ? p[snp] : mn;
+        int snp = 1;
+        for (; snp + 7 <= N; snp += 8) {
+            double v[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v[q] = p[snp + q];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) mn = v[q] < mn ? v[q] : mn;
+        }
+        for (; snp <= N; ++snp) mn = p[snp] < mn ? p[snp] : mn;
         stats[2] = mn;                                     // min marginal
         stats[3] = mn < min_remove ? min_remove : mn;      // cmd.py:157-160
         stats[5] = 1.0;                                    // iteration completed

@@ -138,3 +138,28 @@ def test_recover_terminates_when_evidence_is_spent():
     assert [i["path"] for i in it_g] == [i["path"] for i in it_o] and len(it_g) >= 1
     for a, b in zip(it_g, it_o):
         assert a["removed"] == pytest.approx(b["removed"], rel=1e-9)
+
+
+import glob
+
+GOLDEN_RECOVERY = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "ref_recovery_*.npz")))
+
+
+@pytest.mark.parametrize("path", GOLDEN_RECOVERY, ids=[os.path.basename(p)[:-4] for p in GOLDEN_RECOVERY])
+@pytest.mark.parametrize("resident", [True, False])
+def test_gpu_against_reference_code_golden(path, resident):
+    """Golden vectors made by the reference's own generate_path / reweight_hansel_from_path
+    (tests/golden/make_golden.py): identical haplotypes, likelihoods within 1e-6 relative."""
+    from gretel_b200 import gretel
+    z = np.load(path)
+    N, L, v_site = int(z["N"]), int(z["L"]), str(z["v_site"])
+    h = _mk(z["rank"], z["off"], z["codes"], N, N + 1, L=L, v_site=v_site)
+    assert (h.n_slices, h.n_crumbs) == (int(z["n_slices"]), int(z["n_crumbs"]))
+    assert np.array_equal(h.to_dense(), z["dense_before"])
+    its, _ = gretel.recover(h, N, max_paths=len(z["paths"]), resident=resident)
+    assert len(its) == len(z["paths"])
+    for it, gp, gs in zip(its, z["paths"], z["stats"]):
+        assert list(h.encode_path(it["hansel_path"])) == list(gp)
+        for got, exp in zip((it["hp_current"], it["hp_original"], it["min_marginal"], it["ratio"], it["removed"]), gs):
+            assert got == pytest.approx(exp, rel=RTOL, abs=1e-12)
+    assert np.allclose(h.to_dense(), z["dense_after"], rtol=1e-6, atol=0)

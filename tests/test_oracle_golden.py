@@ -103,3 +103,40 @@ def test_reweight_closed_form():
             assert [(i, j) for (_, _, i, j) in rec.calls] == [
                 (0, 0), (0, 1), (0, 1), (1, 1), (1, 2), (0, 2), (1, 2), (2, 2), (2, 3),
                 (0, 3), (1, 3), (2, 3), (3, 3), (3, 4), (4, 5)]
+
+
+# ---- recovery control flow pinned to the reference's own code --------------------------------
+# tests/golden/ref_recovery_*.npz were produced by tests/golden/make_golden.py, which imports
+# /root/reference/gretel/gretel.py UNMODIFIED (generate_path, reweight_hansel_from_path) and
+# drives it over OracleHansel.  The oracle's restatement of those loops must reproduce them.
+import glob
+
+import pytest
+
+GOLDEN_RECOVERY = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "ref_recovery_*.npz")))
+
+
+@pytest.mark.parametrize("path", GOLDEN_RECOVERY, ids=[os.path.basename(p)[:-4] for p in GOLDEN_RECOVERY])
+def test_oracle_reproduces_reference_recovery(path, c_oracle):
+    z = np.load(path)
+    N, L, v_site = int(z["N"]), int(z["L"]), str(z["v_site"])
+    h = o.load_from_packed(z["rank"], z["off"], z["codes"], N, v_site=v_site)
+    assert (h.n_slices, h.n_crumbs) == (int(z["n_slices"]), int(z["n_crumbs"]))
+    assert np.array_equal(h.m, z["dense_before"])
+    h.L = L
+    its, _ = o.recover(h, N, max_paths=len(z["paths"]))
+    assert len(its) == len(z["paths"]) and len(its) > 0
+    for it, gp, gs in zip(its, z["paths"], z["stats"]):
+        assert [o.CODE[c] for c in it["path"]] == list(gp)
+        assert (it["hp_current"], it["hp_original"], it["min_marginal"], it["ratio"], it["removed"]) == tuple(gs)
+    assert np.array_equal(h.m, z["dense_after"])
+    # and the C twin, on the banded layout
+    W = N + 1
+    band, _ = c_oracle.ingest(z["rank"], z["off"], z["codes"], N, W)
+    cur = band.astype(np.float32)
+    orig = cur.copy()
+    for gp, gs in zip(z["paths"], z["stats"]):
+        pc, res = c_oracle.generate_path(cur, orig, N, W, L, v_site=v_site)
+        assert list(pc) == list(gp) and res == tuple(gs[:3])
+        assert c_oracle.reweight_path(cur, N, W, pc, gs[3]) == gs[4]
+    assert np.array_equal(cur, o.band_of(h, W))
