@@ -214,8 +214,15 @@ def run_ours(args):
     h.counts_buffer()                      # allocate the pending counts outside the timed region
     stream = torch.cuda.ExternalStream(h.stream, device=dev)
 
+    pipe = None
+    if world > 1 and args.segments > 1:
+        pipe = gdist.PipelinedIngest(h, d["rank"], R, segments=args.segments)
+
     def step():
         h.reset_counts()
+        if pipe is not None:
+            pipe.run(t_rank.data_ptr(), t_off.data_ptr(), t_codes.data_ptr())
+            return
         h.ingest_device(t_rank.data_ptr(), t_off.data_ptr(), t_codes.data_ptr(), R)
         if world > 1:
             gdist.allreduce_counts(h)
@@ -358,7 +365,7 @@ def run_ours(args):
                            "[+ all-reduce] + finalize + totals"},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
             "observations_per_step": int(n_obs_global), "wall_s_timed_region": wall_s,
-            "recovery": recovery, "synth_seconds": gen_s, "band_w": W,
+            "recovery": recovery, "synth_seconds": gen_s, "band_w": W, "allreduce_segments": args.segments if world > 1 else 0,
             "ingest_kernel": args.kernel}
     print(json.dumps(line))
     if world > 1:
@@ -376,6 +383,8 @@ def main():
     ap.add_argument("--workload", default="metagenome", choices=sorted(synth.WORKLOADS))
     ap.add_argument("--reads", type=int, default=0, help="reads per GPU (default: the workload's full size)")
     ap.add_argument("--kernel", type=int, default=0, help="ingestion kernel: 0 auto, 1 generic, 2 bit-sliced")
+    ap.add_argument("--segments", type=int, default=4,
+                    help="N>1: ingest in this many launches, all-reducing finished band rows behind the next one")
     ap.add_argument("--recover-paths", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-sample", type=int, default=0)

@@ -280,6 +280,7 @@ k_walk_tables(const double *__restrict__ terms, const double *__restrict__ logm,
             double best = key;
 #pragma unroll
             for (int o = 4; o > 0; o >>= 1) best = fmax(best, __shfl_xor_sync(0xffffffffu, best, o));
+            best = __shfl_sync(0xffffffffu, best, 0);    // lanes 8..31 hold -inf: make the branch below warp-uniform
             const unsigned near = __ballot_sync(0xffffffffu, cand && key >= best - 1e-6);
             int next;
             if (cmask == 0) {

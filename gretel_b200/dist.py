@@ -50,6 +50,66 @@ def allreduce_counts(hansel, group=None):
             dist.all_reduce(totals, op=dist.ReduceOp.SUM, group=group)
 
 
+class PipelinedIngest:
+    """Ingestion of device-resident, rank-sorted reads in ``segments`` launches with the
+    all-reduce of the finished band rows overlapped with the next launch.
+
+    After the reads [0, i) are ingested, every band row pj <= rank[i] + 1 is final on this GPU
+    (a read of rank r only touches rows pj >= r + 2), so that slice of the partial matrix can
+    already be summed across GPUs on a second stream while the kernel works on the next
+    segment.  Only the last segment's all-reduce stays exposed."""
+
+    def __init__(self, hansel, rank_host, n_reads, segments=4, group=None):
+        import torch
+        import torch.distributed as dist
+        self.h, self.group, self.dist, self.torch = hansel, group, dist, torch
+        S = max(1, int(segments))
+        self.cuts = [(n_reads * s) // S for s in range(S + 1)]
+        cell = hansel.band_w * 49
+        # last finished row after each segment; must agree on every rank -> take the minimum
+        rows = [min(int(rank_host[self.cuts[s + 1]]) + 1, hansel.n_snps + 1) for s in range(S - 1)]
+        dev = torch.device("cuda", hansel.device)
+        if dist.is_initialized() and dist.get_world_size(group) > 1 and rows:
+            t = torch.tensor(rows, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+            rows = [int(x) for x in t.tolist()]
+        rows = [max(r, 0) for r in rows] + [hansel.n_snps + 1]
+        for i in range(1, len(rows)):
+            rows[i] = max(rows[i], rows[i - 1])
+        self.row_hi = rows
+        self.cell = cell
+        cptr, cn, tptr, tn = hansel.counts_buffer()
+        self.counts = torch.as_tensor(_DevBuf(cptr, cn, "<i4"), device=dev)
+        self.totals = torch.as_tensor(_DevBuf(tptr, tn, "<i8"), device=dev)
+        self.main = torch.cuda.ExternalStream(hansel.stream, device=dev)
+        self.comm = torch.cuda.Stream(device=dev)
+        self.events = [torch.cuda.Event() for _ in range(S)]
+        self.done = torch.cuda.Event()
+
+    def run(self, rank_ptr, off_ptr, codes_ptr):
+        """Enqueue everything; returns without synchronising (work is ordered on hansel.stream)."""
+        torch, dist = self.torch, self.dist
+        h = self.h
+        self.comm.wait_stream(self.main)                 # counts were zeroed on the main stream
+        lo_row = 0
+        for s in range(len(self.cuts) - 1):
+            a, b = self.cuts[s], self.cuts[s + 1]
+            if b > a:
+                h.ingest_device(rank_ptr + 4 * a, off_ptr + 8 * a, codes_ptr, b - a)
+            self.events[s].record(self.main)
+            hi_row = self.row_hi[s]
+            if hi_row >= lo_row:
+                self.comm.wait_event(self.events[s])
+                with torch.cuda.stream(self.comm):
+                    dist.all_reduce(self.counts[lo_row * self.cell:(hi_row + 1) * self.cell],
+                                    op=dist.ReduceOp.SUM, group=self.group)
+                lo_row = hi_row + 1
+        with torch.cuda.stream(self.comm):
+            dist.all_reduce(self.totals, op=dist.ReduceOp.SUM, group=self.group)
+            self.done.record(self.comm)
+        self.main.wait_event(self.done)
+
+
 def load_from_packed_sharded(rank, off, codes, n_snps, band_w, world_size=None, my_rank=None, device=None,
                              presharded=False, group=None):
     """Every rank calls this with the same packed reads (or, with ``presharded``, its own
