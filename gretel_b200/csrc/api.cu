@@ -45,6 +45,7 @@ int in_band(const hx_matrix *h, int a, int b, int64_t i, int64_t j) {
 void free_all(hx_matrix *h) {
     if (!h) return;
     cudaSetDevice(h->device);
+    hx_lr_free(h);
     if (h->band) cudaFreeAsync(h->band, h->stream);
     if (h->cnt) cudaFreeAsync(h->cnt, h->stream);
     if (h->d_totals) cudaFreeAsync(h->d_totals, h->stream);
@@ -198,7 +199,7 @@ static int ensure_counts_buffer(hx_matrix *h) {
 }
 
 int hx_set_ingest_kernel(hx_matrix *h, int which) {
-    HX_CHECK_ARG(h && which >= 0 && which <= 2);
+    HX_CHECK_ARG(h && which >= 0 && which <= 3);
     h->ingest_kernel = which;
     return HX_OK;
 }

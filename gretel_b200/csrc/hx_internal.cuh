@@ -44,6 +44,7 @@ struct hx_matrix {
     double *d_misc;                  // small outputs (weights etc.)
     void *h_pinned;                  // small pinned host buffer for D2H of scalars
     int ingest_kernel;
+    void *lr_scratch;                // long-read ingestion scratch (ingest_long.cu)
     cudaEvent_t ev0, ev1;
     bool ev_rec;                     // ev0/ev1 have been recorded at least once
     float last_ms[3];
@@ -76,5 +77,9 @@ __host__ __device__ __forceinline__ int64_t hx_cell_off(int64_t W, int64_t pi, i
 // ingest.cu
 int hx_launch_ingest(hx_matrix *h, const int32_t *d_rank, const int64_t *d_off,
                      const uint8_t *d_codes, int64_t n_reads);
+// ingest_long.cu
+int hx_launch_ingest_long(hx_matrix *h, const int32_t *d_rank, const int64_t *d_off,
+                          const uint8_t *d_codes, int64_t n_reads);
+void hx_lr_free(hx_matrix *h);
 // recover.cu
 int hx_ensure_counts(hx_matrix *h);

@@ -487,9 +487,20 @@ int hx_launch_ingest(hx_matrix *h, const int32_t *d_rank, const int64_t *d_off,
     const int kmax = h->W + 1;
     const bool bs_possible = kmax >= 2 && kmax <= BS_KMAX;
     const bool use_bs = h->ingest_kernel == 2 ? bs_possible : (h->ingest_kernel == 0 && bs_possible);
+    const bool use_long = !use_bs && (h->ingest_kernel == 3 || (h->ingest_kernel == 0 && kmax >= 2));
 
     HX_CUDA(cudaEventRecord(h->ev0, h->stream));
-    if (!use_bs) {
+    if (use_long) {
+        HX_CUDA(cudaMemsetAsync(sorted_flag, 1, sizeof(int), h->stream));     // non-zero = sorted
+        k_prepass<<<(unsigned)((n_reads + 255) / 256), 256, 0, h->stream>>>(d_rank, n_reads, h->N, sorted_flag,
+                                                                            h->d_run_end);
+        h->launches++;
+        int rc = hx_launch_ingest_long(h, d_rank, d_off, d_codes, n_reads);
+        if (rc) return rc;
+        k1_pairs_red<GBLOCK><<<ggrid, GBLOCK, 0, h->stream>>>(d_rank, d_off, d_codes, n_reads, h->N, h->W, h->cnt,
+                                                              h->d_totals, h->d_err, sorted_flag, 0);
+        h->launches++;
+    } else if (!use_bs) {
         k1_pairs_red<GBLOCK><<<ggrid, GBLOCK, 0, h->stream>>>(d_rank, d_off, d_codes, n_reads, h->N, h->W, h->cnt,
                                                               h->d_totals, h->d_err, sorted_flag, 1);
         h->launches++;

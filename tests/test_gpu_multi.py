@@ -1,0 +1,73 @@
+"""Two-GPU parity (NCCL): sharded ingestion + (pipelined) all-reduce == single-process oracle.
+Skipped on a 1-GPU box; `gpurun --gpus 2 -- python -m pytest tests/test_gpu_multi.py -m gpu`."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, segments, out):
+    import torch
+    import torch.distributed as dist
+    from gretel_b200 import dist as gdist, synth, util
+    from gretel_b200.hansel import Hansel, REF_SYMBOLS, REF_UNSYMBOLS
+    from oracle import c_oracle
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        w = synth.scaled(synth.WORKLOADS["metagenome"], 150_000)
+        d = synth.generate(w)
+        N, W = w.n_snps, d["max_k"] - 1
+        b = gdist.shard_bounds(d["off"], world)
+        lo, hi = int(b[rank]), int(b[rank + 1])
+        h = Hansel.init_matrix(REF_SYMBOLS, REF_UNSYMBOLS, N, band_w=W, device=rank)
+        h.counts_buffer()
+        dev = torch.device("cuda", rank)
+        t_rank = torch.from_numpy(d["rank"][lo:hi].copy()).to(dev)
+        t_off = torch.from_numpy(d["off"][lo:hi + 1].copy()).to(dev)
+        t_codes = torch.from_numpy(d["codes"]).to(dev)
+        if segments > 1:
+            pipe = gdist.PipelinedIngest(h, d["rank"][lo:hi], hi - lo, segments=segments)
+            h.reset_counts()
+            pipe.run(t_rank.data_ptr(), t_off.data_ptr(), t_codes.data_ptr())
+        else:
+            h.ingest_device(t_rank.data_ptr(), t_off.data_ptr(), t_codes.data_ptr(), hi - lo)
+            gdist.allreduce_counts(h)
+        s, c, v, sent = h.ingest_totals()
+        h.finalize()
+        util.set_totals(h, s, c, v)
+        band = h.band()
+        ref, rt = c_oracle.ingest(d["rank"], d["off"], d["codes"], N, W)
+        assert (s, c, v, sent) == tuple(int(x) for x in rt)
+        assert np.array_equal(band, ref.astype(np.float32))
+        # sharded public entry point from host arrays
+        h2 = gdist.load_from_packed_sharded(d["rank"], d["off"], d["codes"], N, W, device=rank)
+        assert np.array_equal(h2.band(), band) and h2.n_crumbs == c
+        dist.barrier()
+        open(out + str(rank), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("segments", [1, 4])
+def test_two_gpu_sharded_ingest(tmp_path, c_oracle, segments):
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    out = str(tmp_path / "ok")
+    mp.spawn(_worker, args=(2, _free_port(), segments, out), nprocs=2, join=True)
+    assert open(out + "0").read() == "ok" and open(out + "1").read() == "ok"
