@@ -246,6 +246,7 @@ k1_bitsliced(const int32_t *__restrict__ rank, const int64_t *__restrict__ off,
     int *const rareq0 = gk0 + 64;                                     // two buffers of gb*32 ints
     const uint32_t planes_saddr = (uint32_t)__cvta_generic_to_shared(planes0);
     __shared__ int s_rare_n[3];                      // rotating: built / consumed / being cleared
+    __shared__ int s_claim[3];                       // next group to transpose (same rotation): warps claim work
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int64_t per = (n_reads + gridDim.x - 1) / gridDim.x;
@@ -254,7 +255,7 @@ k1_bitsliced(const int32_t *__restrict__ rank, const int64_t *__restrict__ off,
     if (lo >= hi) return;
 
     for (size_t w = threadIdx.x; w < (size_t)rows * cells * 4; w += blockDim.x) tile[w] = make_uint4(0, 0, 0, 0);
-    if (threadIdx.x == 0) s_rare_n[0] = s_rare_n[1] = s_rare_n[2] = 0;
+    if (threadIdx.x == 0) { s_rare_n[0] = s_rare_n[1] = s_rare_n[2] = 0; s_claim[0] = s_claim[1] = s_claim[2] = 0; }
     int rc_build = 1, rc_cons = 0, rc_clear = 2;      // indices into s_rare_n, rotated every phase
 
     // this thread's site pair(s)
@@ -385,10 +386,13 @@ k1_bitsliced(const int32_t *__restrict__ rank, const int64_t *__restrict__ off,
             const int nb = (next.n + 31) >> 5;
             const int r = next.r;
             const int64_t run_stop = next.start + next.n;
-            // builders: the warps that own no active pair of `prev`, unless that leaves too few
-            int nbuild = nwarps - prev_aw, wfirst = prev_aw;
-            if (nbuild < (nwarps + 1) / 2) { nbuild = nwarps; wfirst = 0; }
-            for (int g = warp - wfirst; g >= 0 && g < nb; g += nbuild) {
+            // every warp claims groups until none is left: warps without active pairs of `prev` get here
+            // first and do most of the transposing, the pair-owning warps join when they are done
+            for (;;) {
+                int g = 0;
+                if (lane == 0) g = atomicAdd(&s_claim[rc_build], 1);
+                g = __shfl_sync(0xffffffffu, g, 0);
+                if (g >= nb) break;
                 const int64_t idx = next.start + (int64_t)g * 32 + lane;
                 int64_t o = 0;
                 int kb = 0;
@@ -458,7 +462,7 @@ k1_bitsliced(const int32_t *__restrict__ rank, const int64_t *__restrict__ off,
                 }
             }
         }
-        if (threadIdx.x == 0) s_rare_n[rc_clear] = 0;  // consumed one phase ago, refilled one phase ahead
+        if (threadIdx.x == 0) { s_rare_n[rc_clear] = 0; s_claim[rc_clear] = 0; }   // used one phase ago, reused one phase ahead
         __syncthreads();
         prev = next;
         buf ^= 1;

@@ -318,50 +318,85 @@ k_walk_tables(const double *__restrict__ terms, const double *__restrict__ logm,
     if (lane == 0) flagsd[0] = 0;
 }
 
-// Same walk straight from global memory, for lookbacks too long to stage (L*448 B per site
-// exceeds shared memory): ordered sums as in the reference, no fast path.
-__global__ void __launch_bounds__(32)
-k_walk_global(const double *__restrict__ terms, const double *__restrict__ logm,
-              const int32_t *__restrict__ vseen, int N, int L, int Lw, int flags,
-              uint8_t *__restrict__ path, int *__restrict__ flagsd) {
+// Wide-lookback walk (L*448 B per site does not fit the staged pipeline, e.g. ONT L ~ 300):
+// one warp per candidate symbol, lanes split the lookbacks and combine with warp shuffles;
+// warp 0 then takes the 7-way argmax.  As in k_walk_tables the reordered sum only picks a clear
+// winner; near-ties are re-evaluated in the reference's order by one lane per candidate.
+__global__ void __launch_bounds__(256)
+k_walk_wide(const double *__restrict__ terms, const double *__restrict__ logm,
+            const int32_t *__restrict__ vseen, int N, int L, int Lw, int flags,
+            uint8_t *__restrict__ path, int *__restrict__ flagsd) {
     __shared__ uint8_t ring[HX_RING];
-    const int lane = threadIdx.x;
-    const int s = lane < HX_NSYM ? lane : 0;
+    __shared__ double s_lw[8];
+    __shared__ int s_next;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;   // warp = candidate symbol (7 = idle helper)
     if (flagsd[1]) return;
-    if (lane == 0) { ring[0] = HX_SYM_GAP; path[0] = HX_SYM_GAP; }
-    __syncwarp();
+    if (threadIdx.x == 0) { ring[0] = HX_SYM_GAP; path[0] = HX_SYM_GAP; }
+    __syncthreads();
     for (int snp = 1; snp <= N; ++snp) {
         const double *lmrow = logm + (int64_t)snp * 8;
         const unsigned cmask = (unsigned)lmrow[7];
-        const bool cand = lane < HX_NSYM && ((cmask >> lane) & 1u);
-        double lw = lmrow[s];
         const int lmax = L < snp ? L : snp;
         const int lt = lmax < Lw ? lmax : Lw;
-        const double *base = terms + ((int64_t)snp * Lw) * 56 + s;
-        int l = 1;
-        for (; l + 7 <= lt; l += 8) {
-            double v[8];
+        const bool cand = warp < HX_NSYM && ((cmask >> warp) & 1u);
+        if (cand) {
+            const double *base = terms + ((int64_t)snp * Lw) * 56 + warp;
+            double p = 0.0;
+            for (int l = 1 + lane; l <= lt; l += 32)
+                p += base[((l - 1) * HX_NSYM + ring[(snp - l) & (HX_RING - 1)]) * 8];
+            for (int l = lt + 1 + lane; l <= lmax; l += 32) {       // beyond the band: cells are zero
+                const int v = (flags & HX_F_VSITE_TO) ? vseen[snp] : vseen[snp - l];
+                if (v != 0) p += log10(1.0 / (double)v);
+            }
 #pragma unroll
-            for (int q = 0; q < 8; ++q) v[q] = base[((l + q - 1) * HX_NSYM + ring[(snp - (l + q)) & (HX_RING - 1)]) * 8];
+            for (int o = 16; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
+            if (lane == 0) s_lw[warp] = lmrow[warp] + p;
+        } else if (lane == 0 && warp < 8) {
+            s_lw[warp] = -INFINITY;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            const double key = lane < HX_NSYM ? s_lw[lane] : -INFINITY;
+            double best = key;
 #pragma unroll
-            for (int q = 0; q < 8; ++q) lw += v[q];
+            for (int o = 4; o > 0; o >>= 1) best = fmax(best, __shfl_xor_sync(0xffffffffu, best, o));
+            best = __shfl_sync(0xffffffffu, best, 0);
+            const bool lcand = lane < HX_NSYM && ((cmask >> lane) & 1u);
+            const unsigned near = __ballot_sync(0xffffffffu, lcand && key >= best - 1e-6);
+            int next;
+            if (cmask == 0) {
+                next = -1;
+            } else if (__popc(near) == 1 && best > -300.0 && best < 300.0) {
+                next = __ffs(near) - 1;
+            } else {
+                // exact evaluation in the reference's order, one lane per candidate
+                double lw = 0.0;
+                if (lcand) {
+                    const double *base = terms + ((int64_t)snp * Lw) * 56 + lane;
+                    lw = lmrow[lane];
+                    for (int l = 1; l <= lt; ++l)
+                        lw += base[((l - 1) * HX_NSYM + ring[(snp - l) & (HX_RING - 1)]) * 8];
+                    for (int l = lt + 1; l <= lmax; ++l) {
+                        const int v = (flags & HX_F_VSITE_TO) ? vseen[snp] : vseen[snp - l];
+                        if (v != 0) lw += log10(1.0 / (double)v);
+                    }
+                }
+                const double ws = lcand ? pow(10.0, lw) : 0.0;
+                double wn, tw;
+                next = normalise_and_pick(ws, cmask, &wn, &tw);
+            }
+            if (lane == 0) {
+                s_next = next;
+                if (next >= 0) { ring[snp & (HX_RING - 1)] = (uint8_t)next; path[snp] = (uint8_t)next; }
+            }
         }
-        for (; l <= lt; ++l) lw += base[((l - 1) * HX_NSYM + ring[(snp - l) & (HX_RING - 1)]) * 8];
-        for (; l <= lmax; ++l) {
-            const int v = (flags & HX_F_VSITE_TO) ? vseen[snp] : vseen[snp - l];
-            if (v != 0) lw += log10(1.0 / (double)v);
-        }
-        const double ws = cand ? pow(10.0, lw) : 0.0;
-        double wn, tw;
-        const int next = normalise_and_pick(ws, cmask, &wn, &tw);
-        if (next < 0) {
-            if (lane == 0) { flagsd[0] = snp; flagsd[1] = 1; }
+        __syncthreads();
+        if (s_next < 0) {                                  // gretel.py:176-180
+            if (threadIdx.x == 0) { flagsd[0] = snp; flagsd[1] = 1; }
             return;
         }
-        if (lane == 0) { ring[snp & (HX_RING - 1)] = (uint8_t)next; path[snp] = (uint8_t)next; }
-        __syncwarp();
     }
-    if (lane == 0) flagsd[0] = 0;
+    if (threadIdx.x == 0) flagsd[0] = 0;
 }
 
 // ---- per-site marginals of the chosen path, then ordered sums -------------------------
@@ -536,7 +571,7 @@ int launch_generate(hx_matrix *cur, hx_matrix *orig, int L, int flags, uint8_t *
     int C = (int)((200 * 1024) / (3 * site_bytes));
     if (C > 64) C = 64;
     if (C < 1) {
-        k_walk_global<<<1, 32, 0, cur->stream>>>(cur->d_terms, logm, cur->vseen, N, L, Lw, flags, d_path, cur->d_flags);
+        k_walk_wide<<<1, 256, 0, cur->stream>>>(cur->d_terms, logm, cur->vseen, N, L, Lw, flags, d_path, cur->d_flags);
     } else {
         const size_t wsmem = (size_t)3 * C * site_bytes;
         HX_CUDA(cudaFuncSetAttribute(k_walk_tables, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem));

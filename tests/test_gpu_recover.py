@@ -65,7 +65,7 @@ def test_small_against_literal_python_oracle(seed):
 
 
 @pytest.mark.parametrize("name,n_reads,L", [("hiv", 20_000, None), ("hiv", 20_000, 1), ("hiv", 20_000, 8),
-                                            ("metagenome", 200_000, None), ("ont", 300, 6)])
+                                            ("metagenome", 200_000, None), ("ont", 300, 6), ("ont", 300, None)])
 def test_workload_recovery_against_c_oracle(c_oracle, name, n_reads, L):
     from gretel_b200 import gretel
     w = synth.scaled(synth.WORKLOADS[name], n_reads)
