@@ -207,7 +207,13 @@ def run_ours(args):
     p_rank = torch.from_numpy(d["rank"]).pin_memory()
     p_off = torch.from_numpy(d["off"]).pin_memory()
     p_codes = torch.from_numpy(d["codes"]).pin_memory()
-    h2d_bytes = p_rank.numel() * 4 + p_off.numel() * 8 + p_codes.numel()
+    # ... in the compact wire format the packer emits for the GPU path (uint16 SNP counts, nibble codes)
+    klen, codes4, n_codes = util.compact_packed(d["off"], d["codes"])
+    p_klen = torch.from_numpy(klen).pin_memory()
+    p_codes4 = torch.from_numpy(codes4).pin_memory()
+    h2d_bytes = p_rank.numel() * 4 + p_klen.numel() * 2 + p_codes4.numel()
+    if args.e2e_format == "wide":
+        h2d_bytes = p_rank.numel() * 4 + p_off.numel() * 8 + p_codes.numel()
 
     h = Hansel.init_matrix(REF_SYMBOLS, REF_UNSYMBOLS, N, band_w=W, device=local_rank)
     h.set_ingest_kernel(args.kernel)
@@ -273,7 +279,10 @@ def run_ours(args):
     def e2e_step():
         hh = Hansel.init_matrix(REF_SYMBOLS, REF_UNSYMBOLS, N, band_w=W, device=local_rank)
         hh.set_ingest_kernel(args.kernel)
-        hh.ingest_packed(p_rank.numpy(), p_off.numpy(), p_codes.numpy())
+        if args.e2e_format == "wide":
+            hh.ingest_packed(p_rank.numpy(), p_off.numpy(), p_codes.numpy())
+        else:
+            hh.ingest_packed_compact(p_rank.numpy(), p_klen.numpy(), p_codes4.numpy(), n_codes)
         if world > 1:
             gdist.allreduce_counts(hh)
         s, c, v, _ = hh.ingest_totals()
@@ -361,8 +370,9 @@ def run_ours(args):
             "config": workload_config(args, k_mean, R),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes),
                     "d2h_bytes_per_step": 32 + 4, "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps,
-                    "api": "gretel_b200.util.load_from_packed equivalent: Hansel.init_matrix + ingest_packed(host) "
-                           "[+ all-reduce] + finalize + totals"},
+                    "wire_format": args.e2e_format,
+                    "api": "Hansel.init_matrix + ingest_packed%s(pinned host arrays) [+ all-reduce] + finalize + "
+                           "totals, a new matrix every step" % ("_compact" if args.e2e_format == "compact" else "")},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
             "observations_per_step": int(n_obs_global), "wall_s_timed_region": wall_s,
             "recovery": recovery, "synth_seconds": gen_s, "band_w": W, "allreduce_segments": args.segments if world > 1 else 0,
@@ -383,8 +393,10 @@ def main():
     ap.add_argument("--workload", default="metagenome", choices=sorted(synth.WORKLOADS))
     ap.add_argument("--reads", type=int, default=0, help="reads per GPU (default: the workload's full size)")
     ap.add_argument("--kernel", type=int, default=0, help="ingestion kernel: 0 auto, 1 generic, 2 bit-sliced")
-    ap.add_argument("--segments", type=int, default=4,
+    ap.add_argument("--segments", type=int, default=1,
                     help="N>1: ingest in this many launches, all-reducing finished band rows behind the next one")
+    ap.add_argument("--e2e-format", default="compact", choices=["compact", "wide"],
+                    help="host wire format of the packed reads in the e2e leg (compact: uint16 counts + nibble codes)")
     ap.add_argument("--recover-paths", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-sample", type=int, default=0)

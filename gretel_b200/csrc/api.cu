@@ -6,6 +6,7 @@
 #include <string.h>
 
 #include "hx_internal.cuh"
+#include "scan.cuh"
 
 static thread_local char g_err[512] = "";
 
@@ -27,6 +28,22 @@ __global__ void k_fold_counts(const uint32_t *__restrict__ cnt, float *__restric
 }
 
 __global__ void k_add_one(float *p, float amount) { *p += amount; }
+
+// compact wire format -> the packed arrays the ingestion kernels read
+__global__ void k_widen_klen(const uint16_t *__restrict__ klen, int64_t n, int64_t *__restrict__ out /* n+1 */) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i <= n) out[i] = i < n ? (int64_t)klen[i] : 0;
+}
+
+__global__ void k_unpack_nibbles(const uint32_t *__restrict__ in, int64_t n_words, uint2 *__restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_words) return;
+    const uint32_t w = in[i];                    // 4 bytes = 8 codes, low nibble first
+    uint2 o;
+    o.x = (w & 0xfu) | ((w >> 4 & 0xfu) << 8) | ((w >> 8 & 0xfu) << 16) | ((w >> 12 & 0xfu) << 24);
+    o.y = (w >> 16 & 0xfu) | ((w >> 20 & 0xfu) << 8) | ((w >> 24 & 0xfu) << 16) | ((w >> 28 & 0xfu) << 24);
+    out[i] = o;
+}
 
 __global__ void k_reweight_one(float *p, double ratio, double *removed) {
     const double old = (double)*p;
@@ -53,6 +70,9 @@ void free_all(hx_matrix *h) {
     if (h->s_rank) cudaFreeAsync(h->s_rank, h->stream);
     if (h->s_off) cudaFreeAsync(h->s_off, h->stream);
     if (h->s_codes) cudaFreeAsync(h->s_codes, h->stream);
+    if (h->s_klen) cudaFreeAsync(h->s_klen, h->stream);
+    if (h->s_codes4) cudaFreeAsync(h->s_codes4, h->stream);
+    if (h->s_scan) cudaFreeAsync(h->s_scan, h->stream);
     if (h->scnt) cudaFreeAsync(h->scnt, h->stream);
     if (h->vseen) cudaFreeAsync(h->vseen, h->stream);
     if (h->d_path) cudaFreeAsync(h->d_path, h->stream);
@@ -263,6 +283,70 @@ int hx_ingest_host(hx_matrix *h, const int32_t *rank, const int64_t *off, const 
         if (rc) return rc;
         // kernels index codes by absolute offsets: bias the base pointer by off[0]
         rc = hx_launch_ingest(h, h->s_rank, h->s_off, h->s_codes - off[0], n_reads);
+        if (rc) return rc;
+    }
+    return hx_ingest_totals(h, totals);
+}
+
+int hx_ingest_host_compact(hx_matrix *h, const int32_t *rank, const uint16_t *klen, const uint8_t *codes4,
+                           int64_t n_reads, int64_t n_codes, int64_t totals[4]) {
+    HX_CHECK_ARG(h && totals && n_reads >= 0 && n_codes >= 0);
+    HX_CUDA(cudaSetDevice(h->device));
+    if (n_reads > 0) {
+        HX_CHECK_ARG(rank && klen && (codes4 || n_codes == 0));
+        cudaStream_t st = h->stream;
+        const int64_t n_words = (n_codes + 7) / 8;          // 32-bit words of packed nibbles
+        if (n_reads > h->cap_reads) {
+            if (h->s_rank) cudaFreeAsync(h->s_rank, st);
+            if (h->s_off) cudaFreeAsync(h->s_off, st);
+            h->s_rank = nullptr; h->s_off = nullptr; h->cap_reads = 0;
+            HX_CUDA(cudaMallocAsync((void **)&h->s_rank, sizeof(int32_t) * (size_t)n_reads, st));
+            HX_CUDA(cudaMallocAsync((void **)&h->s_off, sizeof(int64_t) * ((size_t)n_reads + 1), st));
+            h->cap_reads = n_reads;
+        }
+        if (n_words * 8 > h->cap_codes) {
+            if (h->s_codes) cudaFreeAsync(h->s_codes, st);
+            h->s_codes = nullptr; h->cap_codes = 0;
+            HX_CUDA(cudaMallocAsync((void **)&h->s_codes, (size_t)n_words * 8 + 16, st));
+            h->cap_codes = n_words * 8;
+        }
+        if (n_reads > h->cap_klen) {
+            if (h->s_klen) cudaFreeAsync(h->s_klen, st);
+            h->s_klen = nullptr; h->cap_klen = 0;
+            HX_CUDA(cudaMallocAsync((void **)&h->s_klen, sizeof(uint16_t) * (size_t)n_reads, st));
+            h->cap_klen = n_reads;
+        }
+        if (n_words > h->cap_codes4) {
+            if (h->s_codes4) cudaFreeAsync(h->s_codes4, st);
+            h->s_codes4 = nullptr; h->cap_codes4 = 0;
+            HX_CUDA(cudaMallocAsync((void **)&h->s_codes4, sizeof(uint32_t) * (size_t)n_words, st));
+            h->cap_codes4 = n_words;
+        }
+        constexpr int ITEMS = 16;
+        const int64_t n1 = n_reads + 1;
+        const int64_t nblk = (n1 + 256 * ITEMS - 1) / (256 * ITEMS);
+        if (nblk > h->cap_scan) {
+            if (h->s_scan) cudaFreeAsync(h->s_scan, st);
+            h->s_scan = nullptr; h->cap_scan = 0;
+            HX_CUDA(cudaMallocAsync((void **)&h->s_scan, sizeof(int64_t) * (size_t)nblk, st));
+            h->cap_scan = nblk;
+        }
+        HX_CUDA(cudaMemcpyAsync(h->s_rank, rank, sizeof(int32_t) * (size_t)n_reads, cudaMemcpyHostToDevice, st));
+        HX_CUDA(cudaMemcpyAsync(h->s_klen, klen, sizeof(uint16_t) * (size_t)n_reads, cudaMemcpyHostToDevice, st));
+        if (n_codes)
+            HX_CUDA(cudaMemcpyAsync(h->s_codes4, codes4, (size_t)((n_codes + 1) / 2), cudaMemcpyHostToDevice, st));
+        // off = exclusive scan of klen (n+1 entries, off[n] = n_codes); codes = one byte per nibble
+        k_widen_klen<<<(unsigned)((n1 + 255) / 256), 256, 0, st>>>(h->s_klen, n_reads, h->s_off);
+        k_scan_partials<int64_t, 0, ITEMS><<<(unsigned)nblk, 256, 0, st>>>(h->s_off, n1, h->s_scan);
+        k_scan_spine<int64_t, 0><<<1, 32, 0, st>>>(h->s_scan, nblk, nullptr);
+        k_scan_apply<int64_t, 0, ITEMS, true><<<(unsigned)nblk, 256, 0, st>>>(h->s_off, n1, h->s_scan, h->s_off);
+        if (n_words)
+            k_unpack_nibbles<<<(unsigned)((n_words + 255) / 256), 256, 0, st>>>(h->s_codes4, n_words, (uint2 *)h->s_codes);
+        h->launches += 5;
+        HX_CUDA(cudaGetLastError());
+        int rc = ensure_counts_buffer(h);
+        if (rc) return rc;
+        rc = hx_launch_ingest(h, h->s_rank, h->s_off, h->s_codes, n_reads);
         if (rc) return rc;
     }
     return hx_ingest_totals(h, totals);

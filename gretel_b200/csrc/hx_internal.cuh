@@ -26,6 +26,8 @@ struct hx_matrix {
     // staging for hx_ingest_host
     int32_t *s_rank; int64_t *s_off; uint8_t *s_codes;
     int64_t cap_reads, cap_codes;
+    uint16_t *s_klen; uint32_t *s_codes4; int64_t *s_scan;     // compact wire format staging
+    int64_t cap_klen, cap_codes4, cap_scan;
     // recovery scratch
     double *scnt;                    // (N+2)*8 per-site counts + total
     int32_t *vseen;                  // (N+2) valid symbols seen per site

@@ -132,6 +132,20 @@ class Hansel:
         self._touch()
         return tuple(int(x) for x in totals)
 
+    def ingest_packed_compact(self, rank, klen, codes4, n_codes):
+        """ingest_packed in the compact wire format (see util.compact_packed): uint16 SNP counts and
+        nibble-packed codes; offsets and byte codes are rebuilt on the GPU."""
+        rank = np.ascontiguousarray(rank, dtype=np.int32)
+        klen = np.ascontiguousarray(klen, dtype=np.uint16)
+        codes4 = np.ascontiguousarray(codes4, dtype=np.uint8)
+        if len(klen) != len(rank) or len(codes4) < (int(n_codes) + 1) // 2:
+            raise ValueError("klen/codes4 do not match rank/n_codes")
+        totals = np.zeros(4, dtype=np.int64)
+        _lib.check(self._lib.hx_ingest_host_compact(self._h, rank.ctypes.data, klen.ctypes.data, codes4.ctypes.data,
+                                                    len(rank), int(n_codes), totals.ctypes.data))
+        self._touch()
+        return tuple(int(x) for x in totals)
+
     def ingest_totals(self):
         totals = np.zeros(4, dtype=np.int64)
         _lib.check(self._lib.hx_ingest_totals(self._h, totals.ctypes.data))

@@ -25,6 +25,21 @@ def band_width_for(off, floor=1):
     return max(int(np.diff(off).max()) - 1, floor, 1)
 
 
+def compact_packed(off, codes):
+    """(off int64[R+1], codes uint8) -> (klen uint16[R], codes4 uint8[ceil(n/2)], n_codes): the compact
+    wire format of Hansel.ingest_packed_compact (two allele codes per byte, low nibble first)."""
+    off = np.asarray(off, dtype=np.int64)
+    k = np.diff(off)
+    if len(k) and k.max() > 65535:
+        raise ValueError("a read covers more than 65535 SNPs")
+    c = np.ascontiguousarray(codes[off[0]:off[-1]] if len(off) else codes, dtype=np.uint8)
+    n = len(c)
+    if n & 1:
+        c = np.concatenate([c, np.zeros(1, np.uint8)])
+    codes4 = (c[0::2] | (c[1::2] << 4)).astype(np.uint8)
+    return k.astype(np.uint16), codes4, n
+
+
 def load_from_packed(rank, off, codes, n_snps, band_w=None, device=None, hansel=None, finalize=True,
                      quiet=True):
     """Packed reads -> Hansel (util.py:83 + 226-286 + 329-333).

@@ -70,6 +70,11 @@ int hx_sync(hx_matrix *h);
  * Counts accumulate over calls until hx_finalize_counts(). */
 int hx_ingest_host(hx_matrix *h, const int32_t *rank, const int64_t *off, const uint8_t *codes,
                    int64_t n_reads, int64_t totals[4]);
+/* The same, in the compact wire format (half the host->device bytes): klen[r] = SNPs on read r,
+ * codes4 = the allele codes of all reads back to back, two per byte (low nibble first);
+ * n_codes = sum of klen.  Offsets and byte codes are rebuilt on the device. */
+int hx_ingest_host_compact(hx_matrix *h, const int32_t *rank, const uint16_t *klen, const uint8_t *codes4,
+                           int64_t n_reads, int64_t n_codes, int64_t totals[4]);
 /* Device-buffer entry point, asynchronous on the matrix's stream. */
 int hx_ingest_device(hx_matrix *h, const int32_t *d_rank, const int64_t *d_off,
                      const uint8_t *d_codes, int64_t n_reads);

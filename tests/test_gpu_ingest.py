@@ -149,3 +149,35 @@ def test_linearity_and_order_independence():
     idx = np.repeat(off[:-1][perm], k[perm]) + (np.arange(poff[-1]) - np.repeat(poff[:-1], k[perm]))
     pb, pt = _gpu_band(d["rank"][perm], poff, d["codes"][idx], w.n_snps, W)
     assert pt == t_whole and np.array_equal(pb, whole)
+
+
+@pytest.mark.parametrize("name,n_reads", [("hiv", 30_000), ("metagenome", 100_000), ("ont", 300)])
+def test_compact_wire_format(c_oracle, name, n_reads):
+    """hx_ingest_host_compact (uint16 SNP counts + nibble codes, offsets rebuilt by a device scan)."""
+    from gretel_b200 import util
+    from gretel_b200.hansel import Hansel, REF_SYMBOLS, REF_UNSYMBOLS
+    w = synth.scaled(synth.WORKLOADS[name], n_reads)
+    d = synth.generate(w)
+    W = d["max_k"] - 1
+    klen, codes4, n_codes = util.compact_packed(d["off"], d["codes"])
+    assert n_codes == len(d["codes"]) and len(codes4) == (n_codes + 1) // 2
+    ref, rt = c_oracle.ingest(d["rank"], d["off"], d["codes"], w.n_snps, W)
+    h = Hansel.init_matrix(REF_SYMBOLS, REF_UNSYMBOLS, w.n_snps, band_w=W)
+    totals = h.ingest_packed_compact(d["rank"], klen, codes4, n_codes)
+    assert totals == tuple(int(x) for x in rt)
+    assert np.array_equal(h.band(), ref.astype(np.float32))
+
+
+def test_compact_wire_format_edges(c_oracle):
+    from gretel_b200 import util
+    from gretel_b200.hansel import Hansel, REF_SYMBOLS, REF_UNSYMBOLS
+    rng = np.random.default_rng(77)
+    for trial in range(6):
+        N = int(rng.integers(2, 60))
+        rank, off, codes = synth.random_packed(rng, N, int(rng.integers(0, 400)), int(rng.integers(2, 12)), p_special=0.3)
+        W = N + 1
+        klen, codes4, n_codes = util.compact_packed(off, codes)
+        ref, rt = c_oracle.ingest(rank, off, codes, N, W)
+        h = Hansel.init_matrix(REF_SYMBOLS, REF_UNSYMBOLS, N, band_w=W)
+        assert h.ingest_packed_compact(rank, klen, codes4, n_codes) == tuple(int(x) for x in rt)
+        assert np.array_equal(h.band(), ref.astype(np.float32))
