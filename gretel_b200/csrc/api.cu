@@ -219,7 +219,7 @@ static int ensure_counts_buffer(hx_matrix *h) {
 }
 
 int hx_set_ingest_kernel(hx_matrix *h, int which) {
-    HX_CHECK_ARG(h && which >= 0 && which <= 3);
+    HX_CHECK_ARG(h && which >= 0 && which <= 5);
     h->ingest_kernel = which;
     return HX_OK;
 }

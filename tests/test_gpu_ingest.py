@@ -45,7 +45,7 @@ def test_reference_golden_through_gpu(golden_dir):
         assert h.L == 3
 
 
-@pytest.mark.parametrize("kernel", [1, 2, 3])
+@pytest.mark.parametrize("kernel", [1, 2, 3, 4, 5])
 @pytest.mark.parametrize("seed", range(8))
 def test_random_packed_bit_exact(c_oracle, seed, kernel):
     rng = np.random.default_rng(500 + seed)
@@ -60,7 +60,7 @@ def test_random_packed_bit_exact(c_oracle, seed, kernel):
     assert np.array_equal(band, ref.astype(np.float32))
 
 
-@pytest.mark.parametrize("kernel", [1, 2, 3])
+@pytest.mark.parametrize("kernel", [1, 2, 3, 4, 5])
 def test_edge_cases(c_oracle, kernel):
     # empty input, reads with k<2, N=2 (start rule beats end rule), reads ending on the last SNP
     cases = []
@@ -91,7 +91,7 @@ def test_bad_reads_raise():
 
 
 @pytest.mark.parametrize("name,n_reads", [("hiv", 200_000), ("metagenome", 300_000), ("ont", 600)])
-@pytest.mark.parametrize("kernel", [0, 1, 3])
+@pytest.mark.parametrize("kernel", [0, 1, 3, 4, 5])
 def test_workloads_bit_exact(c_oracle, name, n_reads, kernel):
     """Config 2 at full size, configs 3/4 at sizes the C oracle finishes in seconds."""
     w = synth.scaled(synth.WORKLOADS[name], n_reads)
