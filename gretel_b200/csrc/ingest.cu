@@ -221,6 +221,66 @@ __device__ __forceinline__ void bs_rare_read(const uint8_t *__restrict__ c, int 
     }
 }
 
+// Transposes one group of 32 reads (lane = read, kb SNPs each, codes at codes+o) into bit-planes in
+// shared memory: planes[t] = {v, b0, b1, -} with bit r of v set when read r holds A/C/G/T at site t and
+// (b0,b1) the two low code bits of that allele.  No warp votes (they share the quarter-rate XU pipe with
+// POPC): every lane packs 10 sites x 3 flags of its own read into one word and a 32x32 bit-matrix
+// transpose over the warp (5 shuffle stages on the ALU) turns "flags of my read" into "reads per flag".
+// Returns the widest read of the group; rare_or != 0 marks reads holding N, - or _; x0 = first 4 codes.
+template <int KW>
+__device__ __forceinline__ int bs_build_group(const uint8_t *__restrict__ codes, int64_t o, int kb,
+                                              uint32_t pg_addr, uint32_t &rare_or, uint32_t &x0) {
+    const int lane = threadIdx.x & 31;
+    const int kg = __reduce_max_sync(0xffffffffu, kb);
+    const uint8_t *__restrict__ c = codes + o;
+    const unsigned mis = (unsigned)(reinterpret_cast<uintptr_t>(c) & 3u);
+    const uint32_t *__restrict__ cw = reinterpret_cast<const uint32_t *>(c - mis);
+    const int nw = kb ? (int)((mis + kb + 3) >> 2) : 0;
+    uint32_t wd[KW + 1];
+#pragma unroll
+    for (int w = 0; w <= KW; ++w) wd[w] = w < nw ? __ldg(cw + w) : 0u;
+    const unsigned sh = 8u * mis;
+    uint32_t x[KW];
+    rare_or = 0;
+#pragma unroll
+    for (int w = 0; w < KW; ++w) {
+        uint32_t xx = __funnelshift_r(wd[w], wd[w + 1], sh);
+        const int nv = kb - 4 * w;                                // valid bytes in this word
+        const uint32_t vmask = nv >= 4 ? 0xffffffffu : (nv <= 0 ? 0u : ((1u << (8 * nv)) - 1u));
+        rare_or |= xx & 0xfcfcfcfcu & vmask;
+        x[w] = xx | ~vmask;                                       // bytes past the read's end -> 0xff
+    }
+    x0 = x[0];
+    // which (site, flag) this lane will hold after a transpose: flag index = lane
+    const int my_tl = lane / 3, my_plane = lane - 3 * my_tl;
+#pragma unroll
+    for (int t0 = 0; t0 < 4 * KW; t0 += 10) {
+        if (t0 >= kg) break;                                      // warp-uniform
+        uint32_t row = 0;                                         // flags of my read for sites t0..t0+9
+#pragma unroll
+        for (int tl = 0; tl < 10; ++tl) {
+            const int t = t0 + tl;
+            if (t < 4 * KW) {
+                const uint32_t a = (x[t >> 2] >> (8 * (t & 3))) & 0xffu;
+                const uint32_t f = a < 4u ? 2u * a + 1u : 0u;      // v | b0<<1 | b1<<2
+                row |= f << (3 * tl);
+            }
+        }
+        // 32x32 bit transpose across the warp: afterwards bit r of `row` = flag `lane` of read r
+#pragma unroll
+        for (int j = 16; j >= 1; j >>= 1) {
+            const uint32_t m = j == 16 ? 0x0000ffffu : j == 8 ? 0x00ff00ffu : j == 4 ? 0x0f0f0f0fu
+                             : j == 2 ? 0x33333333u : 0x55555555u;
+            const uint32_t y = __shfl_xor_sync(0xffffffffu, row, j);
+            row = (lane & j) ? ((row & ~m) | ((y & ~m) >> j)) : ((row & m) | ((y & m) << j));
+        }
+        const int t = t0 + my_tl;
+        if (lane < 30 && t < kg)
+            asm volatile("st.shared.u32 [%0], %1;" ::"r"(pg_addr + (uint32_t)(t * 16 + my_plane * 4)), "r"(row) : "memory");
+    }
+    return kg;
+}
+
 // One batch of up to `gb` groups (32 reads each) out of a run of reads that share rank r.
 struct BsBatch {
     int64_t start;      // first read
@@ -337,8 +397,9 @@ k1_bitsliced(const int32_t *__restrict__ rank, const int64_t *__restrict__ off,
                         if (a2 < gk[g]) {
                             const uint4 m1 = planes[(size_t)g * kmax + a1];
                             const uint4 m2 = planes[(size_t)g * kmax + a2];
-                            const unsigned x1[4] = {m1.x, m1.y, m1.z, m1.w};
-                            const unsigned x2[4] = {m2.x, m2.y, m2.z, m2.w};
+                            // planes hold (v, b0, b1): A = v&~b0&~b1, C = b0&~b1, G = b1&~b0, T = b0&b1
+                            const unsigned x1[4] = {m1.x & ~(m1.y | m1.z), m1.y & ~m1.z, m1.z & ~m1.y, m1.y & m1.z};
+                            const unsigned x2[4] = {m2.x & ~(m2.y | m2.z), m2.y & ~m2.z, m2.z & ~m2.y, m2.y & m2.z};
 #pragma unroll
                             for (int a = 0; a < 4; ++a)
 #pragma unroll
@@ -406,44 +467,11 @@ k1_bitsliced(const int32_t *__restrict__ rank, const int64_t *__restrict__ off,
                 }
                 n_slices += kb >= 2;
                 n_codes += kb;
-                const int kg = __reduce_max_sync(0xffffffffu, kb);
-                if (lane == 0) gk[g] = kg;
+                uint32_t rare_or, x0;
                 const uint8_t *__restrict__ c = codes + o;
-                const unsigned mis = (unsigned)(reinterpret_cast<uintptr_t>(c) & 3u);
-                const uint32_t *__restrict__ cw = reinterpret_cast<const uint32_t *>(c - mis);
-                const int nw = kb ? (int)((mis + kb + 3) >> 2) : 0;
-                uint32_t wd[KW + 1];
-#pragma unroll
-                for (int w = 0; w <= KW; ++w) wd[w] = w < nw ? __ldg(cw + w) : 0u;
-                const unsigned sh = 8u * mis;
-                // shared-window byte address of this group's planes (keeps the per-site store to one STS)
-                uint32_t pg_addr = planes_saddr + (uint32_t)((buf * gb + g) * kmax) * 16u;
-                asm volatile("" : "+r"(pg_addr));              // keep it in a register (no rematerialisation per site)
-                const unsigned lane_nz = lane;                 // predicate source for the lane-0 store
-                uint32_t rare_or = 0, x0 = 0xffffffffu;
-#pragma unroll
-                for (int w = 0; w < KW; ++w) {
-                    if (4 * w >= kg) break;                        // warp-uniform
-                    uint32_t x = __funnelshift_r(wd[w], wd[w + 1], sh);
-                    const int nv = kb - 4 * w;                    // valid bytes in this word
-                    const uint32_t vmask = nv >= 4 ? 0xffffffffu : (nv <= 0 ? 0u : ((1u << (8 * nv)) - 1u));
-                    rare_or |= x & 0xfcfcfcfcu & vmask;
-                    x |= ~vmask;                                  // bytes past the read's end -> 0xff
-                    if (w == 0) x0 = x;
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        if (4 * w + u >= kg) break;                // warp-uniform
-                        const bool pv = (x & (0xfcu << (8 * u))) == 0;
-                        const unsigned v = __ballot_sync(0xffffffffu, pv);
-                        const unsigned b0 = __ballot_sync(0xffffffffu, pv && (x & (1u << (8 * u))));
-                        const unsigned b1 = __ballot_sync(0xffffffffu, pv && (x & (2u << (8 * u))));
-                        asm volatile(
-                            "{ .reg .pred p; setp.eq.u32 p, %5, 0;\n\t"
-                            "@p st.shared.v4.u32 [%0], {%1, %2, %3, %4}; }" ::"r"(pg_addr + (4 * w + u) * 16),
-                            "r"(v & ~b1 & ~b0), "r"(v & ~b1 & b0), "r"(v & b1 & ~b0), "r"(v & b1 & b0), "r"(lane_nz)
-                            : "memory");
-                    }
-                }
+                const int kg = bs_build_group<KW>(codes, o, kb, planes_saddr + (uint32_t)((buf * gb + g) * kmax) * 16u,
+                                                  rare_or, x0);
+                if (lane == 0) gk[g] = kg;
                 if (kb >= 2) {
                     // start sentinel (util.py:262-266) / end sentinel (:271-275); the start rule wins
                     const unsigned a0 = x0 & 0xffu;
@@ -593,43 +621,11 @@ k1_bitsliced_ws(const int32_t *__restrict__ rank, const int64_t *__restrict__ of
                 }
                 n_slices += kb >= 2;
                 n_codes += kb;
-                const int kg = __reduce_max_sync(0xffffffffu, kb);
-                if (lane == 0) gk[g] = kg;
+                uint32_t rare_or, x0;
                 const uint8_t *__restrict__ c = codes + o;
-                const unsigned mis = (unsigned)(reinterpret_cast<uintptr_t>(c) & 3u);
-                const uint32_t *__restrict__ cw = reinterpret_cast<const uint32_t *>(c - mis);
-                const int nw = kb ? (int)((mis + kb + 3) >> 2) : 0;
-                uint32_t wd[KW + 1];
-#pragma unroll
-                for (int w = 0; w <= KW; ++w) wd[w] = w < nw ? __ldg(cw + w) : 0u;
-                const unsigned sh = 8u * mis;
-                uint32_t pg_addr = planes_saddr + (uint32_t)((b * gb + g) * kmax) * 16u;
-                asm volatile("" : "+r"(pg_addr));
-                const unsigned lane_nz = lane;
-                uint32_t rare_or = 0, x0 = 0xffffffffu;
-#pragma unroll
-                for (int w = 0; w < KW; ++w) {
-                    if (4 * w >= kg) break;                        // warp-uniform
-                    uint32_t x = __funnelshift_r(wd[w], wd[w + 1], sh);
-                    const int nv = kb - 4 * w;
-                    const uint32_t vmask = nv >= 4 ? 0xffffffffu : (nv <= 0 ? 0u : ((1u << (8 * nv)) - 1u));
-                    rare_or |= x & 0xfcfcfcfcu & vmask;
-                    x |= ~vmask;
-                    if (w == 0) x0 = x;
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        if (4 * w + u >= kg) break;                // warp-uniform
-                        const bool pv = (x & (0xfcu << (8 * u))) == 0;
-                        const unsigned v = __ballot_sync(0xffffffffu, pv);
-                        const unsigned b0 = __ballot_sync(0xffffffffu, pv && (x & (1u << (8 * u))));
-                        const unsigned b1 = __ballot_sync(0xffffffffu, pv && (x & (2u << (8 * u))));
-                        asm volatile(
-                            "{ .reg .pred p; setp.eq.u32 p, %5, 0;\n\t"
-                            "@p st.shared.v4.u32 [%0], {%1, %2, %3, %4}; }" ::"r"(pg_addr + (4 * w + u) * 16),
-                            "r"(v & ~b1 & ~b0), "r"(v & ~b1 & b0), "r"(v & b1 & ~b0), "r"(v & b1 & b0), "r"(lane_nz)
-                            : "memory");
-                    }
-                }
+                const int kg = bs_build_group<KW>(codes, o, kb, planes_saddr + (uint32_t)((b * gb + g) * kmax) * 16u,
+                                                  rare_or, x0);
+                if (lane == 0) gk[g] = kg;
                 if (kb >= 2) {
                     const unsigned a0 = x0 & 0xffu;
                     if (r == 0 && sym_valid_from(a0)) {            // util.py:262-266
@@ -734,8 +730,9 @@ k1_bitsliced_ws(const int32_t *__restrict__ rank, const int64_t *__restrict__ of
                         if (a2 < gk[g]) {
                             const uint4 m1 = planes[(size_t)g * kmax + a1];
                             const uint4 m2 = planes[(size_t)g * kmax + a2];
-                            const unsigned x1[4] = {m1.x, m1.y, m1.z, m1.w};
-                            const unsigned x2[4] = {m2.x, m2.y, m2.z, m2.w};
+                            // planes hold (v, b0, b1): A = v&~b0&~b1, C = b0&~b1, G = b1&~b0, T = b0&b1
+                            const unsigned x1[4] = {m1.x & ~(m1.y | m1.z), m1.y & ~m1.z, m1.z & ~m1.y, m1.y & m1.z};
+                            const unsigned x2[4] = {m2.x & ~(m2.y | m2.z), m2.y & ~m2.z, m2.z & ~m2.y, m2.y & m2.z};
 #pragma unroll
                             for (int a = 0; a < 4; ++a)
 #pragma unroll
