@@ -281,6 +281,32 @@ __device__ __forceinline__ int bs_build_group(const uint8_t *__restrict__ codes,
     return kg;
 }
 
+// One thread's site pair (a1,a2) over the nb groups of a plane buffer: 16 x (AND, POPC, ADD) per group
+// of 32 reads.  Shared-window byte addresses are kept in registers and advanced per group (the compiler
+// otherwise rebuilds them from the kernel parameters in every iteration).
+__device__ __forceinline__ void bs_accumulate(uint32_t (&acc)[16], uint32_t buf_saddr, uint32_t gk_addr, int a1, int a2,
+                                              int nb, int kmax) {
+    uint32_t p1 = buf_saddr + (uint32_t)a1 * 16u, p2 = buf_saddr + (uint32_t)a2 * 16u;
+    uint32_t gstep = (uint32_t)kmax * 16u;
+    asm volatile("" : "+r"(p1), "+r"(p2), "+r"(gstep), "+r"(gk_addr));
+    for (int g = 0; g < nb; ++g, p1 += gstep, p2 += gstep, gk_addr += 4u) {
+        int kg;
+        asm volatile("ld.shared.s32 %0, [%1];" : "=r"(kg) : "r"(gk_addr));
+        if (a2 < kg) {
+            uint4 m1, m2;
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(m1.x), "=r"(m1.y), "=r"(m1.z), "=r"(m1.w) : "r"(p1));
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(m2.x), "=r"(m2.y), "=r"(m2.z), "=r"(m2.w) : "r"(p2));
+            // planes hold (v, b0, b1): A = v&~b0&~b1, C = b0&~b1, G = b1&~b0, T = b0&b1
+            const unsigned x1[4] = {m1.x & ~(m1.y | m1.z), m1.y & ~m1.z, m1.z & ~m1.y, m1.y & m1.z};
+            const unsigned x2[4] = {m2.x & ~(m2.y | m2.z), m2.y & ~m2.z, m2.z & ~m2.y, m2.y & m2.z};
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) acc[a * 4 + b] += __popc(x1[a] & x2[b]);
+        }
+    }
+}
+
 // One batch of up to `gb` groups (32 reads each) out of a run of reads that share rank r.
 struct BsBatch {
     int64_t start;      // first read
@@ -305,6 +331,7 @@ k1_bitsliced(const int32_t *__restrict__ rank, const int64_t *__restrict__ off,
     int *const gk0 = reinterpret_cast<int *>(planes0 + (size_t)2 * gb * kmax);   // two buffers of 32 ints
     int *const rareq0 = gk0 + 64;                                     // two buffers of gb*32 ints
     const uint32_t planes_saddr = (uint32_t)__cvta_generic_to_shared(planes0);
+    const uint32_t gk_saddr = (uint32_t)__cvta_generic_to_shared(gk0);
     __shared__ int s_rare_n[3];                      // rotating: built / consumed / being cleared
     __shared__ int s_claim[3];                       // next group to transpose (same rotation): warps claim work
 
@@ -367,7 +394,6 @@ k1_bitsliced(const int32_t *__restrict__ rank, const int64_t *__restrict__ off,
         // ---- consume `prev` (planes buffer buf^1) ---------------------------------------------
         if (prev.n) {
             const int pb = buf ^ 1;
-            const uint4 *planes = planes0 + (size_t)pb * gb * kmax;
             const int *gk = gk0 + pb * 32;
             const int nb = (prev.n + 31) >> 5;
             const int r = prev.r;
@@ -391,22 +417,8 @@ k1_bitsliced(const int32_t *__restrict__ rank, const int64_t *__restrict__ off,
             prev_aw = (bkm * (bkm - 1) / 2 + 31) >> 5;
 #pragma unroll
             for (int q = 0; q < NP; ++q) {
-                const int a1 = t1[q], a2 = t2[q];
-                if (a2 < bkm) {
-                    for (int g = 0; g < nb; ++g) {
-                        if (a2 < gk[g]) {
-                            const uint4 m1 = planes[(size_t)g * kmax + a1];
-                            const uint4 m2 = planes[(size_t)g * kmax + a2];
-                            // planes hold (v, b0, b1): A = v&~b0&~b1, C = b0&~b1, G = b1&~b0, T = b0&b1
-                            const unsigned x1[4] = {m1.x & ~(m1.y | m1.z), m1.y & ~m1.z, m1.z & ~m1.y, m1.y & m1.z};
-                            const unsigned x2[4] = {m2.x & ~(m2.y | m2.z), m2.y & ~m2.z, m2.z & ~m2.y, m2.y & m2.z};
-#pragma unroll
-                            for (int a = 0; a < 4; ++a)
-#pragma unroll
-                                for (int b = 0; b < 4; ++b) acc[q][a * 4 + b] += __popc(x1[a] & x2[b]);
-                        }
-                    }
-                }
+                if (t2[q] < bkm) bs_accumulate(acc[q], planes_saddr + (uint32_t)(pb * gb * kmax) * 16u, gk_saddr + pb * 128u,
+                                               t1[q], t2[q], nb, kmax);
             }
             if (prev.last) {
                 // add this run's counts into the sliding tile (each cell has one owner thread)
@@ -557,6 +569,7 @@ k1_bitsliced_ws(const int32_t *__restrict__ rank, const int64_t *__restrict__ of
     uint4 *const planes0 = tile + (size_t)rows * cells * 4;                      // WS_NBUF x gb x kmax uint4
     int *const gk0 = reinterpret_cast<int *>(planes0 + (size_t)WS_NBUF * gb * kmax);   // WS_NBUF x 32
     const uint32_t planes_saddr = (uint32_t)__cvta_generic_to_shared(planes0);
+    const uint32_t gk_saddr = (uint32_t)__cvta_generic_to_shared(gk0);
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int bw = nwarps - pw;                      // builder warps
@@ -718,28 +731,13 @@ k1_bitsliced_ws(const int32_t *__restrict__ rank, const int64_t *__restrict__ of
                     for (int x = 0; x < 16; ++x) acc[q][x] = 0;
             }
             ws_mbar_wait(ws_smem_u32(&s_full[b]), (bi / WS_NBUF) & 1);
-            const uint4 *planes = planes0 + (size_t)b * gb * kmax;
             const int *gk = gk0 + b * 32;
             const int bkm = __reduce_max_sync(0xffffffffu, lane < nb ? gk[lane] : 0);
             run_kmax = max(run_kmax, bkm);
 #pragma unroll
             for (int q = 0; q < NP; ++q) {
-                const int a1 = t1[q], a2 = t2[q];
-                if (a2 < bkm) {
-                    for (int g = 0; g < nb; ++g) {
-                        if (a2 < gk[g]) {
-                            const uint4 m1 = planes[(size_t)g * kmax + a1];
-                            const uint4 m2 = planes[(size_t)g * kmax + a2];
-                            // planes hold (v, b0, b1): A = v&~b0&~b1, C = b0&~b1, G = b1&~b0, T = b0&b1
-                            const unsigned x1[4] = {m1.x & ~(m1.y | m1.z), m1.y & ~m1.z, m1.z & ~m1.y, m1.y & m1.z};
-                            const unsigned x2[4] = {m2.x & ~(m2.y | m2.z), m2.y & ~m2.z, m2.z & ~m2.y, m2.y & m2.z};
-#pragma unroll
-                            for (int a = 0; a < 4; ++a)
-#pragma unroll
-                                for (int bb = 0; bb < 4; ++bb) acc[q][a * 4 + bb] += __popc(x1[a] & x2[bb]);
-                        }
-                    }
-                }
+                if (t2[q] < bkm) bs_accumulate(acc[q], planes_saddr + (uint32_t)(b * gb * kmax) * 16u, gk_saddr + b * 128u,
+                                               t1[q], t2[q], nb, kmax);
             }
             __syncwarp();
             if (lane == 0) ws_mbar_arrive(ws_smem_u32(&s_empty[b]));
