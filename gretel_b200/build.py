@@ -38,7 +38,8 @@ def needs_build():
 def build_lib(force=False, verbose=False):
     if not force and not needs_build():
         return LIB_PATH
-    cmd = [nvcc_path()] + NVCC_FLAGS + ["-I", os.path.join(_ROOT, "include"), "-I", os.path.join(_HERE, "csrc"),
+    extra = os.environ.get("HX_NVCC_DEFS", "").split()
+    cmd = [nvcc_path()] + NVCC_FLAGS + extra + ["-I", os.path.join(_ROOT, "include"), "-I", os.path.join(_HERE, "csrc"),
                                        "-o", LIB_PATH] + [os.path.join(_HERE, "csrc", s) for s in SOURCES]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or res.returncode != 0:
