@@ -181,3 +181,43 @@ def test_compact_wire_format_edges(c_oracle):
         h = Hansel.init_matrix(REF_SYMBOLS, REF_UNSYMBOLS, N, band_w=W)
         assert h.ingest_packed_compact(rank, klen, codes4, n_codes) == tuple(int(x) for x in rt)
         assert np.array_equal(h.band(), ref.astype(np.float32))
+
+
+@pytest.mark.parametrize("shape", [(600, 40, 300_000, 150), (600, 100, 120_000, 200), (3000, 300, 400_000, 150)],
+                         ids=["7k-reads-per-rank", "wide-reads-deep", "1k-reads-per-rank"])
+@pytest.mark.parametrize("kernel", [0, 4, 5, 3])
+def test_deep_coverage_runs_bit_exact(c_oracle, shape, kernel):
+    """Runs of thousands of reads per rank (several 1024-read batches per run, several CTAs per
+    run) - the regime of the full-size configs - at a size the C oracle checks in a second."""
+    G, N, R, L = shape
+    w = synth.Workload("deep", 1, G, N, R, L, 0.01, 0.004)
+    d = synth.generate(w, seed=5)
+    W = d["max_k"] - 1
+    ref, rt = c_oracle.ingest(d["rank"], d["off"], d["codes"], N, W)
+    band, totals = _gpu_band(d["rank"], d["off"], d["codes"], N, W, kernel)
+    assert totals == tuple(int(x) for x in rt)
+    assert np.array_equal(band, ref.astype(np.float32))
+
+
+def test_adversarial_shapes(c_oracle):
+    """All reads on one rank; only k=2 reads; a read spanning the whole region; isolated ranks far apart."""
+    rng = np.random.default_rng(11)
+    cases = []
+    k = rng.integers(2, 21, size=5000)                              # one rank, 5000 reads
+    off = np.concatenate([[0], np.cumsum(k)]).astype(np.int64)
+    cases.append((np.full(5000, 3, np.int32), off, rng.integers(0, 6, size=off[-1]).astype(np.uint8), 40, 19))
+    off = (np.arange(3001) * 2).astype(np.int64)                    # only pairs, every rank
+    cases.append((np.sort(rng.integers(0, 99, size=3000)).astype(np.int32), off,
+                  rng.integers(0, 4, size=6000).astype(np.uint8), 100, 1))
+    off = np.array([0, 50, 52, 54], np.int64)                       # one read covers everything
+    cases.append((np.array([0, 0, 48], np.int32), off, rng.integers(0, 4, size=54).astype(np.uint8), 50, 49))
+    ranks = np.sort(np.repeat(np.array([0, 500, 1000, 1990], np.int32), 700))   # isolated ranks (ring jumps)
+    k = rng.integers(2, 11, size=len(ranks))
+    off = np.concatenate([[0], np.cumsum(k)]).astype(np.int64)
+    cases.append((ranks, off, rng.integers(0, 5, size=off[-1]).astype(np.uint8), 2000, 9))
+    for rank, off, codes, N, W in cases:
+        ref, rt = c_oracle.ingest(rank, off, codes, N, W)
+        for kernel in (0, 1, 3, 4, 5):
+            band, totals = _gpu_band(rank, off, codes, N, W, kernel)
+            assert totals == tuple(int(x) for x in rt), (N, kernel)
+            assert np.array_equal(band, ref.astype(np.float32)), (N, kernel)
