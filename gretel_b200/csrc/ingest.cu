@@ -307,6 +307,14 @@ __device__ __forceinline__ void bs_accumulate(uint32_t (&acc)[16], uint32_t buf_
     }
 }
 
+// L2 prefetch of the inputs of the batch after the one being transposed (TMA prefetch, no destination):
+// the packed reads are streamed from HBM exactly once, so without it every group build pays two
+// dependent HBM misses (offsets, then codes).
+__device__ __forceinline__ void bs_prefetch_l2(const void *p, uint32_t bytes) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)15;
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"((bytes + 31u) & ~15u) : "memory");
+}
+
 // One batch of up to `gb` groups (32 reads each) out of a run of reads that share rank r.
 struct BsBatch {
     int64_t start;      // first read
@@ -343,6 +351,7 @@ k1_bitsliced(const int32_t *__restrict__ rank, const int64_t *__restrict__ off,
 
     for (size_t w = threadIdx.x; w < (size_t)rows * cells * 4; w += blockDim.x) tile[w] = make_uint4(0, 0, 0, 0);
     if (threadIdx.x == 0) { s_rare_n[0] = s_rare_n[1] = s_rare_n[2] = 0; s_claim[0] = s_claim[1] = s_claim[2] = 0; }
+    const uint32_t pf_bytes = (uint32_t)gb * 32u * (uint32_t)(kmax > 40 ? 32 : 18);   // ~ one batch of codes
     int rc_build = 1, rc_cons = 0, rc_clear = 2;      // indices into s_rare_n, rotated every phase
 
     // this thread's site pair(s)
@@ -388,6 +397,11 @@ k1_bitsliced(const int32_t *__restrict__ rank, const int64_t *__restrict__ off,
             next.n = (int)min((int64_t)gb * 32, run_hi - cur);
             cur += next.n;
             next.last = cur >= run_hi;
+            if (threadIdx.x == 0 && cur < hi) {          // the batch after `next`: its offsets and first rank
+                const int64_t ahead = min((int64_t)gb * 32 + 1, hi - cur + 1);
+                bs_prefetch_l2(off + cur, (uint32_t)(ahead * 8));
+                bs_prefetch_l2(rank + cur, 16);
+            }
         }
         if (!prev.n && !next.n) break;
 
@@ -476,6 +490,8 @@ k1_bitsliced(const int32_t *__restrict__ rank, const int64_t *__restrict__ off,
                         if (r < 0 || (int64_t)r + k64 > N || k64 - 1 > W) errbits |= 1;
                         else kb = (int)k64;
                     }
+                    // last read of the batch: the next batch's codes start right behind it
+                    if (idx + 1 == run_stop && idx + 1 < hi) bs_prefetch_l2(codes + o + k64, pf_bytes);
                 }
                 n_slices += kb >= 2;
                 n_codes += kb;
@@ -592,6 +608,7 @@ k1_bitsliced_ws(const int32_t *__restrict__ rank, const int64_t *__restrict__ of
 
     unsigned long long t_crumbs = 0;
     unsigned n_slices = 0, n_codes = 0, n_notcov = 0, n_sent = 0, n_rcrumbs = 0, errbits = 0;
+    const uint32_t pf_bytes = (uint32_t)gb * 32u * (uint32_t)(kmax > 40 ? 32 : 18);   // ~ one batch of codes
 
     // batch scheduler (identical in every warp)
     int64_t cur = lo, run_hi = lo;
@@ -614,6 +631,11 @@ k1_bitsliced_ws(const int32_t *__restrict__ rank, const int64_t *__restrict__ of
             const int64_t bstart = cur;
             const int bn = (int)min((int64_t)gb * 32, run_hi - cur);
             cur += bn;
+            if (bwid == 0 && lane == 0 && cur < hi) {      // the next batch: its offsets and first rank
+                const int64_t ahead = min((int64_t)gb * 32 + 1, hi - cur + 1);
+                bs_prefetch_l2(off + cur, (uint32_t)(ahead * 8));
+                bs_prefetch_l2(rank + cur, 16);
+            }
             const int r = run_r;
             const int nb = (bn + 31) >> 5;
             const int b = bi % WS_NBUF;
@@ -631,6 +653,8 @@ k1_bitsliced_ws(const int32_t *__restrict__ rank, const int64_t *__restrict__ of
                         if (r < 0 || (int64_t)r + k64 > N || k64 - 1 > W) errbits |= 1;
                         else kb = (int)k64;
                     }
+                    // last read of the batch: the next batch's codes start right behind it
+                    if (idx + 1 == run_stop && idx + 1 < hi) bs_prefetch_l2(codes + o + k64, pf_bytes);
                 }
                 n_slices += kb >= 2;
                 n_codes += kb;
