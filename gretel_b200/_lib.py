@@ -45,12 +45,19 @@ SIGNATURES = {
     "hx_generate_path": (_int, [_p, _p, _i32, _int, _p, _p, C.POINTER(_i32)]),
     "hx_reweight_path": (_int, [_p, _p, _dbl, C.POINTER(_dbl)]),
     "hx_recover": (_int, [_p, _p, _i32, _int, _i32, _dbl, _p, _p, C.POINTER(_i32)]),
+    "hx_pack_bam": (_int, [C.c_char_p, C.c_char_p, _i32, _i32, _p, _i32, _int, _int, _p]),
+    "hx_pack_free": (None, [_p]),
     "hx_band_to_host": (_int, [_p, _p]),
     "hx_band_from_host": (_int, [_p, _p]),
     "hx_to_dense": (_int, [_p, _p]),
     "hx_last_kernel_ms": (_int, [_p, _int, C.POINTER(_flt)]),
     "hx_launch_count": (_int, [_p, C.POINTER(_i64)]),
 }
+
+class HxPacked(C.Structure):
+    _fields_ = [("rank", C.POINTER(C.c_int32)), ("off", C.POINTER(C.c_int64)), ("codes", C.POINTER(C.c_uint8)),
+                ("n_reads", C.c_int64), ("n_codes", C.c_int64), ("n_records", C.c_int64)]
+
 
 _LIB = None
 

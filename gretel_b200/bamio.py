@@ -215,8 +215,31 @@ def pack_reads(records, snp_pos_sorted, start_pos, end_pos, target_tid, stepper=
             np.ascontiguousarray(codes, dtype=np.uint8))
 
 
+def pack_bam_native(bam_path, target_contig, start_pos, end_pos, vcf_handler, stepper="samtools", n_threads=1):
+    """BAM + process_vcf() output -> packed reads, by the multi-threaded C++ packer of libhanselx.so
+    (hx_pack_bam: BGZF inflate + one CIGAR walk per alignment).  Same result as pack_bam()."""
+    import ctypes as C
+
+    from . import _lib
+    lib = _lib.load()
+    snp_pos = np.ascontiguousarray([vcf_handler["snp_rev"][i] for i in range(vcf_handler["N"])], dtype=np.int32)
+    out = _lib.HxPacked()
+    rc = lib.hx_pack_bam(str(bam_path).encode(), str(target_contig).encode(), int(start_pos), int(end_pos),
+                         snp_pos.ctypes.data, len(snp_pos), {"samtools": 0, "all": 1, "nofilter": 2}[stepper],
+                         int(max(1, n_threads)), C.byref(out))
+    _lib.check(rc)
+    try:
+        R, n = int(out.n_reads), int(out.n_codes)
+        rank = np.ctypeslib.as_array(out.rank, shape=(max(R, 1),))[:R].copy()
+        off = np.ctypeslib.as_array(out.off, shape=(R + 1,)).copy()
+        codes = np.ctypeslib.as_array(out.codes, shape=(max(n, 1),))[:n].copy()
+    finally:
+        lib.hx_pack_free(C.byref(out))
+    return rank, off, codes
+
+
 def pack_bam(bam_path, target_contig, start_pos, end_pos, vcf_handler, stepper="samtools"):
-    """BAM + process_vcf() output -> packed reads."""
+    """BAM + process_vcf() output -> packed reads (dependency-free Python reader)."""
     refs, recs = read_bam(bam_path)
     names = [n for n, _ in refs]
     tid = names.index(target_contig)

@@ -7,7 +7,7 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
-SOURCES = ["api.cu", "ingest.cu", "ingest_long.cu", "recover.cu"]
+SOURCES = ["api.cu", "ingest.cu", "ingest_long.cu", "recover.cu", "bampack.cpp"]
 LIB_PATH = os.path.join(_HERE, "libhanselx.so")
 
 NVCC_FLAGS = [
@@ -40,7 +40,7 @@ def build_lib(force=False, verbose=False):
         return LIB_PATH
     extra = os.environ.get("HX_NVCC_DEFS", "").split()
     cmd = [nvcc_path()] + NVCC_FLAGS + extra + ["-I", os.path.join(_ROOT, "include"), "-I", os.path.join(_HERE, "csrc"),
-                                       "-o", LIB_PATH] + [os.path.join(_HERE, "csrc", s) for s in SOURCES]
+                                       "-o", LIB_PATH] + [os.path.join(_HERE, "csrc", s) for s in SOURCES] + ["-lz"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or res.returncode != 0:
         print(res.stdout)

@@ -1,0 +1,277 @@
+// BAM -> packed reads on the CPU: multi-threaded BGZF inflate + one CIGAR walk per alignment.
+//
+// This is the producer side of the boundary (north_star keeps parsing on the CPU).  It replaces the
+// reference's pysam column pileup (gretel/util.py:112-210, one Python object per read x SNP column)
+// and yields exactly what that loop accumulates per read:
+//   * read key / mate separation ....... util.py:149-160 (every BAM record is its own read)
+//   * window ownership / start clamp ... util.py:162-176 (the union over work blocks == one pass)
+//   * allele at a SNP column ........... util.py:180-190, 238 ('-' inside a deletion or ref-skip,
+//                                         else the aligned base; only the first character is used)
+//   * rank ............................. util.py:198  (#SNPs before the read's leftmost position)
+//   * stepper filters .................. cmd.py:39,78 (samtools: UNMAP/SECONDARY/QCFAIL/DUP + orphans)
+//   * reads with < 2 covered SNPs ...... dropped (util.py:230)
+// Same semantics as gretel_b200/bamio.py (the dependency-free Python packer the tests compare against).
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <zlib.h>
+
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "hanselx.h"
+
+void hx_set_error(const char *fmt, ...);
+
+namespace {
+
+struct Block { size_t coff, csize, uoff, usize; };
+
+inline uint16_t rd16(const uint8_t *p) { return (uint16_t)(p[0] | (p[1] << 8)); }
+inline uint32_t rd32(const uint8_t *p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
+inline int32_t rdi32(const uint8_t *p) { return (int32_t)rd32(p); }
+
+// Splits a BGZF file into its blocks (offset/size of the raw deflate payload and of the output).
+bool scan_bgzf(const std::vector<uint8_t> &f, std::vector<Block> &blocks, size_t &total) {
+    size_t p = 0;
+    total = 0;
+    while (p + 18 <= f.size()) {
+        const uint8_t *h = f.data() + p;
+        if (h[0] != 0x1f || h[1] != 0x8b || h[2] != 8 || !(h[3] & 4)) return false;
+        const size_t xlen = rd16(h + 10);
+        size_t q = p + 12, xend = q + xlen;
+        size_t bsize = 0;
+        while (q + 4 <= xend) {
+            const uint8_t *s = f.data() + q;
+            const size_t slen = rd16(s + 2);
+            if (s[0] == 'B' && s[1] == 'C' && slen == 2) bsize = (size_t)rd16(s + 4) + 1;
+            q += 4 + slen;
+        }
+        if (!bsize || p + bsize > f.size()) return false;
+        const size_t usize = rd32(f.data() + p + bsize - 4);
+        blocks.push_back({xend, bsize - (xend - p) - 8, total, usize});
+        total += usize;
+        p += bsize;
+    }
+    return p == f.size();
+}
+
+bool inflate_block(const uint8_t *src, size_t n, uint8_t *dst, size_t m) {
+    if (m == 0) return true;
+    z_stream z;
+    memset(&z, 0, sizeof(z));
+    if (inflateInit2(&z, -15) != Z_OK) return false;
+    z.next_in = const_cast<uint8_t *>(src);
+    z.avail_in = (uInt)n;
+    z.next_out = dst;
+    z.avail_out = (uInt)m;
+    const int rc = inflate(&z, Z_FINISH);
+    inflateEnd(&z);
+    return rc == Z_STREAM_END && z.avail_out == 0;
+}
+
+struct Out {
+    std::vector<int32_t> rank;
+    std::vector<int64_t> klen;
+    std::vector<uint8_t> codes;
+};
+
+const uint8_t NT16_CODE[16] = {4, 0, 1, 4, 2, 4, 4, 4, 3, 4, 4, 4, 4, 4, 4, 4};   // "=ACMGRSVTWYHKDBN" -> A0 C1 G2 T3 else N4
+
+// One alignment -> (rank, codes) appended to `o` when it covers at least two SNPs.
+void pack_record(const uint8_t *rec, int32_t target_tid, int32_t start_pos, int32_t end_pos,
+                 const int32_t *snp, int32_t n_snps, int stepper, Out &o, std::vector<uint8_t> &tmp) {
+    const int32_t tid = rdi32(rec), pos = rdi32(rec + 4);
+    const int l_read_name = rec[8];
+    const int n_cigar = rd16(rec + 12);
+    const int flag = rd16(rec + 14);
+    const int32_t l_seq = rdi32(rec + 16);
+    if (tid != target_tid || pos < 0) return;
+    if (stepper != 2) {
+        if (flag & (0x4 | 0x100 | 0x200 | 0x400)) return;
+        if (stepper == 0 && (flag & 0x1) && !(flag & 0x2)) return;          // orphan rule
+    }
+    if (pos + 1 > end_pos) return;
+    const uint8_t *cig = rec + 32 + l_read_name;
+    const uint8_t *seq = cig + 4 * (size_t)n_cigar;
+    int64_t qalen = 0, rlen = 0;
+    for (int i = 0; i < n_cigar; ++i) {
+        const uint32_t c = rd32(cig + 4 * i);
+        const int op = c & 0xf;
+        const int64_t ln = c >> 4;
+        if (op == 0 || op == 1 || op == 7 || op == 8) qalen += ln;           // M I = X
+        if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) rlen += ln; // M D N = X
+    }
+    int64_t leftmost = (int64_t)pos + 1;
+    if (leftmost < start_pos) {                                               // util.py:165-171
+        if ((int64_t)pos + 1 + qalen < start_pos) return;
+        leftmost = start_pos;
+    }
+    const int32_t *sb = snp, *se = snp + n_snps;
+    const int32_t rank = (int32_t)(std::lower_bound(sb, se, (int32_t)leftmost) - sb);
+    const int64_t last = std::min<int64_t>((int64_t)pos + rlen, end_pos);
+    const int32_t hi = (int32_t)(std::upper_bound(sb, se, (int32_t)std::min<int64_t>(last, INT32_MAX)) - sb);
+    if (hi - rank < 2) return;
+    tmp.clear();
+    int32_t wi = rank;
+    int64_t rpos = (int64_t)pos + 1, qpos = 0;
+    for (int i = 0; i < n_cigar && wi < hi; ++i) {
+        const uint32_t c = rd32(cig + 4 * i);
+        const int op = c & 0xf;
+        const int64_t ln = c >> 4;
+        if (op == 0 || op == 7 || op == 8) {
+            while (wi < hi && snp[wi] < rpos + ln) {
+                if (snp[wi] >= rpos) {
+                    const int64_t q = qpos + (snp[wi] - rpos);
+                    uint8_t code = 4;
+                    if (q < l_seq) {
+                        const uint8_t b = seq[q >> 1];
+                        code = NT16_CODE[(q & 1) ? (b & 0xf) : (b >> 4)];
+                    }
+                    tmp.push_back(code);
+                }
+                ++wi;
+            }
+            rpos += ln; qpos += ln;
+        } else if (op == 2 || op == 3) {
+            while (wi < hi && snp[wi] < rpos + ln) {
+                if (snp[wi] >= rpos) tmp.push_back(5);                           // '-'
+                ++wi;
+            }
+            rpos += ln;
+        } else if (op == 1 || op == 4) {
+            qpos += ln;
+        }
+    }
+    if (tmp.size() < 2) return;
+    o.rank.push_back(rank);
+    o.klen.push_back((int64_t)tmp.size());
+    o.codes.insert(o.codes.end(), tmp.begin(), tmp.end());
+}
+
+}  // namespace
+
+extern "C" {
+
+int hx_pack_bam(const char *bam_path, const char *contig, int32_t start_pos, int32_t end_pos,
+                const int32_t *snp_pos, int32_t n_snps, int stepper, int n_threads, hx_packed *out) {
+    if (!bam_path || !contig || !out || n_snps < 0 || (n_snps && !snp_pos) || stepper < 0 || stepper > 2) {
+        hx_set_error("hx_pack_bam: bad arguments");
+        return HX_E_ARG;
+    }
+    memset(out, 0, sizeof(*out));
+    if (n_threads < 1) n_threads = 1;
+    const bool verbose = getenv("HX_PACK_VERBOSE") != nullptr;
+    auto t0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char *what) {
+        if (!verbose) return;
+        auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[hx_pack_bam] %-10s %.1f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    };
+    FILE *fp = fopen(bam_path, "rb");
+    if (!fp) { hx_set_error("hx_pack_bam: cannot open %s", bam_path); return HX_E_ARG; }
+    fseek(fp, 0, SEEK_END);
+    const long fsz = ftell(fp);
+    fseek(fp, 0, SEEK_SET);
+    std::vector<uint8_t> file((size_t)fsz);
+    if (fsz && fread(file.data(), 1, (size_t)fsz, fp) != (size_t)fsz) { fclose(fp); hx_set_error("hx_pack_bam: short read"); return HX_E_ARG; }
+    fclose(fp);
+    lap("read");
+
+    std::vector<Block> blocks;
+    size_t total = 0;
+    if (!scan_bgzf(file, blocks, total)) { hx_set_error("hx_pack_bam: %s is not a BGZF file", bam_path); return HX_E_ARG; }
+    std::vector<uint8_t> data(total);
+    {
+        std::atomic<size_t> next(0);
+        std::atomic<bool> ok(true);
+        auto work = [&]() {
+            for (;;) {
+                const size_t b = next.fetch_add(1);
+                if (b >= blocks.size()) break;
+                if (!inflate_block(file.data() + blocks[b].coff, blocks[b].csize, data.data() + blocks[b].uoff, blocks[b].usize))
+                    ok = false;
+            }
+        };
+        std::vector<std::thread> th;
+        for (int t = 1; t < n_threads; ++t) th.emplace_back(work);
+        work();
+        for (auto &t : th) t.join();
+        if (!ok) { hx_set_error("hx_pack_bam: inflate failed"); return HX_E_ARG; }
+    }
+    file.clear();
+    file.shrink_to_fit();
+    lap("inflate");
+
+    // header
+    if (total < 12 || memcmp(data.data(), "BAM\1", 4) != 0) { hx_set_error("hx_pack_bam: not a BAM file"); return HX_E_ARG; }
+    size_t p = 4;
+    const int32_t l_text = rdi32(data.data() + p); p += 4 + (size_t)l_text;
+    const int32_t n_ref = rdi32(data.data() + p); p += 4;
+    int32_t target_tid = -1;
+    for (int32_t i = 0; i < n_ref; ++i) {
+        const int32_t l_name = rdi32(data.data() + p); p += 4;
+        if (std::string((const char *)data.data() + p, (size_t)std::max(0, l_name - 1)) == contig) target_tid = i;
+        p += (size_t)l_name + 4;
+    }
+    if (target_tid < 0) { hx_set_error("hx_pack_bam: contig %s not in %s", contig, bam_path); return HX_E_ARG; }
+    // record boundaries
+    std::vector<size_t> recs;
+    while (p + 4 <= total) {
+        const int32_t bs = rdi32(data.data() + p);
+        if (bs < 32 || p + 4 + (size_t)bs > total) break;
+        recs.push_back(p + 4);
+        p += 4 + (size_t)bs;
+    }
+    lap("index");
+    // parallel CIGAR walks over contiguous chunks of records (keeps BAM order)
+    const size_t nrec = recs.size();
+    const int nt = (int)std::min<size_t>((size_t)n_threads, std::max<size_t>(1, nrec / 4096));
+    std::vector<Out> outs((size_t)nt);
+    {
+        auto work = [&](int t) {
+            std::vector<uint8_t> tmp;
+            const size_t a = nrec * (size_t)t / (size_t)nt, b = nrec * (size_t)(t + 1) / (size_t)nt;
+            for (size_t i = a; i < b; ++i)
+                pack_record(data.data() + recs[i], target_tid, start_pos, end_pos, snp_pos, n_snps, stepper, outs[(size_t)t], tmp);
+        };
+        std::vector<std::thread> th;
+        for (int t = 1; t < nt; ++t) th.emplace_back(work, t);
+        work(0);
+        for (auto &t : th) t.join();
+    }
+    lap("walk");
+    int64_t R = 0, C = 0;
+    for (auto &o : outs) { R += (int64_t)o.rank.size(); C += (int64_t)o.codes.size(); }
+    out->rank = (int32_t *)malloc(sizeof(int32_t) * (size_t)std::max<int64_t>(R, 1));
+    out->off = (int64_t *)malloc(sizeof(int64_t) * (size_t)(R + 1));
+    out->codes = (uint8_t *)malloc((size_t)std::max<int64_t>(C, 1));
+    if (!out->rank || !out->off || !out->codes) { hx_pack_free(out); return HX_E_NOMEM; }
+    int64_t r = 0, c = 0;
+    out->off[0] = 0;
+    for (auto &o : outs) {
+        if (!o.rank.empty()) memcpy(out->rank + r, o.rank.data(), sizeof(int32_t) * o.rank.size());
+        for (size_t i = 0; i < o.klen.size(); ++i) { out->off[r + 1] = out->off[r] + o.klen[i]; ++r; }
+        if (!o.codes.empty()) memcpy(out->codes + c, o.codes.data(), o.codes.size());
+        c += (int64_t)o.codes.size();
+    }
+    lap("gather");
+    out->n_reads = R;
+    out->n_codes = C;
+    out->n_records = (int64_t)nrec;
+    return HX_OK;
+}
+
+void hx_pack_free(hx_packed *p) {
+    if (!p) return;
+    free(p->rank); free(p->off); free(p->codes);
+    memset(p, 0, sizeof(*p));
+}
+
+}  // extern "C"

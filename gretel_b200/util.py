@@ -78,7 +78,9 @@ def load_from_bam(bam_path, target_contig, start_pos, end_pos, vcf_handler, use_
     experimental dead branch upstream (never passed, cmd.py:78) and is rejected here."""
     if use_end_sentinels:
         raise NotImplementedError("use_end_sentinels is never enabled by the reference (cmd.py:28,78)")
-    rank, off, codes = bamio.pack_bam(bam_path, target_contig, start_pos, end_pos, vcf_handler, stepper=stepper)
+    # n_threads (the reference's number of BAM iterators, cmd.py:31) drives the native packer's threads
+    rank, off, codes = bamio.pack_bam_native(bam_path, target_contig, start_pos, end_pos, vcf_handler,
+                                             stepper=stepper, n_threads=n_threads)
     if band_w is None:
         # hold every ingested pair; at least N+1 for tiny regions so that the scalar API
         # (add/get_observation on arbitrary i<j) is band-resident like the reference's dense array

@@ -131,6 +131,20 @@ int hx_reweight_path(hx_matrix *h, const uint8_t *path, double ratio, double *re
 int hx_recover(hx_matrix *cur, hx_matrix *orig, int32_t L, int flags, int32_t max_paths,
                double min_remove, uint8_t *paths, double *stats, int32_t *n_found);
 
+/* ---- BAM -> packed reads on the CPU (the producer side of the boundary) ------------ */
+/* Replaces the pysam column pileup of gretel/util.py:112-210: multi-threaded BGZF inflate and one
+ * CIGAR walk per alignment against the sorted 1-based SNP positions.  stepper: 0 = samtools,
+ * 1 = all, 2 = nofilter (gretel/cmd.py:39,78).  The arrays are malloc'ed; release with hx_pack_free. */
+typedef struct {
+    int32_t *rank;      /* [n_reads]   index of the first SNP on the read */
+    int64_t *off;       /* [n_reads+1] */
+    uint8_t *codes;     /* [n_codes]   A0 C1 G2 T3 N4 -5 */
+    int64_t n_reads, n_codes, n_records;
+} hx_packed;
+int hx_pack_bam(const char *bam_path, const char *contig, int32_t start_pos, int32_t end_pos,
+                const int32_t *snp_pos, int32_t n_snps, int stepper, int n_threads, hx_packed *out);
+void hx_pack_free(hx_packed *p);
+
 /* ---- bulk matrix I/O (tests, --dumpmatrix gretel/cmd.py:81-82) ------------------- */
 int hx_band_to_host(hx_matrix *h, float *out /* (N+2)*W*49 */);
 int hx_band_from_host(hx_matrix *h, const float *in);

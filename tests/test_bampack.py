@@ -1,0 +1,81 @@
+"""The native multi-threaded BAM packer (hx_pack_bam, CPU code in libhanselx.so) must produce exactly
+what the dependency-free Python packer produces, which in turn reproduces the reference's ingestion on its
+own fixture (tests/test_oracle_golden.py)."""
+import os
+
+import numpy as np
+import pytest
+
+from gretel_b200 import bamio
+from tests.bamwriter import write_bam
+
+
+def _random_bam(path, rng, n_reads, ref_len=3000):
+    refs = [("ctgA", ref_len), ("ctgB", ref_len)]
+    reads = []
+    for i in range(n_reads):
+        tid = 0 if rng.random() < 0.9 else 1
+        pos = int(rng.integers(0, ref_len - 50))
+        cigar, qlen, rlen = [], 0, 0
+        if rng.random() < 0.2:
+            s = int(rng.integers(1, 8)); cigar.append(("S", s)); qlen += s
+        for _ in range(int(rng.integers(1, 6))):
+            m = int(rng.integers(5, 60)); cigar.append((rng.choice(["M", "=", "X"], p=[0.8, 0.1, 0.1]), m)); qlen += m; rlen += m
+            r = rng.random()
+            if r < 0.25:
+                d = int(rng.integers(1, 12)); cigar.append(("D", d)); rlen += d
+            elif r < 0.45:
+                ins = int(rng.integers(1, 6)); cigar.append(("I", ins)); qlen += ins
+            elif r < 0.5:
+                n = int(rng.integers(5, 40)); cigar.append(("N", n)); rlen += n
+        if cigar[-1][0] in "DIN":
+            cigar.append(("M", 7)); qlen += 7; rlen += 7
+        if rng.random() < 0.2:
+            s = int(rng.integers(1, 8)); cigar.append(("S", s)); qlen += s
+        if pos + rlen > ref_len:
+            continue
+        flag = int(rng.choice([0, 16, 99, 147, 65, 4, 256, 512, 1024, 2048], p=[.3, .3, .1, .1, .05, .03, .03, .03, .03, .03]))
+        seq = "".join(rng.choice(list("ACGTN"), p=[.24, .24, .24, .24, .04], size=qlen))
+        reads.append((tid, pos, flag, "r%d" % i, cigar, seq))
+    reads.sort(key=lambda r: (r[0], r[1]))
+    write_bam(path, refs, reads)
+    return refs
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_native_packer_matches_python(tmp_path, seed):
+    rng = np.random.default_rng(40 + seed)
+    path = str(tmp_path / "t.bam")
+    _random_bam(path, rng, 3000)
+    snps = np.sort(rng.choice(np.arange(1, 3001), size=int(rng.integers(50, 400)), replace=False))
+    for (start, end) in ((1, 3000), (500, 2200)):
+        sel = [int(p) for p in snps if start <= p <= end]
+        vh = {"N": len(sel), "snp_rev": {i: p for i, p in enumerate(sel)}}
+        for stepper in ("samtools", "all", "nofilter"):
+            exp = bamio.pack_bam(path, "ctgA", start, end, vh, stepper=stepper)
+            for threads in (1, 3):
+                got = bamio.pack_bam_native(path, "ctgA", start, end, vh, stepper=stepper, n_threads=threads)
+                for a, b in zip(exp, got):
+                    assert np.array_equal(a, b), (start, end, stepper, threads)
+            assert len(exp[0]) > 50
+
+
+def test_native_packer_on_reference_fixture(golden_dir):
+    v = bamio.process_vcf(os.path.join(golden_dir, "ref_test.vcf.gz"), "hoot", 1, 20)
+    exp = bamio.pack_bam(os.path.join(golden_dir, "ref_test.bam"), "hoot", 1, 20, v)
+    got = bamio.pack_bam_native(os.path.join(golden_dir, "ref_test.bam"), "hoot", 1, 20, v, n_threads=2)
+    for a, b in zip(exp, got):
+        assert np.array_equal(a, b)
+    assert list(got[0]) == [0, 0, 0, 0, 2]
+
+
+def test_native_packer_errors(tmp_path, golden_dir):
+    from gretel_b200 import _lib
+    v = {"N": 1, "snp_rev": {0: 5}}
+    with pytest.raises(_lib.HanselxError):
+        bamio.pack_bam_native(str(tmp_path / "missing.bam"), "hoot", 1, 20, v)
+    with pytest.raises(_lib.HanselxError):
+        bamio.pack_bam_native(os.path.join(golden_dir, "ref_test.bam"), "nope", 1, 20, v)
+    (tmp_path / "junk.bam").write_bytes(b"not a bam file at all")
+    with pytest.raises(_lib.HanselxError):
+        bamio.pack_bam_native(str(tmp_path / "junk.bam"), "hoot", 1, 20, v)
