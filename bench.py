@@ -221,10 +221,18 @@ def run_ours(args):
     stream = torch.cuda.ExternalStream(h.stream, device=dev)
 
     pipe = None
-    if world > 1 and args.segments > 1:
+    fused = None
+    if world > 1 and args.exchange == "fused":
+        fused = gdist.FusedExchange(h)
+    elif world > 1 and args.segments > 1:
         pipe = gdist.PipelinedIngest(h, d["rank"], R, segments=args.segments)
 
     def step():
+        if fused is not None:
+            fused.reset()
+            h.ingest_device(t_rank.data_ptr(), t_off.data_ptr(), t_codes.data_ptr(), R)
+            fused.finish()
+            return
         h.reset_counts()
         if pipe is not None:
             pipe.run(t_rank.data_ptr(), t_off.data_ptr(), t_codes.data_ptr())
@@ -274,6 +282,9 @@ def run_ours(args):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         total_ms = float(tt.item())
     value = n_obs_global * args.steps / (total_ms * 1e-3)
+
+    if fused is not None:
+        fused.close()
 
     # ---- e2e through the public API with host buffers
     def e2e_step():
@@ -390,7 +401,7 @@ def run_ours(args):
                            "totals, a new matrix every step" % ("_compact" if args.e2e_format == "compact" else "")},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
             "observations_per_step": int(n_obs_global), "wall_s_timed_region": wall_s,
-            "recovery": recovery, "synth_seconds": gen_s, "band_w": W, "allreduce_segments": args.segments if world > 1 else 0,
+            "recovery": recovery, "synth_seconds": gen_s, "band_w": W, "allreduce_segments": args.segments if world > 1 else 0, "exchange": args.exchange if world > 1 else None,
             "ingest_kernel": args.kernel}
     print(json.dumps(line))
     if world > 1:
@@ -408,6 +419,9 @@ def main():
     ap.add_argument("--workload", default="metagenome", choices=sorted(synth.WORKLOADS))
     ap.add_argument("--reads", type=int, default=0, help="reads per GPU (default: the workload's full size)")
     ap.add_argument("--kernel", type=int, default=0, help="ingestion kernel: 0 auto, 1 generic, 2 bit-sliced")
+    ap.add_argument("--exchange", default="allreduce", choices=["allreduce", "fused"],
+                    help="N>1: NCCL all-reduce of the partial matrices, or counts added straight into the owning GPU "
+                         "over NVLink peer memory + all-gather of the owned rows")
     ap.add_argument("--segments", type=int, default=1,
                     help="N>1: ingest in this many launches, all-reducing finished band rows behind the next one")
     ap.add_argument("--e2e-format", default="compact", choices=["compact", "wide"],

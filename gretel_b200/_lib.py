@@ -33,6 +33,9 @@ SIGNATURES = {
     "hx_set_ingest_kernel": (_int, [_p, _int]),
     "hx_ingest_totals": (_int, [_p, _p]),
     "hx_counts_buffer": (_int, [_p, _pp, C.POINTER(_i64), _pp, C.POINTER(_i64)]),
+    "hx_counts_ipc_export": (_int, [_p, _i32, _p]),
+    "hx_counts_ipc_import": (_int, [_p, _p, _i32, _i32]),
+    "hx_counts_ipc_close": (_int, [_p]),
     "hx_finalize_counts": (_int, [_p]),
     "hx_reset_counts": (_int, [_p]),
     "hx_add_observation": (_int, [_p, _int, _int, _i32, _i32, _flt]),

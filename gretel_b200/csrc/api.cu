@@ -17,6 +17,31 @@ void hx_set_error(const char *fmt, ...) {
     va_end(ap);
 }
 
+static void release_counts(hx_matrix *h) {
+    for (int g = 0; g < HX_MAX_PEERS; ++g) {
+        if (h->ipc_opened[g]) cudaIpcCloseMemHandle(h->ipc_opened[g]);
+        h->ipc_opened[g] = nullptr;
+        h->peer_host[g] = nullptr;
+    }
+    h->peer_world = 0;
+    if (h->cnt) {
+        if (h->cnt_ipc) { cudaStreamSynchronize(h->stream); cudaFree(h->cnt); }
+        else cudaFreeAsync(h->cnt, h->stream);
+    }
+    h->cnt = nullptr;
+    h->cnt_ipc = false;
+    h->cnt_elems = 0;
+}
+
+HxCnt hx_cnt_ref(const hx_matrix *h) {
+    HxCnt c;
+    c.local = h->cnt;
+    c.peer = h->d_peer_tbl;
+    c.world = h->peer_world > 1 ? h->peer_world : 1;
+    c.rows_per = h->peer_world > 1 ? h->peer_rows_per : 1;
+    return c;
+}
+
 namespace {
 
 __global__ void k_fold_counts(const uint32_t *__restrict__ cnt, float *__restrict__ band, int64_t n) {
@@ -63,8 +88,9 @@ void free_all(hx_matrix *h) {
     if (!h) return;
     cudaSetDevice(h->device);
     hx_lr_free(h);
+    if (h->d_peer_tbl) cudaFree(h->d_peer_tbl);
     if (h->band) cudaFreeAsync(h->band, h->stream);
-    if (h->cnt) cudaFreeAsync(h->cnt, h->stream);
+    release_counts(h);
     if (h->d_totals) cudaFreeAsync(h->d_totals, h->stream);
     if (h->d_err) cudaFreeAsync(h->d_err, h->stream);
     if (h->s_rank) cudaFreeAsync(h->s_rank, h->stream);
@@ -213,8 +239,9 @@ int hx_sync(hx_matrix *h) {
 // ------------------------------------------------------------------------------ ingestion
 static int ensure_counts_buffer(hx_matrix *h) {
     if (h->cnt) return HX_OK;
-    HX_CUDA(cudaMallocAsync((void **)&h->cnt, sizeof(uint32_t) * (size_t)h->band_elems, h->stream));
-    HX_CUDA(cudaMemsetAsync(h->cnt, 0, sizeof(uint32_t) * (size_t)h->band_elems, h->stream));
+    h->cnt_elems = h->band_elems;
+    HX_CUDA(cudaMallocAsync((void **)&h->cnt, sizeof(uint32_t) * (size_t)h->cnt_elems, h->stream));
+    HX_CUDA(cudaMemsetAsync(h->cnt, 0, sizeof(uint32_t) * (size_t)h->cnt_elems, h->stream));
     return HX_OK;
 }
 
@@ -358,16 +385,66 @@ int hx_counts_buffer(hx_matrix *h, void **d_counts, int64_t *n_u32, void **d_tot
     int rc = ensure_counts_buffer(h);
     if (rc) return rc;
     *d_counts = h->cnt;
-    *n_u32 = h->band_elems;
+    *n_u32 = h->cnt_elems;
     *d_totals = h->d_totals;
     *n_i64 = 4;
+    return HX_OK;
+}
+
+int hx_counts_ipc_export(hx_matrix *h, int32_t world, void *handle_out) {
+    HX_CHECK_ARG(h && handle_out && world >= 1 && world <= HX_MAX_PEERS);
+    HX_CUDA(cudaSetDevice(h->device));
+    release_counts(h);
+    const int64_t rows = (int64_t)h->N + 2;
+    const int64_t rows_per = (rows + world - 1) / world;
+    h->cnt_elems = rows_per * world * h->W * HX_CELL;          // padded so that every rank owns rows_per rows
+    HX_CUDA(cudaMalloc((void **)&h->cnt, sizeof(uint32_t) * (size_t)h->cnt_elems));   // IPC needs a plain allocation
+    h->cnt_ipc = true;
+    HX_CUDA(cudaMemsetAsync(h->cnt, 0, sizeof(uint32_t) * (size_t)h->cnt_elems, h->stream));
+    HX_CUDA(cudaStreamSynchronize(h->stream));
+    cudaIpcMemHandle_t hd;
+    HX_CUDA(cudaIpcGetMemHandle(&hd, h->cnt));
+    memcpy(handle_out, &hd, sizeof(hd));
+    h->peer_rows_per = (int)rows_per;
+    return HX_OK;
+}
+
+int hx_counts_ipc_import(hx_matrix *h, const void *handles, int32_t world, int32_t my_rank) {
+    HX_CHECK_ARG(h && handles && world >= 1 && world <= HX_MAX_PEERS && my_rank >= 0 && my_rank < world);
+    if (!h->cnt_ipc) { hx_set_error("hx_counts_ipc_import: call hx_counts_ipc_export first"); return HX_E_STATE; }
+    HX_CUDA(cudaSetDevice(h->device));
+    for (int g = 0; g < world; ++g) {
+        if (g == my_rank) { h->peer_host[g] = h->cnt; continue; }
+        cudaIpcMemHandle_t hd;
+        memcpy(&hd, (const char *)handles + (size_t)g * sizeof(hd), sizeof(hd));
+        void *p = nullptr;
+        HX_CUDA(cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess));
+        h->ipc_opened[g] = p;
+        h->peer_host[g] = (uint32_t *)p;
+    }
+    if (!h->d_peer_tbl) HX_CUDA(cudaMalloc((void **)&h->d_peer_tbl, sizeof(uint32_t *) * HX_MAX_PEERS));
+    HX_CUDA(cudaMemcpy(h->d_peer_tbl, h->peer_host, sizeof(uint32_t *) * HX_MAX_PEERS, cudaMemcpyHostToDevice));
+    h->peer_world = world;
+    return HX_OK;
+}
+
+int hx_counts_ipc_close(hx_matrix *h) {
+    HX_CHECK_ARG(h);
+    HX_CUDA(cudaSetDevice(h->device));
+    HX_CUDA(cudaStreamSynchronize(h->stream));
+    for (int g = 0; g < HX_MAX_PEERS; ++g) {
+        if (h->ipc_opened[g]) HX_CUDA(cudaIpcCloseMemHandle(h->ipc_opened[g]));
+        h->ipc_opened[g] = nullptr;
+        h->peer_host[g] = nullptr;
+    }
+    h->peer_world = 0;                          // counts go to the local buffer again
     return HX_OK;
 }
 
 int hx_reset_counts(hx_matrix *h) {
     HX_CHECK_ARG(h);
     HX_CUDA(cudaSetDevice(h->device));
-    if (h->cnt) HX_CUDA(cudaMemsetAsync(h->cnt, 0, sizeof(uint32_t) * (size_t)h->band_elems, h->stream));
+    if (h->cnt) HX_CUDA(cudaMemsetAsync(h->cnt, 0, sizeof(uint32_t) * (size_t)h->cnt_elems, h->stream));
     HX_CUDA(cudaMemsetAsync(h->d_totals, 0, 8 * sizeof(unsigned long long), h->stream));
     HX_CUDA(cudaMemsetAsync(h->d_err, 0, sizeof(int), h->stream));
     return HX_OK;
@@ -382,8 +459,7 @@ int hx_finalize_counts(hx_matrix *h) {
     h->launches++;
     HX_CUDA(cudaGetLastError());
     HX_CUDA(cudaStreamSynchronize(h->stream));
-    HX_CUDA(cudaFreeAsync(h->cnt, h->stream));
-    h->cnt = nullptr;
+    release_counts(h);
     h->counts_dirty = true;
     return HX_OK;
 }

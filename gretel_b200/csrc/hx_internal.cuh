@@ -14,6 +14,23 @@
 #define HX_RING 4096   // lookback window of chosen symbols kept in shared memory by the walk
 #define HX_MAX_L (HX_RING - 1)
 
+#define HX_MAX_PEERS 8
+// Where count increments go: the local partial band, or - with the fused multi-GPU exchange - the GPU
+// that owns band row pj (rows are dealt out in contiguous blocks of rows_per), reached through NVLink
+// peer memory.  Passed to the ingestion kernels by value.
+struct HxCnt {
+    uint32_t *local;
+    uint32_t *const *peer;           // device array [world] of every rank's buffer (own entry included)
+    int world, rows_per;
+#ifdef __CUDACC__
+    __device__ __forceinline__ uint32_t *cell(int64_t W, int64_t pi, int64_t pj) const {
+        uint32_t *base = local;
+        if (world > 1) base = peer[pj / rows_per];
+        return base + (pj * W + (pj - pi - 1)) * 49;
+    }
+#endif
+};
+
 struct hx_matrix {
     int32_t N, W, device;
     int64_t band_elems;              // (N+2)*W*49
@@ -21,6 +38,12 @@ struct hx_matrix {
     bool own_stream;
     float *band;                     // float32 working matrix (what the Hansel surface reads)
     uint32_t *cnt;                   // integer counts being ingested (lazily allocated)
+    bool cnt_ipc;                    // cnt is a plain cudaMalloc allocation shared through CUDA IPC
+    int64_t cnt_elems;               // allocated uint32 elements (>= band_elems; padded for the fused exchange)
+    uint32_t *peer_host[HX_MAX_PEERS];   // fused exchange: every rank's cnt (own entry = local pointer)
+    uint32_t **d_peer_tbl;           // the same table on the device
+    int peer_world, peer_rows_per;
+    void *ipc_opened[HX_MAX_PEERS];  // pointers returned by cudaIpcOpenMemHandle (to close)
     unsigned long long *d_totals;    // [8] slices, crumbs, covered, sentinels, -, -, -, -
     int *d_err;                      // ingestion error bits
     // staging for hx_ingest_host
@@ -79,6 +102,8 @@ __host__ __device__ __forceinline__ int64_t hx_cell_off(int64_t W, int64_t pi, i
 // ingest.cu
 int hx_launch_ingest(hx_matrix *h, const int32_t *d_rank, const int64_t *d_off,
                      const uint8_t *d_codes, int64_t n_reads);
+// api.cu
+HxCnt hx_cnt_ref(const hx_matrix *h);
 // ingest_long.cu
 int hx_launch_ingest_long(hx_matrix *h, const int32_t *d_rank, const int64_t *d_off,
                           const uint8_t *d_codes, int64_t n_reads);

@@ -54,22 +54,22 @@ __device__ __forceinline__ bool sym_valid_from(unsigned a) {   // util.py:258
 }
 
 // The per-pair rules of util.py:254-281 for one (i,j) of one read (sentinels included).
-__device__ __forceinline__ void add_pair(uint32_t *__restrict__ cnt, int N, int64_t W, int rk, int i,
+__device__ __forceinline__ void add_pair(const HxCnt cnt, int N, int64_t W, int rk, int i,
                                          int j, unsigned a, unsigned b, unsigned long long &sent) {
     const int pi = rk + i + 1, pj = rk + j + 1;
-    atomicAdd(cnt + hx_cell_off(W, pi, pj) + a * HX_NSYM + b, 1u);            // :267,274,280
+    atomicAdd(cnt.cell(W, pi, pj) + a * HX_NSYM + b, 1u);            // :267,274,280
     if (i == 0 && j == 1 && rk == 0) {                                          // :262-266
-        atomicAdd(cnt + hx_cell_off(W, 0, 1) + HX_SYM_GAP * HX_NSYM + a, 1u);
+        atomicAdd(cnt.cell(W, 0, 1) + HX_SYM_GAP * HX_NSYM + a, 1u);
         sent++;
     } else if (pj == N && j - i == 1) {                                         // :271-275
-        atomicAdd(cnt + hx_cell_off(W, N, N + 1) + b * HX_NSYM + HX_SYM_GAP, 1u);
+        atomicAdd(cnt.cell(W, N, N + 1) + b * HX_NSYM + HX_SYM_GAP, 1u);
         sent++;
     }
 }
 
 // One whole read, cooperatively by the calling warp (all 32 lanes converged).
 __device__ __forceinline__ void warp_read_generic(const uint8_t *__restrict__ c, int k, int rk, int N,
-                                                  int64_t W, uint32_t *__restrict__ cnt,
+                                                  int64_t W, const HxCnt cnt,
                                                   unsigned long long &t_crumbs, unsigned long long &t_cov,
                                                   unsigned long long &t_sent, int *err) {
     const int lane = threadIdx.x & 31;
@@ -100,7 +100,7 @@ template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK)
 k1_pairs_red(const int32_t *__restrict__ rank, const int64_t *__restrict__ off,
              const uint8_t *__restrict__ codes, int64_t n_reads, int N, int W,
-             uint32_t *__restrict__ cnt, unsigned long long *__restrict__ totals,
+             const HxCnt cnt, unsigned long long *__restrict__ totals,
              int *__restrict__ err, const int *__restrict__ sorted_flag, int run_if_sorted) {
     // sorted_flag: 1 when the reads are rank-sorted.  run_if_sorted = 0 makes this launch the
     // fallback that only runs when the bit-sliced kernel declined the input.
@@ -164,7 +164,7 @@ struct BsLayout {
 // flushed by this thread (every regular-cell increment is one crumb, util.py:268,276,281).
 __device__ __forceinline__ unsigned long long bs_flush_rows(uint32_t *tile32, int rows, int cells,
                                                             int64_t pj_lo, int64_t pj_hi, int64_t W,
-                                                            uint32_t *__restrict__ cnt) {
+                                                            const HxCnt cnt) {
     unsigned long long sum = 0;
     const int per_row = cells * 16;
     int row = (int)(pj_lo % rows);
@@ -174,7 +174,7 @@ __device__ __forceinline__ unsigned long long bs_flush_rows(uint32_t *tile32, in
             const uint32_t v = base[w];
             if (v) {
                 const int d = (w >> 4) + 1, ab = w & 15;
-                atomicAdd(cnt + hx_cell_off(W, pj - d, pj) + (ab >> 2) * HX_NSYM + (ab & 3), v);
+                atomicAdd(cnt.cell(W, pj - d, pj) + (ab >> 2) * HX_NSYM + (ab & 3), v);
                 base[w] = 0;
                 sum += v;
             }
@@ -187,7 +187,7 @@ __device__ __forceinline__ unsigned long long bs_flush_rows(uint32_t *tile32, in
 // A read that holds N, - or _ : the pairs with such an allele on either side are not in the
 // bit-planes; the whole warp adds them with REDs (lanes over the read's positions).
 __device__ __forceinline__ void bs_rare_read(const uint8_t *__restrict__ c, int kb, int r, int64_t W,
-                                             uint32_t *__restrict__ cnt, unsigned &crumbs, unsigned &notcov,
+                                             const HxCnt cnt, unsigned &crumbs, unsigned &notcov,
                                              unsigned &errbits) {
     const int lane = threadIdx.x & 31;
     const unsigned a_lo = lane < kb ? c[lane] : 0xffu;
@@ -210,10 +210,10 @@ __device__ __forceinline__ void bs_rare_read(const uint8_t *__restrict__ c, int 
                 const unsigned aj = h2 ? a_hi : a_lo;
                 if (j >= kb || aj > 6) continue;
                 if (j > i && ai == HX_SYM_DEL) {                 // '-' is a valid first allele
-                    atomicAdd(cnt + hx_cell_off(W, r + i + 1, r + j + 1) + ai * HX_NSYM + aj, 1u);
+                    atomicAdd(cnt.cell(W, r + i + 1, r + j + 1) + ai * HX_NSYM + aj, 1u);
                     crumbs++;
                 } else if (j < i && aj < 4) {                    // common first allele, rare second
-                    atomicAdd(cnt + hx_cell_off(W, r + j + 1, r + i + 1) + aj * HX_NSYM + ai, 1u);
+                    atomicAdd(cnt.cell(W, r + j + 1, r + i + 1) + aj * HX_NSYM + ai, 1u);
                     crumbs++;
                 }
             }
@@ -323,14 +323,16 @@ struct BsBatch {
     bool first, last;   // first / last batch of its run (within this CTA's slice)
 };
 
-template <int KW, int NP, int MAXT, int MINB>
+template <int KW, int NP, int MAXT, int MINB, bool FUSED>
 __global__ void __launch_bounds__(MAXT, MINB)
 k1_bitsliced(const int32_t *__restrict__ rank, const int64_t *__restrict__ off,
              const uint8_t *__restrict__ codes, int64_t n_reads, int N, int W, int kmax, int gb,
-             uint32_t *__restrict__ cnt, unsigned long long *__restrict__ totals,
+             const HxCnt cnt_in, unsigned long long *__restrict__ totals,
              int *__restrict__ err, const int *__restrict__ sorted_flag,
              const int64_t *__restrict__ run_end) {
     extern __shared__ uint4 smem4[];
+    HxCnt cnt = cnt_in;                              // single-GPU build: the peer path folds away
+    if (!FUSED) { cnt.world = 1; cnt.rows_per = 1; cnt.peer = nullptr; }
     if (!*sorted_flag) return;                       // the generic fallback launch takes over
     const int rows = kmax + 1, cells = kmax - 1;
     uint4 *const tile = smem4;
@@ -504,13 +506,13 @@ k1_bitsliced(const int32_t *__restrict__ rank, const int64_t *__restrict__ off,
                     // start sentinel (util.py:262-266) / end sentinel (:271-275); the start rule wins
                     const unsigned a0 = x0 & 0xffu;
                     if (r == 0 && sym_valid_from(a0)) {
-                        atomicAdd(cnt + hx_cell_off(W, 0, 1) + HX_SYM_GAP * HX_NSYM + a0, 1u);
+                        atomicAdd(cnt.cell(W, 0, 1) + HX_SYM_GAP * HX_NSYM + a0, 1u);
                         n_sent++;
                     }
                     if (r + kb == N && !(kb == 2 && r == 0)) {
                         const unsigned ap = c[kb - 2], bl = c[kb - 1];
                         if (sym_valid_from(ap) && bl <= 6) {
-                            atomicAdd(cnt + hx_cell_off(W, N, N + 1) + bl * HX_NSYM + HX_SYM_GAP, 1u);
+                            atomicAdd(cnt.cell(W, N, N + 1) + bl * HX_NSYM + HX_SYM_GAP, 1u);
                             n_sent++;
                         }
                     }
@@ -569,14 +571,16 @@ struct WsLayout {
     }
 };
 
-template <int KW, int NP, int MAXT, int MINB>
+template <int KW, int NP, int MAXT, int MINB, bool FUSED>
 __global__ void __launch_bounds__(MAXT, MINB)
 k1_bitsliced_ws(const int32_t *__restrict__ rank, const int64_t *__restrict__ off,
                 const uint8_t *__restrict__ codes, int64_t n_reads, int N, int W, int kmax, int gb, int pw,
-                uint32_t *__restrict__ cnt, unsigned long long *__restrict__ totals,
+                const HxCnt cnt_in, unsigned long long *__restrict__ totals,
                 int *__restrict__ err, const int *__restrict__ sorted_flag,
                 const int64_t *__restrict__ run_end) {
     extern __shared__ uint4 smem4[];
+    HxCnt cnt = cnt_in;                              // single-GPU build: the peer path folds away
+    if (!FUSED) { cnt.world = 1; cnt.rows_per = 1; cnt.peer = nullptr; }
     __shared__ __align__(8) unsigned long long s_full[WS_NBUF], s_empty[WS_NBUF];
     if (!*sorted_flag) return;                       // the generic fallback launch takes over
     const int rows = kmax + 1, cells = kmax - 1;
@@ -666,13 +670,13 @@ k1_bitsliced_ws(const int32_t *__restrict__ rank, const int64_t *__restrict__ of
                 if (kb >= 2) {
                     const unsigned a0 = x0 & 0xffu;
                     if (r == 0 && sym_valid_from(a0)) {            // util.py:262-266
-                        atomicAdd(cnt + hx_cell_off(W, 0, 1) + HX_SYM_GAP * HX_NSYM + a0, 1u);
+                        atomicAdd(cnt.cell(W, 0, 1) + HX_SYM_GAP * HX_NSYM + a0, 1u);
                         n_sent++;
                     }
                     if (r + kb == N && !(kb == 2 && r == 0)) {     // util.py:271-275
                         const unsigned ap = c[kb - 2], bl = c[kb - 1];
                         if (sym_valid_from(ap) && bl <= 6) {
-                            atomicAdd(cnt + hx_cell_off(W, N, N + 1) + bl * HX_NSYM + HX_SYM_GAP, 1u);
+                            atomicAdd(cnt.cell(W, N, N + 1) + bl * HX_NSYM + HX_SYM_GAP, 1u);
                             n_sent++;
                         }
                     }
@@ -736,7 +740,7 @@ k1_bitsliced_ws(const int32_t *__restrict__ rank, const int64_t *__restrict__ of
                             const uint32_t v = base[w];
                             if (v) {
                                 const int d = (w >> 4) + 1, ab = w & 15;
-                                atomicAdd(cnt + hx_cell_off(W, pj - d, pj) + (ab >> 2) * HX_NSYM + (ab & 3), v);
+                                atomicAdd(cnt.cell(W, pj - d, pj) + (ab >> 2) * HX_NSYM + (ab & 3), v);
                                 base[w] = 0;
                                 sum += v;
                             }
@@ -795,7 +799,7 @@ k1_bitsliced_ws(const int32_t *__restrict__ rank, const int64_t *__restrict__ of
                     const uint32_t v = base[w];
                     if (v) {
                         const int d = (w >> 4) + 1, ab = w & 15;
-                        atomicAdd(cnt + hx_cell_off(W, pj - d, pj) + (ab >> 2) * HX_NSYM + (ab & 3), v);
+                        atomicAdd(cnt.cell(W, pj - d, pj) + (ab >> 2) * HX_NSYM + (ab & 3), v);
                         sum += v;
                     }
                 }
@@ -825,6 +829,7 @@ int hx_launch_ingest(hx_matrix *h, const int32_t *d_rank, const int64_t *d_off,
     const bool bs_possible = kmax >= 2 && kmax <= BS_KMAX;
     const bool use_bs = (h->ingest_kernel == 2 || h->ingest_kernel == 4 || h->ingest_kernel == 5)
                             ? bs_possible : (h->ingest_kernel == 0 && bs_possible);
+    const bool fused = h->peer_world > 1;
     const bool use_long = !use_bs && (h->ingest_kernel == 3 || (h->ingest_kernel == 0 && kmax >= 2));
 
     HX_CUDA(cudaEventRecord(h->ev0, h->stream));
@@ -835,11 +840,11 @@ int hx_launch_ingest(hx_matrix *h, const int32_t *d_rank, const int64_t *d_off,
         h->launches++;
         int rc = hx_launch_ingest_long(h, d_rank, d_off, d_codes, n_reads);
         if (rc) return rc;
-        k1_pairs_red<GBLOCK><<<ggrid, GBLOCK, 0, h->stream>>>(d_rank, d_off, d_codes, n_reads, h->N, h->W, h->cnt,
+        k1_pairs_red<GBLOCK><<<ggrid, GBLOCK, 0, h->stream>>>(d_rank, d_off, d_codes, n_reads, h->N, h->W, hx_cnt_ref(h),
                                                               h->d_totals, h->d_err, sorted_flag, 0);
         h->launches++;
     } else if (!use_bs) {
-        k1_pairs_red<GBLOCK><<<ggrid, GBLOCK, 0, h->stream>>>(d_rank, d_off, d_codes, n_reads, h->N, h->W, h->cnt,
+        k1_pairs_red<GBLOCK><<<ggrid, GBLOCK, 0, h->stream>>>(d_rank, d_off, d_codes, n_reads, h->N, h->W, hx_cnt_ref(h),
                                                               h->d_totals, h->d_err, sorted_flag, 1);
         h->launches++;
     } else {
@@ -861,7 +866,7 @@ int hx_launch_ingest(hx_matrix *h, const int32_t *d_rank, const int64_t *d_off,
             const size_t smem = WsLayout{kmax, gb}.bytes();
 #define HX_WS_LAUNCH(KW_, NP_, MAXT_, MINB_)                                                                  \
     do {                                                                                                       \
-        auto kern = k1_bitsliced_ws<KW_, NP_, MAXT_, MINB_>;                                                   \
+        auto kern = fused ? k1_bitsliced_ws<KW_, NP_, MAXT_, MINB_, true> : k1_bitsliced_ws<KW_, NP_, MAXT_, MINB_, false>; \
         HX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));           \
         int occ = 1;                                                                                           \
         HX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, block, smem));                       \
@@ -870,7 +875,7 @@ int hx_launch_ingest(hx_matrix *h, const int32_t *d_rank, const int64_t *d_off,
         const int64_t max_useful = (n_reads + 255) / 256;                                                      \
         if (grid > max_useful) grid = max_useful;                                                              \
         kern<<<(unsigned)grid, block, smem, h->stream>>>(d_rank, d_off, d_codes, n_reads, h->N, h->W, kmax,    \
-                                                         gb, pw, h->cnt, h->d_totals, h->d_err, sorted_flag,   \
+                                                         gb, pw, hx_cnt_ref(h), h->d_totals, h->d_err, sorted_flag,   \
                                                          h->d_run_end);                                        \
     } while (0)
             if (np == 2) HX_WS_LAUNCH(14, 2, 1024, 1);
@@ -887,7 +892,7 @@ int hx_launch_ingest(hx_matrix *h, const int32_t *d_rank, const int64_t *d_off,
         if (block > 1024) block = 1024;
 #define HX_BS_LAUNCH(KW_, NP_, MAXT_, MINB_)                                                                  \
     do {                                                                                                       \
-        auto kern = k1_bitsliced<KW_, NP_, MAXT_, MINB_>;                                                      \
+        auto kern = fused ? k1_bitsliced<KW_, NP_, MAXT_, MINB_, true> : k1_bitsliced<KW_, NP_, MAXT_, MINB_, false>;       \
         HX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));           \
         int occ = 1;                                                                                           \
         HX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, block, smem));                       \
@@ -896,7 +901,7 @@ int hx_launch_ingest(hx_matrix *h, const int32_t *d_rank, const int64_t *d_off,
         const int64_t max_useful = (n_reads + 255) / 256;   /* no thinner than 256 reads per CTA */            \
         if (grid > max_useful) grid = max_useful;                                                              \
         kern<<<(unsigned)grid, block, smem, h->stream>>>(d_rank, d_off, d_codes, n_reads, h->N, h->W, kmax,    \
-                                                         gb, h->cnt, h->d_totals, h->d_err, sorted_flag,       \
+                                                         gb, hx_cnt_ref(h), h->d_totals, h->d_err, sorted_flag,       \
                                                          h->d_run_end);                                        \
     } while (0)
         if (np == 2) HX_BS_LAUNCH(14, 2, 1024, 1);
@@ -905,7 +910,7 @@ int hx_launch_ingest(hx_matrix *h, const int32_t *d_rank, const int64_t *d_off,
 #undef HX_BS_LAUNCH
         }
         // fallback for unsorted input: runs only when the flag says the bit-sliced kernel declined
-        k1_pairs_red<GBLOCK><<<ggrid, GBLOCK, 0, h->stream>>>(d_rank, d_off, d_codes, n_reads, h->N, h->W, h->cnt,
+        k1_pairs_red<GBLOCK><<<ggrid, GBLOCK, 0, h->stream>>>(d_rank, d_off, d_codes, n_reads, h->N, h->W, hx_cnt_ref(h),
                                                               h->d_totals, h->d_err, sorted_flag, 0);
         h->launches += 3;
     }

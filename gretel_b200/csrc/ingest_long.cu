@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(256)
 k_lr_transpose(const int32_t *__restrict__ rank, const int64_t *__restrict__ off,
                const uint8_t *__restrict__ codes, int64_t n_reads, int N, int W,
                const int32_t *__restrict__ g_lo, const int64_t *__restrict__ g_len,
-               const int64_t *__restrict__ g_off, uint4 *__restrict__ planes, uint32_t *__restrict__ cnt,
+               const int64_t *__restrict__ g_off, uint4 *__restrict__ planes, const HxCnt cnt,
                unsigned long long *__restrict__ totals, int *__restrict__ err,
                const int *__restrict__ sorted_flag) {
     __shared__ unsigned long long sh_tot[4];
@@ -117,13 +117,13 @@ k_lr_transpose(const int32_t *__restrict__ rank, const int64_t *__restrict__ off
             // start sentinel (util.py:262-266) / end sentinel (:271-275); the start rule wins
             const unsigned a0 = c[0];
             if (r == 0 && lr_valid_from(a0)) {
-                atomicAdd(cnt + hx_cell_off(W, 0, 1) + HX_SYM_GAP * HX_NSYM + a0, 1u);
+                atomicAdd(cnt.cell(W, 0, 1) + HX_SYM_GAP * HX_NSYM + a0, 1u);
                 t_sent++;
             }
             if (r + k == N && !(k == 2 && r == 0)) {
                 const unsigned ap = c[k - 2], bl = c[k - 1];
                 if (lr_valid_from(ap) && bl <= 6) {
-                    atomicAdd(cnt + hx_cell_off(W, N, N + 1) + bl * HX_NSYM + HX_SYM_GAP, 1u);
+                    atomicAdd(cnt.cell(W, N, N + 1) + bl * HX_NSYM + HX_SYM_GAP, 1u);
                     t_sent++;
                 }
             }
@@ -143,7 +143,7 @@ k_lr_transpose(const int32_t *__restrict__ rank, const int64_t *__restrict__ off
                 for (int i = lane; i < j; i += 32) {
                     const unsigned a = c2[i];
                     if (lr_valid_from(a)) {
-                        atomicAdd(cnt + hx_cell_off(W, r2 + i + 1, r2 + j + 1) + a * HX_NSYM + HX_SYM_GAP, 1u);
+                        atomicAdd(cnt.cell(W, r2 + i + 1, r2 + j + 1) + a * HX_NSYM + HX_SYM_GAP, 1u);
                         t_crumbs++;
                     }
                 }
@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(LR_TI * LR_TJ, 2)
 k_lr_tiles(const uint4 *__restrict__ planes, const int64_t *__restrict__ g_off,
            const int32_t *__restrict__ g_lo, const int64_t *__restrict__ g_len,
            const int64_t *__restrict__ first_reach, const int64_t *__restrict__ first_after, int N, int W,
-           int njb, uint32_t *__restrict__ cnt, unsigned long long *__restrict__ totals,
+           int njb, const HxCnt cnt, unsigned long long *__restrict__ totals,
            const int *__restrict__ sorted_flag) {
     if (!*sorted_flag) return;
     const int ib = blockIdx.x / njb, jb = blockIdx.x % njb;
@@ -224,14 +224,16 @@ k_lr_tiles(const uint4 *__restrict__ planes, const int64_t *__restrict__ g_off,
     }
     unsigned long long crumbs = 0;
     if (valid) {
-        uint32_t *cell = cnt + hx_cell_off(W, pi + 1, pj + 1);
+        uint32_t *cell = cnt.cell(W, pi + 1, pj + 1);
+        const bool shared_cell = cnt.world > 1;                // fused exchange: other GPUs add into it too
 #pragma unroll
         for (int a = 0; a < 5; ++a) {
             const int sa = a < 4 ? a : HX_SYM_DEL;
 #pragma unroll
             for (int b = 0; b < 6; ++b) {
                 if (acc[a][b]) {
-                    cell[sa * HX_NSYM + b] += acc[a][b];      // single owner: no atomic needed
+                    if (shared_cell) atomicAdd(cell + sa * HX_NSYM + b, acc[a][b]);
+                    else cell[sa * HX_NSYM + b] += acc[a][b];  // single owner: no atomic needed
                     crumbs += acc[a][b];
                 }
             }
@@ -320,13 +322,13 @@ int hx_launch_ingest_long(hx_matrix *h, const int32_t *d_rank, const int64_t *d_
     const int64_t want = (ng * 32 + 255) / 256;
     const int tgrid = (int)(want < (int64_t)sms * 8 ? want : (int64_t)sms * 8);
     k_lr_transpose<<<tgrid, 256, 0, st>>>(d_rank, d_off, d_codes, n_reads, N, W, s->g_lo, s->g_len, s->g_off,
-                                          s->planes, h->cnt, h->d_totals, h->d_err, h->d_flags + 4);
+                                          s->planes, hx_cnt_ref(h), h->d_totals, h->d_err, h->d_flags + 4);
     k_lr_site_index<<<(N + 255) / 256, 256, 0, st>>>(s->g_lo, s->g_hipm, ng, N, s->first_reach, s->first_after);
     const int nib = (N + LR_TI - 1) / LR_TI;
     const int njb = (W + LR_TI - 1) / LR_TJ + 1;            // J0 = I0 + jb*TJ must reach pi + W for the last row
     k_lr_tiles<<<(unsigned)((int64_t)nib * njb), LR_TI * LR_TJ, 0, st>>>(s->planes, s->g_off, s->g_lo, s->g_len,
                                                                          s->first_reach, s->first_after, N, W, njb,
-                                                                         h->cnt, h->d_totals, h->d_flags + 4);
+                                                                         hx_cnt_ref(h), h->d_totals, h->d_flags + 4);
     h->launches += 3;
     HX_CUDA(cudaGetLastError());
     return HX_OK;

@@ -110,6 +110,56 @@ class PipelinedIngest:
         self.main.wait_event(self.done)
 
 
+class FusedExchange:
+    """Ingestion fused with the cross-GPU sum over NVLink peer memory.
+
+    Band rows are dealt out to the ranks in contiguous blocks; every rank maps every other rank's pending
+    count buffer (CUDA IPC) and the ingestion kernels add each count straight into the GPU that owns its
+    row.  When all kernels are done every rank holds the final sums of its own rows: the 68 MB all-reduce
+    of the partial matrices is replaced by a barrier and an all-gather of the owned rows (1/world of the
+    matrix per rank)."""
+
+    def __init__(self, hansel, group=None):
+        import torch
+        import torch.distributed as dist
+        self.h, self.group, self.dist, self.torch = hansel, group, dist, torch
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        dev = torch.device("cuda", hansel.device)
+        mine = torch.frombuffer(bytearray(hansel.counts_ipc_export(self.world)), dtype=torch.uint8).to(dev)
+        allh = [torch.empty(64, dtype=torch.uint8, device=dev) for _ in range(self.world)]
+        dist.all_gather(allh, mine, group=group)
+        hansel.counts_ipc_import([bytes(t.cpu().numpy().tobytes()) for t in allh], self.rank)
+        cptr, cn, tptr, tn = hansel.counts_buffer()
+        self.counts = torch.as_tensor(_DevBuf(cptr, cn, "<i4"), device=dev)
+        self.totals = torch.as_tensor(_DevBuf(tptr, tn, "<i8"), device=dev)
+        self.own = self.counts.view(self.world, -1)[self.rank]
+        self.main = torch.cuda.ExternalStream(hansel.stream, device=dev)
+        self.token = torch.zeros(1, dtype=torch.int32, device=dev)
+        dist.barrier(group=group)
+
+    def reset(self):
+        """Zero the local buffer; nobody may add into it before every rank has done so."""
+        self.h.reset_counts()
+        with self.torch.cuda.stream(self.main):
+            self.dist.all_reduce(self.token, group=self.group)
+
+    def finish(self, gather=True):
+        """After the ingestion launches: wait for every rank's kernels (the totals all-reduce doubles as the
+        barrier), then collect the owned rows."""
+        with self.torch.cuda.stream(self.main):
+            self.dist.all_reduce(self.totals, op=self.dist.ReduceOp.SUM, group=self.group)
+            if gather:
+                self.dist.all_gather_into_tensor(self.counts, self.own, group=self.group)
+
+    def close(self):
+        """Unmap the peers' buffers; every rank must have done so before any rank frees its own."""
+        self.h.sync()
+        self.dist.barrier(group=self.group)
+        self.h.counts_ipc_close()
+        self.dist.barrier(group=self.group)
+
+
 def load_from_packed_sharded(rank, off, codes, n_snps, band_w, world_size=None, my_rank=None, device=None,
                              presharded=False, group=None):
     """Every rank calls this with the same packed reads (or, with ``presharded``, its own

@@ -170,6 +170,20 @@ class Hansel:
         _lib.check(self._lib.hx_reset_counts(self._h))
         self._touch()
 
+    def counts_ipc_export(self, world):
+        """Fused exchange, step 1: make the pending counts IPC-shareable; returns the 64-byte handle."""
+        buf = C.create_string_buffer(64)
+        _lib.check(self._lib.hx_counts_ipc_export(self._h, int(world), buf))
+        return bytes(buf.raw)
+
+    def counts_ipc_import(self, handles, my_rank):
+        """Fused exchange, step 2: handles = the world handles in rank order (bytes, 64 each)."""
+        blob = b"".join(handles)
+        _lib.check(self._lib.hx_counts_ipc_import(self._h, blob, len(handles), int(my_rank)))
+
+    def counts_ipc_close(self):
+        _lib.check(self._lib.hx_counts_ipc_close(self._h))
+
     def finalize(self):
         _lib.check(self._lib.hx_finalize_counts(self._h))
         self._touch()

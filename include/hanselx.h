@@ -88,6 +88,18 @@ int hx_ingest_totals(hx_matrix *h, int64_t totals[4]);               /* synchron
  * util.py:303-326): device pointer + length of the uint32 counts and of the int64
  * totals, for an integer sum-allreduce by the caller (NCCL). */
 int hx_counts_buffer(hx_matrix *h, void **d_counts, int64_t *n_u32, void **d_totals, int64_t *n_i64);
+/* Fused exchange (one process per GPU, NVLink peer memory): band rows are dealt out to the ranks in
+ * contiguous blocks of ceil((N+2)/world); after export + import every ingestion kernel adds its counts
+ * straight into the GPU that owns the row, so when all ranks' kernels are done each rank holds the final
+ * sums of its own rows and the partial matrices never have to be all-reduced (an all-gather of the owned
+ * rows, or nothing if only the owner needs them, completes the exchange).
+ *   hx_counts_ipc_export  (re)allocates the pending counts as an IPC-shareable buffer, padded to
+ *                         world * rows_per rows, and writes its 64-byte cudaIpcMemHandle_t;
+ *   hx_counts_ipc_import  takes the world handles (own one included, in rank order). */
+int hx_counts_ipc_export(hx_matrix *h, int32_t world, void *handle_out);
+int hx_counts_ipc_import(hx_matrix *h, const void *handles, int32_t world, int32_t my_rank);
+/* Unmap the peers' buffers (every rank must do this before any rank frees its own: barrier around it). */
+int hx_counts_ipc_close(hx_matrix *h);
 /* Fold the integer counts into the float32 working matrix used by everything below
  * (util.py:329-333 happens in the caller from the totals). */
 int hx_finalize_counts(hx_matrix *h);

@@ -39,7 +39,14 @@ def _worker(rank, world, port, segments, out):
         t_rank = torch.from_numpy(d["rank"][lo:hi].copy()).to(dev)
         t_off = torch.from_numpy(d["off"][lo:hi + 1].copy()).to(dev)
         t_codes = torch.from_numpy(d["codes"]).to(dev)
-        if segments > 1:
+        if segments == -1:                                  # fused exchange over NVLink peer memory
+            fx = gdist.FusedExchange(h)
+            for _ in range(2):                               # twice: the reset/barrier protocol must hold
+                fx.reset()
+                h.ingest_device(t_rank.data_ptr(), t_off.data_ptr(), t_codes.data_ptr(), hi - lo)
+                fx.finish()
+            fx.close()
+        elif segments > 1:
             pipe = gdist.PipelinedIngest(h, d["rank"][lo:hi], hi - lo, segments=segments)
             h.reset_counts()
             pipe.run(t_rank.data_ptr(), t_off.data_ptr(), t_codes.data_ptr())
@@ -62,7 +69,7 @@ def _worker(rank, world, port, segments, out):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("segments", [1, 4])
+@pytest.mark.parametrize("segments", [1, 4, -1])
 def test_two_gpu_sharded_ingest(tmp_path, c_oracle, segments):
     import torch
     import torch.multiprocessing as mp
