@@ -162,6 +162,42 @@ def run_reference(args):
     return 0
 
 
+def recovery_cpu_baseline(device):
+    """One haplotype on BASELINE.json configs[1] (HIV-like, ~1k SNPs) recovered by the literal Python
+    restatement of gretel.py:102-189 + :79-98 over a dense Hansel (the reference's way: one Python call per
+    branch / per pair), next to the same haplotype on the GPU.  The dense matrix is taken from the GPU
+    ingestion so that the CPU side only pays for recovery."""
+    from gretel_b200 import util
+    from oracle import hansel_oracle as o
+    w = synth.scaled(synth.WORKLOADS["hiv"], 20_000)
+    d = synth.generate(w)
+    N = w.n_snps
+    h = util.load_from_packed(d["rank"], d["off"], d["codes"], N, band_w=d["max_k"] - 1, device=device)
+    ho = o.OracleHansel.init_matrix(o.SYMBOLS, o.UNSYMBOLS, N)
+    ho.m[...] = h.to_dense()
+    ho.L = h.L
+    horig = ho.copy()
+    t0 = time.perf_counter()
+    path, prob, mn = o.generate_path(N, ho, horig)
+    t_gen = time.perf_counter() - t0
+    t_rw = None
+    if path is not None:
+        t0 = time.perf_counter()
+        o.reweight_hansel_from_path(ho, path, max(mn, 0.01))
+        t_rw = time.perf_counter() - t0
+    orig = h.copy()
+    t0 = time.perf_counter()
+    res = h.generate_path_codes(orig)
+    if res[0] is not None:
+        h.reweight_path_codes(res[0], max(res[3], 0.01))
+    t_gpu = time.perf_counter() - t0
+    same = (path is None and res[0] is None) or (path is not None and res[0] is not None and
+                                                  [o.CODE[x] for x in path] == list(res[0]))
+    return {"workload": "configs[1] hiv: %d SNPs, 20000 reads, L=%d" % (N, h.L), "cores": 1, "kind": "port",
+            "generate_path_s": t_gen, "reweight_s": t_rw, "gpu_generate_plus_reweight_s": t_gpu,
+            "same_haplotype": bool(same)}
+
+
 # ----------------------------------------------------------------------------------- our arm
 def run_ours(args):
     import torch
@@ -353,6 +389,8 @@ def run_ours(args):
                         "real DRAM traffic (traffic, dram_frac) stays at the compulsory input+band bytes"}
 
     # ---- CPU baseline: the reference's per-pair Python loop on a bounded sample, all cores
+    if args.no_cpu_baseline:
+        args.recovery_cpu_baseline = False
     cpu = None
     if not args.no_cpu_baseline:
         from oracle import py_baseline as pb
@@ -389,6 +427,8 @@ def run_ours(args):
                 sweep.append({"L": L, "haplotypes": int(len(pp)), "seconds": time.perf_counter() - t0})
                 hc.close()
             recovery["sweep_L1_8_50_haplotypes"] = sweep
+        if args.recovery_cpu_baseline:
+            recovery["cpu_port"] = recovery_cpu_baseline(local_rank)
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
@@ -430,6 +470,9 @@ def main():
     ap.add_argument("--recovery-sweep", action="store_true", default=True,
                     help="also time configs[4]: 50 haplotypes at L=1..8 (a few seconds)")
     ap.add_argument("--no-recovery-sweep", dest="recovery_sweep", action="store_false")
+    ap.add_argument("--recovery-cpu-baseline", action="store_true", default=True,
+                    help="also recover one ~1k-SNP haplotype with the literal Python restatement (~10-20 s of CPU)")
+    ap.add_argument("--no-recovery-cpu-baseline", dest="recovery_cpu_baseline", action="store_false")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-sample", type=int, default=0)
     args = ap.parse_args()

@@ -87,8 +87,10 @@ int main() {
         ms = timeit([&] { k_red_f4<<<grid, block>>>((float*)buf, nw, iters); });
         printf("RED.v4.f32 random,   %4llu MB : %.1f Gops/s (x4 elements)\n", (unsigned long long)mb, nops / ms / 1e6);
     }
+    CK(cudaFuncSetAttribute(k_atoms, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
     for (int nwords : {32, 1024, 16384}) {
         float ms = timeit([&] { k_atoms<<<grid, block, 65536>>>(out, iters, nwords); });
+        CK(cudaGetLastError());
         printf("ATOMS.u32 random over %5d words: %.1f Gops/s (%.2f lanes/clk/SM)\n", nwords, nops / ms / 1e6, nops / ms / 1e6 / sms / 1.9);
     }
     { float ms = timeit([&] { k_popc<<<grid, block>>>(out, iters); });
