@@ -224,19 +224,123 @@ k_lr_tiles(const uint4 *__restrict__ planes, const int64_t *__restrict__ g_off,
     }
     unsigned long long crumbs = 0;
     if (valid) {
-        uint32_t *cell = cnt.cell(W, pi + 1, pj + 1);
+        uint32_t *__restrict__ cell = cnt.cell(W, pi + 1, pj + 1);
         const bool shared_cell = cnt.world > 1;                // fused exchange: other GPUs add into it too
 #pragma unroll
         for (int a = 0; a < 5; ++a) {
             const int sa = a < 4 ? a : HX_SYM_DEL;
+            if (shared_cell) {
 #pragma unroll
-            for (int b = 0; b < 6; ++b) {
-                if (acc[a][b]) {
-                    if (shared_cell) atomicAdd(cell + sa * HX_NSYM + b, acc[a][b]);
-                    else cell[sa * HX_NSYM + b] += acc[a][b];  // single owner: no atomic needed
-                    crumbs += acc[a][b];
+                for (int b = 0; b < 6; ++b)
+                    if (acc[a][b]) atomicAdd(cell + sa * HX_NSYM + b, acc[a][b]);
+            } else {
+                // single owner: no atomic needed; the six loads of a row go out together, then the stores
+                uint32_t old[6];
+#pragma unroll
+                for (int b = 0; b < 6; ++b) old[b] = cell[sa * HX_NSYM + b];
+#pragma unroll
+                for (int b = 0; b < 6; ++b)
+                    if (acc[a][b]) cell[sa * HX_NSYM + b] = old[b] + acc[a][b];
+            }
+#pragma unroll
+            for (int b = 0; b < 6; ++b) crumbs += acc[a][b];
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) crumbs += __shfl_xor_sync(0xffffffffu, crumbs, o);
+    if ((threadIdx.x & 31) == 0 && crumbs) atomicAdd(&totals[1], crumbs);
+}
+
+// ---- tiles, planes staged through shared memory (dense coverage) --------------------------------
+__global__ void __launch_bounds__(LR_TI * LR_TJ, 2)
+k_lr_tiles_staged(const uint4 *__restrict__ planes, const int64_t *__restrict__ g_off,
+           const int32_t *__restrict__ g_lo, const int64_t *__restrict__ g_len,
+           const int64_t *__restrict__ first_reach, const int64_t *__restrict__ first_after, int N, int W,
+           int njb, const HxCnt cnt, unsigned long long *__restrict__ totals,
+           const int *__restrict__ sorted_flag) {
+    if (!*sorted_flag) return;
+    const int ib = blockIdx.x / njb, jb = blockIdx.x % njb;
+    const int I0 = ib * LR_TI, J0 = I0 + jb * LR_TJ;
+    if (J0 >= N) return;
+    const int ti = threadIdx.x / LR_TJ, tj = threadIdx.x % LR_TJ;
+    const int pi = I0 + ti, pj = J0 + tj;
+    const bool valid = pi < N && pj < N && pj > pi && pj - pi <= W;
+    // groups that can cover a pair of this tile: started at or before the last pi, reach past J0
+    const int ilast = min(I0 + LR_TI - 1, N - 1);
+    const int64_t g_begin = first_reach[J0];
+    const int64_t g_end = first_after[ilast];
+    uint32_t acc[5][6];
+#pragma unroll
+    for (int a = 0; a < 5; ++a)
+#pragma unroll
+        for (int b = 0; b < 6; ++b) acc[a][b] = 0;
+    // The planes of the tile's 16 + 32 sites are staged through shared memory with cp.async, two groups
+    // ahead of the one being counted (4 stages, one barrier per group): the loads of a group no longer
+    // stall the 30 x (AND, POPC, ADD) of the previous ones.
+    constexpr int NST = 4, DEPTH = 2, ENT = LR_TI + LR_TJ;
+    __shared__ uint4 st_planes[NST][ENT][2];
+    __shared__ int st_active[NST];
+    const uint32_t st_base = (uint32_t)__cvta_generic_to_shared(&st_planes[0][0][0]);
+    for (int64_t g = g_begin; g < g_end + DEPTH; ++g) {
+        const int stage = (int)((g - g_begin) % NST);
+        if (g < g_end) {
+            const int lo = g_lo[g];
+            const int len = (int)g_len[g];
+            const bool active = lo + len > J0;             // uniform: does the group reach the tile's columns
+            if (threadIdx.x == 0) st_active[stage] = active;
+            if (active && threadIdx.x < 2 * ENT) {
+                const int e = threadIdx.x >> 1, half = threadIdx.x & 1;
+                const int site = e < LR_TI ? I0 + e : J0 + (e - LR_TI);
+                const int u = site - lo;
+                const uint32_t dst = st_base + (uint32_t)(((stage * ENT + e) * 2 + half) * 16);
+                if (u >= 0 && u < len) {
+                    const uint4 *src = planes + 2 * (g_off[g] + u) + half;
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+                } else {
+                    asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(dst), "r"(0u) : "memory");
                 }
             }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        const int64_t gc = g - DEPTH;
+        if (gc >= g_begin) {
+            asm volatile("cp.async.wait_group %0;" ::"n"(DEPTH) : "memory");
+            __syncthreads();
+            const int sc = (int)((gc - g_begin) % NST);
+            if (st_active[sc] && valid) {
+                const uint4 m1a = st_planes[sc][ti][0], m1b = st_planes[sc][ti][1];
+                const uint4 m2a = st_planes[sc][LR_TI + tj][0], m2b = st_planes[sc][LR_TI + tj][1];
+                const unsigned x1[5] = {m1a.x, m1a.y, m1a.z, m1a.w, m1b.y};            // A C G T -   (first allele)
+                const unsigned x2[6] = {m2a.x, m2a.y, m2a.z, m2a.w, m2b.x, m2b.y};     // A C G T N - (second allele)
+#pragma unroll
+                for (int a = 0; a < 5; ++a)
+#pragma unroll
+                    for (int b = 0; b < 6; ++b) acc[a][b] += __popc(x1[a] & x2[b]);
+            }
+        }
+    }
+    unsigned long long crumbs = 0;
+    if (valid) {
+        uint32_t *__restrict__ cell = cnt.cell(W, pi + 1, pj + 1);
+        const bool shared_cell = cnt.world > 1;                // fused exchange: other GPUs add into it too
+#pragma unroll
+        for (int a = 0; a < 5; ++a) {
+            const int sa = a < 4 ? a : HX_SYM_DEL;
+            if (shared_cell) {
+#pragma unroll
+                for (int b = 0; b < 6; ++b)
+                    if (acc[a][b]) atomicAdd(cell + sa * HX_NSYM + b, acc[a][b]);
+            } else {
+                // single owner: no atomic needed; the six loads of a row go out together, then the stores
+                uint32_t old[6];
+#pragma unroll
+                for (int b = 0; b < 6; ++b) old[b] = cell[sa * HX_NSYM + b];
+#pragma unroll
+                for (int b = 0; b < 6; ++b)
+                    if (acc[a][b]) cell[sa * HX_NSYM + b] = old[b] + acc[a][b];
+            }
+#pragma unroll
+            for (int b = 0; b < 6; ++b) crumbs += acc[a][b];
         }
     }
 #pragma unroll
@@ -326,9 +430,16 @@ int hx_launch_ingest_long(hx_matrix *h, const int32_t *d_rank, const int64_t *d_
     k_lr_site_index<<<(N + 255) / 256, 256, 0, st>>>(s->g_lo, s->g_hipm, ng, N, s->first_reach, s->first_after);
     const int nib = (N + LR_TI - 1) / LR_TI;
     const int njb = (W + LR_TI - 1) / LR_TJ + 1;            // J0 = I0 + jb*TJ must reach pi + W for the last row
-    k_lr_tiles<<<(unsigned)((int64_t)nib * njb), LR_TI * LR_TJ, 0, st>>>(s->planes, s->g_off, s->g_lo, s->g_len,
-                                                                         s->first_reach, s->first_after, N, W, njb,
-                                                                         hx_cnt_ref(h), h->d_totals, h->d_flags + 4);
+    // measured (B200, ONT-like reads): with ~10 reads per SNP rank the cp.async-staged tiles win (9.2 vs
+    // 11.3 ms for 100k reads), with ~2 per rank the per-group barrier costs more than it hides (3.8 vs 1.4 ms)
+    if (n_reads >= 6 * (int64_t)N)
+        k_lr_tiles_staged<<<(unsigned)((int64_t)nib * njb), LR_TI * LR_TJ, 0, st>>>(
+            s->planes, s->g_off, s->g_lo, s->g_len, s->first_reach, s->first_after, N, W, njb, hx_cnt_ref(h),
+            h->d_totals, h->d_flags + 4);
+    else
+        k_lr_tiles<<<(unsigned)((int64_t)nib * njb), LR_TI * LR_TJ, 0, st>>>(
+            s->planes, s->g_off, s->g_lo, s->g_len, s->first_reach, s->first_after, N, W, njb, hx_cnt_ref(h),
+            h->d_totals, h->d_flags + 4);
     h->launches += 3;
     HX_CUDA(cudaGetLastError());
     return HX_OK;
