@@ -110,7 +110,7 @@ void free_all(hx_matrix *h) {
     if (h->d_run_end) cudaFreeAsync(h->d_run_end, h->stream);
     if (h->d_misc) cudaFreeAsync(h->d_misc, h->stream);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    if (h->h_pinned) cudaFreeHost(h->h_pinned);
+    free(h->h_pinned);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
@@ -174,7 +174,9 @@ int hx_create(int32_t n_snps, int32_t band_w, int32_t device, hx_matrix **out) {
     HX_TRY(cudaMemsetAsync(h->d_flags, 0, 8 * sizeof(int), h->stream));
     HX_TRY(cudaMallocAsync((void **)&h->d_misc, 32 * sizeof(double), h->stream));
     HX_TRY(cudaMallocAsync((void **)&h->d_run_end, sizeof(int64_t) * ((size_t)n_snps + 2), h->stream));
-    HX_TRY(cudaMallocHost(&h->h_pinned, 256));
+    h->h_pinned = calloc(1, 256);     // scalars come back through pageable memory: a pinned allocation per
+                                      // matrix costs more (cudaMallocHost/cudaFreeHost) than it saves
+    if (!h->h_pinned) { free_all(h); return HX_E_NOMEM; }
     HX_TRY(cudaStreamSynchronize(h->stream));
 #undef HX_TRY
     *out = h;

@@ -67,7 +67,7 @@ struct hx_matrix {
     int *d_flags;                    // [0] hole site / abort flag, [1..] misc
     int64_t *d_run_end;              // (N+1) end (exclusive) of the run of reads with each rank
     double *d_misc;                  // small outputs (weights etc.)
-    void *h_pinned;                  // small pinned host buffer for D2H of scalars
+    void *h_pinned;                  // small host buffer for D2H of scalars
     int ingest_kernel;
     void *lr_scratch;                // long-read ingestion scratch (ingest_long.cu)
     cudaEvent_t ev0, ev1;

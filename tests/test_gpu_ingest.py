@@ -221,3 +221,27 @@ def test_adversarial_shapes(c_oracle):
             band, totals = _gpu_band(rank, off, codes, N, W, kernel)
             assert totals == tuple(int(x) for x in rt), (N, kernel)
             assert np.array_equal(band, ref.astype(np.float32)), (N, kernel)
+
+
+def test_full_size_config3_bit_exact(c_oracle):
+    """BASELINE.json configs[2] at FULL size (10M x 150 bp reads, 10k SNPs, 1.1 G observations): the GPU band
+    equals the C oracle's bit for bit, and so do the totals (n_slices, n_crumbs, covered SNPs, sentinels)."""
+    d = synth.generate(synth.WORKLOADS["metagenome"])
+    N, W = d["n_snps"], d["max_k"] - 1
+    band, totals = _gpu_band(d["rank"], d["off"], d["codes"], N, W, 0)
+    ref, rt = c_oracle.ingest(d["rank"], d["off"], d["codes"], N, W)
+    assert totals == tuple(int(x) for x in rt)
+    assert totals[1] > 1_000_000_000
+    assert np.array_equal(band, ref.astype(np.float32))
+
+
+def test_config4_60pct_size_bit_exact(c_oracle):
+    """BASELINE.json configs[3] shape (ONT-like, ~300 SNPs/read) at 62% of its size: 2.9 G observations
+    through the cp.async-staged tile kernel, bit for bit against the C oracle."""
+    d = synth.generate(synth.scaled(synth.WORKLOADS["ont"], 62_000))
+    N, W = d["n_snps"], d["max_k"] - 1
+    assert len(d["rank"]) >= 6 * N                      # dense enough for the staged tiles
+    band, totals = _gpu_band(d["rank"], d["off"], d["codes"], N, W, 0)
+    ref, rt = c_oracle.ingest(d["rank"], d["off"], d["codes"], N, W)
+    assert totals == tuple(int(x) for x in rt)
+    assert np.array_equal(band, ref.astype(np.float32))
