@@ -233,6 +233,26 @@ def test_full_size_config3_bit_exact(c_oracle):
     assert totals == tuple(int(x) for x in rt)
     assert totals[1] > 1_000_000_000
     assert np.array_equal(band, ref.astype(np.float32))
+    # ... and the first haplotypes recovered from that full-size matrix (10k sites, L = 15)
+    from gretel_b200 import util
+    from gretel_b200.hansel import Hansel, REF_SYMBOLS, REF_UNSYMBOLS
+    h = Hansel.init_matrix(REF_SYMBOLS, REF_UNSYMBOLS, N, band_w=W)
+    h.load_band(band)
+    util.set_totals(h, totals[0], totals[1], totals[2])
+    assert h.L == 15
+    orig = h.copy()
+    cur = ref.astype(np.float32)
+    cur0 = cur.copy()
+    for _ in range(3):
+        pc, res = c_oracle.generate_path(cur, cur0, N, W, h.L)
+        got = h.generate_path_codes(orig)
+        assert pc is not None and got[0] is not None
+        assert np.array_equal(got[0], pc)
+        for a, b in zip(got[1:], res):
+            assert a == pytest.approx(b, rel=1e-6)
+        ratio = max(res[2], 0.01)
+        assert h.reweight_path_codes(got[0], ratio) == pytest.approx(c_oracle.reweight_path(cur, N, W, pc, ratio), rel=1e-9)
+    assert np.array_equal(h.band(), cur)
 
 
 def test_config4_60pct_size_bit_exact(c_oracle):
