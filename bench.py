@@ -275,7 +275,10 @@ def run_ours(args):
             return
         h.ingest_device(t_rank.data_ptr(), t_off.data_ptr(), t_codes.data_ptr(), R)
         if world > 1:
-            gdist.allreduce_counts(h)
+            if args.exchange == "reduce":
+                gdist.reduce_counts(h, dst=0)
+            else:
+                gdist.allreduce_counts(h)
 
     def barrier():
         if world > 1:
@@ -459,9 +462,10 @@ def main():
     ap.add_argument("--workload", default="metagenome", choices=sorted(synth.WORKLOADS))
     ap.add_argument("--reads", type=int, default=0, help="reads per GPU (default: the workload's full size)")
     ap.add_argument("--kernel", type=int, default=0, help="ingestion kernel: 0 auto, 1 generic, 2 bit-sliced")
-    ap.add_argument("--exchange", default="allreduce", choices=["allreduce", "fused"],
-                    help="N>1: NCCL all-reduce of the partial matrices, or counts added straight into the owning GPU "
-                         "over NVLink peer memory + all-gather of the owned rows")
+    ap.add_argument("--exchange", default="allreduce", choices=["allreduce", "reduce", "fused"],
+                    help="N>1: NCCL all-reduce of the partial matrices (default, as north_star names it); reduce onto "
+                         "rank 0 only (recovery runs there); or counts added straight into the owning GPU over "
+                         "NVLink peer memory + all-gather of the owned rows")
     ap.add_argument("--segments", type=int, default=1,
                     help="N>1: ingest in this many launches, all-reducing finished band rows behind the next one")
     ap.add_argument("--e2e-format", default="compact", choices=["compact", "wide"],

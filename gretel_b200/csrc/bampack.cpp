@@ -156,6 +156,68 @@ void pack_record(const uint8_t *rec, int32_t target_tid, int32_t start_pos, int3
 
 }  // namespace
 
+namespace {
+
+// Whole BAM in memory: inflated bytes, target contig id and the offset of every alignment record.
+struct LoadedBam {
+    std::vector<uint8_t> data;
+    std::vector<size_t> recs;
+    int32_t target_tid = -1;
+    int32_t target_len = 0;
+};
+
+int load_bam(const char *bam_path, const char *contig, int n_threads, LoadedBam &lb) {
+    FILE *fp = fopen(bam_path, "rb");
+    if (!fp) { hx_set_error("cannot open %s", bam_path); return HX_E_ARG; }
+    fseek(fp, 0, SEEK_END);
+    const long fsz = ftell(fp);
+    fseek(fp, 0, SEEK_SET);
+    std::vector<uint8_t> file((size_t)fsz);
+    if (fsz && fread(file.data(), 1, (size_t)fsz, fp) != (size_t)fsz) { fclose(fp); hx_set_error("short read on %s", bam_path); return HX_E_ARG; }
+    fclose(fp);
+    std::vector<Block> blocks;
+    size_t total = 0;
+    if (!scan_bgzf(file, blocks, total)) { hx_set_error("%s is not a BGZF file", bam_path); return HX_E_ARG; }
+    lb.data.resize(total);
+    std::atomic<size_t> next(0);
+    std::atomic<bool> ok(true);
+    auto work = [&]() {
+        for (;;) {
+            const size_t b = next.fetch_add(1);
+            if (b >= blocks.size()) break;
+            if (!inflate_block(file.data() + blocks[b].coff, blocks[b].csize, lb.data.data() + blocks[b].uoff, blocks[b].usize))
+                ok = false;
+        }
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < n_threads; ++t) th.emplace_back(work);
+    work();
+    for (auto &t : th) t.join();
+    if (!ok) { hx_set_error("inflate failed on %s", bam_path); return HX_E_ARG; }
+    const uint8_t *d = lb.data.data();
+    if (total < 12 || memcmp(d, "BAM\1", 4) != 0) { hx_set_error("%s is not a BAM file", bam_path); return HX_E_ARG; }
+    size_t p = 4;
+    const int32_t l_text = rdi32(d + p); p += 4 + (size_t)l_text;
+    const int32_t n_ref = rdi32(d + p); p += 4;
+    for (int32_t i = 0; i < n_ref; ++i) {
+        const int32_t l_name = rdi32(d + p); p += 4;
+        const bool hit = std::string((const char *)d + p, (size_t)std::max(0, l_name - 1)) == contig;
+        p += (size_t)l_name;
+        if (hit) { lb.target_tid = i; lb.target_len = rdi32(d + p); }
+        p += 4;
+    }
+    if (lb.target_tid < 0) { hx_set_error("contig %s not in %s", contig, bam_path); return HX_E_ARG; }
+    while (p + 4 <= total) {
+        const int32_t bs = rdi32(d + p);
+        if (bs < 32 || p + 4 + (size_t)bs > total) break;
+        lb.recs.push_back(p + 4);
+        p += 4 + (size_t)bs;
+    }
+    return HX_OK;
+}
+
+}  // namespace
+
 extern "C" {
 
 int hx_pack_bam(const char *bam_path, const char *contig, int32_t start_pos, int32_t end_pos,
@@ -174,61 +236,16 @@ int hx_pack_bam(const char *bam_path, const char *contig, int32_t start_pos, int
         fprintf(stderr, "[hx_pack_bam] %-10s %.1f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
         t0 = t1;
     };
-    FILE *fp = fopen(bam_path, "rb");
-    if (!fp) { hx_set_error("hx_pack_bam: cannot open %s", bam_path); return HX_E_ARG; }
-    fseek(fp, 0, SEEK_END);
-    const long fsz = ftell(fp);
-    fseek(fp, 0, SEEK_SET);
-    std::vector<uint8_t> file((size_t)fsz);
-    if (fsz && fread(file.data(), 1, (size_t)fsz, fp) != (size_t)fsz) { fclose(fp); hx_set_error("hx_pack_bam: short read"); return HX_E_ARG; }
-    fclose(fp);
-    lap("read");
-
-    std::vector<Block> blocks;
-    size_t total = 0;
-    if (!scan_bgzf(file, blocks, total)) { hx_set_error("hx_pack_bam: %s is not a BGZF file", bam_path); return HX_E_ARG; }
-    std::vector<uint8_t> data(total);
+    LoadedBam lb;
     {
-        std::atomic<size_t> next(0);
-        std::atomic<bool> ok(true);
-        auto work = [&]() {
-            for (;;) {
-                const size_t b = next.fetch_add(1);
-                if (b >= blocks.size()) break;
-                if (!inflate_block(file.data() + blocks[b].coff, blocks[b].csize, data.data() + blocks[b].uoff, blocks[b].usize))
-                    ok = false;
-            }
-        };
-        std::vector<std::thread> th;
-        for (int t = 1; t < n_threads; ++t) th.emplace_back(work);
-        work();
-        for (auto &t : th) t.join();
-        if (!ok) { hx_set_error("hx_pack_bam: inflate failed"); return HX_E_ARG; }
+        const int rc = load_bam(bam_path, contig, n_threads, lb);
+        if (rc) return rc;
     }
-    file.clear();
-    file.shrink_to_fit();
-    lap("inflate");
-
-    // header
-    if (total < 12 || memcmp(data.data(), "BAM\1", 4) != 0) { hx_set_error("hx_pack_bam: not a BAM file"); return HX_E_ARG; }
-    size_t p = 4;
-    const int32_t l_text = rdi32(data.data() + p); p += 4 + (size_t)l_text;
-    const int32_t n_ref = rdi32(data.data() + p); p += 4;
-    int32_t target_tid = -1;
-    for (int32_t i = 0; i < n_ref; ++i) {
-        const int32_t l_name = rdi32(data.data() + p); p += 4;
-        if (std::string((const char *)data.data() + p, (size_t)std::max(0, l_name - 1)) == contig) target_tid = i;
-        p += (size_t)l_name + 4;
-    }
-    if (target_tid < 0) { hx_set_error("hx_pack_bam: contig %s not in %s", contig, bam_path); return HX_E_ARG; }
-    // record boundaries
-    std::vector<size_t> recs;
-    while (p + 4 <= total) {
-        const int32_t bs = rdi32(data.data() + p);
-        if (bs < 32 || p + 4 + (size_t)bs > total) break;
-        recs.push_back(p + 4);
-        p += 4 + (size_t)bs;
-    }
+    const std::vector<uint8_t> &data = lb.data;
+    const std::vector<size_t> &recs = lb.recs;
+    const int32_t target_tid = lb.target_tid;
+    const size_t total = data.size();
+    (void)total;
     lap("index");
     // parallel CIGAR walks over contiguous chunks of records (keeps BAM order)
     const size_t nrec = recs.size();
@@ -265,6 +282,73 @@ int hx_pack_bam(const char *bam_path, const char *contig, int32_t start_pos, int
     out->n_reads = R;
     out->n_codes = C;
     out->n_records = (int64_t)nrec;
+    return HX_OK;
+}
+
+/* Per-position A,C,G,T counts over [start0, end0) of a contig from every alignment (no filter, no base
+ * quality threshold): what gretel/snpper.py:30 asks pysam's count_coverage for.  out[4][end0-start0]. */
+int hx_count_coverage(const char *bam_path, const char *contig, int32_t start0, int32_t end0, int n_threads,
+                      uint32_t *out) {
+    if (!bam_path || !contig || !out || start0 < 0 || end0 < start0) { hx_set_error("hx_count_coverage: bad arguments"); return HX_E_ARG; }
+    if (n_threads < 1) n_threads = 1;
+    LoadedBam lb;
+    int rc = load_bam(bam_path, contig, n_threads, lb);
+    if (rc) return rc;
+    const int64_t len = (int64_t)end0 - start0;
+    memset(out, 0, sizeof(uint32_t) * 4 * (size_t)len);
+    const size_t nrec = lb.recs.size();
+    const int nt = (int)std::min<size_t>((size_t)n_threads, std::max<size_t>(1, nrec / 4096));
+    std::vector<std::vector<uint32_t>> part((size_t)nt);
+    auto work = [&](int t) {
+        std::vector<uint32_t> &c = part[(size_t)t];
+        c.assign(4 * (size_t)len, 0u);
+        const size_t a = nrec * (size_t)t / (size_t)nt, b = nrec * (size_t)(t + 1) / (size_t)nt;
+        for (size_t i = a; i < b; ++i) {
+            const uint8_t *rec = lb.data.data() + lb.recs[i];
+            const int32_t tid = rdi32(rec), pos = rdi32(rec + 4);
+            if (tid != lb.target_tid || pos < 0) continue;
+            const int l_read_name = rec[8];
+            const int n_cigar = rd16(rec + 12);
+            const int32_t l_seq = rdi32(rec + 16);
+            const uint8_t *cig = rec + 32 + l_read_name;
+            const uint8_t *seq = cig + 4 * (size_t)n_cigar;
+            int64_t rpos = pos, qpos = 0;
+            for (int ci = 0; ci < n_cigar; ++ci) {
+                const uint32_t cv = rd32(cig + 4 * ci);
+                const int op = cv & 0xf;
+                const int64_t ln = cv >> 4;
+                if (op == 0 || op == 7 || op == 8) {
+                    for (int64_t j = 0; j < ln; ++j) {
+                        const int64_t r = rpos + j, q = qpos + j;
+                        if (r < start0 || r >= end0 || q >= l_seq) continue;
+                        const uint8_t bb = seq[q >> 1];
+                        const uint8_t code = NT16_CODE[(q & 1) ? (bb & 0xf) : (bb >> 4)];
+                        if (code < 4) c[(size_t)code * (size_t)len + (size_t)(r - start0)]++;
+                    }
+                    rpos += ln; qpos += ln;
+                } else if (op == 2 || op == 3) {
+                    rpos += ln;
+                } else if (op == 1 || op == 4) {
+                    qpos += ln;
+                }
+            }
+        }
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < nt; ++t) th.emplace_back(work, t);
+    work(0);
+    for (auto &t : th) t.join();
+    for (int t = 0; t < nt; ++t)
+        for (size_t i = 0; i < 4 * (size_t)len; ++i) out[i] += part[(size_t)t][i];
+    return HX_OK;
+}
+
+int hx_bam_contig_length(const char *bam_path, const char *contig, int32_t *length) {
+    if (!bam_path || !contig || !length) { hx_set_error("hx_bam_contig_length: bad arguments"); return HX_E_ARG; }
+    LoadedBam lb;
+    int rc = load_bam(bam_path, contig, 1, lb);
+    if (rc) return rc;
+    *length = lb.target_len;
     return HX_OK;
 }
 

@@ -35,6 +35,22 @@ class _DevBuf:
                                          "version": 2, "strides": None}
 
 
+def reduce_counts(hansel, dst=0, group=None):
+    """Sum the pending integer counts and totals onto rank ``dst`` only (recovery runs on one GPU, so the
+    other ranks do not need the full matrix): about half the traffic of the all-reduce."""
+    import torch
+    import torch.distributed as dist
+    cptr, cn, tptr, tn = hansel.counts_buffer()
+    dev = torch.device("cuda", hansel.device)
+    with torch.cuda.device(dev):
+        s = torch.cuda.ExternalStream(hansel.stream, device=dev)
+        with torch.cuda.stream(s):
+            counts = torch.as_tensor(_DevBuf(cptr, cn, "<i4"), device=dev)
+            totals = torch.as_tensor(_DevBuf(tptr, tn, "<i8"), device=dev)
+            dist.reduce(counts, dst=dst, op=dist.ReduceOp.SUM, group=group)
+            dist.all_reduce(totals, op=dist.ReduceOp.SUM, group=group)
+
+
 def allreduce_counts(hansel, group=None):
     """Sum the pending integer counts and totals of ``hansel`` across ranks, in place."""
     import torch

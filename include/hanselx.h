@@ -156,6 +156,11 @@ typedef struct {
 int hx_pack_bam(const char *bam_path, const char *contig, int32_t start_pos, int32_t end_pos,
                 const int32_t *snp_pos, int32_t n_snps, int stepper, int n_threads, hx_packed *out);
 void hx_pack_free(hx_packed *p);
+/* Per-position A,C,G,T counts over 0-based [start0,end0) of a contig from every alignment, no filters:
+ * what gretel/snpper.py:30 asks pysam.count_coverage for.  out[4*(end0-start0)], A row first. */
+int hx_count_coverage(const char *bam_path, const char *contig, int32_t start0, int32_t end0, int n_threads,
+                      uint32_t *out);
+int hx_bam_contig_length(const char *bam_path, const char *contig, int32_t *length);
 
 /* ---- bulk matrix I/O (tests, --dumpmatrix gretel/cmd.py:81-82) ------------------- */
 int hx_band_to_host(hx_matrix *h, float *out /* (N+2)*W*49 */);

@@ -79,3 +79,52 @@ def test_native_packer_errors(tmp_path, golden_dir):
     (tmp_path / "junk.bam").write_bytes(b"not a bam file at all")
     with pytest.raises(_lib.HanselxError):
         bamio.pack_bam_native(str(tmp_path / "junk.bam"), "hoot", 1, 20, v)
+
+
+def _py_coverage(path, contig, start0, end0):
+    refs, recs = bamio.read_bam(path)
+    tid = [n for n, _ in refs].index(contig)
+    out = np.zeros((4, end0 - start0), dtype=np.uint32)
+    code = {"A": 0, "C": 1, "G": 2, "T": 3}
+    for r in recs:
+        if r.tid != tid or r.pos < 0:
+            continue
+        rpos, qpos = r.pos, 0
+        for op, ln in r.cigar:
+            if op in (0, 7, 8):
+                for j in range(ln):
+                    p = rpos + j
+                    if start0 <= p < end0 and r.seq[qpos + j] in code:
+                        out[code[r.seq[qpos + j]], p - start0] += 1
+                rpos += ln; qpos += ln
+            elif op in (2, 3):
+                rpos += ln
+            elif op in (1, 4):
+                qpos += ln
+    return out
+
+
+def test_snpper_matches_python(tmp_path, golden_dir):
+    """gretel/snpper.py:30-41 on the native reader: per-position base counts and the called sites."""
+    import io
+    from gretel_b200 import snpper
+    rng = np.random.default_rng(9)
+    path = str(tmp_path / "s.bam")
+    _random_bam(path, rng, 2500)
+    for (s0, e0) in ((0, 3000), (400, 1900)):
+        exp = _py_coverage(path, "ctgA", s0, e0)
+        for th in (1, 3):
+            assert np.array_equal(snpper.count_coverage(path, "ctgA", s0, e0, n_threads=th), exp)
+    assert snpper.contig_length(path, "ctgB") == 3000
+    buf = io.StringIO()
+    assert snpper.main(["--bam", path, "--contig", "ctgA", "-s", "401", "-e", "1900", "--depth", "2"], out=buf) == 0
+    lines = buf.getvalue().strip().split("\n")
+    assert lines[0] == "##fileformat=VCFv4.2"
+    exp = _py_coverage(path, "ctgA", 400, 1900)
+    sites = [i + 401 for i in np.nonzero((exp > 2).sum(axis=0) > 1)[0]]
+    assert [int(l.split("\t")[1]) for l in lines[1:]] == sites and len(sites) > 10
+    assert lines[1].split("\t")[3:] == ["A", "C,T,G", "0", ".", "INFO"]
+    # the reference's toy BAM: reads 1-4 disagree at positions 1 and 2 of 'hoot' (A, C, T, T)
+    buf = io.StringIO()
+    snpper.main(["--bam", os.path.join(golden_dir, "ref_test.bam"), "--contig", "hoot"], out=buf)
+    assert [int(l.split("\t")[1]) for l in buf.getvalue().strip().split("\n")[1:]] == [1, 2, 10]
