@@ -10,6 +10,7 @@
 // All probability arithmetic is float64 on float32-stored cells, in the same
 // operation order as oracle/hansel_oracle.c, compiled with -fmad=false so that +,-,*,/
 // round exactly like the CPU; only log10/pow may differ from glibc by an ulp.
+#include <limits.h>
 #include <math.h>
 
 #include "hx_internal.cuh"
@@ -120,19 +121,30 @@ k_edge_one(const float *__restrict__ band, const double *__restrict__ scnt,
 // (0.0 where the Laplace denominator is 0, i.e. the term is dropped), for every symbol a
 // the path could hold at snp-l.  logm[snp*8+s] = log10(count_s / total); logm[snp*8+7] holds
 // the candidate mask as a double.
+#define HX_QSCALE 1048576.0      // fixed-point scale of the quantised walk tables (2^20)
+#define HX_QSUNK (INT_MIN / 2)    // log weight of a non-candidate: below any real sum, far from overflow
+
+// The int32 twin (quantised walk) has Lq >= Lw rows per site; rows beyond Lw are zero so that every lane of
+// k_walk_q owns a real row.  qflag[0] is raised if a term is too large for the fixed-point sums.
 __global__ void k_walk_terms(const float *__restrict__ band, const int32_t *__restrict__ vseen, int N, int W,
-                             int Lw, int flags, double *__restrict__ terms) {
+                             int Lw, int flags, double *__restrict__ terms, int32_t *__restrict__ termsq, int Lq,
+                             int *__restrict__ qflag) {
+    const int Lr = Lw > Lq ? Lw : Lq;
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t total = (int64_t)(N + 1) * Lw * 8;
+    const int64_t total = (int64_t)(N + 1) * Lr * 8;
     if (idx >= total) return;
     const int s = (int)(idx & 7);
-    const int l = (int)((idx >> 3) % Lw) + 1;
-    const int snp = (int)((idx >> 3) / Lw);
-    double *out = terms + (((int64_t)snp * Lw + (l - 1)) * HX_NSYM) * 8 + s;   // [snp][l][a][8]: 448-byte blocks
+    const int l = (int)((idx >> 3) % Lr) + 1;
+    const int snp = (int)((idx >> 3) / Lr);
+    double *out = l <= Lw ? terms + (((int64_t)snp * Lw + (l - 1)) * HX_NSYM) * 8 + s : nullptr;   // [snp][l][a][8]
+    int32_t *outq = l <= Lq ? termsq + (((int64_t)snp * Lq + (l - 1)) * HX_NSYM) * 8 + s : nullptr;
     const int pf = snp - l;
-    if (s >= HX_NSYM || snp < 1 || pf < 0) {
+    if (s >= HX_NSYM || snp < 1 || pf < 0 || l > Lw) {
 #pragma unroll
-        for (int a = 0; a < HX_NSYM; ++a) out[a * 8] = 0.0;
+        for (int a = 0; a < HX_NSYM; ++a) {
+            if (out) out[a * 8] = 0.0;
+            if (outq) outq[a * 8] = 0;
+        }
         return;
     }
     const float *cell = band + hx_cell_off(W, pf, snp);
@@ -144,11 +156,21 @@ __global__ void k_walk_terms(const float *__restrict__ band, const int32_t *__re
     }
     const int v = (flags & HX_F_VSITE_TO) ? vseen[snp] : vseen[pf];
     const double den = (double)v + sup;
+    bool unsafe = false;
 #pragma unroll
-    for (int a = 0; a < HX_NSYM; ++a) out[a * 8] = den != 0 ? log10((1.0 + obs[a]) / den) : 0.0;
+    for (int a = 0; a < HX_NSYM; ++a) {
+        const double t = den != 0 ? log10((1.0 + obs[a]) / den) : 0.0;
+        out[a * 8] = t;
+        if (outq) {
+            unsafe |= !(fabs(t) < 15.0);
+            outq[a * 8] = __double2int_rn(fmax(fmin(t, 15.0), -15.0) * HX_QSCALE);
+        }
+    }
+    if (unsafe) *qflag = 1;
 }
 
-__global__ void k_walk_logm(const double *__restrict__ scnt, int N, int flags, double *__restrict__ logm) {
+__global__ void k_walk_logm(const double *__restrict__ scnt, int N, int flags, double *__restrict__ logm,
+                            int32_t *__restrict__ logmq) {
     const int snp = blockIdx.x * blockDim.x + threadIdx.x;
     if (snp > N) return;
     const double total = scnt[(int64_t)snp * 8 + 7];
@@ -157,10 +179,13 @@ __global__ void k_walk_logm(const double *__restrict__ scnt, int N, int flags, d
     for (int s = 0; s < HX_NSYM; ++s) {
         const double c = scnt[(int64_t)snp * 8 + s];
         const bool cand = c > 0 && !(skip_unsym && (s == HX_SYM_N || s == HX_SYM_GAP));
-        logm[(int64_t)snp * 8 + s] = cand ? log10(c / total) : 0.0;
+        const double lm = cand ? log10(c / total) : 0.0;
+        logm[(int64_t)snp * 8 + s] = lm;
+        if (logmq) logmq[(int64_t)snp * 8 + s] = cand ? __double2int_rn(lm * HX_QSCALE) : HX_QSUNK;
         if (cand) mask |= 1u << s;
     }
     logm[(int64_t)snp * 8 + 7] = (double)mask;
+    if (logmq) logmq[(int64_t)snp * 8 + 7] = HX_QSUNK;
 }
 
 // ---- TMA / mbarrier helpers (1-D bulk copies of the walk tables into shared memory) -------
@@ -318,6 +343,155 @@ k_walk_tables(const double *__restrict__ terms, const double *__restrict__ logm,
     if (lane == 0) flagsd[0] = 0;
 }
 
+// Quantised walk (L <= 32, all lookbacks inside the band).  The log terms are kept as 2^-20 fixed point, so a
+// candidate's log weight is an exact integer sum in any order.  Lane = (lookback group g = lane/8, candidate
+// q = lane%8).  Only the lookback-1 term depends on the symbol chosen at the previous site, so the walk is
+// software-pipelined: while site s is being decided, every lane already sums the lookback >= 2 terms of site
+// s+1 for its (g,q) (their history is known; rows 1+g, 5+g, ... of the table, NIT per lane) and two shuffles fold
+// the four groups.  The serial chain per site is one shared-memory load, an add, a warp max (REDUX), a ballot
+// and a find-first-set.  A candidate wins outright only if it leads by more than 1.6e-4 in log10 weight (ten
+// times the worst-case quantisation error of 33 terms); otherwise - and whenever 10**x could under/overflow,
+// or a term did not fit the fixed-point range - the site is re-evaluated exactly, in the reference's order,
+// from the float64 tables (gretel.py:166-174 semantics, first max wins a tie).
+// History: h[t] byte b = 32 * symbol chosen 4t+b+1 sites back (byte granular so one PRMT yields a row offset).
+__device__ __forceinline__ int lds32(uint32_t addr) {
+    int v;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+
+template <int NIT>
+__global__ void __launch_bounds__(32)
+k_walk_q(const int32_t *__restrict__ termsq, const int32_t *__restrict__ logmq, const double *__restrict__ terms,
+         const double *__restrict__ logm, int N, int L, int C, uint8_t *__restrict__ path,
+         int *__restrict__ flagsd) {
+    extern __shared__ __align__(128) unsigned char smraw[];
+    __shared__ __align__(8) unsigned long long bars[3];
+    constexpr int Lq = 4 * NIT + 1;
+    constexpr uint32_t site_t_bytes = (uint32_t)Lq * 224u;             // int32 terms of one site
+    const int lane = threadIdx.x;
+    if (flagsd[1]) return;
+    const bool force_exact = flagsd[2] != 0;
+    const uint32_t chunk_t_bytes = (uint32_t)C * site_t_bytes;
+    const uint32_t sm_terms = smem_u32(smraw);                                   // [3][C][Lq][7][8] int32
+    const uint32_t sm_logm = sm_terms + 3u * chunk_t_bytes;                      // [3][C][8] int32
+    const int nchunks = (N + C - 1) / C;
+    if (lane == 0) {
+        path[0] = HX_SYM_GAP;
+        for (int b = 0; b < 3; ++b) mbar_init(smem_u32(&bars[b]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    auto issue = [&](int k) {
+        if (k >= nchunks) return;
+        const int b = k % 3;
+        const int first = 1 + k * C;
+        const int ns = min(C, N - first + 1);
+        const uint32_t bar = smem_u32(&bars[b]);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(bar, (uint32_t)ns * (site_t_bytes + 32u));
+        bulk_g2s(sm_terms + (uint32_t)b * chunk_t_bytes, termsq + (int64_t)first * Lq * 56,
+                 (uint32_t)ns * site_t_bytes, bar);
+        bulk_g2s(sm_logm + (uint32_t)b * C * 32u, logmq + (int64_t)first * 8, (uint32_t)ns * 32u, bar);
+    };
+    if (lane == 0) { issue(0); issue(1); }
+    const uint32_t q4 = 4u * (uint32_t)(lane & 7);
+    const uint32_t g = (uint32_t)lane >> 3;
+    const uint32_t look_off = (1u + g) * 224u + q4;         // this lane's first look-ahead row, its candidate slot
+    const uint32_t psel = 0x4440u | g;                      // PRMT selector: byte g of a history word
+    uint32_t h[NIT + 1];
+#pragma unroll
+    for (int t = 0; t <= NIT; ++t) h[t] = 0;
+    h[0] = HX_SYM_GAP * 32u;
+    uint32_t prev32 = HX_SYM_GAP * 32u;                     // 32 * symbol at the previous site
+    unsigned mine = 0;                                      // lane's slot of the 32-site output block
+    const int margin_q = 168;                               // 1.6e-4 * 2^20
+    const int floor_q = -300 * 1048576;                     // 10**x must stay representable
+#ifdef HX_WALK_STATS
+    int n_exact = 0;
+#endif
+    mbar_wait(smem_u32(&bars[0]), 0u);
+    int R = lds32(sm_logm + q4);                            // site 1 has only lookback 1
+    for (int k = 0; k < nchunks; ++k) {
+        __syncwarp();
+        if (lane == 0) issue(k + 2);
+        if (k + 1 < nchunks) mbar_wait(smem_u32(&bars[(k + 1) % 3]), (uint32_t)(((k + 1) / 3) & 1));
+        const int first = 1 + k * C;
+        const int ns = min(C, N - first + 1);
+        const uint32_t ct_n = sm_terms + (uint32_t)((k + 1) % 3) * chunk_t_bytes;
+        const uint32_t cl_n = sm_logm + (uint32_t)((k + 1) % 3) * C * 32u;
+        uint32_t csite = sm_terms + (uint32_t)(k % 3) * chunk_t_bytes;     // current site's table
+        uint32_t clm = sm_logm + (uint32_t)(k % 3) * C * 32u;
+        for (int j = 0; j < ns; ++j) {
+            const int snp = first + j;
+            // ---- look ahead: lookback >= 2 terms of site snp+1 (independent of this site's choice).  After the
+            // last site this reads the next buffer's stale bytes; the result is never used.
+            const bool wrap = j + 1 == ns;
+            const uint32_t nsite = wrap ? ct_n : csite + site_t_bytes;
+            const uint32_t nlm = wrap ? cl_n : clm + 32u;
+            int acc = 0;
+#pragma unroll
+            for (int t = 0; t < NIT; ++t)
+                acc += lds32(nsite + look_off + (uint32_t)t * 896u + __byte_perm(h[t], 0u, psel));
+            acc += __shfl_xor_sync(0xffffffffu, acc, 8);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+            const int Rn = acc + lds32(nlm + q4);
+            // ---- the serial chain: lookback-1 term of this site for the symbol just chosen
+            const int tot = R + lds32(csite + q4 + prev32);
+            const int best = __reduce_max_sync(0xffffffffu, tot);
+            const unsigned near = __ballot_sync(0xffffffffu, tot >= best - margin_q) & 0xffu;
+            int next = 31 - __clz(near);                     // == ffs-1 when exactly one candidate is near
+            if ((near & (near - 1)) != 0 || best <= floor_q || force_exact) {
+                const unsigned cmask = (unsigned)logm[(int64_t)snp * 8 + 7];
+                if (cmask == 0) next = -1;
+                else {
+#ifdef HX_WALK_STATS
+                    ++n_exact;
+#endif
+                    // exact evaluation from the float64 tables in the reference's order (lane = candidate)
+                    const int lmax = L < snp ? L : snp;
+                    const int s = lane < HX_NSYM ? lane : 0;
+                    const bool cand = lane < HX_NSYM && ((cmask >> lane) & 1u);
+                    const double *base = terms + ((int64_t)snp * L) * 56 + s;
+                    double lw = logm[(int64_t)snp * 8 + s];
+#pragma unroll
+                    for (int l = 1; l <= 4 * NIT + 1; ++l) {
+                        if (l <= lmax) {
+                            const unsigned al = (h[(l - 1) >> 2] >> (8 * ((l - 1) & 3) + 5)) & 7u;
+                            lw += base[((l - 1) * HX_NSYM + al) * 8];
+                        }
+                    }
+                    const double ws = cand ? pow(10.0, lw) : 0.0;
+                    double wn, tw;
+                    next = normalise_and_pick(ws, cmask, &wn, &tw);
+                }
+                if (next < 0) {                          // gretel.py:176-180
+                    if (lane == 0) { flagsd[0] = snp; flagsd[1] = 1; }
+                    for (int k2 = k + 1; k2 <= k + 2 && k2 < nchunks; ++k2)
+                        mbar_wait(smem_u32(&bars[k2 % 3]), (uint32_t)((k2 / 3) & 1));
+                    return;
+                }
+            }
+            prev32 = (uint32_t)next << 5;
+#pragma unroll
+            for (int t = NIT; t >= 1; --t) h[t] = __funnelshift_l(h[t - 1], h[t], 8);
+            h[0] = (h[0] << 8) | prev32;
+            mine = lane == ((snp - 1) & 31) ? (unsigned)next : mine;
+            if (((snp - 1) & 31) == 31 || snp == N) {    // a block of 32 sites (or the tail) is complete
+                const int at = ((snp - 1) & ~31) + 1 + lane;
+                if (at <= snp) path[at] = (uint8_t)mine;
+            }
+            R = Rn;
+            csite = nsite;
+            clm = nlm;
+        }
+    }
+#ifdef HX_WALK_STATS
+    if (lane == 0) printf("k_walk_q: N=%d L=%d exact sites=%d\n", N, L, n_exact);
+#endif
+    if (lane == 0) flagsd[0] = 0;
+}
+
 // Wide-lookback walk (L*448 B per site does not fit the staged pipeline, e.g. ONT L ~ 300):
 // one warp per candidate symbol, lanes split the lookbacks and combine with warp shuffles;
 // warp 0 then takes the 7-way argmax.  As in k_walk_tables the reordered sum only picks a clear
@@ -415,41 +589,59 @@ __global__ void k_path_stats(const double *__restrict__ scnt_cur, const double *
     site[2 * stride + snp] = m;
 }
 
-// lanes 0,1,2 each run one strictly ordered accumulation (same order as gretel.py:185-189)
-__global__ void __launch_bounds__(32)
+// Three threads each run one strictly ordered accumulation (same order as gretel.py:185-189) out of shared
+// memory while warps 2..7 stage the next block of per-site values, so the ordered adds never wait on HBM.
+constexpr int HX_SUM_CH = 896;
+
+__global__ void __launch_bounds__(256)
 k_path_sum(const double *__restrict__ site, int N, double min_remove, double *__restrict__ stats,
            const int *__restrict__ flagsd) {
-    const int lane = threadIdx.x;
-    if (flagsd[1]) { if (lane == 0) stats[5] = 0.0; return; }
+    __shared__ double buf[2][3][HX_SUM_CH];
+    const int tid = threadIdx.x;
+    if (flagsd[1]) { if (tid == 0) stats[5] = 0.0; return; }
     const int64_t stride = (int64_t)N + 2;
-    if (lane < 2) {
-        double acc = 0.0;
-        const double *p = site + lane * stride;
-        int snp = 1;
-        for (; snp + 7 <= N; snp += 8) {                   // loads first, then the ordered adds
-            double v[8];
+    const int nch = (N + HX_SUM_CH - 1) / HX_SUM_CH;
+    auto stage = [&](int c, int t0, int nt) {
+        const int base = 1 + c * HX_SUM_CH;
+        const int n = min(HX_SUM_CH, N - base + 1);
+        for (int a = 0; a < 3; ++a)
+            for (int x = t0; x < n; x += nt) buf[c & 1][a][x] = site[a * stride + base + x];
+    };
+    stage(0, tid, 256);
+    __syncthreads();
+    const int role = tid < 2 ? tid : (tid == 32 ? 2 : -1);     // two ordered sums in warp 0, the min in warp 1
+    double acc = role == 2 ? INFINITY : 0.0;
+    for (int c = 0; c < nch; ++c) {
+        if (tid >= 64) {
+            if (c + 1 < nch) stage(c + 1, tid - 64, 192);
+        } else if (role >= 0) {
+            const int n = min(HX_SUM_CH, N - c * HX_SUM_CH);
+            const double *p = buf[c & 1][role];
+            int x = 0;
+            for (; x + 8 <= n; x += 8) {                       // loads first, then the ordered chain
+                double v[8];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) v[q] = p[snp + q];
+                for (int q = 0; q < 8; ++q) v[q] = p[x + q];
+                if (role < 2) {
 #pragma unroll
-            for (int q = 0; q < 8; ++q) acc += v[q];
+                    for (int q = 0; q < 8; ++q) acc += v[q];
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) acc = v[q] < acc ? v[q] : acc;
+                }
+            }
+            for (; x < n; ++x) {
+                if (role < 2) acc += p[x];
+                else acc = p[x] < acc ? p[x] : acc;
+            }
         }
-        for (; snp <= N; ++snp) acc += p[snp];
-        stats[lane] = acc;                                 // hp_current, hp_original
-    } else if (lane == 2) {
-        double mn = INFINITY;
-        const double *p = site + 2 * stride;
-        int snp = 1;
-        for (; snp + 7 <= N; snp += 8) {
-            double v[8];
-#pragma unroll
-            for (int q = 0; q < 8; ++q) v[q] = p[snp + q];
-#pragma unroll
-            for (int q = 0; q < 8; ++q) mn = v[q] < mn ? v[q] : mn;
-        }
-        for (; snp <= N; ++snp) mn = p[snp] < mn ? p[snp] : mn;
-        stats[2] = mn;                                     // min marginal
-        stats[3] = mn < min_remove ? min_remove : mn;      // cmd.py:157-160
-        stats[5] = 1.0;                                    // iteration completed
+        __syncthreads();
+    }
+    if (role >= 0 && role < 2) stats[role] = acc;              // hp_current, hp_original
+    else if (role == 2) {
+        stats[2] = acc;                                        // min marginal
+        stats[3] = acc < min_remove ? min_remove : acc;        // cmd.py:157-160
+        stats[5] = 1.0;                                        // iteration completed
     }
 }
 
@@ -559,18 +751,45 @@ int launch_generate(hx_matrix *cur, hx_matrix *orig, int L, int flags, uint8_t *
     const int N = cur->N;
     const int Lw = L < cur->W ? (L < 1 ? 1 : L) : cur->W;          // lookbacks that stay inside the band
     const int64_t n_terms = ((int64_t)N + 2) * Lw * HX_NSYM * 8;
-    rc = ensure_buf((void **)&cur->d_terms, &cur->cap_terms, (n_terms + ((int64_t)N + 2) * 8) * (int64_t)sizeof(double), cur->stream);
+    // float64 tables, then (quantised walk only) their int32 fixed-point twins with Lq >= L rows per site
+    const bool use_q = L >= 1 && L <= 32 && L <= cur->W;
+    const int nit = use_q ? (L - 1 + 3) / 4 : 0;
+    const int Lq = use_q ? 4 * nit + 1 : 0;
+    const int64_t n_all = n_terms + ((int64_t)N + 2) * 8;
+    const int64_t n_termsq = ((int64_t)N + 2) * Lq * HX_NSYM * 8;
+    const int64_t n_allq = n_termsq + ((int64_t)N + 2) * 8;
+    rc = ensure_buf((void **)&cur->d_terms, &cur->cap_terms, (n_all + (use_q ? (n_allq + 1) / 2 + 8 : 0)) * (int64_t)sizeof(double),
+                    cur->stream);
     if (rc) return rc;
     double *logm = cur->d_terms + n_terms;
-    const int64_t tthreads = (int64_t)(N + 1) * Lw * 8;
+    int32_t *termsq = use_q ? reinterpret_cast<int32_t *>(cur->d_terms + n_all) : nullptr;
+    int32_t *logmq = use_q ? termsq + n_termsq : nullptr;
+    const int64_t tthreads = (int64_t)(N + 1) * (Lw > Lq ? Lw : Lq) * 8;
     k_walk_terms<<<(unsigned)((tthreads + 255) / 256), 256, 0, cur->stream>>>(cur->band, cur->vseen, N, cur->W, Lw,
-                                                                              flags, cur->d_terms);
-    k_walk_logm<<<(N + 1 + 127) / 128, 128, 0, cur->stream>>>(cur->scnt, N, flags, logm);
+                                                                              flags, cur->d_terms, termsq, Lq,
+                                                                              cur->d_flags + 2);
+    k_walk_logm<<<(N + 1 + 127) / 128, 128, 0, cur->stream>>>(cur->scnt, N, flags, logm, logmq);
     // sites per staged chunk: three chunks (terms + log-marginals) must fit in shared memory
     const int64_t site_bytes = (int64_t)Lw * 448 + 64;
     int C = (int)((200 * 1024) / (3 * site_bytes));
     if (C > 64) C = 64;
-    if (C < 1) {
+    if (use_q) {
+        const int64_t qsite = (int64_t)Lq * 224 + 32;
+        int Cq = (int)((200 * 1024) / (3 * qsite));
+        if (Cq > 128) Cq = 128;
+        const size_t qsmem = (size_t)3 * Cq * qsite;
+#define HX_WALK_Q(NIT)                                                                                              \
+    case NIT:                                                                                                       \
+        HX_CUDA(cudaFuncSetAttribute(k_walk_q<NIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qsmem));      \
+        k_walk_q<NIT><<<1, 32, qsmem, cur->stream>>>(termsq, logmq, cur->d_terms, logm, N, L, Cq, d_path,           \
+                                                     cur->d_flags);                                                 \
+        break;
+        switch (nit) {
+            HX_WALK_Q(0) HX_WALK_Q(1) HX_WALK_Q(2) HX_WALK_Q(3) HX_WALK_Q(4) HX_WALK_Q(5) HX_WALK_Q(6) HX_WALK_Q(7)
+            HX_WALK_Q(8)
+        }
+#undef HX_WALK_Q
+    } else if (C < 1) {
         k_walk_wide<<<1, 256, 0, cur->stream>>>(cur->d_terms, logm, cur->vseen, N, L, Lw, flags, d_path, cur->d_flags);
     } else {
         const size_t wsmem = (size_t)3 * C * site_bytes;
@@ -581,7 +800,7 @@ int launch_generate(hx_matrix *cur, hx_matrix *orig, int L, int flags, uint8_t *
     cur->launches += 2;
     k_path_stats<<<(N + 255) / 256, 256, 0, cur->stream>>>(cur->scnt, orig->scnt, N, d_path, cur->d_site,
                                                            cur->d_flags);
-    k_path_sum<<<1, 32, 0, cur->stream>>>(cur->d_site, N, min_remove, d_stats, cur->d_flags);
+    k_path_sum<<<1, 256, 0, cur->stream>>>(cur->d_site, N, min_remove, d_stats, cur->d_flags);
     cur->launches += 3;
     HX_CUDA(cudaGetLastError());
     return HX_OK;
@@ -661,7 +880,7 @@ int hx_generate_path(hx_matrix *cur, hx_matrix *orig, int32_t L, int flags, uint
         if (rc) return rc;
         HX_CUDA(cudaStreamSynchronize(orig->stream));
     }
-    HX_CUDA(cudaMemsetAsync(cur->d_flags, 0, 2 * sizeof(int), cur->stream));
+    HX_CUDA(cudaMemsetAsync(cur->d_flags, 0, 3 * sizeof(int), cur->stream));
     HX_CUDA(cudaEventRecord(cur->ev0, cur->stream));
     rc = launch_generate(cur, orig, L, flags, cur->d_path, cur->d_stats, 0.0);
     if (rc) return rc;
@@ -688,7 +907,7 @@ int hx_reweight_path(hx_matrix *h, const uint8_t *path, double ratio, double *re
     HX_CUDA(cudaSetDevice(h->device));
     int rc = ensure_buf((void **)&h->d_path, &h->cap_path, (int64_t)h->N + 2, h->stream);
     if (rc) return rc;
-    HX_CUDA(cudaMemsetAsync(h->d_flags, 0, 2 * sizeof(int), h->stream));
+    HX_CUDA(cudaMemsetAsync(h->d_flags, 0, 3 * sizeof(int), h->stream));
     HX_CUDA(cudaMemcpyAsync(h->d_path, path, (size_t)h->N + 1, cudaMemcpyHostToDevice, h->stream));
     HX_CUDA(cudaEventRecord(h->ev0, h->stream));
     rc = launch_reweight(h, h->d_path, nullptr, ratio, h->d_misc);
@@ -718,7 +937,7 @@ int hx_recover(hx_matrix *cur, hx_matrix *orig, int32_t L, int flags, int32_t ma
         if (rc) return rc;
         HX_CUDA(cudaStreamSynchronize(orig->stream));
     }
-    HX_CUDA(cudaMemsetAsync(cur->d_flags, 0, 2 * sizeof(int), cur->stream));
+    HX_CUDA(cudaMemsetAsync(cur->d_flags, 0, 3 * sizeof(int), cur->stream));
     HX_CUDA(cudaMemsetAsync(cur->d_stats, 0, 8 * sizeof(double) * (size_t)max_paths, cur->stream));
     HX_CUDA(cudaEventRecord(cur->ev0, cur->stream));
     for (int it = 0; it < max_paths; ++it) {
