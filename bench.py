@@ -250,6 +250,16 @@ def run_ours(args):
     h2d_bytes = p_rank.numel() * 4 + p_klen.numel() * 2 + p_codes4.numel()
     if args.e2e_format == "wide":
         h2d_bytes = p_rank.numel() * 4 + p_off.numel() * 8 + p_codes.numel()
+    # ... or in the dense wire format (uint8 rank deltas and SNP counts, 2-bit alleles + exception list), in a
+    # few chunks so that each chunk's copy overlaps the previous chunk's pair expansion
+    dense_chunks = []
+    if args.e2e_format == "dense":
+        _keep = []
+        for c in util.dense_chunks(d["rank"], d["off"], d["codes"], args.e2e_chunks):
+            pinned = torch.from_numpy(c.blob).pin_memory()
+            _keep.append(pinned)
+            dense_chunks.append(c.rebased(pinned.numpy()))
+        h2d_bytes = sum(c.nbytes for c in dense_chunks)
 
     h = Hansel.init_matrix(REF_SYMBOLS, REF_UNSYMBOLS, N, band_w=W, device=local_rank)
     h.set_ingest_kernel(args.kernel)
@@ -331,6 +341,9 @@ def run_ours(args):
         hh.set_ingest_kernel(args.kernel)
         if args.e2e_format == "wide":
             hh.ingest_packed(p_rank.numpy(), p_off.numpy(), p_codes.numpy())
+        elif args.e2e_format == "dense":
+            for c in dense_chunks:
+                hh.ingest_packed_dense(c, wait=False)
         else:
             hh.ingest_packed_compact(p_rank.numpy(), p_klen.numpy(), p_codes4.numpy(), n_codes)
         if world > 1:
@@ -441,7 +454,8 @@ def run_ours(args):
                     "d2h_bytes_per_step": 32 + 4, "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps,
                     "wire_format": args.e2e_format,
                     "api": "Hansel.init_matrix + ingest_packed%s(pinned host arrays) [+ all-reduce] + finalize + "
-                           "totals, a new matrix every step" % ("_compact" if args.e2e_format == "compact" else "")},
+                           "totals, a new matrix every step" % {"compact": "_compact", "wide": "",
+                                                                 "dense": "_dense x%d chunks" % max(len(dense_chunks), 1)}[args.e2e_format]},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
             "observations_per_step": int(n_obs_global), "wall_s_timed_region": wall_s,
             "recovery": recovery, "synth_seconds": gen_s, "band_w": W, "allreduce_segments": args.segments if world > 1 else 0, "exchange": args.exchange if world > 1 else None,
@@ -468,8 +482,11 @@ def main():
                          "NVLink peer memory + all-gather of the owned rows")
     ap.add_argument("--segments", type=int, default=1,
                     help="N>1: ingest in this many launches, all-reducing finished band rows behind the next one")
-    ap.add_argument("--e2e-format", default="compact", choices=["compact", "wide"],
-                    help="host wire format of the packed reads in the e2e leg (compact: uint16 counts + nibble codes)")
+    ap.add_argument("--e2e-format", default="dense", choices=["dense", "compact", "wide"],
+                    help="host wire format of the packed reads in the e2e leg (dense: uint8 rank deltas/SNP counts + "
+                         "2-bit alleles; compact: int32 ranks + uint16 counts + nibble codes; wide: the packed arrays)")
+    ap.add_argument("--e2e-chunks", type=int, default=3,
+                    help="dense format: chunks per step (copy of chunk i+1 overlaps the expansion of chunk i)")
     ap.add_argument("--recover-paths", type=int, default=5)
     ap.add_argument("--recovery-sweep", action="store_true", default=True,
                     help="also time configs[4]: 50 haplotypes at L=1..8 (a few seconds)")

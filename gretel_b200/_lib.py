@@ -29,6 +29,7 @@ SIGNATURES = {
     "hx_sync": (_int, [_p]),
     "hx_ingest_host": (_int, [_p, _p, _p, _p, _i64, _p]),
     "hx_ingest_host_compact": (_int, [_p, _p, _p, _p, _i64, _i64, _p]),
+    "hx_ingest_host_dense": (_int, [_p, _p, _p, _p, _i64, _p, _i32, _p, _p, _i64, _i64, _i64, _p]),
     "hx_ingest_device": (_int, [_p, _p, _p, _p, _i64]),
     "hx_set_ingest_kernel": (_int, [_p, _int]),
     "hx_ingest_totals": (_int, [_p, _p]),

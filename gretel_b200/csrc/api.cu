@@ -88,6 +88,7 @@ void free_all(hx_matrix *h) {
     if (!h) return;
     cudaSetDevice(h->device);
     hx_lr_free(h);
+    hx_wire_free(h);
     if (h->d_peer_tbl) cudaFree(h->d_peer_tbl);
     if (h->band) cudaFreeAsync(h->band, h->stream);
     release_counts(h);
@@ -239,13 +240,15 @@ int hx_sync(hx_matrix *h) {
 }
 
 // ------------------------------------------------------------------------------ ingestion
-static int ensure_counts_buffer(hx_matrix *h) {
+}  // extern "C"
+int hx_ensure_counts_buffer(hx_matrix *h) {
     if (h->cnt) return HX_OK;
     h->cnt_elems = h->band_elems;
     HX_CUDA(cudaMallocAsync((void **)&h->cnt, sizeof(uint32_t) * (size_t)h->cnt_elems, h->stream));
     HX_CUDA(cudaMemsetAsync(h->cnt, 0, sizeof(uint32_t) * (size_t)h->cnt_elems, h->stream));
     return HX_OK;
 }
+extern "C" {
 
 int hx_set_ingest_kernel(hx_matrix *h, int which) {
     HX_CHECK_ARG(h && which >= 0 && which <= 5);
@@ -259,7 +262,7 @@ int hx_ingest_device(hx_matrix *h, const int32_t *d_rank, const int64_t *d_off,
     if (n_reads == 0) return HX_OK;
     HX_CHECK_ARG(d_rank && d_off && d_codes);
     HX_CUDA(cudaSetDevice(h->device));
-    int rc = ensure_counts_buffer(h);
+    int rc = hx_ensure_counts_buffer(h);
     if (rc) return rc;
     return hx_launch_ingest(h, d_rank, d_off, d_codes, n_reads);
 }
@@ -272,6 +275,7 @@ int hx_ingest_totals(hx_matrix *h, int64_t totals[4]) {
     HX_CUDA(cudaMemcpyAsync(hp, h->d_totals, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
     HX_CUDA(cudaMemcpyAsync(he, h->d_err, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     HX_CUDA(cudaStreamSynchronize(h->stream));
+    hx_wire_trace_dump();
     if (h->ev_rec) cudaEventElapsedTime(&h->last_ms[0], h->ev0, h->ev1);
     for (int i = 0; i < 4; ++i) totals[i] = (int64_t)hp[i];
     if (*he) {
@@ -308,7 +312,7 @@ int hx_ingest_host(hx_matrix *h, const int32_t *rank, const int64_t *off, const 
         HX_CUDA(cudaMemcpyAsync(h->s_rank, rank, sizeof(int32_t) * (size_t)n_reads, cudaMemcpyHostToDevice, h->stream));
         HX_CUDA(cudaMemcpyAsync(h->s_off, off, sizeof(int64_t) * ((size_t)n_reads + 1), cudaMemcpyHostToDevice, h->stream));
         HX_CUDA(cudaMemcpyAsync(h->s_codes, codes + off[0], (size_t)n_codes, cudaMemcpyHostToDevice, h->stream));
-        int rc = ensure_counts_buffer(h);
+        int rc = hx_ensure_counts_buffer(h);
         if (rc) return rc;
         // kernels index codes by absolute offsets: bias the base pointer by off[0]
         rc = hx_launch_ingest(h, h->s_rank, h->s_off, h->s_codes - off[0], n_reads);
@@ -373,7 +377,7 @@ int hx_ingest_host_compact(hx_matrix *h, const int32_t *rank, const uint16_t *kl
             k_unpack_nibbles<<<(unsigned)((n_words + 255) / 256), 256, 0, st>>>(h->s_codes4, n_words, (uint2 *)h->s_codes);
         h->launches += 5;
         HX_CUDA(cudaGetLastError());
-        int rc = ensure_counts_buffer(h);
+        int rc = hx_ensure_counts_buffer(h);
         if (rc) return rc;
         rc = hx_launch_ingest(h, h->s_rank, h->s_off, h->s_codes, n_reads);
         if (rc) return rc;
@@ -384,7 +388,7 @@ int hx_ingest_host_compact(hx_matrix *h, const int32_t *rank, const uint16_t *kl
 int hx_counts_buffer(hx_matrix *h, void **d_counts, int64_t *n_u32, void **d_totals, int64_t *n_i64) {
     HX_CHECK_ARG(h && d_counts && n_u32 && d_totals && n_i64);
     HX_CUDA(cudaSetDevice(h->device));
-    int rc = ensure_counts_buffer(h);
+    int rc = hx_ensure_counts_buffer(h);
     if (rc) return rc;
     *d_counts = h->cnt;
     *n_u32 = h->cnt_elems;

@@ -31,6 +31,14 @@ struct HxCnt {
 #endif
 };
 
+#define HX_WIRE_SETS 3
+// One staging set of the dense wire format (wire.cu): raw shipped bytes + the rebuilt packed arrays
+struct hx_wire_set {
+    void *raw; int32_t *rank; int64_t *off; uint8_t *codes; int64_t *partials;
+    int64_t cap_raw, cap_rank, cap_off, cap_codes, cap_partials;
+    cudaEvent_t copied, consumed;
+};
+
 struct hx_matrix {
     int32_t N, W, device;
     int64_t band_elems;              // (N+2)*W*49
@@ -51,6 +59,8 @@ struct hx_matrix {
     int64_t cap_reads, cap_codes;
     uint16_t *s_klen; uint32_t *s_codes4; int64_t *s_scan;     // compact wire format staging
     int64_t cap_klen, cap_codes4, cap_scan;
+    hx_wire_set wire[HX_WIRE_SETS]; int wire_next;   // dense wire format: rotating staging sets
+    cudaStream_t copy_stream;                // host->device copies of the dense format
     // recovery scratch
     double *scnt;                    // (N+2)*8 per-site counts + total
     int32_t *vseen;                  // (N+2) valid symbols seen per site
@@ -104,6 +114,10 @@ int hx_launch_ingest(hx_matrix *h, const int32_t *d_rank, const int64_t *d_off,
                      const uint8_t *d_codes, int64_t n_reads);
 // api.cu
 HxCnt hx_cnt_ref(const hx_matrix *h);
+int hx_ensure_counts_buffer(hx_matrix *h);
+// wire.cu
+void hx_wire_free(hx_matrix *h);
+void hx_wire_trace_dump();
 // ingest_long.cu
 int hx_launch_ingest_long(hx_matrix *h, const int32_t *d_rank, const int64_t *d_off,
                           const uint8_t *d_codes, int64_t n_reads);

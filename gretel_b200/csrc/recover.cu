@@ -11,6 +11,7 @@
 // operation order as oracle/hansel_oracle.c, compiled with -fmad=false so that +,-,*,/
 // round exactly like the CPU; only log10/pow may differ from glibc by an ulp.
 #include <limits.h>
+#include <stdlib.h>
 #include <math.h>
 
 #include "hx_internal.cuh"
@@ -752,7 +753,8 @@ int launch_generate(hx_matrix *cur, hx_matrix *orig, int L, int flags, uint8_t *
     const int Lw = L < cur->W ? (L < 1 ? 1 : L) : cur->W;          // lookbacks that stay inside the band
     const int64_t n_terms = ((int64_t)N + 2) * Lw * HX_NSYM * 8;
     // float64 tables, then (quantised walk only) their int32 fixed-point twins with Lq >= L rows per site
-    const bool use_q = L >= 1 && L <= 32 && L <= cur->W;
+    static const bool no_q = getenv("HX_WALK_NOQ") != nullptr;   // debugging: force the float64 walk kernels
+    const bool use_q = !no_q && L >= 1 && L <= 32 && L <= cur->W;
     const int nit = use_q ? (L - 1 + 3) / 4 : 0;
     const int Lq = use_q ? 4 * nit + 1 : 0;
     const int64_t n_all = n_terms + ((int64_t)N + 2) * 8;

@@ -146,9 +146,32 @@ class Hansel:
         self._touch()
         return tuple(int(x) for x in totals)
 
+    def ingest_packed_dense(self, dense, wait=True):
+        """ingest_packed in the dense wire format (util.dense_packed / util.DensePacked).  ``wait=False`` only
+        enqueues the chunk (copy on a second stream): call ingest_totals() after the last chunk; the arrays of
+        ``dense`` must stay alive and untouched until then."""
+        d = dense
+        for a in d.arrays():
+            if not a.flags["C_CONTIGUOUS"]:
+                raise ValueError("dense arrays must be contiguous")
+        if len(d.rank_delta) != d.n_reads or len(d.klen) != d.n_reads or len(d.codes2) < (d.n_codes + 3) // 4:
+            raise ValueError("dense arrays do not match n_reads/n_codes")
+        totals = np.zeros(4, dtype=np.int64)
+        if not wait:
+            self._dense_keepalive = getattr(self, "_dense_keepalive", []) + [d]
+        _lib.check(self._lib.hx_ingest_host_dense(
+            self._h, d.rank_delta.ctypes.data, d.esc_idx.ctypes.data, d.esc_delta.ctypes.data, len(d.esc_idx),
+            d.klen.ctypes.data, int(d.klen.dtype.itemsize), d.codes2.ctypes.data, d.exc_pos.ctypes.data,
+            len(d.exc_pos), d.n_reads, d.n_codes, totals.ctypes.data if wait else None))
+        self._touch()
+        return tuple(int(x) for x in totals) if wait else None
+
     def ingest_totals(self):
         totals = np.zeros(4, dtype=np.int64)
-        _lib.check(self._lib.hx_ingest_totals(self._h, totals.ctypes.data))
+        try:
+            _lib.check(self._lib.hx_ingest_totals(self._h, totals.ctypes.data))
+        finally:
+            self._dense_keepalive = []
         return tuple(int(x) for x in totals)
 
     def set_ingest_kernel(self, which):

@@ -40,6 +40,100 @@ def compact_packed(off, codes):
     return k.astype(np.uint16), codes4, n
 
 
+class DensePacked:
+    """Rank-sorted packed reads in the dense wire format of hx_ingest_host_dense (include/hanselx.h): uint8 rank
+    deltas (255 = listed in esc_idx/esc_delta), uint8|uint16 SNP counts, 2-bit alleles with the N/-/_ positions
+    listed in exc_pos.  ``chunks(n)`` splits at read boundaries for the overlapped (asynchronous) ingestion."""
+    __slots__ = ("rank_delta", "esc_idx", "esc_delta", "klen", "codes2", "exc_pos", "n_reads", "n_codes", "blob")
+
+    def __init__(self, rank_delta, esc_idx, esc_delta, klen, codes2, exc_pos, n_reads, n_codes):
+        self.rank_delta, self.esc_idx, self.esc_delta = rank_delta, esc_idx, esc_delta
+        self.klen, self.codes2, self.exc_pos = klen, codes2, exc_pos
+        self.n_reads, self.n_codes = int(n_reads), int(n_codes)
+        self.blob = None            # the single host buffer the arrays are views of (dense_packed), if any
+
+    def rebased(self, blob):
+        """The same chunk as views of ``blob`` (a copy of self.blob, e.g. in pinned memory)."""
+        base = self.blob.ctypes.data
+        def view(a):
+            o = a.ctypes.data - base
+            return blob[o:o + a.nbytes].view(a.dtype)
+        out = DensePacked(*[view(a) for a in self.arrays()], self.n_reads, self.n_codes)
+        out.blob = blob
+        return out
+
+    @property
+    def nbytes(self):
+        return sum(int(a.nbytes) for a in (self.rank_delta, self.esc_idx, self.esc_delta, self.klen, self.codes2,
+                                           self.exc_pos))
+
+    def arrays(self):
+        return (self.rank_delta, self.esc_idx, self.esc_delta, self.klen, self.codes2, self.exc_pos)
+
+
+def dense_packed(rank, off, codes):
+    """(rank int32[R] non-decreasing, off int64[R+1], codes uint8) -> DensePacked."""
+    rank = np.asarray(rank, dtype=np.int64)
+    off = np.asarray(off, dtype=np.int64)
+    k = np.diff(off)
+    d = np.diff(rank, prepend=0)
+    if len(d) and d.min() < 0:
+        raise ValueError("the dense wire format needs reads sorted by rank")
+    if len(k) and k.max() > 65535:
+        raise ValueError("a read covers more than 65535 SNPs")
+    esc_idx = np.nonzero(d >= 255)[0].astype(np.int64)
+    c = np.ascontiguousarray(codes[off[0]:off[-1]] if len(off) else codes, dtype=np.uint8)
+    n = len(c)
+    if n >= 1 << 32:
+        raise ValueError("more than 2^32 alleles in one call: split the reads into chunks")
+    if n and c.max() > 6:
+        raise ValueError("allele code > 6")
+    exc = np.nonzero(c >= 4)[0].astype(np.uint32)
+    f = np.where(c >= 4, c - 4, c).astype(np.uint8)
+    if n & 3:
+        f = np.concatenate([f, np.zeros(4 - (n & 3), np.uint8)])
+    # one host buffer laid out like the device staging set (16-byte aligned sections, wire.cu), so that the
+    # library ships it with a single copy
+    R, kb = len(k), (1 if (len(k) == 0 or k.max() < 256) else 2)
+    al = lambda x: (int(x) + 15) & ~15
+    n_words = (n + 15) // 16
+    o_kl = al(R)
+    o_c2 = o_kl + al(R * kb)
+    o_ex = o_c2 + al(n_words * 4)
+    o_ei = o_ex + al(len(exc) * 4)
+    o_ed = o_ei + al(len(esc_idx) * 8)
+    blob = np.zeros(o_ed + al(len(esc_idx) * 4) + 16, dtype=np.uint8)
+    rank_delta = blob[0:R]
+    rank_delta[:] = np.minimum(d, 255)
+    klen = blob[o_kl:o_kl + R * kb].view(np.uint8 if kb == 1 else np.uint16)
+    klen[:] = k
+    codes2 = blob[o_c2:o_c2 + (n + 3) // 4]
+    codes2[:] = f[0::4] | (f[1::4] << 2) | (f[2::4] << 4) | (f[3::4] << 6)
+    exc_pos = blob[o_ex:o_ex + 4 * len(exc)].view(np.uint32)
+    exc_pos[:] = exc
+    ei = blob[o_ei:o_ei + 8 * len(esc_idx)].view(np.int64)
+    ei[:] = esc_idx
+    ed = blob[o_ed:o_ed + 4 * len(esc_idx)].view(np.int32)
+    ed[:] = d[esc_idx]
+    out = DensePacked(rank_delta, ei, ed, klen, codes2, exc_pos, R, n)
+    out.blob = blob
+    return out
+
+
+def dense_chunks(rank, off, codes, n_chunks):
+    """Split rank-sorted packed reads into ``n_chunks`` DensePacked pieces of about equal allele count."""
+    off = np.asarray(off, dtype=np.int64)
+    R = len(off) - 1
+    n_chunks = max(1, min(int(n_chunks), max(R, 1)))
+    targets = off[0] + (off[-1] - off[0]) * np.arange(1, n_chunks) // n_chunks
+    cuts = [0] + [int(x) for x in np.searchsorted(off, targets, side="left")] + [R]
+    out = []
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        if b > a:
+            out.append(dense_packed(rank[a:b], off[a:b + 1], codes))
+    return out
+
+
 def load_from_packed(rank, off, codes, n_snps, band_w=None, device=None, hansel=None, finalize=True,
                      quiet=True):
     """Packed reads -> Hansel (util.py:83 + 226-286 + 329-333).

@@ -75,6 +75,20 @@ int hx_ingest_host(hx_matrix *h, const int32_t *rank, const int64_t *off, const 
  * n_codes = sum of klen.  Offsets and byte codes are rebuilt on the device. */
 int hx_ingest_host_compact(hx_matrix *h, const int32_t *rank, const uint16_t *klen, const uint8_t *codes4,
                            int64_t n_reads, int64_t n_codes, int64_t totals[4]);
+/* The dense wire format for rank-sorted reads (about 6 bytes per 15-SNP read instead of 13.5): what the CPU
+ * packer should emit for the GPU path.  See gretel_b200/csrc/wire.cu and gretel_b200.util.dense_packed.
+ *   rank_delta uint8[n_reads]   rank[r]-rank[r-1] (rank[-1] = 0); 255 => the true delta is esc_delta[k] where
+ *                               esc_idx[k] == r (esc_idx ascending; first read of a chunk, or a gap >= 255 sites)
+ *   klen       uint8[n_reads] (klen_bytes = 1) or uint16[n_reads] (klen_bytes = 2): SNPs on read r
+ *   codes2     2 bits per allele, four per byte, low bits first (A0 C1 G2 T3); N, '-' and '_' store code-4 and
+ *              are listed, by index into the allele stream, in exc_pos[n_exc] (ascending)
+ * totals != NULL: synchronous like hx_ingest_host.  totals == NULL: the call only enqueues (copies on a second
+ * stream, rotating staging sets), so feeding the reads in a few chunks overlaps each copy with the previous chunk's
+ * pair expansion; the host buffers must stay untouched until hx_ingest_totals() or hx_sync() returns. */
+int hx_ingest_host_dense(hx_matrix *h, const uint8_t *rank_delta, const int64_t *esc_idx, const int32_t *esc_delta,
+                         int64_t n_esc, const void *klen, int32_t klen_bytes, const uint8_t *codes2,
+                         const uint32_t *exc_pos, int64_t n_exc, int64_t n_reads, int64_t n_codes,
+                         int64_t totals[4]);
 /* Device-buffer entry point, asynchronous on the matrix's stream. */
 int hx_ingest_device(hx_matrix *h, const int32_t *d_rank, const int64_t *d_off,
                      const uint8_t *d_codes, int64_t n_reads);

@@ -183,6 +183,80 @@ def test_compact_wire_format_edges(c_oracle):
         assert np.array_equal(h.band(), ref.astype(np.float32))
 
 
+@pytest.mark.parametrize("name,n_reads", [("hiv", 30_000), ("metagenome", 100_000), ("ont", 300)])
+@pytest.mark.parametrize("n_chunks", [1, 3])
+def test_dense_wire_format(c_oracle, name, n_reads, n_chunks):
+    """hx_ingest_host_dense: uint8 rank deltas, uint8/uint16 SNP counts, 2-bit alleles + exception list; one
+    synchronous call, or chunks enqueued back to back (copy of chunk i+1 overlapping chunk i)."""
+    from gretel_b200 import util
+    from gretel_b200.hansel import Hansel, REF_SYMBOLS, REF_UNSYMBOLS
+    w = synth.scaled(synth.WORKLOADS[name], n_reads)
+    d = synth.generate(w)
+    W = d["max_k"] - 1
+    ref, rt = c_oracle.ingest(d["rank"], d["off"], d["codes"], w.n_snps, W)
+    h = Hansel.init_matrix(REF_SYMBOLS, REF_UNSYMBOLS, w.n_snps, band_w=W)
+    if n_chunks == 1:
+        dense = util.dense_packed(d["rank"], d["off"], d["codes"])
+        assert dense.klen.dtype == (np.uint16 if d["max_k"] > 255 else np.uint8)
+        totals = h.ingest_packed_dense(dense)
+    else:
+        chunks = util.dense_chunks(d["rank"], d["off"], d["codes"], n_chunks)
+        assert len(chunks) == n_chunks and sum(c.n_reads for c in chunks) == len(d["rank"])
+        for c in chunks:
+            assert h.ingest_packed_dense(c, wait=False) is None
+        totals = h.ingest_totals()
+    assert totals == tuple(int(x) for x in rt)
+    assert np.array_equal(h.band(), ref.astype(np.float32))
+
+
+def test_dense_wire_format_edges(c_oracle):
+    """Empty input, reads of 0/1 SNPs, many N/-/_ alleles, rank gaps >= 255 (escapes), lengths that are not a
+    multiple of the 16-read / 16-allele decode granules, repeated calls on one matrix."""
+    from gretel_b200 import util
+    from gretel_b200.hansel import Hansel, REF_SYMBOLS, REF_UNSYMBOLS
+    rng = np.random.default_rng(78)
+    escapes = 0
+    for trial in range(8):
+        N = int(rng.integers(2, 60)) if trial < 5 else int(rng.integers(2000, 6000))
+        n_reads = (int(rng.integers(0, 400)) if trial else 0) if trial < 5 else int(rng.integers(8, 20))
+        rank, off, codes = synth.random_packed(rng, N, n_reads, int(rng.integers(2, 12)), p_special=0.3)
+        W = min(N + 1, 12)
+        dense = util.dense_packed(rank, off, codes)
+        assert len(dense.esc_idx) == int((np.diff(rank.astype(np.int64), prepend=0) >= 255).sum())
+        escapes += len(dense.esc_idx)                           # sparse reads over thousands of sites
+        ref, rt = c_oracle.ingest(rank, off, codes, N, W)
+        h = Hansel.init_matrix(REF_SYMBOLS, REF_UNSYMBOLS, N, band_w=W)
+        assert h.ingest_packed_dense(dense) == tuple(int(x) for x in rt)
+        assert np.array_equal(h.band(), ref.astype(np.float32))
+        # a second, asynchronous pass over the same reads doubles every count
+        h2 = Hansel.init_matrix(REF_SYMBOLS, REF_UNSYMBOLS, N, band_w=W)
+        for c in util.dense_chunks(rank, off, codes, 2) * 2:
+            h2.ingest_packed_dense(c, wait=False)
+        assert h2.ingest_totals() == tuple(2 * int(x) for x in rt)
+        assert np.array_equal(h2.band(), 2 * ref.astype(np.float32))
+    assert escapes > 0
+
+
+def test_dense_wire_format_rejects_bad_input():
+    from gretel_b200 import util, _lib
+    from gretel_b200.hansel import Hansel, REF_SYMBOLS, REF_UNSYMBOLS
+    with pytest.raises(ValueError):
+        util.dense_packed(np.array([3, 1], np.int32), np.array([0, 2, 4], np.int64), np.zeros(4, np.uint8))
+    # an exception index past the allele stream, and a 2-bit field of 3 at an exception (code 7)
+    rank, off = np.array([0, 1], np.int32), np.array([0, 3, 6], np.int64)
+    dense = util.dense_packed(rank, off, np.array([0, 1, 5, 2, 3, 0], np.uint8))
+    for bad in ("pos", "field"):
+        d2 = util.DensePacked(dense.rank_delta, dense.esc_idx, dense.esc_delta, dense.klen, dense.codes2.copy(),
+                              dense.exc_pos.copy(), dense.n_reads, dense.n_codes)
+        if bad == "pos":
+            d2.exc_pos[0] = 600
+        else:
+            d2.codes2[0] |= 3 << 4                               # allele 2 (the exception) -> field 3 -> code 7
+        h = Hansel.init_matrix(REF_SYMBOLS, REF_UNSYMBOLS, 6, band_w=4)
+        with pytest.raises(_lib.HanselxError):
+            h.ingest_packed_dense(d2)
+
+
 @pytest.mark.parametrize("shape", [(600, 40, 300_000, 150), (600, 100, 120_000, 200), (3000, 300, 400_000, 150)],
                          ids=["7k-reads-per-rank", "wide-reads-deep", "1k-reads-per-rank"])
 @pytest.mark.parametrize("kernel", [0, 4, 5, 3])

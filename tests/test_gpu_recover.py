@@ -140,6 +140,73 @@ def test_recover_terminates_when_evidence_is_spent():
         assert a["removed"] == pytest.approx(b["removed"], rel=1e-9)
 
 
+def _is_rounding_noise_tie(packed, N, L, pc, pg):
+    """True if the first site where two walks differ is one where the literal oracle's weights of the two
+    choices agree to 1e-12 relative: the candidates tie in real arithmetic and the reference's own pick hangs on
+    the last ulp of libm's log10/pow (not reproducible between libm builds, let alone on the device)."""
+    s0 = int(np.nonzero(np.asarray(pc) != np.asarray(pg))[0][0])
+    ho = o.load_from_packed(*packed, N)
+    ho.L = L
+    syms = "ACGTN-_"
+    ew = ho.get_edge_weights_at(s0, [syms[c] for c in pc[:s0]])
+    a, b = ew[syms[pc[s0]]], ew[syms[pg[s0]]]
+    return abs(a - b) <= 1e-12 * max(a, b)
+
+
+def _walk_vs_c_oracle(c_oracle, h, band, N, W, L, iters=3, packed=None):
+    cur, orig = band.astype(np.float32).copy(), band.astype(np.float32).copy()
+    h.L = L
+    orig_h = h.copy()
+    for it in range(iters):
+        pc, res = c_oracle.generate_path(cur, orig, N, W, L)
+        r = h.generate_path_codes(orig_h)
+        if pc is None:
+            assert r[0] is None and r[1] == res
+            return
+        assert r[0] is not None
+        if not np.array_equal(r[0], pc):
+            assert packed is not None and it == 0 and _is_rounding_noise_tie(packed, N, L, pc, r[0]), \
+                "L=%d iteration %d" % (L, it)
+            return
+        for a, b in zip(r[1:], res):
+            assert a == pytest.approx(b, rel=RTOL)
+        ratio = max(res[2], 0.01)
+        assert h.reweight_path_codes(r[0], ratio) == pytest.approx(c_oracle.reweight_path(cur, N, W, pc, ratio),
+                                                                   rel=1e-9)
+    assert np.array_equal(h.band(), cur)
+
+
+@pytest.mark.parametrize("L", list(range(1, 35)) + [40, 47])
+def test_every_lookback_depth(c_oracle, L):
+    """One case per lookback depth: each instantiation of the fixed-point walk (L <= 32 inside the band), the
+    staged float64 walk beyond it and lookbacks that leave the band.  Thin random evidence gives many exact ties,
+    so the exact re-evaluation (first maximum wins, gretel.py:166-174) is exercised at every depth.  A walk may
+    leave the oracle's only at a rounding-noise tie (see _is_rounding_noise_tie)."""
+    rng = np.random.default_rng(4200 + L)
+    N = 150
+    rank, off, codes = synth.random_packed(rng, N, 900, 38, p_special=0.05)
+    W = int(np.diff(off).max()) - 1
+    band, _ = c_oracle.ingest(rank, off, codes, N, W)
+    h = _mk(rank, off, codes, N, W)
+    _walk_vs_c_oracle(c_oracle, h, band, N, W, L, packed=(rank, off, codes))
+
+
+def test_walk_leaves_fixed_point_range(c_oracle):
+    """Counts so large that a log10 term does not fit the fixed-point table: the walk must notice and decide
+    every site from the float64 terms."""
+    rng = np.random.default_rng(77)
+    N = 60
+    rank, off, codes = synth.random_packed(rng, N, 600, 12, p_special=0.05)
+    W = int(np.diff(off).max()) - 1
+    band, _ = c_oracle.ingest(rank, off, codes, N, W)
+    band = band.astype(np.float32)
+    band[band > 0] *= np.float32(1e17)
+    band[10:50:7] *= np.float32(1e3)
+    h = _mk(rank, off, codes, N, W)
+    h.load_band(band)
+    _walk_vs_c_oracle(c_oracle, h, band, N, W, 6, iters=2)
+
+
 import glob
 
 GOLDEN_RECOVERY = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "ref_recovery_*.npz")))

@@ -1,0 +1,48 @@
+"""Host-side encoders of the wire formats (no GPU): decoding them with numpy gives the packed reads back."""
+import numpy as np
+import pytest
+
+from gretel_b200 import synth, util
+
+
+def _decode_dense(d):
+    delta = d.rank_delta.astype(np.int64)
+    delta[d.esc_idx] = d.esc_delta
+    rank = np.cumsum(delta).astype(np.int32)
+    off = np.zeros(d.n_reads + 1, np.int64)
+    np.cumsum(d.klen.astype(np.int64), out=off[1:])
+    f = np.stack([(d.codes2 >> s) & 3 for s in (0, 2, 4, 6)], axis=1).reshape(-1)[:d.n_codes].astype(np.uint8)
+    f[d.exc_pos] += 4
+    return rank, off, f
+
+
+@pytest.mark.parametrize("seed", range(5))
+def test_dense_packed_round_trip(seed):
+    rng = np.random.default_rng(seed)
+    N = [8, 50, 3000, 20000, 400][seed]
+    rank, off, codes = synth.random_packed(rng, N, int(rng.integers(1, 300)), [4, 11, 9, 7, 300][seed],
+                                           p_special=0.2)
+    d = util.dense_packed(rank, off, codes)
+    r2, o2, c2 = _decode_dense(d)
+    assert np.array_equal(r2, rank) and np.array_equal(o2, off) and np.array_equal(c2, codes)
+    assert d.klen.dtype == (np.uint16 if np.diff(off).max() > 255 else np.uint8)
+    assert d.nbytes < rank.nbytes + off.nbytes + codes.nbytes
+    pieces = util.dense_chunks(rank, off, codes, 3)
+    assert sum(p.n_reads for p in pieces) == len(rank) and sum(p.n_codes for p in pieces) == len(codes)
+    got = [_decode_dense(p) for p in pieces]
+    assert np.array_equal(np.concatenate([g[0] for g in got]), rank)
+    assert np.array_equal(np.concatenate([g[2] for g in got]), codes)
+
+
+def test_dense_packed_needs_sorted_reads():
+    with pytest.raises(ValueError):
+        util.dense_packed(np.array([2, 1], np.int32), np.array([0, 2, 4], np.int64), np.zeros(4, np.uint8))
+
+
+def test_compact_packed_round_trip():
+    rng = np.random.default_rng(9)
+    rank, off, codes = synth.random_packed(rng, 40, 101, 9, p_special=0.2)
+    klen, codes4, n = util.compact_packed(off, codes)
+    assert n == len(codes) and np.array_equal(np.cumsum(klen), off[1:])
+    back = np.stack([codes4 & 15, codes4 >> 4], axis=1).reshape(-1)[:n]
+    assert np.array_equal(back, codes)
