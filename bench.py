@@ -348,8 +348,8 @@ def run_ours(args):
             hh.ingest_packed_compact(p_rank.numpy(), p_klen.numpy(), p_codes4.numpy(), n_codes)
         if world > 1:
             gdist.allreduce_counts(hh)
+        hh.finalize()                      # enqueue the fold into the float matrix, then one wait for everything
         s, c, v, _ = hh.ingest_totals()
-        hh.finalize()
         util.set_totals(hh, s, c, v)
         return hh
 

@@ -29,6 +29,8 @@ SIGNATURES = {
     "hx_sync": (_int, [_p]),
     "hx_ingest_host": (_int, [_p, _p, _p, _p, _i64, _p]),
     "hx_ingest_host_compact": (_int, [_p, _p, _p, _p, _i64, _i64, _p]),
+    "hx_dense_encode": (_int, [_p, _p, _p, _i64, _int, _p]),
+    "hx_dense_free": (None, [_p]),
     "hx_ingest_host_dense": (_int, [_p, _p, _p, _p, _i64, _p, _i32, _p, _p, _i64, _i64, _i64, _p]),
     "hx_ingest_device": (_int, [_p, _p, _p, _p, _i64]),
     "hx_set_ingest_kernel": (_int, [_p, _int]),
@@ -63,6 +65,13 @@ SIGNATURES = {
 class HxPacked(C.Structure):
     _fields_ = [("rank", C.POINTER(C.c_int32)), ("off", C.POINTER(C.c_int64)), ("codes", C.POINTER(C.c_uint8)),
                 ("n_reads", C.c_int64), ("n_codes", C.c_int64), ("n_records", C.c_int64)]
+
+
+class HxDense(C.Structure):
+    _fields_ = [("blob", C.POINTER(C.c_uint8)), ("blob_bytes", C.c_int64), ("n_reads", C.c_int64),
+                ("n_codes", C.c_int64), ("n_exc", C.c_int64), ("n_esc", C.c_int64), ("o_klen", C.c_int64),
+                ("o_codes2", C.c_int64), ("o_exc", C.c_int64), ("o_esc_idx", C.c_int64), ("o_esc_delta", C.c_int64),
+                ("klen_bytes", C.c_int32)]
 
 
 _LIB = None

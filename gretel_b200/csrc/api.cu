@@ -464,8 +464,8 @@ int hx_finalize_counts(hx_matrix *h) {
     k_fold_counts<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->cnt, h->band, n);
     h->launches++;
     HX_CUDA(cudaGetLastError());
-    HX_CUDA(cudaStreamSynchronize(h->stream));
-    release_counts(h);
+    if (h->cnt_ipc) HX_CUDA(cudaStreamSynchronize(h->stream));   // a shared allocation is freed with cudaFree
+    release_counts(h);                                           // (stream-ordered otherwise: no host wait here)
     h->counts_dirty = true;
     return HX_OK;
 }

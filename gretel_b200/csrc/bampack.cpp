@@ -352,6 +352,131 @@ int hx_bam_contig_length(const char *bam_path, const char *contig, int32_t *leng
     return HX_OK;
 }
 
+// ---- dense wire format encoder (CPU side of hx_ingest_host_dense; layout documented in wire.cu) ----------
+static inline int64_t al16(int64_t x) { return (x + 15) & ~(int64_t)15; }
+
+int hx_dense_encode(const int32_t *rank, const int64_t *off, const uint8_t *codes, int64_t n_reads, int n_threads,
+                    hx_dense *out) {
+    if (!out || n_reads < 0 || (n_reads > 0 && (!rank || !off || !codes))) {
+        hx_set_error("hx_dense_encode: bad arguments");
+        return HX_E_ARG;
+    }
+    memset(out, 0, sizeof(*out));
+    const int64_t c0 = n_reads ? off[0] : 0, n_codes = n_reads ? off[n_reads] - c0 : 0;
+    if (n_codes < 0 || n_codes >= ((int64_t)1 << 32)) {
+        hx_set_error("hx_dense_encode: %lld alleles in one chunk (limit 2^32 - 1): split the reads", (long long)n_codes);
+        return HX_E_ARG;
+    }
+    const int nt = (int)std::max<int64_t>(1, std::min<int64_t>(n_threads, 1 + n_reads / 65536));
+    // pass 1: per-thread maxima and counts over a contiguous range of reads (and of their alleles)
+    std::vector<int64_t> n_esc(nt, 0), n_exc(nt, 0), kmax(nt, 0);
+    std::vector<int> bad(nt, 0);
+    auto range = [&](int t, int64_t &a, int64_t &b) { a = n_reads * t / nt; b = n_reads * (t + 1) / nt; };
+    auto pass1 = [&](int t) {
+        int64_t a, b;
+        range(t, a, b);
+        for (int64_t r = a; r < b; ++r) {
+            const int64_t d = (int64_t)rank[r] - (r ? (int64_t)rank[r - 1] : 0), k = off[r + 1] - off[r];
+            if (d < 0 || k < 0 || k > 65535) bad[t] = d < 0 ? 1 : 2;
+            if (d >= 255) n_esc[t]++;
+            kmax[t] = std::max(kmax[t], k);
+        }
+        if (b > a && !bad[t])
+            for (int64_t i = off[a]; i < off[b]; ++i) {
+                if (codes[i] > 6) bad[t] = 3;
+                n_exc[t] += codes[i] >= 4;
+            }
+    };
+    {
+        std::vector<std::thread> th;
+        for (int t = 1; t < nt; ++t) th.emplace_back(pass1, t);
+        pass1(0);
+        for (auto &x : th) x.join();
+    }
+    int64_t tot_esc = 0, tot_exc = 0, km = 0;
+    for (int t = 0; t < nt; ++t) {
+        if (bad[t]) {
+            hx_set_error("hx_dense_encode: %s", bad[t] == 1 ? "reads are not sorted by rank"
+                                               : bad[t] == 2 ? "a read covers more than 65535 SNPs (or off[] decreases)"
+                                                             : "allele code > 6");
+            return HX_E_ARG;
+        }
+        const int64_t e = n_esc[t], x = n_exc[t];
+        n_esc[t] = tot_esc; n_exc[t] = tot_exc;       // exclusive prefix: where each thread writes its lists
+        tot_esc += e; tot_exc += x;
+        km = std::max(km, kmax[t]);
+    }
+    const int kb = km < 256 ? 1 : 2;
+    const int64_t n_words = (n_codes + 15) / 16;
+    const int64_t o_kl = al16(n_reads), o_c2 = o_kl + al16(n_reads * kb), o_ex = o_c2 + al16(n_words * 4);
+    const int64_t o_ei = o_ex + al16(tot_exc * 4), o_ed = o_ei + al16(tot_esc * 8), bytes = o_ed + al16(tot_esc * 4) + 16;
+    uint8_t *blob = (uint8_t *)calloc(1, (size_t)bytes);
+    if (!blob) { hx_set_error("hx_dense_encode: out of memory (%lld bytes)", (long long)bytes); return HX_E_NOMEM; }
+    uint32_t *exc = (uint32_t *)(blob + o_ex);
+    int64_t *ei = (int64_t *)(blob + o_ei);
+    int32_t *ed = (int32_t *)(blob + o_ed);
+    // pass 2: a thread's alleles start at off[a]-c0, which need not be a multiple of 4: boundaries move up to the
+    // next byte so that every output byte has exactly one writer
+    auto pass2 = [&](int t) {
+        int64_t a, b;
+        range(t, a, b);
+        int64_t ne = n_esc[t];
+        for (int64_t r = a; r < b; ++r) {
+            const int64_t d = (int64_t)rank[r] - (r ? (int64_t)rank[r - 1] : 0), k = off[r + 1] - off[r];
+            blob[r] = (uint8_t)std::min<int64_t>(d, 255);
+            if (d >= 255) { ei[ne] = r; ed[ne] = (int32_t)d; ++ne; }
+            if (kb == 1) blob[o_kl + r] = (uint8_t)k; else ((uint16_t *)(blob + o_kl))[r] = (uint16_t)k;
+        }
+        if (b <= a) return;
+        // alleles [lo, hi) of the stream, rounded so that every output byte has exactly one writer
+        int64_t lo = off[a] - c0, hi = off[b] - c0;
+        lo = t == 0 ? 0 : (lo + 3) & ~(int64_t)3;
+        hi = t == nt - 1 ? n_codes : (hi + 3) & ~(int64_t)3;
+        hi = std::min(hi, n_codes);
+        uint8_t *c2 = blob + o_c2;
+        for (int64_t i = lo; i < hi; i += 4) {
+            uint8_t byte = 0;
+            const int64_t m = std::min<int64_t>(4, n_codes - i);
+            for (int64_t j = 0; j < m; ++j) {
+                const uint8_t c = codes[c0 + i + j];
+                byte |= (uint8_t)((c >= 4 ? c - 4 : c) << (2 * j));
+            }
+            c2[i >> 2] = byte;
+        }
+    };
+    {
+        std::vector<std::thread> th;
+        for (int t = 1; t < nt; ++t) th.emplace_back(pass2, t);
+        pass2(0);
+        for (auto &x : th) x.join();
+    }
+    // exception positions: per-thread slots were sized by read ranges, so fill them by read ranges too
+    auto pass3 = [&](int t) {
+        int64_t a, b;
+        range(t, a, b);
+        if (b <= a) return;
+        int64_t nx = n_exc[t];
+        for (int64_t i = off[a] - c0; i < off[b] - c0; ++i)
+            if (codes[c0 + i] >= 4) exc[nx++] = (uint32_t)i;
+    };
+    {
+        std::vector<std::thread> th;
+        for (int t = 1; t < nt; ++t) th.emplace_back(pass3, t);
+        pass3(0);
+        for (auto &x : th) x.join();
+    }
+    out->blob = blob; out->blob_bytes = bytes; out->n_reads = n_reads; out->n_codes = n_codes;
+    out->n_exc = tot_exc; out->n_esc = tot_esc; out->klen_bytes = kb;
+    out->o_klen = o_kl; out->o_codes2 = o_c2; out->o_exc = o_ex; out->o_esc_idx = o_ei; out->o_esc_delta = o_ed;
+    return HX_OK;
+}
+
+void hx_dense_free(hx_dense *d) {
+    if (!d) return;
+    free(d->blob);
+    memset(d, 0, sizeof(*d));
+}
+
 void hx_pack_free(hx_packed *p) {
     if (!p) return;
     free(p->rank); free(p->off); free(p->codes);

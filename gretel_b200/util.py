@@ -71,8 +71,39 @@ class DensePacked:
         return (self.rank_delta, self.esc_idx, self.esc_delta, self.klen, self.codes2, self.exc_pos)
 
 
+def dense_packed_native(rank, off, codes, n_threads=8):
+    """dense_packed by the C++ encoder of libhanselx.so (hx_dense_encode); byte-identical output."""
+    import ctypes as C
+
+    from . import _lib
+    lib = _lib.load()
+    rank = np.ascontiguousarray(rank, dtype=np.int32)
+    off = np.ascontiguousarray(off, dtype=np.int64)
+    codes = np.ascontiguousarray(codes, dtype=np.uint8)
+    if len(off) != len(rank) + 1:
+        raise ValueError("off must have len(rank)+1 entries")
+    out = _lib.HxDense()
+    rc = lib.hx_dense_encode(rank.ctypes.data, off.ctypes.data, codes.ctypes.data, len(rank), int(n_threads), C.byref(out))
+    if rc == _lib.HX_E_ARG:
+        raise ValueError(lib.hx_last_error().decode())
+    _lib.check(rc)
+    try:
+        blob = np.ctypeslib.as_array(out.blob, shape=(int(out.blob_bytes),)).copy()
+        R, n, kb = int(out.n_reads), int(out.n_codes), int(out.klen_bytes)
+        d = DensePacked(blob[0:R],
+                        blob[out.o_esc_idx:out.o_esc_idx + 8 * out.n_esc].view(np.int64),
+                        blob[out.o_esc_delta:out.o_esc_delta + 4 * out.n_esc].view(np.int32),
+                        blob[out.o_klen:out.o_klen + R * kb].view(np.uint8 if kb == 1 else np.uint16),
+                        blob[out.o_codes2:out.o_codes2 + (n + 3) // 4],
+                        blob[out.o_exc:out.o_exc + 4 * out.n_exc].view(np.uint32), R, n)
+        d.blob = blob
+    finally:
+        lib.hx_dense_free(C.byref(out))
+    return d
+
+
 def dense_packed(rank, off, codes):
-    """(rank int32[R] non-decreasing, off int64[R+1], codes uint8) -> DensePacked."""
+    """(rank int32[R] non-decreasing, off int64[R+1], codes uint8) -> DensePacked (numpy encoder)."""
     rank = np.asarray(rank, dtype=np.int64)
     off = np.asarray(off, dtype=np.int64)
     k = np.diff(off)
@@ -134,17 +165,37 @@ def dense_chunks(rank, off, codes, n_chunks):
     return out
 
 
+DENSE_MIN_READS = 200_000      # below this the host->device copy is not what bounds ingestion
+DENSE_CHUNK_CODES = 40_000_000
+
+
 def load_from_packed(rank, off, codes, n_snps, band_w=None, device=None, hansel=None, finalize=True,
-                     quiet=True):
+                     quiet=True, wire="auto", n_threads=8):
     """Packed reads -> Hansel (util.py:83 + 226-286 + 329-333).
 
     With ``finalize=False`` the integer counts stay pending so that partial matrices of
-    several GPUs can be summed first (see gretel_b200.dist)."""
+    several GPUs can be summed first (see gretel_b200.dist).  ``wire``: "wide" ships the packed arrays as they
+    are; "dense" re-encodes rank-sorted reads into the dense wire format (native encoder) and feeds them in
+    chunks whose copies overlap the pair expansion; "auto" picks dense for large sorted inputs."""
     if hansel is None:
         if band_w is None:
             band_w = band_width_for(off)
         hansel = Hansel.init_matrix(REF_SYMBOLS, REF_UNSYMBOLS, n_snps, band_w=band_w, device=device)
-    slices, crumbs, covered, _sent = hansel.ingest_packed(rank, off, codes)
+    rank = np.asarray(rank)
+    if wire == "auto":
+        wire = "dense" if (len(rank) >= DENSE_MIN_READS and bool(np.all(rank[1:] >= rank[:-1]))) else "wide"
+    if wire == "dense":
+        off = np.asarray(off, dtype=np.int64)
+        n_chunks = max(2, int((off[-1] - off[0]) // DENSE_CHUNK_CODES) + 1) if len(rank) > 1 else 1
+        targets = off[0] + (off[-1] - off[0]) * np.arange(1, n_chunks) // n_chunks
+        cuts = [0] + [int(x) for x in np.searchsorted(off, targets, side="left")] + [len(rank)]
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            if b > a:
+                hansel.ingest_packed_dense(dense_packed_native(rank[a:b], off[a:b + 1], codes, n_threads=n_threads),
+                                           wait=False)
+        slices, crumbs, covered, _sent = hansel.ingest_totals()
+    else:
+        slices, crumbs, covered, _sent = hansel.ingest_packed(rank, off, codes)
     if finalize:
         hansel.finalize()
         set_totals(hansel, slices, crumbs, covered, quiet=quiet)

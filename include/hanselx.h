@@ -170,6 +170,18 @@ typedef struct {
 int hx_pack_bam(const char *bam_path, const char *contig, int32_t start_pos, int32_t end_pos,
                 const int32_t *snp_pos, int32_t n_snps, int stepper, int n_threads, hx_packed *out);
 void hx_pack_free(hx_packed *p);
+/* Packed reads (rank-sorted) -> the dense wire format of hx_ingest_host_dense, as one malloc'ed buffer whose
+ * sections sit at the given byte offsets (rank_delta at 0): shipping it takes a single host->device copy.
+ * CPU code (n_threads workers).  HX_E_ARG if the reads are not sorted by rank.  Release with hx_dense_free. */
+typedef struct hx_dense {
+    uint8_t *blob;
+    int64_t blob_bytes, n_reads, n_codes, n_exc, n_esc;
+    int64_t o_klen, o_codes2, o_exc, o_esc_idx, o_esc_delta;
+    int32_t klen_bytes;
+} hx_dense;
+int hx_dense_encode(const int32_t *rank, const int64_t *off, const uint8_t *codes, int64_t n_reads, int n_threads,
+                    hx_dense *out);
+void hx_dense_free(hx_dense *d);
 /* Per-position A,C,G,T counts over 0-based [start0,end0) of a contig from every alignment, no filters:
  * what gretel/snpper.py:30 asks pysam.count_coverage for.  out[4*(end0-start0)], A row first. */
 int hx_count_coverage(const char *bam_path, const char *contig, int32_t start0, int32_t end0, int n_threads,

@@ -237,6 +237,19 @@ def test_dense_wire_format_edges(c_oracle):
     assert escapes > 0
 
 
+def test_load_from_packed_picks_dense_for_large_sorted_input():
+    """util.load_from_packed(wire="auto"): native encoder + chunked overlapped ingestion == the wide path."""
+    from gretel_b200 import util
+    d = synth.generate(synth.scaled(synth.WORKLOADS["metagenome"], 250_000))
+    N, W = d["n_snps"], d["max_k"] - 1
+    assert len(d["rank"]) >= util.DENSE_MIN_READS
+    a = util.load_from_packed(d["rank"], d["off"], d["codes"], N, band_w=W, wire="wide")
+    b = util.load_from_packed(d["rank"], d["off"], d["codes"], N, band_w=W)
+    assert (a.n_slices, a.n_crumbs, a.L) == (b.n_slices, b.n_crumbs, b.L)
+    assert np.array_equal(a.band(), b.band())
+    assert b.launch_count() > a.launch_count()              # the decode kernels ran
+
+
 def test_dense_wire_format_rejects_bad_input():
     from gretel_b200 import util, _lib
     from gretel_b200.hansel import Hansel, REF_SYMBOLS, REF_UNSYMBOLS

@@ -46,3 +46,31 @@ def test_compact_packed_round_trip():
     assert n == len(codes) and np.array_equal(np.cumsum(klen), off[1:])
     back = np.stack([codes4 & 15, codes4 >> 4], axis=1).reshape(-1)[:n]
     assert np.array_equal(back, codes)
+
+
+@pytest.mark.parametrize("seed", range(5))
+def test_native_dense_encoder_matches_numpy(seed):
+    """hx_dense_encode (C++, threaded) produces the same bytes as util.dense_packed."""
+    rng = np.random.default_rng(100 + seed)
+    N = [8, 50, 3000, 20000, 400][seed]
+    n_reads = [7, 300, 150, 200_000, 90][seed]          # 200k reads: several encoder threads
+    rank, off, codes = synth.random_packed(rng, N, n_reads, [4, 11, 9, 7, 300][seed], p_special=0.2)
+    a = util.dense_packed(rank, off, codes)
+    b = util.dense_packed_native(rank, off, codes, n_threads=4)
+    assert (a.n_reads, a.n_codes) == (b.n_reads, b.n_codes)
+    for x, y in zip(a.arrays(), b.arrays()):
+        assert x.dtype == y.dtype and np.array_equal(x, y)
+    assert np.array_equal(a.blob, b.blob)
+    # a chunk that starts in the middle of the allele stream (off[0] != 0)
+    if len(rank) > 4:
+        h = len(rank) // 2
+        a2 = util.dense_packed(rank[h:], off[h:], codes)
+        b2 = util.dense_packed_native(rank[h:], off[h:], codes, n_threads=3)
+        assert np.array_equal(a2.blob, b2.blob)
+
+
+def test_native_dense_encoder_rejects_bad_input():
+    with pytest.raises(ValueError):
+        util.dense_packed_native(np.array([2, 1], np.int32), np.array([0, 2, 4], np.int64), np.zeros(4, np.uint8))
+    with pytest.raises(ValueError):
+        util.dense_packed_native(np.array([0, 1], np.int32), np.array([0, 2, 4], np.int64), np.array([0, 9, 1, 2], np.uint8))
