@@ -485,7 +485,7 @@ def main():
     ap.add_argument("--e2e-format", default="dense", choices=["dense", "compact", "wide"],
                     help="host wire format of the packed reads in the e2e leg (dense: uint8 rank deltas/SNP counts + "
                          "2-bit alleles; compact: int32 ranks + uint16 counts + nibble codes; wide: the packed arrays)")
-    ap.add_argument("--e2e-chunks", type=int, default=3,
+    ap.add_argument("--e2e-chunks", type=int, default=4,
                     help="dense format: chunks per step (copy of chunk i+1 overlaps the expansion of chunk i)")
     ap.add_argument("--recover-paths", type=int, default=5)
     ap.add_argument("--recovery-sweep", action="store_true", default=True,

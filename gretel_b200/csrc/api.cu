@@ -163,16 +163,17 @@ int hx_create(int32_t n_snps, int32_t band_w, int32_t device, hx_matrix **out) {
     HX_TRY(cudaEventCreate(&h->ev0));
     HX_TRY(cudaEventCreate(&h->ev1));
     HX_TRY(cudaMallocAsync((void **)&h->band, sizeof(float) * (size_t)h->band_elems, h->stream));
-    HX_TRY(cudaMemsetAsync(h->band, 0, sizeof(float) * (size_t)h->band_elems, h->stream));
+    HX_TRY(hx_fill_async(h->band, 0, sizeof(float) * (size_t)h->band_elems, h->stream));
     HX_TRY(cudaMallocAsync((void **)&h->d_totals, 8 * sizeof(unsigned long long), h->stream));
-    HX_TRY(cudaMemsetAsync(h->d_totals, 0, 8 * sizeof(unsigned long long), h->stream));
+    HX_TRY(hx_fill_async(h->d_totals, 0, 8 * sizeof(unsigned long long), h->stream));
     HX_TRY(cudaMallocAsync((void **)&h->d_err, sizeof(int), h->stream));
-    HX_TRY(cudaMemsetAsync(h->d_err, 0, sizeof(int), h->stream));
+    HX_TRY(hx_fill_async(h->d_err, 0, sizeof(int), h->stream));
     HX_TRY(cudaMallocAsync((void **)&h->scnt, sizeof(double) * 8 * ((size_t)n_snps + 2), h->stream));
     HX_TRY(cudaMallocAsync((void **)&h->vseen, sizeof(int32_t) * ((size_t)n_snps + 2), h->stream));
     HX_TRY(cudaMallocAsync((void **)&h->d_site, sizeof(double) * 3 * ((size_t)n_snps + 2), h->stream));
     HX_TRY(cudaMallocAsync((void **)&h->d_flags, 8 * sizeof(int), h->stream));
-    HX_TRY(cudaMemsetAsync(h->d_flags, 0, 8 * sizeof(int), h->stream));
+    HX_TRY(hx_fill_async(h->d_flags, 0, 8 * sizeof(int), h->stream));
+    HX_TRY(hx_fill_async(h->d_flags + 5, 1, sizeof(int), h->stream));      // "sorted" for callers that guarantee it
     HX_TRY(cudaMallocAsync((void **)&h->d_misc, 32 * sizeof(double), h->stream));
     HX_TRY(cudaMallocAsync((void **)&h->d_run_end, sizeof(int64_t) * ((size_t)n_snps + 2), h->stream));
     h->h_pinned = calloc(1, 256);     // scalars come back through pageable memory: a pinned allocation per
@@ -245,7 +246,7 @@ int hx_ensure_counts_buffer(hx_matrix *h) {
     if (h->cnt) return HX_OK;
     h->cnt_elems = h->band_elems;
     HX_CUDA(cudaMallocAsync((void **)&h->cnt, sizeof(uint32_t) * (size_t)h->cnt_elems, h->stream));
-    HX_CUDA(cudaMemsetAsync(h->cnt, 0, sizeof(uint32_t) * (size_t)h->cnt_elems, h->stream));
+    HX_CUDA(hx_fill_async(h->cnt, 0, sizeof(uint32_t) * (size_t)h->cnt_elems, h->stream));
     return HX_OK;
 }
 extern "C" {
@@ -406,7 +407,7 @@ int hx_counts_ipc_export(hx_matrix *h, int32_t world, void *handle_out) {
     h->cnt_elems = rows_per * world * h->W * HX_CELL;          // padded so that every rank owns rows_per rows
     HX_CUDA(cudaMalloc((void **)&h->cnt, sizeof(uint32_t) * (size_t)h->cnt_elems));   // IPC needs a plain allocation
     h->cnt_ipc = true;
-    HX_CUDA(cudaMemsetAsync(h->cnt, 0, sizeof(uint32_t) * (size_t)h->cnt_elems, h->stream));
+    HX_CUDA(hx_fill_async(h->cnt, 0, sizeof(uint32_t) * (size_t)h->cnt_elems, h->stream));
     HX_CUDA(cudaStreamSynchronize(h->stream));
     cudaIpcMemHandle_t hd;
     HX_CUDA(cudaIpcGetMemHandle(&hd, h->cnt));
@@ -450,9 +451,9 @@ int hx_counts_ipc_close(hx_matrix *h) {
 int hx_reset_counts(hx_matrix *h) {
     HX_CHECK_ARG(h);
     HX_CUDA(cudaSetDevice(h->device));
-    if (h->cnt) HX_CUDA(cudaMemsetAsync(h->cnt, 0, sizeof(uint32_t) * (size_t)h->cnt_elems, h->stream));
-    HX_CUDA(cudaMemsetAsync(h->d_totals, 0, 8 * sizeof(unsigned long long), h->stream));
-    HX_CUDA(cudaMemsetAsync(h->d_err, 0, sizeof(int), h->stream));
+    if (h->cnt) HX_CUDA(hx_fill_async(h->cnt, 0, sizeof(uint32_t) * (size_t)h->cnt_elems, h->stream));
+    HX_CUDA(hx_fill_async(h->d_totals, 0, 8 * sizeof(unsigned long long), h->stream));
+    HX_CUDA(hx_fill_async(h->d_err, 0, sizeof(int), h->stream));
     return HX_OK;
 }
 

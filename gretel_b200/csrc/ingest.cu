@@ -814,12 +814,29 @@ k1_bitsliced_ws(const int32_t *__restrict__ rank, const int64_t *__restrict__ of
 
 }  // namespace
 
+static int launch_ingest(hx_matrix *h, const int32_t *d_rank, const int64_t *d_off, const uint8_t *d_codes,
+                         int64_t n_reads, int64_t *run_end);
+
 int hx_launch_ingest(hx_matrix *h, const int32_t *d_rank, const int64_t *d_off,
                      const uint8_t *d_codes, int64_t n_reads) {
+    return launch_ingest(h, d_rank, d_off, d_codes, n_reads, nullptr);
+}
+
+// The caller guarantees non-decreasing ranks and has filled run_end[N+1] (end of each rank's run of reads; the
+// dense wire format's decode does both): no sortedness pre-pass, no generic fallback launch.
+int hx_launch_ingest_presorted(hx_matrix *h, const int32_t *d_rank, const int64_t *d_off,
+                               const uint8_t *d_codes, int64_t n_reads, int64_t *run_end) {
+    return launch_ingest(h, d_rank, d_off, d_codes, n_reads, run_end);
+}
+
+static int launch_ingest(hx_matrix *h, const int32_t *d_rank, const int64_t *d_off, const uint8_t *d_codes,
+                         int64_t n_reads, int64_t *run_end) {
     if (n_reads <= 0) return HX_OK;
+    const bool presorted = run_end != nullptr;
+    if (!presorted) run_end = h->d_run_end;
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
-    int *sorted_flag = h->d_flags + 4;
+    int *sorted_flag = presorted ? h->d_flags + 5 : h->d_flags + 4;    // [5] is set once, at creation
     constexpr int GBLOCK = 256;
     const int64_t gwant = (n_reads + (GBLOCK / 32) - 1) / (GBLOCK / 32);
     const int ggrid = (int)(gwant < (int64_t)sms * 8 ? gwant : (int64_t)sms * 8);
@@ -834,23 +851,30 @@ int hx_launch_ingest(hx_matrix *h, const int32_t *d_rank, const int64_t *d_off,
 
     HX_CUDA(cudaEventRecord(h->ev0, h->stream));
     if (use_long) {
-        HX_CUDA(cudaMemsetAsync(sorted_flag, 1, sizeof(int), h->stream));     // non-zero = sorted
-        k_prepass<<<(unsigned)((n_reads + 255) / 256), 256, 0, h->stream>>>(d_rank, n_reads, h->N, sorted_flag,
-                                                                            h->d_run_end);
-        h->launches++;
-        int rc = hx_launch_ingest_long(h, d_rank, d_off, d_codes, n_reads);
+        if (!presorted) {
+            HX_CUDA(hx_fill_async(sorted_flag, 1, sizeof(int), h->stream));     // non-zero = sorted
+            k_prepass<<<(unsigned)((n_reads + 255) / 256), 256, 0, h->stream>>>(d_rank, n_reads, h->N, sorted_flag,
+                                                                                run_end);
+            h->launches++;
+        }
+        int rc = hx_launch_ingest_long(h, d_rank, d_off, d_codes, n_reads, sorted_flag);
         if (rc) return rc;
-        k1_pairs_red<GBLOCK><<<ggrid, GBLOCK, 0, h->stream>>>(d_rank, d_off, d_codes, n_reads, h->N, h->W, hx_cnt_ref(h),
-                                                              h->d_totals, h->d_err, sorted_flag, 0);
-        h->launches++;
+        if (!presorted) {
+            k1_pairs_red<GBLOCK><<<ggrid, GBLOCK, 0, h->stream>>>(d_rank, d_off, d_codes, n_reads, h->N, h->W,
+                                                                  hx_cnt_ref(h), h->d_totals, h->d_err, sorted_flag, 0);
+            h->launches++;
+        }
     } else if (!use_bs) {
         k1_pairs_red<GBLOCK><<<ggrid, GBLOCK, 0, h->stream>>>(d_rank, d_off, d_codes, n_reads, h->N, h->W, hx_cnt_ref(h),
                                                               h->d_totals, h->d_err, sorted_flag, 1);
         h->launches++;
     } else {
-        HX_CUDA(cudaMemsetAsync(sorted_flag, 1, sizeof(int), h->stream));     // non-zero = sorted
-        k_prepass<<<(unsigned)((n_reads + 255) / 256), 256, 0, h->stream>>>(d_rank, n_reads, h->N, sorted_flag,
-                                                                            h->d_run_end);
+        if (!presorted) {
+            HX_CUDA(hx_fill_async(sorted_flag, 1, sizeof(int), h->stream));     // non-zero = sorted
+            k_prepass<<<(unsigned)((n_reads + 255) / 256), 256, 0, h->stream>>>(d_rank, n_reads, h->N, sorted_flag,
+                                                                                run_end);
+            h->launches += 2;
+        }
         const int npairs = kmax * (kmax - 1) / 2;
         // measured (B200): the warp-specialised variant wins for wide reads (config 2: 0.097 vs 0.118 ms),
         // the barrier-phased one for narrow reads (config 3: 0.725 vs 0.751 ms)
@@ -876,7 +900,7 @@ int hx_launch_ingest(hx_matrix *h, const int32_t *d_rank, const int64_t *d_off,
         if (grid > max_useful) grid = max_useful;                                                              \
         kern<<<(unsigned)grid, block, smem, h->stream>>>(d_rank, d_off, d_codes, n_reads, h->N, h->W, kmax,    \
                                                          gb, pw, hx_cnt_ref(h), h->d_totals, h->d_err, sorted_flag,   \
-                                                         h->d_run_end);                                        \
+                                                         run_end);                                        \
     } while (0)
             if (np == 2) HX_WS_LAUNCH(14, 2, 1024, 1);
             else if (kmax > 32) HX_WS_LAUNCH(14, 1, 1024, 1);
@@ -902,17 +926,20 @@ int hx_launch_ingest(hx_matrix *h, const int32_t *d_rank, const int64_t *d_off,
         if (grid > max_useful) grid = max_useful;                                                              \
         kern<<<(unsigned)grid, block, smem, h->stream>>>(d_rank, d_off, d_codes, n_reads, h->N, h->W, kmax,    \
                                                          gb, hx_cnt_ref(h), h->d_totals, h->d_err, sorted_flag,       \
-                                                         h->d_run_end);                                        \
+                                                         run_end);                                        \
     } while (0)
         if (np == 2) HX_BS_LAUNCH(14, 2, 1024, 1);
         else if (kmax > 32) HX_BS_LAUNCH(14, 1, 1024, 1);
         else HX_BS_LAUNCH(8, 1, 512, 2);
 #undef HX_BS_LAUNCH
         }
+        h->launches++;
         // fallback for unsorted input: runs only when the flag says the bit-sliced kernel declined
-        k1_pairs_red<GBLOCK><<<ggrid, GBLOCK, 0, h->stream>>>(d_rank, d_off, d_codes, n_reads, h->N, h->W, hx_cnt_ref(h),
-                                                              h->d_totals, h->d_err, sorted_flag, 0);
-        h->launches += 3;
+        if (!presorted) {
+            k1_pairs_red<GBLOCK><<<ggrid, GBLOCK, 0, h->stream>>>(d_rank, d_off, d_codes, n_reads, h->N, h->W,
+                                                                  hx_cnt_ref(h), h->d_totals, h->d_err, sorted_flag, 0);
+            h->launches++;
+        }
     }
     HX_CUDA(cudaGetLastError());
     HX_CUDA(cudaEventRecord(h->ev1, h->stream));

@@ -383,7 +383,7 @@ void hx_lr_free(hx_matrix *h) {
 }
 
 int hx_launch_ingest_long(hx_matrix *h, const int32_t *d_rank, const int64_t *d_off,
-                          const uint8_t *d_codes, int64_t n_reads) {
+                          const uint8_t *d_codes, int64_t n_reads, const int *sorted_flag) {
     if (!h->lr_scratch) h->lr_scratch = new hx_lr_scratch();
     hx_lr_scratch *s = (hx_lr_scratch *)h->lr_scratch;
     cudaStream_t st = h->stream;
@@ -426,7 +426,7 @@ int hx_launch_ingest_long(hx_matrix *h, const int32_t *d_rank, const int64_t *d_
     const int64_t want = (ng * 32 + 255) / 256;
     const int tgrid = (int)(want < (int64_t)sms * 8 ? want : (int64_t)sms * 8);
     k_lr_transpose<<<tgrid, 256, 0, st>>>(d_rank, d_off, d_codes, n_reads, N, W, s->g_lo, s->g_len, s->g_off,
-                                          s->planes, hx_cnt_ref(h), h->d_totals, h->d_err, h->d_flags + 4);
+                                          s->planes, hx_cnt_ref(h), h->d_totals, h->d_err, sorted_flag);
     k_lr_site_index<<<(N + 255) / 256, 256, 0, st>>>(s->g_lo, s->g_hipm, ng, N, s->first_reach, s->first_after);
     const int nib = (N + LR_TI - 1) / LR_TI;
     const int njb = (W + LR_TI - 1) / LR_TJ + 1;            // J0 = I0 + jb*TJ must reach pi + W for the last row
@@ -435,11 +435,11 @@ int hx_launch_ingest_long(hx_matrix *h, const int32_t *d_rank, const int64_t *d_
     if (n_reads >= 6 * (int64_t)N)
         k_lr_tiles_staged<<<(unsigned)((int64_t)nib * njb), LR_TI * LR_TJ, 0, st>>>(
             s->planes, s->g_off, s->g_lo, s->g_len, s->first_reach, s->first_after, N, W, njb, hx_cnt_ref(h),
-            h->d_totals, h->d_flags + 4);
+            h->d_totals, sorted_flag);
     else
         k_lr_tiles<<<(unsigned)((int64_t)nib * njb), LR_TI * LR_TJ, 0, st>>>(
             s->planes, s->g_off, s->g_lo, s->g_len, s->first_reach, s->first_after, N, W, njb, hx_cnt_ref(h),
-            h->d_totals, h->d_flags + 4);
+            h->d_totals, sorted_flag);
     h->launches += 3;
     HX_CUDA(cudaGetLastError());
     return HX_OK;

@@ -10,7 +10,7 @@
 //
 // One pass of partial sums, a spine and an apply pass yield both scans (ranks inclusive, offsets exclusive).
 // hx_ingest_host_dense(..., totals = NULL) only enqueues: copies go on a second stream into one of three staging
-// sets, so the copy of chunk i+1 overlaps the decode + pair expansion of chunk i.
+// sets and the decode on a third, so the copy and decode of chunk i+1 overlap the pair expansion of chunk i.
 #include <algorithm>
 #include <stdlib.h>
 
@@ -137,7 +137,8 @@ template <int KB>
 __global__ void __launch_bounds__(256)
 k_dense_apply(const uint8_t *__restrict__ rd, const void *__restrict__ kl, int64_t n,
               const int64_t *__restrict__ esc_idx, const int32_t *__restrict__ esc_delta, int64_t n_esc,
-              const int64_t *__restrict__ partials, int32_t *__restrict__ rank, int64_t *__restrict__ off /* n+1 */) {
+              const int64_t *__restrict__ partials, int32_t *__restrict__ rank, int64_t *__restrict__ off /* n+1 */,
+              int N, int64_t *__restrict__ run_end) {
     __shared__ int64_t sh[2][8];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t j0 = (int64_t)blockIdx.x * WB + (int64_t)threadIdx.x * WI;
@@ -157,11 +158,22 @@ k_dense_apply(const uint8_t *__restrict__ rd, const void *__restrict__ kl, int64
     int64_t run_d = partials[2 * (int64_t)blockIdx.x] + id - sd;
     int64_t run_k = partials[2 * (int64_t)blockIdx.x + 1] + ik - sk;
     for (int w = 0; w < warp; ++w) { run_d += sh[0][w]; run_k += sh[1][w]; }
+    // the delta of the read after this thread's 16: run_end[r] = index after the last read of rank r (what
+    // k_prepass of ingest.cu records), so the pair expansion needs no pass of its own over the ranks
+    int32_t d_next = 0;
+    if (j0 + WI < n) {
+        d_next = (int32_t)rd[j0 + WI];
+        if (n_esc && d_next == 255) d_next = esc_lookup(esc_idx, esc_delta, n_esc, j0 + WI);
+    }
 #pragma unroll
     for (int i = 0; i < WI; ++i) {
         const int64_t j = j0 + i;
         run_d += d[i];
-        if (j < n) rank[j] = (int32_t)run_d;
+        if (j < n) {
+            rank[j] = (int32_t)run_d;
+            const int32_t dn = i + 1 < WI ? d[i + 1] : d_next;          // d[] is 0 beyond n
+            if ((j + 1 == n || dn != 0) && run_d <= N) run_end[run_d] = j + 1;
+        }
         if (j <= n) off[j] = run_k;
         run_k += k[i];
     }
@@ -197,7 +209,7 @@ inline int64_t al16(int64_t x) { return (x + 15) & ~(int64_t)15; }
 // next hx_ingest_totals() (debugging aid for the copy/compute overlap)
 struct WireTrace {
     static constexpr int MAXC = 32;
-    cudaEvent_t ev[MAXC][4];
+    cudaEvent_t ev[MAXC][5];
     int64_t bytes[MAXC];
     int n = 0;
     bool made = false;
@@ -230,10 +242,10 @@ void hx_wire_trace_dump() {
     if (!g_trace_on || g_trace.n == 0) return;
     cudaEventSynchronize(g_trace.ev[g_trace.n - 1][3]);
     for (int c = 0; c < g_trace.n; ++c) {
-        float t[4];
-        for (int i = 0; i < 4; ++i) cudaEventElapsedTime(&t[i], g_trace.ev[0][0], g_trace.ev[c][i]);
-        fprintf(stderr, "[wire] chunk %d: copy %.3f..%.3f ms (%.1f GB/s)  decode ..%.3f  expand ..%.3f\n", c, t[0], t[1],
-                g_trace.bytes[c] / ((t[1] - t[0]) * 1e6), t[2], t[3]);
+        float t[5];
+        for (int i = 0; i < 5; ++i) cudaEventElapsedTime(&t[i], g_trace.ev[0][0], g_trace.ev[c][i]);
+        fprintf(stderr, "[wire] chunk %d: copy %.3f..%.3f ms (%.1f GB/s)  decode ..%.3f  expand %.3f..%.3f\n", c, t[0], t[1],
+                g_trace.bytes[c] / ((t[1] - t[0]) * 1e6), t[2], t[4], t[3]);
     }
     g_trace.n = 0;
 }
@@ -246,12 +258,16 @@ void hx_wire_free(hx_matrix *h) {
         if (w.off) cudaFreeAsync(w.off, h->stream);
         if (w.codes) cudaFreeAsync(w.codes, h->stream);
         if (w.partials) cudaFreeAsync(w.partials, h->stream);
+        if (w.run_end) cudaFreeAsync(w.run_end, h->stream);
         if (w.copied) cudaEventDestroy(w.copied);
         if (w.consumed) cudaEventDestroy(w.consumed);
+        if (w.decoded) cudaEventDestroy(w.decoded);
         w = hx_wire_set{};
     }
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    if (h->decode_stream) cudaStreamDestroy(h->decode_stream);
     h->copy_stream = nullptr;
+    h->decode_stream = nullptr;
 }
 
 extern "C" int hx_ingest_host_dense(hx_matrix *h, const uint8_t *rank_delta, const int64_t *esc_idx,
@@ -267,6 +283,8 @@ extern "C" int hx_ingest_host_dense(hx_matrix *h, const uint8_t *rank_delta, con
         HX_CHECK_ARG(n_esc == 0 || (esc_idx && esc_delta));
         cudaStream_t st = h->stream;
         if (!h->copy_stream) HX_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+        if (!h->decode_stream) HX_CUDA(cudaStreamCreateWithFlags(&h->decode_stream, cudaStreamNonBlocking));
+        cudaStream_t ds = h->decode_stream;
         hx_wire_set &w = h->wire[h->wire_next];
         h->wire_next = (h->wire_next + 1) % HX_WIRE_SETS;
         const int64_t n_words = (n_codes + 15) / 16;        // 32-bit words of 2-bit alleles
@@ -283,6 +301,7 @@ extern "C" int hx_ingest_host_dense(hx_matrix *h, const uint8_t *rank_delta, con
             if (!ws.copied) {
                 HX_CUDA(cudaEventCreateWithFlags(&ws.copied, cudaEventDisableTiming));
                 HX_CUDA(cudaEventCreateWithFlags(&ws.consumed, cudaEventDisableTiming));
+                HX_CUDA(cudaEventCreateWithFlags(&ws.decoded, cudaEventDisableTiming));
             }
             bool grew = false;
             auto room = [](int64_t b) { return b + b / 8 + 256; };
@@ -292,6 +311,7 @@ extern "C" int hx_ingest_host_dense(hx_matrix *h, const uint8_t *rank_delta, con
             if (!rc && 8 * (n_reads + 1) + 16 > ws.cap_off) rc = ensure((void **)&ws.off, &ws.cap_off, room(8 * (n_reads + 1) + 16), st, &grew);
             if (!rc && n_words * 16 + 32 > ws.cap_codes) rc = ensure((void **)&ws.codes, &ws.cap_codes, room(n_words * 16 + 32), st, &grew);
             if (!rc && 16 * nblk + 16 > ws.cap_partials) rc = ensure((void **)&ws.partials, &ws.cap_partials, room(16 * nblk + 16), st, &grew);
+            if (!rc && 8 * ((int64_t)h->N + 2) > ws.cap_run_end) rc = ensure((void **)&ws.run_end, &ws.cap_run_end, 8 * ((int64_t)h->N + 2), st, &grew);
             if (rc) return rc;
             if (grew) HX_CUDA(cudaEventRecord(ws.consumed, st));
         }
@@ -320,36 +340,40 @@ extern "C" int hx_ingest_host_dense(hx_matrix *h, const uint8_t *rank_delta, con
         }
         trace_mark(1, cs);
         HX_CUDA(cudaEventRecord(w.copied, cs));
-        HX_CUDA(cudaStreamWaitEvent(st, w.copied, 0));
+        // the decode runs on its own stream: it overlaps the previous chunk's expansion and the next chunk's copy
+        HX_CUDA(cudaStreamWaitEvent(ds, w.copied, 0));
         const int64_t *d_ei = reinterpret_cast<const int64_t *>(raw + o_ei);
         const int32_t *d_ed = reinterpret_cast<const int32_t *>(raw + o_ed);
         if (klen_bytes == 1) {
-            k_dense_partials<1><<<(unsigned)nblk, 256, 0, st>>>(raw + o_rd, raw + o_kl, n_reads, d_ei, d_ed, n_esc, w.partials);
-            k_dense_spine<<<1, 1024, 0, st>>>(w.partials, nblk);
-            k_dense_apply<1><<<(unsigned)nblk, 256, 0, st>>>(raw + o_rd, raw + o_kl, n_reads, d_ei, d_ed, n_esc, w.partials,
-                                                            w.rank, w.off);
+            k_dense_partials<1><<<(unsigned)nblk, 256, 0, ds>>>(raw + o_rd, raw + o_kl, n_reads, d_ei, d_ed, n_esc, w.partials);
+            k_dense_spine<<<1, 1024, 0, ds>>>(w.partials, nblk);
+            k_dense_apply<1><<<(unsigned)nblk, 256, 0, ds>>>(raw + o_rd, raw + o_kl, n_reads, d_ei, d_ed, n_esc, w.partials,
+                                                            w.rank, w.off, h->N, w.run_end);
         } else {
-            k_dense_partials<2><<<(unsigned)nblk, 256, 0, st>>>(raw + o_rd, raw + o_kl, n_reads, d_ei, d_ed, n_esc, w.partials);
-            k_dense_spine<<<1, 1024, 0, st>>>(w.partials, nblk);
-            k_dense_apply<2><<<(unsigned)nblk, 256, 0, st>>>(raw + o_rd, raw + o_kl, n_reads, d_ei, d_ed, n_esc, w.partials,
-                                                            w.rank, w.off);
+            k_dense_partials<2><<<(unsigned)nblk, 256, 0, ds>>>(raw + o_rd, raw + o_kl, n_reads, d_ei, d_ed, n_esc, w.partials);
+            k_dense_spine<<<1, 1024, 0, ds>>>(w.partials, nblk);
+            k_dense_apply<2><<<(unsigned)nblk, 256, 0, ds>>>(raw + o_rd, raw + o_kl, n_reads, d_ei, d_ed, n_esc, w.partials,
+                                                            w.rank, w.off, h->N, w.run_end);
         }
         h->launches += 3;
         if (n_words) {
-            k_unpack_2bit<<<(unsigned)((n_words + 255) / 256), 256, 0, st>>>(reinterpret_cast<const uint32_t *>(raw + o_c2),
+            k_unpack_2bit<<<(unsigned)((n_words + 255) / 256), 256, 0, ds>>>(reinterpret_cast<const uint32_t *>(raw + o_c2),
                                                                             n_words, reinterpret_cast<uint4 *>(w.codes));
             h->launches++;
         }
         if (n_exc) {
-            k_patch_exceptions<<<(unsigned)((n_exc + 255) / 256), 256, 0, st>>>(
+            k_patch_exceptions<<<(unsigned)((n_exc + 255) / 256), 256, 0, ds>>>(
                 reinterpret_cast<const uint32_t *>(raw + o_ex), n_exc, n_codes, w.codes, h->d_err);
             h->launches++;
         }
         HX_CUDA(cudaGetLastError());
-        trace_mark(2, st);
+        trace_mark(2, ds);
+        HX_CUDA(cudaEventRecord(w.decoded, ds));
+        HX_CUDA(cudaStreamWaitEvent(st, w.decoded, 0));
         int rc = hx_ensure_counts_buffer(h);
         if (rc) return rc;
-        rc = hx_launch_ingest(h, w.rank, w.off, w.codes, n_reads);
+        trace_mark(4, st);
+        rc = hx_launch_ingest_presorted(h, w.rank, w.off, w.codes, n_reads, w.run_end);
         if (rc) return rc;
         trace_mark(3, st);
         if (g_trace_on && g_trace.n < WireTrace::MAXC) g_trace.bytes[g_trace.n++] = raw_bytes;
