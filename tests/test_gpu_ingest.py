@@ -183,6 +183,27 @@ def test_compact_wire_format_edges(c_oracle):
         assert np.array_equal(h.band(), ref.astype(np.float32))
 
 
+@pytest.mark.parametrize("kernel,name,n_reads", [(5, "hiv", 20_000), (5, "metagenome", 60_000), (4, "hiv", 20_000)])
+def test_bitsliced_kernels_repeatable_under_stress(c_oracle, kernel, name, n_reads):
+    """The warp-specialised kernel hands bit-planes from builder warps to counting warps through full/empty
+    mbarriers (compute-sanitizer's racecheck does not model those and flags every such hand-over, see
+    profiles/r1_sanitizer.txt): 200 back-to-back launches must all give the oracle's matrix bit for bit."""
+    from gretel_b200.hansel import Hansel, REF_SYMBOLS, REF_UNSYMBOLS
+    w = synth.scaled(synth.WORKLOADS[name], n_reads)
+    d = synth.generate(w)
+    N, W = w.n_snps, d["max_k"] - 1
+    ref, rt = c_oracle.ingest(d["rank"], d["off"], d["codes"], N, W)
+    ref = ref.astype(np.float32)
+    h = Hansel.init_matrix(REF_SYMBOLS, REF_UNSYMBOLS, N, band_w=W)
+    h.set_ingest_kernel(kernel)
+    reps = 200
+    assert reps * float(ref.max()) < 2 ** 24               # the float32 matrix stays exact
+    for it in range(reps):
+        totals = h.ingest_packed(d["rank"], d["off"], d["codes"])       # counts and totals accumulate
+    assert totals == tuple(reps * int(x) for x in rt)
+    assert np.array_equal(h.band(), reps * ref)
+
+
 @pytest.mark.parametrize("name,n_reads", [("hiv", 30_000), ("metagenome", 100_000), ("ont", 300)])
 @pytest.mark.parametrize("n_chunks", [1, 3])
 def test_dense_wire_format(c_oracle, name, n_reads, n_chunks):
