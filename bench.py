@@ -287,6 +287,8 @@ def run_ours(args):
         if world > 1:
             if args.exchange == "reduce":
                 gdist.reduce_counts(h, dst=0)
+            elif args.exchange == "packed":
+                gdist.allreduce_counts_packed(h)
             else:
                 gdist.allreduce_counts(h)
 
@@ -347,7 +349,7 @@ def run_ours(args):
         else:
             hh.ingest_packed_compact(p_rank.numpy(), p_klen.numpy(), p_codes4.numpy(), n_codes)
         if world > 1:
-            gdist.allreduce_counts(hh)
+            (gdist.allreduce_counts_packed if args.exchange == "packed" else gdist.allreduce_counts)(hh)
         hh.finalize()                      # enqueue the fold into the float matrix, then one wait for everything
         s, c, v, _ = hh.ingest_totals()
         util.set_totals(hh, s, c, v)
@@ -476,8 +478,9 @@ def main():
     ap.add_argument("--workload", default="metagenome", choices=sorted(synth.WORKLOADS))
     ap.add_argument("--reads", type=int, default=0, help="reads per GPU (default: the workload's full size)")
     ap.add_argument("--kernel", type=int, default=0, help="ingestion kernel: 0 auto, 1 generic, 2 bit-sliced")
-    ap.add_argument("--exchange", default="allreduce", choices=["allreduce", "reduce", "fused"],
-                    help="N>1: NCCL all-reduce of the partial matrices (default, as north_star names it); reduce onto "
+    ap.add_argument("--exchange", default="allreduce", choices=["allreduce", "packed", "reduce", "fused"],
+                    help="N>1: NCCL all-reduce of the partial matrices (default, as north_star names it); the same "
+                         "all-reduce over counts packed into uint16 lanes (half the bytes); reduce onto "
                          "rank 0 only (recovery runs there); or counts added straight into the owning GPU over "
                          "NVLink peer memory + all-gather of the owned rows")
     ap.add_argument("--segments", type=int, default=1,

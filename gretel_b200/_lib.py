@@ -28,6 +28,8 @@ SIGNATURES = {
     "hx_set_stream": (_int, [_p, _p]),
     "hx_sync": (_int, [_p]),
     "hx_ingest_host": (_int, [_p, _p, _p, _p, _i64, _p]),
+    "hx_counts_pack": (_int, [_p, _i32, _pp, C.POINTER(_i64)]),
+    "hx_counts_unpack": (_int, [_p, C.POINTER(_i32)]),
     "hx_ingest_host_compact": (_int, [_p, _p, _p, _p, _i64, _i64, _p]),
     "hx_dense_encode": (_int, [_p, _p, _p, _i64, _int, _p]),
     "hx_dense_free": (None, [_p]),

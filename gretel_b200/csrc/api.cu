@@ -54,6 +54,36 @@ __global__ void k_fold_counts(const uint32_t *__restrict__ cnt, float *__restric
 
 __global__ void k_add_one(float *p, float amount) { *p += amount; }
 
+// ---- packed exchange: the 49 uint32 counts of a site pair travel as 49 x uint16 in 25 words.  Summing the
+// words as uint32 across GPUs is exact as long as no 16-bit lane carries, i.e. every count <= 65535/world on
+// every rank; the pack kernel raises a flag word otherwise and the caller falls back to the plain exchange.
+#define HX_PACK_WORDS 25
+__global__ void k_pack_counts(const uint32_t *__restrict__ cnt, int64_t n_pairs, uint32_t lim16,
+                              uint32_t *__restrict__ packed, int64_t flag_at) {
+    // one thread per packed word: words of consecutive threads are consecutive in memory
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pairs * HX_PACK_WORDS) return;
+    const int64_t p = i / HX_PACK_WORDS;
+    const int w = (int)(i - p * HX_PACK_WORDS);
+    const uint32_t *c = cnt + p * HX_CELL + 2 * w;
+    const uint32_t lo = c[0], hi = 2 * w + 1 < HX_CELL ? c[1] : 0u;
+    if (lo > lim16 || hi > lim16) packed[flag_at] = 1u;
+    packed[i] = (lo & 0xffffu) | (hi << 16);
+}
+
+__global__ void k_unpack_counts(const uint32_t *__restrict__ packed, int64_t n_pairs, uint32_t *__restrict__ cnt,
+                                int64_t flag_at) {
+    if (packed[flag_at] != 0u) return;                                 // some rank overflowed: leave the partials
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pairs * HX_PACK_WORDS) return;
+    const int64_t p = i / HX_PACK_WORDS;
+    const int w = (int)(i - p * HX_PACK_WORDS);
+    const uint32_t v = packed[i];
+    uint32_t *c = cnt + p * HX_CELL + 2 * w;
+    c[0] = v & 0xffffu;
+    if (2 * w + 1 < HX_CELL) c[1] = v >> 16;
+}
+
 // compact wire format -> the packed arrays the ingestion kernels read
 __global__ void k_widen_klen(const uint16_t *__restrict__ klen, int64_t n, int64_t *__restrict__ out /* n+1 */) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -110,6 +140,7 @@ void free_all(hx_matrix *h) {
     if (h->d_flags) cudaFreeAsync(h->d_flags, h->stream);
     if (h->d_run_end) cudaFreeAsync(h->d_run_end, h->stream);
     if (h->d_misc) cudaFreeAsync(h->d_misc, h->stream);
+    if (h->d_pack) cudaFreeAsync(h->d_pack, h->stream);
     if (h->stream) cudaStreamSynchronize(h->stream);
     free(h->h_pinned);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -395,6 +426,47 @@ int hx_counts_buffer(hx_matrix *h, void **d_counts, int64_t *n_u32, void **d_tot
     *n_u32 = h->cnt_elems;
     *d_totals = h->d_totals;
     *n_i64 = 4;
+    return HX_OK;
+}
+
+int hx_counts_pack(hx_matrix *h, int32_t world, void **d_packed, int64_t *n_u32) {
+    HX_CHECK_ARG(h && d_packed && n_u32 && world >= 1 && world <= 65535);
+    HX_CUDA(cudaSetDevice(h->device));
+    int rc = hx_ensure_counts_buffer(h);
+    if (rc) return rc;
+    const int64_t n_pairs = h->band_elems / HX_CELL;
+    const int64_t flag_at = (n_pairs * HX_PACK_WORDS + 3) & ~(int64_t)3;      // 16-byte aligned trailer
+    const int64_t words = flag_at + 4;
+    if (words > h->cap_pack) {
+        if (h->d_pack) cudaFreeAsync(h->d_pack, h->stream);
+        h->d_pack = nullptr; h->cap_pack = 0;
+        HX_CUDA(cudaMallocAsync((void **)&h->d_pack, sizeof(uint32_t) * (size_t)words, h->stream));
+        h->cap_pack = words;
+    }
+    HX_CUDA(hx_fill_async(h->d_pack + n_pairs * HX_PACK_WORDS, 0, (size_t)(words - n_pairs * HX_PACK_WORDS) * 4, h->stream));
+    const int64_t n_w = n_pairs * HX_PACK_WORDS;
+    k_pack_counts<<<(unsigned)((n_w + 255) / 256), 256, 0, h->stream>>>(h->cnt, n_pairs, 65535u / (uint32_t)world,
+                                                                        h->d_pack, flag_at);
+    h->launches++;
+    HX_CUDA(cudaGetLastError());
+    *d_packed = h->d_pack;
+    *n_u32 = words;
+    return HX_OK;
+}
+
+int hx_counts_unpack(hx_matrix *h, int32_t *overflowed) {
+    HX_CHECK_ARG(h && overflowed && h->d_pack && h->cnt);
+    HX_CUDA(cudaSetDevice(h->device));
+    const int64_t n_pairs = h->band_elems / HX_CELL;
+    const int64_t flag_at = (n_pairs * HX_PACK_WORDS + 3) & ~(int64_t)3;
+    const int64_t n_w = n_pairs * HX_PACK_WORDS;
+    k_unpack_counts<<<(unsigned)((n_w + 255) / 256), 256, 0, h->stream>>>(h->d_pack, n_pairs, h->cnt, flag_at);
+    h->launches++;
+    HX_CUDA(cudaGetLastError());
+    uint32_t *hp = (uint32_t *)h->h_pinned + 40;
+    HX_CUDA(cudaMemcpyAsync(hp, h->d_pack + flag_at, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    HX_CUDA(cudaStreamSynchronize(h->stream));
+    *overflowed = *hp != 0;
     return HX_OK;
 }
 

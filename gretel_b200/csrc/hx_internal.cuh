@@ -77,6 +77,8 @@ struct hx_matrix {
     int *d_flags;                    // [0] hole site / abort flag, [1..] misc
     int64_t *d_run_end;              // (N+1) end (exclusive) of the run of reads with each rank
     double *d_misc;                  // small outputs (weights etc.)
+    uint32_t *d_pack;                // packed counts for the cross-GPU exchange (api.cu)
+    int64_t cap_pack;
     void *h_pinned;                  // small host buffer for D2H of scalars
     int ingest_kernel;
     void *lr_scratch;                // long-read ingestion scratch (ingest_long.cu)
@@ -109,6 +111,11 @@ void hx_set_error(const char *fmt, ...);
 // host->device copies of the overlapped ingestion (measured: +0.08 ms per ingestion launch while a copy is in flight).
 #ifdef __CUDACC__
 static __global__ void k_fill_bytes(uint8_t *p, unsigned v, size_t bytes) {
+    if (reinterpret_cast<uintptr_t>(p) & 15) {        // unaligned (small) fills: plain byte stores
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < bytes; i += (size_t)gridDim.x * blockDim.x)
+            p[i] = (uint8_t)v;
+        return;
+    }
     const size_t n16 = bytes / 16;
     const uint4 w = make_uint4(v, v, v, v);
     uint4 *p16 = reinterpret_cast<uint4 *>(p);
@@ -116,7 +123,7 @@ static __global__ void k_fill_bytes(uint8_t *p, unsigned v, size_t bytes) {
     if (blockIdx.x == 0)
         for (size_t i = n16 * 16 + threadIdx.x; i < bytes; i += blockDim.x) p[i] = (uint8_t)v;
 }
-static inline cudaError_t hx_fill_async(void *p, int byte, size_t bytes, cudaStream_t st) {   // p 16-byte aligned
+static inline cudaError_t hx_fill_async(void *p, int byte, size_t bytes, cudaStream_t st) {
     if (!bytes) return cudaSuccess;
     const unsigned b = (unsigned)byte & 0xffu, v = b * 0x01010101u;
     const size_t want = (bytes / 16 + 255) / 256;

@@ -184,6 +184,19 @@ class Hansel:
         _lib.check(self._lib.hx_counts_buffer(self._h, C.byref(a), C.byref(na), C.byref(b), C.byref(nb)))
         return a.value, na.value, b.value, nb.value
 
+    def counts_pack(self, world):
+        """(device ptr, n uint32) of the pending counts packed for a cheaper sum all-reduce (hx_counts_pack)."""
+        a, na = C.c_void_p(), C.c_int64()
+        _lib.check(self._lib.hx_counts_pack(self._h, int(world), C.byref(a), C.byref(na)))
+        return a.value, na.value
+
+    def counts_unpack(self):
+        """Write the all-reduced packed sums back; False if a lane overflowed (counts untouched)."""
+        o = C.c_int32()
+        _lib.check(self._lib.hx_counts_unpack(self._h, C.byref(o)))
+        self._touch()
+        return o.value == 0
+
     def ingest_device(self, d_rank_ptr, d_off_ptr, d_codes_ptr, n_reads):
         """Asynchronous ingestion of packed reads already resident on this GPU (raw device pointers)."""
         _lib.check(self._lib.hx_ingest_device(self._h, d_rank_ptr, d_off_ptr, d_codes_ptr, int(n_reads)))

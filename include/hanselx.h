@@ -102,6 +102,13 @@ int hx_ingest_totals(hx_matrix *h, int64_t totals[4]);               /* synchron
  * util.py:303-326): device pointer + length of the uint32 counts and of the int64
  * totals, for an integer sum-allreduce by the caller (NCCL). */
 int hx_counts_buffer(hx_matrix *h, void **d_counts, int64_t *n_u32, void **d_totals, int64_t *n_i64);
+/* The same exchange with half the bytes: hx_counts_pack() copies the pending counts into a packed device
+ * buffer (49 x uint16 per site pair in 25 words; the last 4 words are an overflow flag), the caller
+ * sum-all-reduces its n_u32 uint32 words, and hx_counts_unpack() writes the sums back into the counts.  Lane
+ * sums are exact when every count is <= 65535/world on every rank; otherwise *overflowed is 1, the counts are
+ * untouched and the caller must fall back to hx_counts_buffer().  hx_counts_unpack synchronises. */
+int hx_counts_pack(hx_matrix *h, int32_t world, void **d_packed, int64_t *n_u32);
+int hx_counts_unpack(hx_matrix *h, int32_t *overflowed);
 /* Fused exchange (one process per GPU, NVLink peer memory): band rows are dealt out to the ranks in
  * contiguous blocks of ceil((N+2)/world); after export + import every ingestion kernel adds its counts
  * straight into the GPU that owns the row, so when all ranks' kernels are done each rank holds the final

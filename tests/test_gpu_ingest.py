@@ -258,6 +258,39 @@ def test_dense_wire_format_edges(c_oracle):
     assert escapes > 0
 
 
+def test_packed_exchange_format_single_gpu(c_oracle):
+    """hx_counts_pack / hx_counts_unpack (the multi-GPU exchange with uint16 lanes): doubling the packed words
+    stands in for a 2-rank sum all-reduce; an input that could overflow a lane is refused untouched."""
+    import torch
+    from gretel_b200.dist import _DevBuf
+    from gretel_b200.hansel import Hansel, REF_SYMBOLS, REF_UNSYMBOLS
+    rng = np.random.default_rng(5)
+    N = 300
+    rank, off, codes = synth.random_packed(rng, N, 20_000, 14, p_special=0.1)
+    W = int(np.diff(off).max()) - 1
+    ref, rt = c_oracle.ingest(rank, off, codes, N, W)
+    h = Hansel.init_matrix(REF_SYMBOLS, REF_UNSYMBOLS, N, band_w=W)
+    h.ingest_packed(rank, off, codes)
+    ptr, n = h.counts_pack(2)
+    assert n == (((N + 2) * W * 25 + 3) & ~3) + 4
+    dev = torch.device("cuda", h.device)
+    packed = torch.as_tensor(_DevBuf(ptr, n, "<i4"), device=dev)
+    with torch.cuda.stream(torch.cuda.ExternalStream(h.stream, device=dev)):
+        packed.add_(packed)
+    assert h.counts_unpack()
+    assert np.array_equal(h.band(), 2 * ref.astype(np.float32))
+    # the same counts cannot be summed over 20000 ranks in 16-bit lanes: refused, counts left as they were
+    h2 = Hansel.init_matrix(REF_SYMBOLS, REF_UNSYMBOLS, N, band_w=W)
+    h2.ingest_packed(rank, off, codes)
+    assert ref.max() > 65535 // 20000
+    ptr, n = h2.counts_pack(20000)
+    packed = torch.as_tensor(_DevBuf(ptr, n, "<i4"), device=dev)
+    with torch.cuda.stream(torch.cuda.ExternalStream(h2.stream, device=dev)):
+        packed.add_(packed)
+    assert not h2.counts_unpack()
+    assert np.array_equal(h2.band(), ref.astype(np.float32))
+
+
 def test_load_from_packed_picks_dense_for_large_sorted_input():
     """util.load_from_packed(wire="auto"): native encoder + chunked overlapped ingestion == the wide path."""
     from gretel_b200 import util

@@ -46,6 +46,9 @@ def _worker(rank, world, port, segments, out):
                 h.ingest_device(t_rank.data_ptr(), t_off.data_ptr(), t_codes.data_ptr(), hi - lo)
                 fx.finish()
             fx.close()
+        elif segments == -2:                                # packed exchange (uint16 lanes)
+            h.ingest_device(t_rank.data_ptr(), t_off.data_ptr(), t_codes.data_ptr(), hi - lo)
+            assert gdist.allreduce_counts_packed(h)
         elif segments > 1:
             pipe = gdist.PipelinedIngest(h, d["rank"][lo:hi], hi - lo, segments=segments)
             h.reset_counts()
@@ -69,7 +72,7 @@ def _worker(rank, world, port, segments, out):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("segments", [1, 4, -1])
+@pytest.mark.parametrize("segments", [1, 4, -1, -2])
 def test_two_gpu_sharded_ingest(tmp_path, c_oracle, segments):
     import torch
     import torch.multiprocessing as mp
