@@ -173,8 +173,9 @@ int hx_device_count(int *n) {
 // stream.  Creating and destroying a matrix costs ~0.25 ms of driver calls (3 streams, a dozen events, ~40
 // stream-ordered allocations) - as much as a whole 2.5M-read ingestion chunk.  HX_NO_MATRIX_CACHE=1 disables it.
 namespace {
-std::mutex g_park_mu;
-std::vector<hx_matrix *> g_parked;
+// heap-allocated and never destroyed: a handle may be released while the process is already exiting
+std::mutex &g_park_mu = *new std::mutex;
+std::vector<hx_matrix *> &g_parked = *new std::vector<hx_matrix *>;
 constexpr size_t HX_PARK_MAX = 4;
 constexpr int64_t HX_PARK_MAX_ELEMS = (int64_t)1 << 28;      // do not sit on bands above 1 GiB
 const bool g_park_on = getenv("HX_NO_MATRIX_CACHE") == nullptr;
