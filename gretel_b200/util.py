@@ -151,17 +151,23 @@ def dense_packed(rank, off, codes):
     return out
 
 
-def dense_chunks(rank, off, codes, n_chunks):
-    """Split rank-sorted packed reads into ``n_chunks`` DensePacked pieces of about equal allele count."""
+def dense_chunks(rank, off, codes, n_chunks, weights=None, native=False, n_threads=8):
+    """Split rank-sorted packed reads into DensePacked pieces at read boundaries: ``n_chunks`` pieces of about
+    equal allele count, or pieces proportional to ``weights`` (a shorter last piece shortens the part of the
+    pipeline that cannot overlap a copy)."""
     off = np.asarray(off, dtype=np.int64)
     R = len(off) - 1
-    n_chunks = max(1, min(int(n_chunks), max(R, 1)))
-    targets = off[0] + (off[-1] - off[0]) * np.arange(1, n_chunks) // n_chunks
+    if weights is None:
+        n_chunks = max(1, min(int(n_chunks), max(R, 1)))
+        weights = [1.0] * n_chunks
+    w = np.cumsum(np.asarray(weights, dtype=np.float64))
+    targets = off[0] + ((off[-1] - off[0]) * (w[:-1] / w[-1])).astype(np.int64)
     cuts = [0] + [int(x) for x in np.searchsorted(off, targets, side="left")] + [R]
+    enc = (lambda r, o, c: dense_packed_native(r, o, c, n_threads=n_threads)) if native else dense_packed
     out = []
     for a, b in zip(cuts[:-1], cuts[1:]):
         if b > a:
-            out.append(dense_packed(rank[a:b], off[a:b + 1], codes))
+            out.append(enc(rank[a:b], off[a:b + 1], codes))
     return out
 
 

@@ -4,11 +4,13 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from gretel_b200 import synth, util
 from gretel_b200.hansel import Hansel, REF_SYMBOLS, REF_UNSYMBOLS
-n_chunks = int(sys.argv[1]) if len(sys.argv) > 1 else 4
+arg = sys.argv[1] if len(sys.argv) > 1 else "4"
+weights = [float(x) for x in arg.split(":")] if ":" in arg else None
+n_chunks = len(weights) if weights else int(arg)
 d = synth.generate(synth.WORKLOADS["metagenome"])
 N, W = d["n_snps"], d["max_k"] - 1
 keep, chunks = [], []
-for c in util.dense_chunks(d["rank"], d["off"], d["codes"], n_chunks):
+for c in util.dense_chunks(d["rank"], d["off"], d["codes"], n_chunks, weights=weights, native=True):
     pinned = torch.from_numpy(c.blob).pin_memory()
     keep.append(pinned)
     chunks.append(c.rebased(pinned.numpy()))
