@@ -214,7 +214,6 @@ int reset_parked(hx_matrix *h) {
     HX_CUDA(hx_fill_async(h->d_totals, 0, 8 * sizeof(unsigned long long), h->stream));
     HX_CUDA(hx_fill_async(h->d_err, 0, sizeof(int), h->stream));
     HX_CUDA(hx_fill_async(h->d_flags, 0, 8 * sizeof(int), h->stream));
-    HX_CUDA(hx_fill_async(h->d_flags + 5, 1, sizeof(int), h->stream));
     h->counts_dirty = true;
     h->ev_rec = false;
     h->launches = 0;
@@ -275,7 +274,6 @@ int hx_create(int32_t n_snps, int32_t band_w, int32_t device, hx_matrix **out) {
     HX_TRY(cudaMallocAsync((void **)&h->d_site, sizeof(double) * 3 * ((size_t)n_snps + 2), h->stream));
     HX_TRY(cudaMallocAsync((void **)&h->d_flags, 8 * sizeof(int), h->stream));
     HX_TRY(hx_fill_async(h->d_flags, 0, 8 * sizeof(int), h->stream));
-    HX_TRY(hx_fill_async(h->d_flags + 5, 1, sizeof(int), h->stream));      // "sorted" for callers that guarantee it
     HX_TRY(cudaMallocAsync((void **)&h->d_misc, 32 * sizeof(double), h->stream));
     HX_TRY(cudaMallocAsync((void **)&h->d_run_end, sizeof(int64_t) * ((size_t)n_snps + 2), h->stream));
     h->h_pinned = calloc(1, 256);     // scalars come back through pageable memory: a pinned allocation per

@@ -141,7 +141,7 @@ __host__ __device__ __forceinline__ int64_t hx_cell_off(int64_t W, int64_t pi, i
 int hx_launch_ingest(hx_matrix *h, const int32_t *d_rank, const int64_t *d_off,
                      const uint8_t *d_codes, int64_t n_reads);
 int hx_launch_ingest_presorted(hx_matrix *h, const int32_t *d_rank, const int64_t *d_off,
-                               const uint8_t *d_codes, int64_t n_reads, int64_t *run_end);
+                               const uint8_t *d_codes, int64_t n_reads, int64_t *run_end, const int *ok);
 // api.cu
 HxCnt hx_cnt_ref(const hx_matrix *h);
 int hx_ensure_counts_buffer(hx_matrix *h);

@@ -103,8 +103,10 @@ k1_pairs_red(const int32_t *__restrict__ rank, const int64_t *__restrict__ off,
              const HxCnt cnt, unsigned long long *__restrict__ totals,
              int *__restrict__ err, const int *__restrict__ sorted_flag, int run_if_sorted) {
     // sorted_flag: 1 when the reads are rank-sorted.  run_if_sorted = 0 makes this launch the
-    // fallback that only runs when the bit-sliced kernel declined the input.
-    if (!run_if_sorted && *sorted_flag) return;
+    // fallback that only runs when the bit-sliced kernel declined the input; 1 = run regardless;
+    // 2 = run only if the flag is set (a pre-decoded chunk that passed its consistency check).
+    if (run_if_sorted == 0 && *sorted_flag) return;
+    if (run_if_sorted == 2 && !*sorted_flag) return;
     const int lane = threadIdx.x & 31;
     const int64_t nwarps = (int64_t)gridDim.x * (BLOCK / 32);
     unsigned long long t_slices = 0, t_crumbs = 0, t_cov = 0, t_sent = 0;
@@ -815,28 +817,29 @@ k1_bitsliced_ws(const int32_t *__restrict__ rank, const int64_t *__restrict__ of
 }  // namespace
 
 static int launch_ingest(hx_matrix *h, const int32_t *d_rank, const int64_t *d_off, const uint8_t *d_codes,
-                         int64_t n_reads, int64_t *run_end);
+                         int64_t n_reads, int64_t *run_end, const int *ok);
 
 int hx_launch_ingest(hx_matrix *h, const int32_t *d_rank, const int64_t *d_off,
                      const uint8_t *d_codes, int64_t n_reads) {
-    return launch_ingest(h, d_rank, d_off, d_codes, n_reads, nullptr);
+    return launch_ingest(h, d_rank, d_off, d_codes, n_reads, nullptr, nullptr);
 }
 
 // The caller guarantees non-decreasing ranks and has filled run_end[N+1] (end of each rank's run of reads; the
-// dense wire format's decode does both): no sortedness pre-pass, no generic fallback launch.
+// dense wire format's decode does both): no sortedness pre-pass, no generic fallback launch.  *ok (device) is
+// non-zero when the chunk decoded consistently; the kernels do nothing otherwise.
 int hx_launch_ingest_presorted(hx_matrix *h, const int32_t *d_rank, const int64_t *d_off,
-                               const uint8_t *d_codes, int64_t n_reads, int64_t *run_end) {
-    return launch_ingest(h, d_rank, d_off, d_codes, n_reads, run_end);
+                               const uint8_t *d_codes, int64_t n_reads, int64_t *run_end, const int *ok) {
+    return launch_ingest(h, d_rank, d_off, d_codes, n_reads, run_end, ok);
 }
 
 static int launch_ingest(hx_matrix *h, const int32_t *d_rank, const int64_t *d_off, const uint8_t *d_codes,
-                         int64_t n_reads, int64_t *run_end) {
+                         int64_t n_reads, int64_t *run_end, const int *ok) {
     if (n_reads <= 0) return HX_OK;
     const bool presorted = run_end != nullptr;
     if (!presorted) run_end = h->d_run_end;
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
-    int *sorted_flag = presorted ? h->d_flags + 5 : h->d_flags + 4;    // [5] is set once, at creation
+    const int *sorted_flag = presorted ? ok : h->d_flags + 4;
     constexpr int GBLOCK = 256;
     const int64_t gwant = (n_reads + (GBLOCK / 32) - 1) / (GBLOCK / 32);
     const int ggrid = (int)(gwant < (int64_t)sms * 8 ? gwant : (int64_t)sms * 8);
@@ -852,8 +855,8 @@ static int launch_ingest(hx_matrix *h, const int32_t *d_rank, const int64_t *d_o
     HX_CUDA(cudaEventRecord(h->ev0, h->stream));
     if (use_long) {
         if (!presorted) {
-            HX_CUDA(hx_fill_async(sorted_flag, 1, sizeof(int), h->stream));     // non-zero = sorted
-            k_prepass<<<(unsigned)((n_reads + 255) / 256), 256, 0, h->stream>>>(d_rank, n_reads, h->N, sorted_flag,
+            HX_CUDA(hx_fill_async(h->d_flags + 4, 1, sizeof(int), h->stream));     // non-zero = sorted
+            k_prepass<<<(unsigned)((n_reads + 255) / 256), 256, 0, h->stream>>>(d_rank, n_reads, h->N, h->d_flags + 4,
                                                                                 run_end);
             h->launches++;
         }
@@ -866,12 +869,12 @@ static int launch_ingest(hx_matrix *h, const int32_t *d_rank, const int64_t *d_o
         }
     } else if (!use_bs) {
         k1_pairs_red<GBLOCK><<<ggrid, GBLOCK, 0, h->stream>>>(d_rank, d_off, d_codes, n_reads, h->N, h->W, hx_cnt_ref(h),
-                                                              h->d_totals, h->d_err, sorted_flag, 1);
+                                                              h->d_totals, h->d_err, sorted_flag, presorted ? 2 : 1);
         h->launches++;
     } else {
         if (!presorted) {
-            HX_CUDA(hx_fill_async(sorted_flag, 1, sizeof(int), h->stream));     // non-zero = sorted
-            k_prepass<<<(unsigned)((n_reads + 255) / 256), 256, 0, h->stream>>>(d_rank, n_reads, h->N, sorted_flag,
+            HX_CUDA(hx_fill_async(h->d_flags + 4, 1, sizeof(int), h->stream));     // non-zero = sorted
+            k_prepass<<<(unsigned)((n_reads + 255) / 256), 256, 0, h->stream>>>(d_rank, n_reads, h->N, h->d_flags + 4,
                                                                                 run_end);
             h->launches += 2;
         }

@@ -67,7 +67,10 @@ __device__ __forceinline__ void load_reads(const uint8_t *__restrict__ rd, const
     if (n_esc) {
 #pragma unroll
         for (int i = 0; i < WI; ++i)
-            if (d[i] == 255) d[i] = esc_lookup(esc_idx, esc_delta, n_esc, j0 + i);
+            if (d[i] == 255) {
+                const int32_t e = esc_lookup(esc_idx, esc_delta, n_esc, j0 + i);
+                d[i] = e < 0 ? 0 : e;              // ranks must never decrease: the expansion relies on it
+            }
     }
 }
 
@@ -97,7 +100,10 @@ k_dense_partials(const uint8_t *__restrict__ rd, const void *__restrict__ kl, in
 }
 
 // exclusive scan of the block partials: one CTA, 1024 blocks per step
-__global__ void __launch_bounds__(1024) k_dense_spine(int64_t *__restrict__ partials, int64_t nblk) {
+// ... and the consistency check of the chunk: the SNP counts must add up to the allele count the caller stated
+// (otherwise offsets would run past the unpacked codes).  *ok gates the pair expansion of this chunk.
+__global__ void __launch_bounds__(1024) k_dense_spine(int64_t *__restrict__ partials, int64_t nblk, int64_t n_codes,
+                                                      int *__restrict__ ok, int *__restrict__ err) {
     __shared__ int64_t sh[2][32];
     __shared__ int64_t carry[2];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -131,6 +137,11 @@ __global__ void __launch_bounds__(1024) k_dense_spine(int64_t *__restrict__ part
         if (threadIdx.x == 0) { carry[0] += sh[0][31]; carry[1] += sh[1][31]; }
         __syncthreads();
     }
+    if (threadIdx.x == 0) {
+        const bool good = carry[1] == n_codes;
+        *ok = good ? 1 : 0;
+        if (!good) atomicOr(err, 1);
+    }
 }
 
 template <int KB>
@@ -163,14 +174,17 @@ k_dense_apply(const uint8_t *__restrict__ rd, const void *__restrict__ kl, int64
     int32_t d_next = 0;
     if (j0 + WI < n) {
         d_next = (int32_t)rd[j0 + WI];
-        if (n_esc && d_next == 255) d_next = esc_lookup(esc_idx, esc_delta, n_esc, j0 + WI);
+        if (n_esc && d_next == 255) {
+            d_next = esc_lookup(esc_idx, esc_delta, n_esc, j0 + WI);
+            if (d_next < 0) d_next = 0;
+        }
     }
 #pragma unroll
     for (int i = 0; i < WI; ++i) {
         const int64_t j = j0 + i;
         run_d += d[i];
         if (j < n) {
-            rank[j] = (int32_t)run_d;
+            rank[j] = (int32_t)(run_d <= (int64_t)N + 1 ? run_d : (int64_t)N + 1);   // > N is invalid anyway; stays monotonic
             const int32_t dn = i + 1 < WI ? d[i + 1] : d_next;          // d[] is 0 beyond n
             if ((j + 1 == n || dn != 0) && run_d <= N) run_end[run_d] = j + 1;
         }
@@ -310,7 +324,7 @@ extern "C" int hx_ingest_host_dense(hx_matrix *h, const uint8_t *rank_delta, con
             if (!rc && 4 * n_reads + 16 > ws.cap_rank) rc = ensure((void **)&ws.rank, &ws.cap_rank, room(4 * n_reads + 16), st, &grew);
             if (!rc && 8 * (n_reads + 1) + 16 > ws.cap_off) rc = ensure((void **)&ws.off, &ws.cap_off, room(8 * (n_reads + 1) + 16), st, &grew);
             if (!rc && n_words * 16 + 32 > ws.cap_codes) rc = ensure((void **)&ws.codes, &ws.cap_codes, room(n_words * 16 + 32), st, &grew);
-            if (!rc && 16 * nblk + 16 > ws.cap_partials) rc = ensure((void **)&ws.partials, &ws.cap_partials, room(16 * nblk + 16), st, &grew);
+            if (!rc && 16 * nblk + 32 > ws.cap_partials) rc = ensure((void **)&ws.partials, &ws.cap_partials, room(16 * nblk + 32), st, &grew);
             if (!rc && 8 * ((int64_t)h->N + 2) > ws.cap_run_end) rc = ensure((void **)&ws.run_end, &ws.cap_run_end, 8 * ((int64_t)h->N + 2), st, &grew);
             if (rc) return rc;
             if (grew) HX_CUDA(cudaEventRecord(ws.consumed, st));
@@ -342,16 +356,17 @@ extern "C" int hx_ingest_host_dense(hx_matrix *h, const uint8_t *rank_delta, con
         HX_CUDA(cudaEventRecord(w.copied, cs));
         // the decode runs on its own stream: it overlaps the previous chunk's expansion and the next chunk's copy
         HX_CUDA(cudaStreamWaitEvent(ds, w.copied, 0));
+        int *ok = reinterpret_cast<int *>(w.partials + 2 * nblk);          // behind the block partials
         const int64_t *d_ei = reinterpret_cast<const int64_t *>(raw + o_ei);
         const int32_t *d_ed = reinterpret_cast<const int32_t *>(raw + o_ed);
         if (klen_bytes == 1) {
             k_dense_partials<1><<<(unsigned)nblk, 256, 0, ds>>>(raw + o_rd, raw + o_kl, n_reads, d_ei, d_ed, n_esc, w.partials);
-            k_dense_spine<<<1, 1024, 0, ds>>>(w.partials, nblk);
+            k_dense_spine<<<1, 1024, 0, ds>>>(w.partials, nblk, n_codes, ok, h->d_err);
             k_dense_apply<1><<<(unsigned)nblk, 256, 0, ds>>>(raw + o_rd, raw + o_kl, n_reads, d_ei, d_ed, n_esc, w.partials,
                                                             w.rank, w.off, h->N, w.run_end);
         } else {
             k_dense_partials<2><<<(unsigned)nblk, 256, 0, ds>>>(raw + o_rd, raw + o_kl, n_reads, d_ei, d_ed, n_esc, w.partials);
-            k_dense_spine<<<1, 1024, 0, ds>>>(w.partials, nblk);
+            k_dense_spine<<<1, 1024, 0, ds>>>(w.partials, nblk, n_codes, ok, h->d_err);
             k_dense_apply<2><<<(unsigned)nblk, 256, 0, ds>>>(raw + o_rd, raw + o_kl, n_reads, d_ei, d_ed, n_esc, w.partials,
                                                             w.rank, w.off, h->N, w.run_end);
         }
@@ -373,7 +388,7 @@ extern "C" int hx_ingest_host_dense(hx_matrix *h, const uint8_t *rank_delta, con
         int rc = hx_ensure_counts_buffer(h);
         if (rc) return rc;
         trace_mark(4, st);
-        rc = hx_launch_ingest_presorted(h, w.rank, w.off, w.codes, n_reads, w.run_end);
+        rc = hx_launch_ingest_presorted(h, w.rank, w.off, w.codes, n_reads, w.run_end, ok);
         if (rc) return rc;
         trace_mark(3, st);
         if (g_trace_on && g_trace.n < WireTrace::MAXC) g_trace.bytes[g_trace.n++] = raw_bytes;

@@ -312,16 +312,31 @@ def test_dense_wire_format_rejects_bad_input():
     # an exception index past the allele stream, and a 2-bit field of 3 at an exception (code 7)
     rank, off = np.array([0, 1], np.int32), np.array([0, 3, 6], np.int64)
     dense = util.dense_packed(rank, off, np.array([0, 1, 5, 2, 3, 0], np.uint8))
-    for bad in ("pos", "field"):
-        d2 = util.DensePacked(dense.rank_delta, dense.esc_idx, dense.esc_delta, dense.klen, dense.codes2.copy(),
-                              dense.exc_pos.copy(), dense.n_reads, dense.n_codes)
+    for bad in ("pos", "field", "n_codes", "klen", "escape"):
+        d2 = util.DensePacked(dense.rank_delta.copy(), dense.esc_idx, dense.esc_delta, dense.klen.copy(),
+                              dense.codes2.copy(), dense.exc_pos.copy(), dense.n_reads, dense.n_codes)
         if bad == "pos":
             d2.exc_pos[0] = 600
-        else:
+        elif bad == "field":
             d2.codes2[0] |= 3 << 4                               # allele 2 (the exception) -> field 3 -> code 7
+        elif bad == "n_codes":
+            d2.n_codes = 5                                       # SNP counts add up to 6
+            d2.exc_pos = d2.exc_pos[:0]
+        elif bad == "klen":
+            d2.klen[1] = 200                                     # offsets would run past the alleles shipped
+        else:                                                    # a negative escape delta: ranks would decrease
+            d2.rank_delta[1] = 255
+            d2.esc_idx, d2.esc_delta = np.array([1], np.int64), np.array([-7], np.int32)
         h = Hansel.init_matrix(REF_SYMBOLS, REF_UNSYMBOLS, 6, band_w=4)
+        if bad == "escape":
+            h.ingest_packed_dense(d2)                            # clamped to "same rank": still a valid input
+            continue
         with pytest.raises(_lib.HanselxError):
             h.ingest_packed_dense(d2)
+        h.close()
+    # the library is still usable afterwards (no sticky CUDA error)
+    h = Hansel.init_matrix(REF_SYMBOLS, REF_UNSYMBOLS, 6, band_w=4)
+    assert h.ingest_packed_dense(dense)[0] == 2
 
 
 @pytest.mark.parametrize("shape", [(600, 40, 300_000, 150), (600, 100, 120_000, 200), (3000, 300, 400_000, 150)],
