@@ -127,6 +127,27 @@ def workload_config(args, k_mean=None, n_reads=None):
 
 
 # ----------------------------------------------------------------------------------- reference arm
+def popc_floor(rank, off, kernel_ms):
+    """The compute floor of the bit-sliced kernel: 16 POPC per (site pair x group of 32 same-rank reads), issued
+    by whole warps over the t2-major pair prefix, on the quarter-rate XU pipe (15.5 lanes/clk/SM measured,
+    profiles/r1_microbench.txt).  Returned beside the HBM figures: it is the hardware bound this kernel is
+    closest to, and the kernel is still several times above it (issue slots / phase barriers)."""
+    k = np.diff(off).astype(np.int64)
+    R = len(rank)
+    if R == 0:
+        return None
+    start = np.flatnonzero(np.r_[True, rank[1:] != rank[:-1]])
+    pos = np.arange(R) - np.repeat(start, np.diff(np.r_[start, R]))
+    gid = np.cumsum(np.r_[True, pos[1:] % 32 == 0]) - 1
+    kg = np.zeros(int(gid[-1]) + 1, np.int64)
+    np.maximum.at(kg, gid, k)
+    lane_ops = int((16 * ((kg * (kg - 1) // 2 + 31) // 32) * 32).sum())
+    lanes_per_clk_sm, sms, mhz = 15.5, 148, 1965.0
+    floor_ms = lane_ops / (lanes_per_clk_sm * sms * mhz * 1e6) * 1e3
+    return {"pipe": "xu (POPC)", "lane_ops_per_launch": lane_ops, "peak_lanes_per_clk_per_sm": lanes_per_clk_sm,
+            "floor_ms": floor_ms, "frac": floor_ms / kernel_ms}
+
+
 def run_reference(args):
     """The reference's own CPU implementation of the path (per-pair Python calls into a NumPy
     array, forked workers over read chunks: gretel/util.py:242-286, 294-326), restated in
@@ -397,11 +418,13 @@ def run_ours(args):
             traffic = tj.get(key, tj.get(args.workload))
         except Exception:
             traffic = None
+    pipe = popc_floor(d["rank"], d["off"], kms) if d["max_k"] <= 52 else None
     roofline = {"bound": "hbm", "kernel": "ingestion (pair expansion)", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "kernel_ms": kms, "algorithmic_bytes_per_obs": b_obs(k_mean),
                 "obs_per_launch": local_obs,
                 "dram_frac": (traffic / (kms * 1e-3) / 1e9 / peak) if traffic else None,
+                "pipe_floor": pipe,
                 "note": "algorithmic bytes charge one uint32 read-modify-write per observation (SURVEY 8d); the "
                         "kernel counts 32 reads at a time in registers/shared memory, so frac can exceed 1 while "
                         "real DRAM traffic (traffic, dram_frac) stays at the compulsory input+band bytes"}
