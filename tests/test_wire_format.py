@@ -74,3 +74,20 @@ def test_native_dense_encoder_rejects_bad_input():
         util.dense_packed_native(np.array([2, 1], np.int32), np.array([0, 2, 4], np.int64), np.zeros(4, np.uint8))
     with pytest.raises(ValueError):
         util.dense_packed_native(np.array([0, 1], np.int32), np.array([0, 2, 4], np.int64), np.array([0, 9, 1, 2], np.uint8))
+
+
+def test_dense_encoders_agree_on_random_shapes():
+    """Property check over many small random inputs (empty read lists, reads of 0 or 1 SNPs, all-rare reads,
+    huge rank gaps, allele streams whose length is not a multiple of 4 or 16): numpy and C++ encoders produce the
+    same bytes and decode back to the input."""
+    rng = np.random.default_rng(2026)
+    for trial in range(150):
+        n_reads = int(rng.integers(0, 40))
+        N = int(rng.choice([3, 17, 300, 70000]))
+        max_k = int(rng.integers(0, min(N, 9) + 1))
+        rank, off, codes = synth.random_packed(rng, N, n_reads, max_k, p_special=float(rng.choice([0.0, 0.3, 1.0])))
+        a = util.dense_packed(rank, off, codes)
+        b = util.dense_packed_native(rank, off, codes, n_threads=int(rng.integers(1, 4)))
+        assert np.array_equal(a.blob, b.blob), trial
+        r2, o2, c2 = _decode_dense(a)
+        assert np.array_equal(r2, rank) and np.array_equal(o2, off) and np.array_equal(c2, codes), trial
