@@ -242,32 +242,39 @@ __device__ __forceinline__ int bs_build_group(const uint8_t *__restrict__ codes,
 #pragma unroll
     for (int w = 0; w <= KW; ++w) wd[w] = w < nw ? __ldg(cw + w) : 0u;
     const unsigned sh = 8u * mis;
-    uint32_t x[KW];
+    const int kb8 = 8 * kb;
+    // Four sites per 32-bit operation: g12[w] = the 3-bit flags (v | b0<<1 | b1<<2, 0 for N/-/_ and past the
+    // read's end) of sites 4w..4w+3.  Words the group's widest read does not reach are skipped (warp-uniform).
+    uint32_t g12[KW];
     rare_or = 0;
+    x0 = 0xffffffffu;
 #pragma unroll
     for (int w = 0; w < KW; ++w) {
-        uint32_t xx = __funnelshift_r(wd[w], wd[w + 1], sh);
-        const int nv = kb - 4 * w;                                // valid bytes in this word
-        const uint32_t vmask = nv >= 4 ? 0xffffffffu : (nv <= 0 ? 0u : ((1u << (8 * nv)) - 1u));
-        rare_or |= xx & 0xfcfcfcfcu & vmask;
-        x[w] = xx | ~vmask;                                       // bytes past the read's end -> 0xff
+        g12[w] = 0;
+        if (w == 0 || 4 * w < kg) {
+            const uint32_t xx = __funnelshift_r(wd[w], wd[w + 1], sh);
+            const int c8 = min(max(kb8 - 32 * w, 0), 32);         // valid bits of this word
+            uint32_t inval;                                       // bytes past the read's end
+            asm("shl.b32 %0, %1, %2;" : "=r"(inval) : "r"(0xffffffffu), "r"(c8));   // shl clamps: c8 = 32 -> 0
+            rare_or |= xx & 0xfcfcfcfcu & ~inval;
+            const uint32_t x = xx | inval;                        // -> 0xff
+            if (w == 0) x0 = x;
+            const uint32_t u = (x >> 2) & 0x3f3f3f3fu;            // any of bits 2..7 set => not A/C/G/T
+            const uint32_t v = (((u + 0x3f3f3f3fu) & 0x40404040u) >> 6) ^ 0x01010101u;   // 1 per valid byte
+            const uint32_t f = ((x & 0x03030303u) * 2u + 0x01010101u) & (v * 7u);        // 2a+1 or 0 per byte
+            g12[w] = (f & 7u) | ((f >> 5) & 0x38u) | ((f >> 10) & 0x1c0u) | ((f >> 15) & 0xe00u);
+        }
     }
-    x0 = x[0];
     // which (site, flag) this lane will hold after a transpose: flag index = lane
     const int my_tl = lane / 3, my_plane = lane - 3 * my_tl;
 #pragma unroll
     for (int t0 = 0; t0 < 4 * KW; t0 += 10) {
         if (t0 >= kg) break;                                      // warp-uniform
-        uint32_t row = 0;                                         // flags of my read for sites t0..t0+9
-#pragma unroll
-        for (int tl = 0; tl < 10; ++tl) {
-            const int t = t0 + tl;
-            if (t < 4 * KW) {
-                const uint32_t a = (x[t >> 2] >> (8 * (t & 3))) & 0xffu;
-                const uint32_t f = a < 4u ? 2u * a + 1u : 0u;      // v | b0<<1 | b1<<2
-                row |= f << (3 * tl);
-            }
-        }
+        // flags of my read for sites t0..t0+9: 20 sites are five 12-bit groups
+        const int c = t0 / 10, wb = 5 * (c >> 1);
+        auto G = [&](int i) -> uint32_t { return i < KW ? g12[i] : 0u; };
+        uint32_t row = (c & 1) ? ((G(wb + 2) >> 6) | (G(wb + 3) << 6) | (G(wb + 4) << 18))
+                               : (G(wb) | (G(wb + 1) << 12) | ((G(wb + 2) & 0x3fu) << 24));
         // 32x32 bit transpose across the warp: afterwards bit r of `row` = flag `lane` of read r
 #pragma unroll
         for (int j = 16; j >= 1; j >>= 1) {
