@@ -275,13 +275,18 @@ __device__ __forceinline__ int bs_build_group(const uint8_t *__restrict__ codes,
         auto G = [&](int i) -> uint32_t { return i < KW ? g12[i] : 0u; };
         uint32_t row = (c & 1) ? ((G(wb + 2) >> 6) | (G(wb + 3) << 6) | (G(wb + 4) << 18))
                                : (G(wb) | (G(wb + 1) << 12) | ((G(wb + 2) & 0x3fu) << 24));
-        // 32x32 bit transpose across the warp: afterwards bit r of `row` = flag `lane` of read r
+        // 32x32 bit transpose across the warp: afterwards bit r of `row` = flag `lane` of read r.  A stage keeps
+        // half of the own word and takes the other half from the partner, shifted by j; as a rotation (the
+        // wrapped bits fall outside the mask) that is shuffle + funnel shift + one bit-select.
 #pragma unroll
         for (int j = 16; j >= 1; j >>= 1) {
             const uint32_t m = j == 16 ? 0x0000ffffu : j == 8 ? 0x00ff00ffu : j == 4 ? 0x0f0f0f0fu
                              : j == 2 ? 0x33333333u : 0x55555555u;
+            const bool up = (lane & j) != 0;
+            const uint32_t take = up ? m : ~m;                    // bits that come from the partner
             const uint32_t y = __shfl_xor_sync(0xffffffffu, row, j);
-            row = (lane & j) ? ((row & ~m) | ((y & ~m) >> j)) : ((row & m) | ((y & m) << j));
+            const uint32_t yr = __funnelshift_l(y, y, up ? 32 - j : j);
+            row = (row & ~take) | (yr & take);
         }
         const int t = t0 + my_tl;
         if (lane < 30 && t < kg)
