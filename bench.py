@@ -444,6 +444,13 @@ def run_ours(args):
                "sample": "%d consecutive reads (%d observations) from the middle of rank 0's shard, %d forked "
                          "workers, oracle/py_baseline.py (per-pair Python calls as gretel/util.py:242-286)" % (
                              sample_reads, c_cr, cores)}
+        try:                                   # the same loop in one process, on 1/cores of the sample
+            one = max(2000, sample_reads // cores)
+            s1, o1 = d["rank"][lo:lo + one], d["off"][lo:lo + one + 1]
+            c1, t1 = pb.timed_ingest(s1, o1 - o1[0], d["codes"][o1[0]:o1[-1]], N, W, n_procs=1)
+            cpu["one_core"] = {"value": c1 / t1, "unit": UNIT, "cores": 1, "sample": "%d reads" % one}
+        except Exception as e:                 # never let the secondary figure break the bench line
+            cpu["one_core"] = {"error": str(e)}
 
     # ---- secondary metric: haplotype recovery seconds on this matrix (rank 0, one GPU)
     recovery = None
