@@ -355,6 +355,32 @@ def run_ours(args):
         total_ms = float(tt.item())
     value = n_obs_global * args.steps / (total_ms * 1e-3)
 
+    # ---- parity probe: one more complete step (ingestion + exchange), then an independent recount of what
+    # every band row must hold (hx_probe_expected_rows, summed over ranks) against the row sums of the
+    # counters the step left behind, and the grand total against n_crumbs + sentinel increments.
+    step()
+    barrier()
+    rows_exp = torch.zeros(N + 2, dtype=torch.int64, device=dev)
+    rows_got = torch.zeros(N + 2, dtype=torch.int64, device=dev)
+    torch.cuda.synchronize()
+    h.probe_expected_rows(t_rank.data_ptr(), t_off.data_ptr(), t_codes.data_ptr(), R, rows_exp.data_ptr())
+    h.counts_row_sums(rows_got.data_ptr())
+    h.sync()
+    if world > 1:
+        dist.all_reduce(rows_exp, op=dist.ReduceOp.SUM)
+    pt = h.ingest_totals()
+    holder = rank == 0 or args.exchange != "reduce"          # "reduce" leaves the sums on rank 0 only
+    rows_ok = bool(torch.equal(rows_exp, rows_got)) if holder else True
+    sum_ok = int(rows_got.sum().item()) == int(pt[1]) + int(pt[3]) if holder else True
+    pok = torch.tensor([int(rows_ok and sum_ok)], device=dev)
+    if world > 1:
+        dist.all_reduce(pok, op=dist.ReduceOp.MIN)
+    parity_probe = {"ok": bool(pok.item()), "rows_equal": rows_ok, "sum_equals_crumbs_plus_sentinels": sum_ok,
+                    "rows": N + 2, "band_sum": int(rows_got.sum().item()), "n_crumbs": int(pt[1]),
+                    "sentinel_increments": int(pt[3]), "ranks_checked": world if args.exchange != "reduce" else 1,
+                    "how": "hx_probe_expected_rows (one thread per read, independent of the ingestion kernels) "
+                           "summed over ranks vs hx_counts_row_sums of the exchanged counts"}
+
     if fused is not None:
         fused.close()
 
@@ -488,7 +514,7 @@ def run_ours(args):
                     "api": "Hansel.init_matrix + ingest_packed%s(pinned host arrays) [+ all-reduce] + finalize + "
                            "totals, a new matrix every step" % {"compact": "_compact", "wide": "",
                                                                  "dense": "_dense x%d chunks" % max(len(dense_chunks), 1)}[args.e2e_format]},
-            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+            "gpu_launches": int(launches), "parity_probe": parity_probe, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
             "observations_per_step": int(n_obs_global), "wall_s_timed_region": wall_s,
             "recovery": recovery, "synth_seconds": gen_s, "band_w": W, "allreduce_segments": args.segments if world > 1 else 0, "exchange": args.exchange if world > 1 else None,
             "ingest_kernel": args.kernel}

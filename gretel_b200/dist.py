@@ -111,13 +111,16 @@ class PipelinedIngest:
         self.cuts = [(n_reads * s) // S for s in range(S + 1)]
         cell = hansel.band_w * 49
         # last finished row after each segment; must agree on every rank -> take the minimum
-        rows = [min(int(rank_host[self.cuts[s + 1]]) + 1, hansel.n_snps + 1) for s in range(S - 1)]
+        # (rank-0 reads also add the start sentinel into row 1, util.py:262-266: while the cut still lies
+        # inside them nothing is final yet)
+        rows = [min(int(rank_host[self.cuts[s + 1]]) + 1, hansel.n_snps + 1) if int(rank_host[self.cuts[s + 1]]) > 0
+                else -1 for s in range(S - 1)]
         dev = torch.device("cuda", hansel.device)
         if dist.is_initialized() and dist.get_world_size(group) > 1 and rows:
             t = torch.tensor(rows, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
             rows = [int(x) for x in t.tolist()]
-        rows = [max(r, 0) for r in rows] + [hansel.n_snps + 1]
+        rows = [max(r, -1) for r in rows] + [hansel.n_snps + 1]
         for i in range(1, len(rows)):
             rows[i] = max(rows[i], rows[i - 1])
         self.row_hi = rows

@@ -206,6 +206,16 @@ class Hansel:
         _lib.check(self._lib.hx_reset_counts(self._h))
         self._touch()
 
+    def probe_expected_rows(self, d_rank_ptr, d_off_ptr, d_codes_ptr, n_reads, d_rows_ptr):
+        """Parity probe: add what device-resident reads must leave in every band row into uint64[N+2] at
+        ``d_rows_ptr`` (an independent recount of gretel/util.py:254-281; asynchronous on the stream)."""
+        _lib.check(self._lib.hx_probe_expected_rows(self._h, d_rank_ptr, d_off_ptr, d_codes_ptr, int(n_reads),
+                                                    d_rows_ptr))
+
+    def counts_row_sums(self, d_rows_ptr):
+        """Parity probe: row sums of the pending integer counts into uint64[N+2] at ``d_rows_ptr``."""
+        _lib.check(self._lib.hx_counts_row_sums(self._h, d_rows_ptr))
+
     def counts_ipc_export(self, world):
         """Fused exchange, step 1: make the pending counts IPC-shareable; returns the 64-byte handle."""
         buf = C.create_string_buffer(64)

@@ -195,6 +195,15 @@ int hx_count_coverage(const char *bam_path, const char *contig, int32_t start0, 
                       uint32_t *out);
 int hx_bam_contig_length(const char *bam_path, const char *contig, int32_t *length);
 
+/* ---- parity probe (bench.py parity_probe, multi-GPU tests) ------------------------ */
+/* An independent recount of gretel/util.py:254-281: adds into d_rows[N+2] (device, uint64) the number of
+ * increments (observations + sentinel increments) the reads must leave in every band row pj.  Accumulates, so
+ * several shards (or ranks, after an integer all-reduce of d_rows) can be summed. */
+int hx_probe_expected_rows(hx_matrix *h, const int32_t *d_rank, const int64_t *d_off, const uint8_t *d_codes,
+                           int64_t n_reads, uint64_t *d_rows);
+/* Row sums of the pending integer counts (after any cross-GPU exchange): d_rows[N+2] (device, uint64). */
+int hx_counts_row_sums(hx_matrix *h, uint64_t *d_rows);
+
 /* ---- bulk matrix I/O (tests, --dumpmatrix gretel/cmd.py:81-82) ------------------- */
 int hx_band_to_host(hx_matrix *h, float *out /* (N+2)*W*49 */);
 int hx_band_from_host(hx_matrix *h, const float *in);

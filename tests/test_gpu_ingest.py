@@ -379,13 +379,25 @@ def test_adversarial_shapes(c_oracle):
             assert np.array_equal(band, ref.astype(np.float32)), (N, kernel)
 
 
+_CONFIG3 = {}
+
+
+def _config3(c_oracle):
+    """BASELINE.json configs[2] at full size, generated and ingested by the C oracle once per session."""
+    if not _CONFIG3:
+        d = synth.generate(synth.WORKLOADS["metagenome"])
+        N, W = d["n_snps"], d["max_k"] - 1
+        ref, rt = c_oracle.ingest(d["rank"], d["off"], d["codes"], N, W)
+        _CONFIG3.update(d=d, N=N, W=W, ref=ref, rt=rt)
+    return _CONFIG3
+
+
 def test_full_size_config3_bit_exact(c_oracle):
     """BASELINE.json configs[2] at FULL size (10M x 150 bp reads, 10k SNPs, 1.1 G observations): the GPU band
     equals the C oracle's bit for bit, and so do the totals (n_slices, n_crumbs, covered SNPs, sentinels)."""
-    d = synth.generate(synth.WORKLOADS["metagenome"])
-    N, W = d["n_snps"], d["max_k"] - 1
+    c3 = _config3(c_oracle)
+    d, N, W, ref, rt = c3["d"], c3["N"], c3["W"], c3["ref"], c3["rt"]
     band, totals = _gpu_band(d["rank"], d["off"], d["codes"], N, W, 0)
-    ref, rt = c_oracle.ingest(d["rank"], d["off"], d["codes"], N, W)
     assert totals == tuple(int(x) for x in rt)
     assert totals[1] > 1_000_000_000
     assert np.array_equal(band, ref.astype(np.float32))
@@ -411,13 +423,80 @@ def test_full_size_config3_bit_exact(c_oracle):
     assert np.array_equal(h.band(), cur)
 
 
-def test_config4_60pct_size_bit_exact(c_oracle):
-    """BASELINE.json configs[3] shape (ONT-like, ~300 SNPs/read) at 62% of its size: 2.9 G observations
-    through the cp.async-staged tile kernel, bit for bit against the C oracle."""
-    d = synth.generate(synth.scaled(synth.WORKLOADS["ont"], 62_000))
+@pytest.mark.parametrize("L", range(1, 9))
+def test_config5_recovery_sweep_parity(c_oracle, L):
+    """BASELINE.json configs[4]: the 10k-SNP matrix of configs[2] at full size, up to 50 ranked haplotypes at
+    lookback L (the sweep bench.py times), through the resident driver loop hx_recover (gretel/cmd.py:148-161):
+    every haplotype identical to the C oracle's, every scalar within 1e-6 relative, the reweighted matrix equal."""
+    from gretel_b200 import util
+    from gretel_b200.hansel import Hansel, REF_SYMBOLS, REF_UNSYMBOLS
+    c3 = _config3(c_oracle)
+    N, W, ref, rt = c3["N"], c3["W"], c3["ref"], c3["rt"]
+    h = Hansel.init_matrix(REF_SYMBOLS, REF_UNSYMBOLS, N, band_w=W)
+    h.load_band(ref.astype(np.float32))
+    util.set_totals(h, int(rt[0]), int(rt[1]), int(rt[2]))
+    orig = h.copy()
+    h.L = L
+    paths, stats = h.recover_codes(orig, 50, 0.01)
+    cur = ref.astype(np.float32)
+    cur0 = cur.copy()
+    n = 0
+    for it in range(50):
+        pc, res = c_oracle.generate_path(cur, cur0, N, W, L)
+        if pc is None:
+            break
+        ratio = max(res[2], 0.01)
+        removed = c_oracle.reweight_path(cur, N, W, pc, ratio)
+        assert it < len(paths), "the GPU loop stopped early at haplotype %d" % it
+        assert np.array_equal(paths[it], pc), "L=%d haplotype %d differs from the oracle" % (L, it)
+        for got, exp in zip(stats[it], (res[0], res[1], res[2], ratio, removed)):
+            assert got == pytest.approx(exp, rel=1e-6)
+        n += 1
+    assert len(paths) == n and n >= 10
+    assert np.array_equal(h.band(), cur)
+    h.close()
+    orig.close()
+
+
+def test_config4_full_size_bit_exact(c_oracle):
+    """BASELINE.json configs[3] at FULL size (100k ONT-like reads, ~300 SNPs/read, 4.7 G observations) through the
+    cp.async-staged tile kernel, bit for bit against the C oracle."""
+    d = synth.generate(synth.WORKLOADS["ont"])
     N, W = d["n_snps"], d["max_k"] - 1
     assert len(d["rank"]) >= 6 * N                      # dense enough for the staged tiles
     band, totals = _gpu_band(d["rank"], d["off"], d["codes"], N, W, 0)
     ref, rt = c_oracle.ingest(d["rank"], d["off"], d["codes"], N, W)
     assert totals == tuple(int(x) for x in rt)
+    assert totals[1] > 4_000_000_000
     assert np.array_equal(band, ref.astype(np.float32))
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_parity_probe_counts_what_the_oracle_counts(c_oracle, seed):
+    """hx_probe_expected_rows (the independent per-row recount bench.py's parity_probe relies on) equals the row
+    sums of the C oracle's band, and hx_counts_row_sums equals the row sums of what the GPU ingested."""
+    import torch
+    from gretel_b200.hansel import Hansel, REF_SYMBOLS, REF_UNSYMBOLS
+    rng = np.random.default_rng(800 + seed)
+    N = int(rng.integers(3, 300))
+    rank, off, codes = synth.random_packed(rng, N, int(rng.integers(10, 4000)), int(rng.integers(2, 30)),
+                                           p_special=0.2)
+    W = max(1, int(np.diff(off).max()) - 1)
+    ref, rt = c_oracle.ingest(rank, off, codes, N, W)
+    dev = torch.device("cuda", 0)
+    t_rank, t_off, t_codes = (torch.from_numpy(np.ascontiguousarray(x)).to(dev) for x in (rank, off, codes))
+    if t_codes.numel() == 0:
+        t_codes = torch.zeros(16, dtype=torch.uint8, device=dev)
+    rows_exp = torch.zeros(N + 2, dtype=torch.int64, device=dev)
+    rows_got = torch.zeros(N + 2, dtype=torch.int64, device=dev)
+    torch.cuda.synchronize()
+    h = Hansel.init_matrix(REF_SYMBOLS, REF_UNSYMBOLS, N, band_w=W)
+    h.ingest_device(t_rank.data_ptr(), t_off.data_ptr(), t_codes.data_ptr(), len(rank))
+    h.probe_expected_rows(t_rank.data_ptr(), t_off.data_ptr(), t_codes.data_ptr(), len(rank), rows_exp.data_ptr())
+    h.counts_row_sums(rows_got.data_ptr())
+    h.sync()
+    want = ref.reshape(N + 2, -1).sum(axis=1).astype(np.int64)
+    assert np.array_equal(rows_exp.cpu().numpy(), want)
+    assert np.array_equal(rows_got.cpu().numpy(), want)
+    assert int(want.sum()) == int(rt[1]) + int(rt[3])
+    h.close()

@@ -28,9 +28,21 @@ def _worker(rank, world, port, segments, out):
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
-        w = synth.scaled(synth.WORKLOADS["metagenome"], 150_000)
-        d = synth.generate(w)
-        N, W = w.n_snps, d["max_k"] - 1
+        if segments == 40:
+            # a short gene window: most reads start before start_pos and are clamped to rank 0, so the segment
+            # cuts of the pipelined all-reduce fall inside the rank-0 reads (row 1 holds their start sentinels)
+            rng = np.random.default_rng(3)
+            N = 60
+            k = rng.integers(2, 21, size=90_000)
+            rk = np.sort(np.where(rng.random(len(k)) < 0.7, 0, rng.integers(0, N - 20, size=len(k)))).astype(np.int32)
+            off = np.concatenate([[0], np.cumsum(k)]).astype(np.int64)
+            d = {"rank": rk, "off": off, "codes": rng.integers(0, 6, size=int(off[-1])).astype(np.uint8), "max_k": 20}
+            segments = 4
+        else:
+            w = synth.scaled(synth.WORKLOADS["metagenome"], 150_000)
+            d = synth.generate(w)
+            N = w.n_snps
+        W = d["max_k"] - 1
         b = gdist.shard_bounds(d["off"], world)
         lo, hi = int(b[rank]), int(b[rank + 1])
         h = Hansel.init_matrix(REF_SYMBOLS, REF_UNSYMBOLS, N, band_w=W, device=rank)
@@ -72,7 +84,7 @@ def _worker(rank, world, port, segments, out):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("segments", [1, 4, -1, -2])
+@pytest.mark.parametrize("segments", [1, 4, 40, -1, -2])
 def test_two_gpu_sharded_ingest(tmp_path, c_oracle, segments):
     import torch
     import torch.multiprocessing as mp
