@@ -352,7 +352,7 @@ int hx_ensure_counts_buffer(hx_matrix *h) {
 extern "C" {
 
 int hx_set_ingest_kernel(hx_matrix *h, int which) {
-    HX_CHECK_ARG(h && which >= 0 && which <= 5);
+    HX_CHECK_ARG(h && which >= 0 && which <= 6);
     h->ingest_kernel = which;
     return HX_OK;
 }

@@ -142,6 +142,10 @@ int hx_launch_ingest(hx_matrix *h, const int32_t *d_rank, const int64_t *d_off,
                      const uint8_t *d_codes, int64_t n_reads);
 int hx_launch_ingest_presorted(hx_matrix *h, const int32_t *d_rank, const int64_t *d_off,
                                const uint8_t *d_codes, int64_t n_reads, int64_t *run_end, const int *ok);
+// ingest_umma.cu
+bool hx_umma_possible(const hx_matrix *h);
+int hx_launch_ingest_umma(hx_matrix *h, const int32_t *d_rank, const int64_t *d_off, const uint8_t *d_codes,
+                          int64_t n_reads, const int64_t *run_end, const int *sorted_flag);
 // api.cu
 HxCnt hx_cnt_ref(const hx_matrix *h);
 int hx_ensure_counts_buffer(hx_matrix *h);

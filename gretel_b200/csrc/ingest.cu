@@ -19,39 +19,12 @@
 //                  REDs once no later read of the CTA can touch it.  Rare alleles
 //                  (N, -, _), sentinels and totals are handled per read on the side.
 #include "hx_internal.cuh"
+#include "ingest_common.cuh"
 
 namespace {
 
 constexpr int BS_KMAX = 52;      // widest read (in SNPs) the bit-sliced kernel takes
 constexpr int BS_GB = 32;        // most groups (of 32 reads) per build/accumulate batch
-
-__device__ __forceinline__ unsigned long long warp_sum_ull(unsigned long long v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-
-// Block-level accumulation of the four ingestion totals into global memory.
-__device__ __forceinline__ void flush_totals(unsigned long long t0, unsigned long long t1,
-                                             unsigned long long t2, unsigned long long t3,
-                                             unsigned long long *totals) {
-    __shared__ unsigned long long sh[4];
-    if (threadIdx.x < 4) sh[threadIdx.x] = 0;
-    __syncthreads();
-    t0 = warp_sum_ull(t0); t1 = warp_sum_ull(t1); t2 = warp_sum_ull(t2); t3 = warp_sum_ull(t3);
-    if ((threadIdx.x & 31) == 0) {
-        if (t0) atomicAdd(&sh[0], t0);
-        if (t1) atomicAdd(&sh[1], t1);
-        if (t2) atomicAdd(&sh[2], t2);
-        if (t3) atomicAdd(&sh[3], t3);
-    }
-    __syncthreads();
-    if (threadIdx.x < 4 && sh[threadIdx.x]) atomicAdd(&totals[threadIdx.x], sh[threadIdx.x]);
-}
-
-__device__ __forceinline__ bool sym_valid_from(unsigned a) {   // util.py:258
-    return a != HX_SYM_N && a != HX_SYM_GAP && a <= 6;
-}
 
 // The per-pair rules of util.py:254-281 for one (i,j) of one read (sentinels included).
 __device__ __forceinline__ void add_pair(const HxCnt cnt, int N, int64_t W, int rk, int i,
@@ -128,10 +101,11 @@ k1_pairs_red(const int32_t *__restrict__ rank, const int64_t *__restrict__ off,
 // Pre-pass over the rank array: clears *flag when the reads are not rank-sorted and records
 // where the run of reads of each rank ends (exclusive), so the main kernel never searches.
 __global__ void k_prepass(const int32_t *__restrict__ rank, int64_t n_reads, int N, int *__restrict__ flag,
-                          int64_t *__restrict__ run_end) {
+                          int64_t *__restrict__ run_end, int *__restrict__ err) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_reads) return;
     const int r = rank[i];
+    if (r < 0 || r > N) atomicOr(err, 1);            // the tensor-core kernel walks run_end and never sees this read
     if (i + 1 < n_reads) {
         const int r2 = rank[i + 1];
         if (r > r2) *flag = 0;
@@ -184,43 +158,6 @@ __device__ __forceinline__ unsigned long long bs_flush_rows(uint32_t *tile32, in
         if (++row == rows) row = 0;
     }
     return sum;
-}
-
-// A read that holds N, - or _ : the pairs with such an allele on either side are not in the
-// bit-planes; the whole warp adds them with REDs (lanes over the read's positions).
-__device__ __forceinline__ void bs_rare_read(const uint8_t *__restrict__ c, int kb, int r, int64_t W,
-                                             const HxCnt cnt, unsigned &crumbs, unsigned &notcov,
-                                             unsigned &errbits) {
-    const int lane = threadIdx.x & 31;
-    const unsigned a_lo = lane < kb ? c[lane] : 0xffu;
-    const unsigned a_hi = lane + 32 < kb ? c[lane + 32] : 0xffu;
-    const unsigned m_lo = __ballot_sync(0xffffffffu, a_lo >= 4 && a_lo != 0xffu);
-    const unsigned m_hi = __ballot_sync(0xffffffffu, a_hi >= 4 && a_hi != 0xffu);
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
-        unsigned m = half ? m_hi : m_lo;
-        while (m) {
-            const int src = __ffs(m) - 1;
-            m &= m - 1;
-            const unsigned ai = __shfl_sync(0xffffffffu, half ? a_hi : a_lo, src);
-            const int i = src + 32 * half;
-            if (ai > 6) { errbits |= 2; continue; }
-            if (lane == 0 && (ai == HX_SYM_N || ai == HX_SYM_GAP)) notcov++;
-#pragma unroll
-            for (int h2 = 0; h2 < 2; ++h2) {
-                const int j = lane + 32 * h2;
-                const unsigned aj = h2 ? a_hi : a_lo;
-                if (j >= kb || aj > 6) continue;
-                if (j > i && ai == HX_SYM_DEL) {                 // '-' is a valid first allele
-                    atomicAdd(cnt.cell(W, r + i + 1, r + j + 1) + ai * HX_NSYM + aj, 1u);
-                    crumbs++;
-                } else if (j < i && aj < 4) {                    // common first allele, rare second
-                    atomicAdd(cnt.cell(W, r + j + 1, r + i + 1) + aj * HX_NSYM + ai, 1u);
-                    crumbs++;
-                }
-            }
-        }
-    }
 }
 
 // Transposes one group of 32 reads (lane = read, kb SNPs each, codes at codes+o) into bit-planes in
@@ -319,14 +256,6 @@ __device__ __forceinline__ void bs_accumulate(uint32_t (&acc)[16], uint32_t buf_
                 for (int b = 0; b < 4; ++b) acc[a * 4 + b] += __popc(x1[a] & x2[b]);
         }
     }
-}
-
-// L2 prefetch of the inputs of the batch after the one being transposed (TMA prefetch, no destination):
-// the packed reads are streamed from HBM exactly once, so without it every group build pays two
-// dependent HBM misses (offsets, then codes).
-__device__ __forceinline__ void bs_prefetch_l2(const void *p, uint32_t bytes) {
-    const uintptr_t a = reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)15;
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"((bytes + 31u) & ~15u) : "memory");
 }
 
 // One batch of up to `gb` groups (32 reads each) out of a run of reads that share rank r.
@@ -554,28 +483,6 @@ k1_bitsliced(const int32_t *__restrict__ rank, const int64_t *__restrict__ off,
 // at a CTA-wide barrier.  The pair warps keep the sliding tile and synchronise among themselves
 // with a named barrier at run boundaries.
 constexpr int WS_NBUF = 3;
-
-__device__ __forceinline__ uint32_t ws_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void ws_mbar_init(uint32_t bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void ws_mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void ws_mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "WS_WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra WS_DONE_%=;\n\t"
-        "bra WS_WAIT_%=;\n\t"
-        "WS_DONE_%=:\n\t}" ::"r"(bar),
-        "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ void ws_pair_barrier(int nthreads) {
-    asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
-}
 
 struct WsLayout {
     int kmax, gb;
@@ -859,8 +766,10 @@ static int launch_ingest(hx_matrix *h, const int32_t *d_rank, const int64_t *d_o
     // crumbs in a read are all distinct cells, so W+1 bounds the SNPs per read
     const int kmax = h->W + 1;
     const bool bs_possible = kmax >= 2 && kmax <= BS_KMAX;
-    const bool use_bs = (h->ingest_kernel == 2 || h->ingest_kernel == 4 || h->ingest_kernel == 5)
+    const bool use_bs = (h->ingest_kernel == 2 || h->ingest_kernel == 4 || h->ingest_kernel == 5 || h->ingest_kernel == 6)
                             ? bs_possible : (h->ingest_kernel == 0 && bs_possible);
+    // tensor-core kernel (ingest_umma.cu): default for rank-sorted reads of at most 32 SNPs
+    const bool use_umma = use_bs && hx_umma_possible(h) && (h->ingest_kernel == 0 || h->ingest_kernel == 6);
     const bool fused = h->peer_world > 1;
     const bool use_long = !use_bs && (h->ingest_kernel == 3 || (h->ingest_kernel == 0 && kmax >= 2));
 
@@ -869,7 +778,7 @@ static int launch_ingest(hx_matrix *h, const int32_t *d_rank, const int64_t *d_o
         if (!presorted) {
             HX_CUDA(hx_fill_async(h->d_flags + 4, 1, sizeof(int), h->stream));     // non-zero = sorted
             k_prepass<<<(unsigned)((n_reads + 255) / 256), 256, 0, h->stream>>>(d_rank, n_reads, h->N, h->d_flags + 4,
-                                                                                run_end);
+                                                                                run_end, h->d_err);
             h->launches++;
         }
         int rc = hx_launch_ingest_long(h, d_rank, d_off, d_codes, n_reads, sorted_flag);
@@ -886,11 +795,16 @@ static int launch_ingest(hx_matrix *h, const int32_t *d_rank, const int64_t *d_o
     } else {
         if (!presorted) {
             HX_CUDA(hx_fill_async(h->d_flags + 4, 1, sizeof(int), h->stream));     // non-zero = sorted
+            if (use_umma) HX_CUDA(hx_fill_async(run_end, 0xff, sizeof(int64_t) * ((size_t)h->N + 2), h->stream));   // -1 = no reads
             k_prepass<<<(unsigned)((n_reads + 255) / 256), 256, 0, h->stream>>>(d_rank, n_reads, h->N, h->d_flags + 4,
-                                                                                run_end);
+                                                                                run_end, h->d_err);
             h->launches += 2;
         }
         const int npairs = kmax * (kmax - 1) / 2;
+        if (use_umma) {
+            int rc = hx_launch_ingest_umma(h, d_rank, d_off, d_codes, n_reads, run_end, sorted_flag);
+            if (rc) return rc;
+        } else
         // measured (B200): the warp-specialised variant wins for wide reads (config 2: 0.097 vs 0.118 ms),
         // the barrier-phased one for narrow reads (config 3: 0.725 vs 0.751 ms)
         if (h->ingest_kernel == 5 || (h->ingest_kernel != 4 && kmax > 32)) {

@@ -359,6 +359,8 @@ extern "C" int hx_ingest_host_dense(hx_matrix *h, const uint8_t *rank_delta, con
         int *ok = reinterpret_cast<int *>(w.partials + 2 * nblk);          // behind the block partials
         const int64_t *d_ei = reinterpret_cast<const int64_t *>(raw + o_ei);
         const int32_t *d_ed = reinterpret_cast<const int32_t *>(raw + o_ed);
+        HX_CUDA(hx_fill_async(w.run_end, 0xff, sizeof(int64_t) * ((size_t)h->N + 2), ds));   // -1 = rank without reads
+        h->launches++;
         if (klen_bytes == 1) {
             k_dense_partials<1><<<(unsigned)nblk, 256, 0, ds>>>(raw + o_rd, raw + o_kl, n_reads, d_ei, d_ed, n_esc, w.partials);
             k_dense_spine<<<1, 1024, 0, ds>>>(w.partials, nblk, n_codes, ok, h->d_err);

@@ -95,7 +95,9 @@ int hx_ingest_device(hx_matrix *h, const int32_t *d_rank, const int64_t *d_off,
 /* Select the ingestion kernel: 0 = auto, 1 = per-pair global reductions (generic),
  * 2 = bit-sliced shared-memory tiles (rank-sorted reads of <= 52 SNPs),
  * 3 = bit-plane transpose + owner-computes tiles (rank-sorted long reads),
- * 4 / 5 = force the barrier-phased / the warp-specialised variant of kernel 2 (2 picks by read width). */
+ * 4 / 5 = force the barrier-phased / the warp-specialised variant of kernel 2 (2 picks by read width),
+ * 6 = tensor-core kernel (int8 tcgen05.mma over one-hot allele rows; rank-sorted reads of <= 32 SNPs; what
+ * auto picks for such reads). */
 int hx_set_ingest_kernel(hx_matrix *h, int which);
 int hx_ingest_totals(hx_matrix *h, int64_t totals[4]);               /* synchronises */
 /* Partial-matrix exchange across GPUs (the reference's fork-shared matrix,
