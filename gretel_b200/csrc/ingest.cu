@@ -769,7 +769,10 @@ static int launch_ingest(hx_matrix *h, const int32_t *d_rank, const int64_t *d_o
     const bool use_bs = (h->ingest_kernel == 2 || h->ingest_kernel == 4 || h->ingest_kernel == 5 || h->ingest_kernel == 6)
                             ? bs_possible : (h->ingest_kernel == 0 && bs_possible);
     // tensor-core kernel (ingest_umma.cu): default for rank-sorted reads of at most 32 SNPs
-    const bool use_umma = use_bs && hx_umma_possible(h) && (h->ingest_kernel == 0 || h->ingest_kernel == 6);
+    // (auto: when a rank's run of reads is deep enough to fill MMAs - measured: 1000 reads per rank 0.42 vs 0.63 ms,
+    // 20 reads per rank 0.25 vs 0.19 ms against the bit-sliced kernel)
+    const bool use_umma = use_bs && hx_umma_possible(h) &&
+                          (h->ingest_kernel == 6 || (h->ingest_kernel == 0 && n_reads >= 64 * ((int64_t)h->N + 1)));
     const bool fused = h->peer_world > 1;
     const bool use_long = !use_bs && (h->ingest_kernel == 3 || (h->ingest_kernel == 0 && kmax >= 2));
 

@@ -36,16 +36,17 @@ __device__ __forceinline__ bool sym_valid_from(unsigned a) {   // util.py:258
 
 // A read that holds N, - or _ : the pairs with such an allele on either side are not in the
 // bit-planes; the whole warp adds them with REDs (lanes over the read's positions).
+template <bool HI = true>   // HI = false: reads of at most 32 SNPs (one allele per lane)
 __device__ __forceinline__ void bs_rare_read(const uint8_t *__restrict__ c, int kb, int r, int64_t W,
                                              const HxCnt cnt, unsigned &crumbs, unsigned &notcov,
                                              unsigned &errbits) {
     const int lane = threadIdx.x & 31;
     const unsigned a_lo = lane < kb ? c[lane] : 0xffu;
-    const unsigned a_hi = lane + 32 < kb ? c[lane + 32] : 0xffu;
+    const unsigned a_hi = HI && lane + 32 < kb ? c[lane + 32] : 0xffu;
     const unsigned m_lo = __ballot_sync(0xffffffffu, a_lo >= 4 && a_lo != 0xffu);
-    const unsigned m_hi = __ballot_sync(0xffffffffu, a_hi >= 4 && a_hi != 0xffu);
+    const unsigned m_hi = HI ? __ballot_sync(0xffffffffu, a_hi >= 4 && a_hi != 0xffu) : 0u;
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
+    for (int half = 0; half < (HI ? 2 : 1); ++half) {
         unsigned m = half ? m_hi : m_lo;
         while (m) {
             const int src = __ffs(m) - 1;
@@ -55,7 +56,7 @@ __device__ __forceinline__ void bs_rare_read(const uint8_t *__restrict__ c, int 
             if (ai > 6) { errbits |= 2; continue; }
             if (lane == 0 && (ai == HX_SYM_N || ai == HX_SYM_GAP)) notcov++;
 #pragma unroll
-            for (int h2 = 0; h2 < 2; ++h2) {
+            for (int h2 = 0; h2 < (HI ? 2 : 1); ++h2) {
                 const int j = lane + 32 * h2;
                 const unsigned aj = h2 ? a_hi : a_lo;
                 if (j >= kb || aj > 6) continue;
@@ -98,6 +99,21 @@ __device__ __forceinline__ void ws_mbar_wait(uint32_t bar, uint32_t parity) {
         "WS_DONE_%=:\n\t}" ::"r"(bar),
         "r"(parity)
         : "memory");
+}
+// the same with a back-off between polls: for waits that normally last microseconds (many warps waiting)
+__device__ __forceinline__ void ws_mbar_wait_sleep(uint32_t bar, uint32_t parity) {
+    for (;;) {
+        uint32_t done;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (done) break;
+        __nanosleep(200);
+    }
 }
 __device__ __forceinline__ void ws_pair_barrier(int nthreads) {
     asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");

@@ -24,20 +24,29 @@
 
 namespace {
 
-constexpr int UM_NSTAGE = 4;                 // X tiles in flight
-constexpr int UM_XBYTES = 32768;             // bytes per X tile
-constexpr int UM_EXP_WARPS = 16;             // expander warps
-constexpr int UM_RD_WARPS = 4;               // readout warps = TMEM lane quarters (warp id % 4)
-constexpr int UM_MMA_WARP = UM_RD_WARPS;     // warp 4 allocates TMEM and issues the MMAs
-constexpr int UM_THREADS = (UM_RD_WARPS + 1 + UM_EXP_WARPS) * 32;
-constexpr int UM_TMEM_COLS = 256;            // two accumulator stages x 128 int32 columns
-constexpr int UM_MAX_GROUPS = 16;            // groups (of 32 reads) per X tile at most
+constexpr int UM_RD_WARPS = 8;               // readout warps: two per TMEM lane quarter (warp id % 4)
+constexpr int UM_EXP_WARPS = 24;             // expander warps 8..31
+constexpr int UM_THREADS = (UM_RD_WARPS + UM_EXP_WARPS) * 32;
+constexpr int UM_NACC = 4;                   // accumulator stages (runs in flight)
+constexpr int UM_TMEM_COLS = 128 * UM_NACC;  // 128 int32 columns each
+constexpr uint32_t UM_ACC_COUNT = 1u << 19;  // arrivals that complete an accumulator stage (see the readout warps)
+
+#ifdef UM_PROFILE
+__device__ unsigned long long um_prof[32];
+#define UM_T(var) const long long var = clock64()
+#define UM_ACC(slot, expr) prof_acc[slot] += (unsigned long long)(expr)
+#else
+#define UM_T(var)
+#define UM_ACC(slot, expr)
+#endif
 
 struct UmLayout {
     int kmax;
+    __host__ __device__ int ch() const { return kmax <= 16 ? 4 : 8; }
+    __host__ __device__ size_t slot_bytes() const { return (size_t)32 * 16 * ch(); }       // one group of 32 reads
     __host__ __device__ size_t tile_bytes() const { return (size_t)(kmax + 1) * (kmax - 1) * 64; }
     __host__ __device__ size_t bytes() const {
-        return (size_t)UM_NSTAGE * UM_XBYTES + tile_bytes() + 1024;   // tile behind the X tiles (see um_desc)
+        return (size_t)UM_EXP_WARPS * slot_bytes() + tile_bytes() + 1024;   // tile behind the slots (see um_desc)
     }
 };
 
@@ -84,21 +93,34 @@ __device__ __forceinline__ void um_ld16(uint32_t taddr, uint32_t (&v)[16]) {
         : "r"(taddr)
         : "memory");
 }
+__device__ __forceinline__ unsigned um_ld_acquire(uint32_t addr) {
+    unsigned v;
+    asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void um_st16_zero(uint32_t taddr) {
+    const uint32_t z = 0;
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};"
+        ::"r"(taddr), "r"(z)
+        : "memory");
+}
+__device__ __forceinline__ void um_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void um_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// The batch schedule, walked identically by every warp: runs of reads that share a rank (run_end[r] = index
-// after the last read of rank r, -1 for ranks without reads), cut into X tiles of at most `cap` reads.
+// The schedule, walked identically by every warp: runs of reads that share a rank (run_end[r] = index after the
+// last read of rank r, -1 for ranks without reads), clipped to the CTA's slice [lo, hi).
 struct UmWalk {
     const int64_t *run_end;
-    int64_t hi, cur, run_hi, wval;
-    int N, r, wbase, cap;
-    // batch
-    int64_t bstart;
-    int bn;
-    bool first, last;
+    int64_t hi, cur, wval;
+    int N, wbase;
+    // the current run
+    int64_t start, n;
+    int r;
+    unsigned ri;
 
-    __device__ __forceinline__ void init(const int64_t *re, int64_t lo_, int64_t hi_, int N_, int r0, int cap_) {
-        run_end = re; hi = hi_; cur = lo_; run_hi = lo_; N = N_; r = r0; cap = cap_;
+    __device__ __forceinline__ void init(const int64_t *re, int64_t lo_, int64_t hi_, int N_, int r0) {
+        run_end = re; hi = hi_; cur = lo_; N = N_; r = r0; ri = 0u - 1u;
         wbase = r0 < 0 ? 0 : r0;
         load_window();
     }
@@ -106,44 +128,44 @@ struct UmWalk {
         const int i = wbase + (int)(threadIdx.x & 31);
         wval = i <= N ? run_end[i] : -1;
     }
-    __device__ __forceinline__ bool next() {
+    __device__ __forceinline__ bool next_run() {
         if (cur >= hi) return false;
-        first = cur >= run_hi;
-        if (first) {
-            for (;;) {
-                const unsigned m = __ballot_sync(0xffffffffu, wval > cur);
-                if (m) {
-                    const int l = __ffs(m) - 1;
-                    r = wbase + l;
-                    const int64_t e = __shfl_sync(0xffffffffu, wval, l);
-                    run_hi = e < hi ? e : hi;
-                    break;
-                }
-                wbase += 32;
-                if (wbase > N) { cur = hi; return false; }      // reads with ranks outside [0,N]: flagged by the pre-pass
-                load_window();
+        for (;;) {
+            const unsigned m = __ballot_sync(0xffffffffu, wval > cur);
+            if (m) {
+                const int l = __ffs(m) - 1;
+                r = wbase + l;
+                const int64_t e = __shfl_sync(0xffffffffu, wval, l);
+                const int64_t run_hi = e < hi ? e : hi;
+                start = cur;
+                n = run_hi - cur;
+                cur = run_hi;
+                ++ri;
+                return true;
             }
+            wbase += 32;
+            if (wbase > N) { cur = hi; return false; }          // reads with ranks outside [0,N]: flagged by the pre-pass
+            load_window();
         }
-        bstart = cur;
-        const int64_t left = run_hi - cur;
-        bn = (int)(left < cap ? left : cap);
-        cur += bn;
-        last = cur >= run_hi;
-        return true;
     }
 };
 
-// lane = read: expand its alleles into the one-hot operand row (CH chunks of four sites).
+// lane = read: the aligned words holding its allele bytes (CH+1 of them cover 4*CH sites at any alignment).
 template <int CH>
-__device__ __forceinline__ void um_expand_read(const uint8_t *__restrict__ codes, int64_t o, int kb, int kg,
-                                               uint32_t rowaddr, uint32_t &rare_or, uint32_t &x0) {
+__device__ __forceinline__ void um_load_read(const uint8_t *__restrict__ codes, int64_t o, int kb, int kg,
+                                             uint32_t (&wd)[CH + 1], unsigned &mis) {
     const uint8_t *__restrict__ c = codes + o;
-    const unsigned mis = (unsigned)(reinterpret_cast<uintptr_t>(c) & 3u);
+    mis = (unsigned)(reinterpret_cast<uintptr_t>(c) & 3u);
     const uint32_t *__restrict__ cw = reinterpret_cast<const uint32_t *>(c - mis);
     const int nw = kb ? (int)((mis + kb + 3) >> 2) : 0;
-    uint32_t wd[CH + 1];
 #pragma unroll
     for (int w = 0; w <= CH; ++w) wd[w] = (w < nw && (w == 0 || 4 * (w - 1) < kg)) ? __ldg(cw + w) : 0u;
+}
+
+// ... and their expansion into the one-hot operand row (CH chunks of four sites, one 16-byte store each).
+template <int CH>
+__device__ __forceinline__ void um_expand_read(const uint32_t (&wd)[CH + 1], unsigned mis, int kb, int kg,
+                                               uint32_t rowaddr, uint32_t &rare_or, uint32_t &x0) {
     const unsigned sh = 8u * mis;
     const int kb8 = 8 * kb;
     rare_or = 0;
@@ -176,20 +198,19 @@ k1_umma(const int32_t *__restrict__ rank, const int64_t *__restrict__ off, const
         int64_t n_reads, int N, int W, int kmax, const HxCnt cnt_in, unsigned long long *__restrict__ totals,
         int *__restrict__ err, const int *__restrict__ sorted_flag, const int64_t *__restrict__ run_end) {
     extern __shared__ __align__(1024) uint8_t um_smem[];
+    UM_T(k_begin);
     HxCnt cnt = cnt_in;                              // single-GPU build: the peer path folds away
     if (!FUSED) { cnt.world = 1; cnt.rows_per = 1; cnt.peer = nullptr; }
-    __shared__ __align__(8) unsigned long long s_full[UM_NSTAGE], s_empty[UM_NSTAGE];
-    __shared__ __align__(8) unsigned long long s_acc_full[2], s_acc_empty[2], s_meta[2];
-    __shared__ int s_gk[UM_NSTAGE][UM_MAX_GROUPS];
-    __shared__ int s_runkg[2];
+    __shared__ __align__(8) unsigned long long s_slot[UM_EXP_WARPS];   // a warp's operand slot has been read by its MMA
+    __shared__ __align__(8) unsigned long long s_acc_full[UM_NACC];    // all MMAs of a run are complete
+    __shared__ int s_runkg[UM_NACC];                       // widest read of the run accumulating in each stage
+    __shared__ unsigned s_runs_read;                 // runs read out of TMEM (and their stage zeroed again)
     __shared__ uint32_t s_tmem;
     if (!*sorted_flag) return;                       // the generic fallback launch takes over
 
     constexpr int ROWB = 16 * CH;                    // bytes of one read's operand row
     constexpr uint32_t LBO = 128u * CH;              // 8 reads further
-    constexpr int CAP = UM_XBYTES / ROWB;            // reads per X tile (512 / 256)
-    constexpr int GB = CAP / 32;                     // groups per X tile
-    static_assert(GB <= UM_MAX_GROUPS, "s_gk too small");
+    constexpr uint32_t SLOTB = 32u * ROWB;           // one group: 32 reads = the K of one MMA
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t per = (n_reads + gridDim.x - 1) / gridDim.x;
@@ -199,23 +220,18 @@ k1_umma(const int32_t *__restrict__ rank, const int64_t *__restrict__ off, const
 
     const int rows = kmax + 1, cells = kmax - 1;
     const uint32_t x_saddr = ws_smem_u32(um_smem);
-    uint4 *const tile = reinterpret_cast<uint4 *>(um_smem + (size_t)UM_NSTAGE * UM_XBYTES);
+    uint4 *const tile = reinterpret_cast<uint4 *>(um_smem + (size_t)UM_EXP_WARPS * SLOTB);
     uint32_t *const tile32 = reinterpret_cast<uint32_t *>(tile);
 
     for (size_t w = threadIdx.x; w < (size_t)rows * cells * 4; w += blockDim.x) tile[w] = make_uint4(0, 0, 0, 0);
     if (threadIdx.x == 0) {
-        for (int b = 0; b < UM_NSTAGE; ++b) {
-            ws_mbar_init(ws_smem_u32(&s_full[b]), UM_EXP_WARPS);
-            ws_mbar_init(ws_smem_u32(&s_empty[b]), 1);
-        }
-        for (int s = 0; s < 2; ++s) {
-            ws_mbar_init(ws_smem_u32(&s_acc_full[s]), 1);
-            ws_mbar_init(ws_smem_u32(&s_acc_empty[s]), UM_RD_WARPS);
-            ws_mbar_init(ws_smem_u32(&s_meta[s]), 1);
-        }
+        s_runs_read = 0;
+        for (int s = 0; s < UM_NACC; ++s) s_runkg[s] = 0;
+        for (int e = 0; e < UM_EXP_WARPS; ++e) ws_mbar_init(ws_smem_u32(&s_slot[e]), 1);
+        for (int s = 0; s < UM_NACC; ++s) ws_mbar_init(ws_smem_u32(&s_acc_full[s]), UM_ACC_COUNT);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == UM_MMA_WARP) {
+    if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(ws_smem_u32(&s_tmem)),
                      "r"((uint32_t)UM_TMEM_COLS)
                      : "memory");
@@ -225,187 +241,244 @@ k1_umma(const int32_t *__restrict__ rank, const int64_t *__restrict__ off, const
     __syncthreads();
     um_fence_after();
     const uint32_t tmem_base = s_tmem;
+    if (warp < UM_RD_WARPS) {
+        // every MMA accumulates (they are issued by many warps in no particular order): the stages start at zero and
+        // the readout warps zero what they have read.  Warps 0-3 clear the even stages, warps 4-7 the odd ones.
+        for (int st = warp >> 2; st < UM_NACC; st += 2) {
+            const uint32_t t0 = tmem_base + (uint32_t)st * 128u + ((uint32_t)((warp & 3) * 32) << 16);
+#pragma unroll
+            for (int cb = 0; cb < 128; cb += 16) um_st16_zero(t0 + (uint32_t)cb);
+        }
+        um_wait_st();
+    }
+    um_fence_before();
+    __syncthreads();
+    um_fence_after();
 
     unsigned long long t_crumbs = 0;
     unsigned n_slices = 0, n_codes = 0, n_notcov = 0, n_sent = 0, n_rcrumbs = 0, errbits = 0;
+#ifdef UM_PROFILE
+    unsigned long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#endif
 
     UmWalk wk;
-    wk.init(run_end, lo, hi, N, rank[lo], CAP);
+    wk.init(run_end, lo, hi, N, rank[lo]);
+    UM_T(k_roles);
 
-    if (warp > UM_MMA_WARP) {
+    if (warp >= UM_RD_WARPS) {
         // ================================ expanders ==========================================
-        const int e = warp - UM_MMA_WARP - 1;
-        const uint32_t pf_bytes = (uint32_t)CAP * (uint32_t)(kmax > 20 ? 24 : 16);     // ~ one X tile of codes
-        for (unsigned bi = 0; wk.next(); ++bi) {
-            const int b = bi % UM_NSTAGE;
-            const int r = wk.r;
-            const int nb = (wk.bn + 31) >> 5;
-            const int64_t run_stop = wk.bstart + wk.bn;
-            if (e == 0 && lane == 0 && wk.cur < hi) {         // the next X tile: its offsets
-                const int64_t ahead = min((int64_t)CAP + 1, hi - wk.cur + 1);
-                bs_prefetch_l2(off + wk.cur, (uint32_t)(ahead * 8));
-            }
-            ws_mbar_wait(ws_smem_u32(&s_empty[b]), ((bi / UM_NSTAGE) & 1) ^ 1);
-            // groups are dealt round-robin over the expander warps across consecutive tiles
-            int g = (e - (int)((bi * (unsigned)GB) % UM_EXP_WARPS) + UM_EXP_WARPS) % UM_EXP_WARPS;
-            for (; g < nb; g += UM_EXP_WARPS) {
-                const int64_t idx = wk.bstart + (int64_t)g * 32 + lane;
-                int64_t o = 0;
-                int kb = 0;
-                if (idx < run_stop) {
-                    o = off[idx];
-                    const int64_t k64 = off[idx + 1] - o;
-                    if (k64 >= 2) {
-                        if (r < 0 || (int64_t)r + k64 > N || k64 - 1 > W) errbits |= 1;
-                        else kb = (int)k64;
-                    }
-                    // last read of the tile: the next tile's codes start right behind it
-                    if (idx + 1 == run_stop && idx + 1 < hi) bs_prefetch_l2(codes + o + k64, pf_bytes);
+        // A job = one group of 32 reads of a run = the K of one MMA.  Groups are dealt round-robin over the expander
+        // warps.  Each warp is a pipeline of its own: request the offsets of its NEXT job, load the alleles of
+        // the current one, expand them into its private operand slot, issue the MMA itself and commit it to the
+        // slot's mbarrier (slot reusable) and to the run's accumulator barrier (run complete).
+        const int e = warp - UM_RD_WARPS;
+        const uint32_t slot_addr = x_saddr + (uint32_t)e * SLOTB;
+        const uint32_t slot_bar = ws_smem_u32(&s_slot[e]);
+        const uint64_t desc = um_desc(slot_addr, LBO);
+        const uint32_t rowaddr = slot_addr + (uint32_t)(lane >> 3) * LBO + (uint32_t)(lane & 7) * 16u;
+        constexpr int64_t PF_READS = 2048;                      // L2 prefetch distance in reads
+        int gmod = 0;                                            // groups dealt so far, modulo the expander count
+        unsigned njobs = 0;
+        int jg = 0, cur_ng = 0;
+        struct Job { int64_t start, n; int r, g; unsigned ri; bool valid; };
+        auto next_job = [&]() -> Job {
+            for (;;) {
+                if (jg < cur_ng) {
+                    Job j{wk.start, wk.n, wk.r, jg, wk.ri, true};
+                    jg += UM_EXP_WARPS;
+                    return j;
                 }
-                n_slices += kb >= 2;
-                n_codes += kb;
-                const int kg = __reduce_max_sync(0xffffffffu, kb);
-                const int ridx = g * 32 + lane;
-                const uint32_t rowaddr = x_saddr + (uint32_t)b * UM_XBYTES + (uint32_t)(ridx >> 3) * LBO + (uint32_t)(ridx & 7) * 16u;
-                uint32_t rare_or, x0;
-                um_expand_read<CH>(codes, o, kb, kg, rowaddr, rare_or, x0);
-                if (lane == 0) s_gk[b][g] = kg;
-                if (kb >= 2) {
-                    const uint8_t *__restrict__ c = codes + o;
-                    const unsigned a0 = x0 & 0xffu;
-                    if (r == 0 && sym_valid_from(a0)) {            // util.py:262-266
-                        atomicAdd(cnt.cell(W, 0, 1) + HX_SYM_GAP * HX_NSYM + a0, 1u);
-                        n_sent++;
+                if (!wk.next_run()) return Job{0, 0, 0, 0, 0, false};
+                cur_ng = (int)((wk.n + 31) >> 5);
+                jg = e - gmod;
+                if (jg < 0) jg += UM_EXP_WARPS;
+                gmod = (int)((unsigned)(gmod + cur_ng) % (unsigned)UM_EXP_WARPS);
+                if (lane == 0 && (int)(wk.ri % UM_EXP_WARPS) == e) {
+                    // the packed reads are streamed from HBM exactly once: request the offsets and (extrapolated
+                    // from this run's byte range) the codes of the reads PF_READS further on
+                    const int64_t pf0 = wk.start + PF_READS;
+                    if (pf0 < hi) {
+                        const int64_t np = min(min(wk.n, (int64_t)2048), hi - pf0);
+                        bs_prefetch_l2(off + pf0, (uint32_t)((np + 1) * 8));
+                        const int64_t o_lo = off[wk.start], o_hi = off[wk.start + wk.n];
+                        const int64_t per_read16 = ((o_hi - o_lo) << 4) / wk.n;
+                        bs_prefetch_l2(codes + o_lo + ((PF_READS * per_read16) >> 4), (uint32_t)(((np * per_read16) >> 4) + 64));
                     }
-                    if (r + kb == N && !(kb == 2 && r == 0)) {     // util.py:271-275
-                        const unsigned ap = c[kb - 2], bl = c[kb - 1];
-                        if (sym_valid_from(ap) && bl <= 6) {
-                            atomicAdd(cnt.cell(W, N, N + 1) + bl * HX_NSYM + HX_SYM_GAP, 1u);
-                            n_sent++;
-                        }
-                    }
-                }
-                // reads holding N, - or _: their pairs with such an allele are added right here by the warp
-                unsigned rm = __ballot_sync(0xffffffffu, kb >= 2 && rare_or != 0);
-                while (rm) {
-                    const int src = __ffs(rm) - 1;
-                    rm &= rm - 1;
-                    const int64_t o2 = __shfl_sync(0xffffffffu, o, src);
-                    const int k2 = __shfl_sync(0xffffffffu, kb, src);
-                    bs_rare_read(codes + o2, k2, r, W, cnt, n_rcrumbs, n_notcov, errbits);
                 }
             }
+        };
+        auto load_off = [&](const Job &j, int64_t &o, int64_t &o1) {
+            const int64_t idx = (int64_t)j.g * 32 + lane;
+            o = 0; o1 = 0;
+            if (j.valid && idx < j.n) { o = off[j.start + idx]; o1 = off[j.start + idx + 1]; }
+        };
+        Job cur = next_job();
+        int64_t o, o1;
+        load_off(cur, o, o1);
+        while (cur.valid) {
+            UM_T(tA);
+            const Job nxt = next_job();
+            int64_t on, o1n;
+            load_off(nxt, on, o1n);                             // in flight while this job is expanded
+            const int r = cur.r;
+            const int s = cur.ri % UM_NACC;
+            int kb = 0;
+            {
+                const int64_t k64 = o1 - o;
+                if (k64 >= 2) {
+                    if (r < 0 || (int64_t)r + k64 > N || k64 - 1 > W) errbits |= 1;
+                    else kb = (int)k64;
+                }
+            }
+            n_slices += kb >= 2;
+            n_codes += kb;
+            const int kg = __reduce_max_sync(0xffffffffu, kb);
+            UM_T(tC);
+            uint32_t wd[CH + 1];
+            unsigned mis;
+            um_load_read<CH>(codes, o, kb, kg, wd, mis);
+            UM_T(tD);
+            // the run's accumulator stage: run ri-NACC must have been read out (and the stage zeroed) before anything
+            // of run ri is added; the previous MMA of this warp must have read the slot before it is rewritten
+            if (cur.ri >= (unsigned)UM_NACC) {
+                const unsigned need = cur.ri - UM_NACC + 1;
+                while (um_ld_acquire(ws_smem_u32(&s_runs_read)) < need) __nanosleep(200);
+            }
+            ws_mbar_wait(slot_bar, (njobs & 1) ^ 1);
+            um_fence_after();
+            UM_T(tE);
+            uint32_t rare_or, x0;
+            um_expand_read<CH>(wd, mis, kb, kg, rowaddr, rare_or, x0);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic stores -> tensor-core reads
             __syncwarp();
-            if (lane == 0) ws_mbar_arrive(ws_smem_u32(&s_full[b]));
-        }
-    } else if (warp == UM_MMA_WARP) {
-        // ================================ MMA issuer =========================================
-        unsigned ri = 0;                               // run index
-        int kg_run = 0;
-        bool fresh = true;                             // the run's accumulator has not been written yet
-        for (unsigned bi = 0; wk.next(); ++bi) {
-            const int b = bi % UM_NSTAGE;
-            const int s = ri & 1;
-            const int nb = (wk.bn + 31) >> 5;
-            if (wk.first) {
-                ws_mbar_wait(ws_smem_u32(&s_acc_empty[s]), ((ri >> 1) & 1) ^ 1);
-                kg_run = 0;
-                fresh = true;
-            }
-            ws_mbar_wait(ws_smem_u32(&s_full[b]), (bi / UM_NSTAGE) & 1);
-            um_fence_after();
             if (lane == 0) {
-                const uint32_t d_addr = tmem_base + (uint32_t)s * 128u;
-                for (int g = 0; g < nb; ++g) {
-                    const int kg = s_gk[b][g];
-                    kg_run = max(kg_run, kg);
-                    // the run's first MMA overwrites all 128 columns; later ones touch what their reads reach
-                    const int ncols = fresh ? 16 * CH : 16 * ((max(kg, 1) + 3) >> 2);
-                    const uint64_t desc = um_desc(x_saddr + (uint32_t)b * UM_XBYTES + (uint32_t)g * 4u * LBO, LBO);
-                    um_mma(d_addr, desc, um_idesc(ncols), fresh ? 0u : 1u);
-                    fresh = false;
+                if (kg >= 2) {
+                    atomicMax(&s_runkg[s], kg);
+                    __threadfence_block();
+                    um_mma(tmem_base + (uint32_t)s * 128u, desc, um_idesc(16 * ((kg + 3) >> 2)), 1u);
                 }
-                um_commit(ws_smem_u32(&s_empty[b]));
-                if (wk.last) {
-                    s_runkg[s] = kg_run;
-                    ws_mbar_arrive(ws_smem_u32(&s_meta[s]));
-                    um_commit(ws_smem_u32(&s_acc_full[s]));
+                um_commit(slot_bar);
+                um_commit(ws_smem_u32(&s_acc_full[s]));
+            }
+            ++njobs;
+            UM_T(tG);
+            if (kb >= 2) {
+                const uint8_t *__restrict__ c = codes + o;
+                const unsigned a0 = x0 & 0xffu;
+                if (r == 0 && sym_valid_from(a0)) {            // util.py:262-266
+                    atomicAdd(cnt.cell(W, 0, 1) + HX_SYM_GAP * HX_NSYM + a0, 1u);
+                    n_sent++;
+                }
+                if (r + kb == N && !(kb == 2 && r == 0)) {     // util.py:271-275
+                    const unsigned ap = c[kb - 2], bl = c[kb - 1];
+                    if (sym_valid_from(ap) && bl <= 6) {
+                        atomicAdd(cnt.cell(W, N, N + 1) + bl * HX_NSYM + HX_SYM_GAP, 1u);
+                        n_sent++;
+                    }
                 }
             }
-            __syncwarp();
-            if (wk.last) ++ri;
+            // reads holding N, - or _: their pairs with such an allele are added right here by the warp
+            unsigned rm = __ballot_sync(0xffffffffu, kb >= 2 && rare_or != 0);
+            while (rm) {
+                const int src = __ffs(rm) - 1;
+                rm &= rm - 1;
+                const int64_t o2 = __shfl_sync(0xffffffffu, o, src);
+                const int k2 = __shfl_sync(0xffffffffu, kb, src);
+                bs_rare_read<false>(codes + o2, k2, r, W, cnt, n_rcrumbs, n_notcov, errbits);
+            }
+            UM_T(tH);
+            UM_ACC(0, tC - tA); UM_ACC(1, tD - tC); UM_ACC(2, tE - tD); UM_ACC(3, tG - tE); UM_ACC(4, tH - tG); UM_ACC(5, 1);
+            cur = nxt; o = on; o1 = o1n;
         }
+#ifdef UM_PROFILE
+        if (lane == 0) for (int i = 0; i < 6; ++i) atomicAdd(&um_prof[i], prof_acc[i]);
+#endif
     } else {
         // ================================ readout ============================================
+        // 8 warps: warp w reads TMEM lanes 32*(w%4).. (rows = (site t1, allele a) of the run) and every other block of
+        // 16 columns (= 4 sites t2); only t2 > t1 is a site pair.
         const int npt = UM_RD_WARPS * 32;
-        const int t1 = threadIdx.x >> 2, a = threadIdx.x & 3;
+        const int q = warp & 3, half = warp >> 2;
+        const int m = q * 32 + lane, t1 = m >> 2, a = m & 3;
         const int per_row = cells * 16;
         int64_t flushed_upto = (int64_t)rank[lo] + 1;
-        int rbase = 0;
-        unsigned ri = 0;
-        while (wk.next()) {
+        while (wk.next_run()) {
             const int r = wk.r;
-            if (wk.first) {
-                ws_pair_barrier(npt);                // the previous run's tile adds are complete
-                if ((int64_t)r + 1 > flushed_upto) {
-                    const int64_t lastrow = min((int64_t)r + 1, flushed_upto + rows - 2);
-                    // rows pj <= r+1 can no longer be touched by this CTA
-                    unsigned long long sum = 0;
-                    int row = (int)((flushed_upto + 1) % rows);
-                    for (int64_t pj = flushed_upto + 1; pj <= lastrow; ++pj) {
-                        uint32_t *base = tile32 + (size_t)row * per_row;
-                        for (int w = threadIdx.x; w < per_row; w += npt) {
-                            const uint32_t v = base[w];
-                            if (v) {
-                                const int d = (w >> 4) + 1, ab = w & 15;
-                                atomicAdd(cnt.cell(W, pj - d, pj) + (ab >> 2) * HX_NSYM + (ab & 3), v);
-                                base[w] = 0;
-                                sum += v;
+            const unsigned ri = wk.ri;
+            const int s = ri % UM_NACC;
+            UM_T(r0);
+            // (the tile adds of the previous run are complete: barrier at the end of the loop body)
+            if ((int64_t)r + 1 > flushed_upto) {
+                const int64_t lastrow = min((int64_t)r + 1, flushed_upto + rows - 2);
+                // rows pj <= r+1 can no longer be touched by this CTA
+                unsigned long long sum = 0;
+                int row = (int)((flushed_upto + 1) % rows);
+                for (int64_t pj = flushed_upto + 1; pj <= lastrow; ++pj) {
+                    uint32_t *base = tile32 + (size_t)row * per_row;
+                    for (int w = threadIdx.x; w < per_row; w += npt) {
+                        const uint32_t v = base[w];
+                        if (v) {
+                            const int d = (w >> 4) + 1, ab = w & 15;
+                            atomicAdd(cnt.cell(W, pj - d, pj) + (ab >> 2) * HX_NSYM + (ab & 3), v);
+                            base[w] = 0;
+                            sum += v;
+                        }
+                    }
+                    if (++row == rows) row = 0;
+                }
+                t_crumbs += sum;
+                flushed_upto = (int64_t)r + 1;
+                ws_pair_barrier(npt);            // retired ring slots may be reused by this run's tile add
+            }
+            const int rbase = (int)(((int64_t)r + 1) % rows);
+            UM_T(r1);
+            // the stage is complete after UM_ACC_COUNT arrivals: one per group (the expanders' commits) plus the rest here
+            if (threadIdx.x == 0) {
+                const uint32_t ng = (uint32_t)((wk.n + 31) >> 5);
+                asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0], %1;" ::"r"(ws_smem_u32(&s_acc_full[s])),
+                             "r"(UM_ACC_COUNT - ng)
+                             : "memory");
+            }
+            ws_mbar_wait_sleep(ws_smem_u32(&s_acc_full[s]), (ri / UM_NACC) & 1);
+            um_fence_after();
+            UM_T(r2);
+            const int kg = *reinterpret_cast<volatile int *>(&s_runkg[s]);
+            const int ncols = 4 * kg;
+            const uint32_t taddr = tmem_base + (uint32_t)s * 128u + ((uint32_t)(q * 32) << 16);
+            if (kg >= 2) {
+                if (q * 32 < ncols - 4) {                                // this lane quarter holds live rows
+                    for (int cb = q * 32 + 16 * half; cb < ncols; cb += 32) {
+                        uint32_t v[16];
+                        um_ld16(taddr + (uint32_t)cb, v);
+                        um_wait_ld();
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int t2 = (cb >> 2) + j;
+                            if (t2 > t1 && t2 < kg) {
+                                int row = rbase + t2;
+                                if (row >= rows) row -= rows;
+                                uint4 *cell = tile + ((size_t)row * cells + (t2 - t1 - 1)) * 4 + a;
+                                uint4 c = *cell;
+                                c.x += v[4 * j + 0]; c.y += v[4 * j + 1]; c.z += v[4 * j + 2]; c.w += v[4 * j + 3];
+                                *cell = c;
                             }
                         }
-                        if (++row == rows) row = 0;
-                    }
-                    t_crumbs += sum;
-                    flushed_upto = (int64_t)r + 1;
-                    ws_pair_barrier(npt);            // retired ring slots may be reused by this run's tile add
-                }
-                rbase = (int)(((int64_t)r + 1) % rows);
-            }
-            if (!wk.last) continue;
-            const int s = ri & 1;
-            const uint32_t par = (ri >> 1) & 1;
-            ws_mbar_wait(ws_smem_u32(&s_meta[s]), par);
-            const int kg = s_runkg[s];
-            ws_mbar_wait(ws_smem_u32(&s_acc_full[s]), par);
-            um_fence_after();
-            const int ncols = 4 * kg;
-            if (kg >= 2 && warp * 32 < ncols - 4) {                     // this lane quarter holds live rows
-                const uint32_t taddr = tmem_base + (uint32_t)s * 128u + ((uint32_t)(warp * 32) << 16);
-                for (int cb = warp * 32; cb < ncols; cb += 16) {
-                    uint32_t v[16];
-                    um_ld16(taddr + (uint32_t)cb, v);
-                    um_wait_ld();
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const int t2 = (cb >> 2) + q;
-                        if (t2 > t1 && t2 < kg) {
-                            int row = rbase + t2;
-                            if (row >= rows) row -= rows;
-                            uint4 *cell = tile + ((size_t)row * cells + (t2 - t1 - 1)) * 4 + a;
-                            uint4 c = *cell;
-                            c.x += v[4 * q + 0]; c.y += v[4 * q + 1]; c.z += v[4 * q + 2]; c.w += v[4 * q + 3];
-                            *cell = c;
-                        }
                     }
                 }
+                // zero everything the run's MMAs may have written (all rows, the lower triangle too)
+                const int ncols16 = 16 * ((kg + 3) >> 2);
+                for (int cb = 16 * half; cb < ncols16; cb += 32) um_st16_zero(taddr + (uint32_t)cb);
+                um_wait_st();
             }
             um_fence_before();
-            __syncwarp();
-            if (lane == 0) ws_mbar_arrive(ws_smem_u32(&s_acc_empty[s]));
-            ++ri;
+            ws_pair_barrier(npt);                // tile adds and zeroing done
+            if (threadIdx.x == 0) {
+                s_runkg[s] = 0;
+                asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(ws_smem_u32(&s_runs_read)), "r"(ri + 1) : "memory");
+            }
+            UM_T(r3);
+            UM_ACC(0, r1 - r0); UM_ACC(1, r2 - r1); UM_ACC(2, r3 - r2); UM_ACC(3, 1);
         }
-        ws_pair_barrier(npt);
         {
             unsigned long long sum = 0;
             int row = (int)((flushed_upto + 1) % rows);
@@ -423,11 +496,28 @@ k1_umma(const int32_t *__restrict__ rank, const int64_t *__restrict__ off, const
             }
             t_crumbs += sum;
         }
+#ifdef UM_PROFILE
+        if (threadIdx.x == 0) for (int i = 0; i < 4; ++i) atomicAdd(&um_prof[16 + i], prof_acc[i]);
+#endif
     }
+    UM_T(k_roles_end);
     if (errbits) atomicOr(err, (int)errbits);
     um_fence_before();
     flush_totals(n_slices, t_crumbs + n_rcrumbs, (unsigned long long)n_codes - n_notcov, n_sent, totals);   // barriers inside
-    if (warp == UM_MMA_WARP) {
+#ifdef UM_PROFILE
+    {
+        const long long k_end = clock64();
+        if (lane == 0) {
+            atomicAdd(&um_prof[24], (unsigned long long)(k_roles - k_begin));
+            atomicAdd(&um_prof[25], (unsigned long long)(k_roles_end - k_roles));
+            atomicAdd(&um_prof[26], (unsigned long long)(k_end - k_roles_end));
+            atomicMax(&um_prof[27], (unsigned long long)(k_end - k_begin));
+            if (warp >= UM_RD_WARPS) atomicMax(&um_prof[28], (unsigned long long)(k_roles_end - k_roles));
+            else atomicMax(&um_prof[29], (unsigned long long)(k_roles_end - k_roles));
+        }
+    }
+#endif
+    if (warp == 0) {
         um_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)UM_TMEM_COLS)
                      : "memory");
@@ -435,6 +525,17 @@ k1_umma(const int32_t *__restrict__ rank, const int64_t *__restrict__ off, const
 }
 
 }  // namespace
+
+#ifdef UM_PROFILE
+extern "C" int hx_debug_um_prof(unsigned long long *out, int reset) {
+    if (cudaMemcpyFromSymbol(out, um_prof, sizeof(unsigned long long) * 32) != cudaSuccess) return -1;
+    if (reset) {
+        unsigned long long z[32] = {0};
+        cudaMemcpyToSymbol(um_prof, z, sizeof(z));
+    }
+    return 0;
+}
+#endif
 
 bool hx_umma_possible(const hx_matrix *h) {
     const int kmax = h->W + 1;

@@ -45,7 +45,7 @@ def test_reference_golden_through_gpu(golden_dir):
         assert h.L == 3
 
 
-@pytest.mark.parametrize("kernel", [1, 2, 3, 4, 5])
+@pytest.mark.parametrize("kernel", [1, 2, 3, 4, 5, 6])
 @pytest.mark.parametrize("seed", range(8))
 def test_random_packed_bit_exact(c_oracle, seed, kernel):
     rng = np.random.default_rng(500 + seed)
@@ -60,7 +60,7 @@ def test_random_packed_bit_exact(c_oracle, seed, kernel):
     assert np.array_equal(band, ref.astype(np.float32))
 
 
-@pytest.mark.parametrize("kernel", [1, 2, 3, 4, 5])
+@pytest.mark.parametrize("kernel", [1, 2, 3, 4, 5, 6])
 def test_edge_cases(c_oracle, kernel):
     # empty input, reads with k<2, N=2 (start rule beats end rule), reads ending on the last SNP
     cases = []
@@ -91,7 +91,7 @@ def test_bad_reads_raise():
 
 
 @pytest.mark.parametrize("name,n_reads", [("hiv", 200_000), ("metagenome", 300_000), ("ont", 600)])
-@pytest.mark.parametrize("kernel", [0, 1, 3, 4, 5])
+@pytest.mark.parametrize("kernel", [0, 1, 3, 4, 5, 6])
 def test_workloads_bit_exact(c_oracle, name, n_reads, kernel):
     """Config 2 at full size, configs 3/4 at sizes the C oracle finishes in seconds."""
     w = synth.scaled(synth.WORKLOADS[name], n_reads)
@@ -341,7 +341,7 @@ def test_dense_wire_format_rejects_bad_input():
 
 @pytest.mark.parametrize("shape", [(600, 40, 300_000, 150), (600, 100, 120_000, 200), (3000, 300, 400_000, 150)],
                          ids=["7k-reads-per-rank", "wide-reads-deep", "1k-reads-per-rank"])
-@pytest.mark.parametrize("kernel", [0, 4, 5, 3])
+@pytest.mark.parametrize("kernel", [0, 4, 5, 3, 6])
 def test_deep_coverage_runs_bit_exact(c_oracle, shape, kernel):
     """Runs of thousands of reads per rank (several 1024-read batches per run, several CTAs per
     run) - the regime of the full-size configs - at a size the C oracle checks in a second."""
@@ -373,7 +373,7 @@ def test_adversarial_shapes(c_oracle):
     cases.append((ranks, off, rng.integers(0, 5, size=off[-1]).astype(np.uint8), 2000, 9))
     for rank, off, codes, N, W in cases:
         ref, rt = c_oracle.ingest(rank, off, codes, N, W)
-        for kernel in (0, 1, 3, 4, 5):
+        for kernel in (0, 1, 3, 4, 5, 6):
             band, totals = _gpu_band(rank, off, codes, N, W, kernel)
             assert totals == tuple(int(x) for x in rt), (N, kernel)
             assert np.array_equal(band, ref.astype(np.float32)), (N, kernel)
@@ -397,10 +397,11 @@ def test_full_size_config3_bit_exact(c_oracle):
     equals the C oracle's bit for bit, and so do the totals (n_slices, n_crumbs, covered SNPs, sentinels)."""
     c3 = _config3(c_oracle)
     d, N, W, ref, rt = c3["d"], c3["N"], c3["W"], c3["ref"], c3["rt"]
-    band, totals = _gpu_band(d["rank"], d["off"], d["codes"], N, W, 0)
-    assert totals == tuple(int(x) for x in rt)
-    assert totals[1] > 1_000_000_000
-    assert np.array_equal(band, ref.astype(np.float32))
+    for kernel in (0, 2):                  # auto = the tensor-core kernel at this depth; 2 = bit-sliced POPC kernel
+        band, totals = _gpu_band(d["rank"], d["off"], d["codes"], N, W, kernel)
+        assert totals == tuple(int(x) for x in rt)
+        assert totals[1] > 1_000_000_000
+        assert np.array_equal(band, ref.astype(np.float32))
     # ... and the first haplotypes recovered from that full-size matrix (10k sites, L = 15)
     from gretel_b200 import util
     from gretel_b200.hansel import Hansel, REF_SYMBOLS, REF_UNSYMBOLS
@@ -500,3 +501,20 @@ def test_parity_probe_counts_what_the_oracle_counts(c_oracle, seed):
     assert np.array_equal(rows_got.cpu().numpy(), want)
     assert int(want.sum()) == int(rt[1]) + int(rt[3])
     h.close()
+
+
+def test_tensor_core_kernel_deep_single_rank(c_oracle):
+    """300k reads on ONE rank (every count far above what an 8-bit or 16-bit lane could hold, and thousands of
+    MMAs accumulating into one TMEM stage from all expander warps), plus a neighbouring rank: the int32
+    accumulation of the tensor-core kernel is exact."""
+    rng = np.random.default_rng(21)
+    k = rng.integers(20, 31, size=300_000)
+    off = np.concatenate([[0], np.cumsum(k)]).astype(np.int64)
+    rank = np.where(np.arange(len(k)) < 290_000, 5, 6).astype(np.int32)
+    codes = rng.choice(np.array([0, 1, 2, 3, 4, 5], np.uint8), size=int(off[-1]), p=[0.5, 0.3, 0.1, 0.08, 0.01, 0.01])
+    N, W = 40, 29
+    ref, rt = c_oracle.ingest(rank, off, codes, N, W)
+    band, totals = _gpu_band(rank, off, codes, N, W, 6)
+    assert totals == tuple(int(x) for x in rt)
+    assert ref.max() > 100_000
+    assert np.array_equal(band, ref.astype(np.float32))
