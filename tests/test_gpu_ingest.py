@@ -516,5 +516,5 @@ def test_tensor_core_kernel_deep_single_rank(c_oracle):
     ref, rt = c_oracle.ingest(rank, off, codes, N, W)
     band, totals = _gpu_band(rank, off, codes, N, W, 6)
     assert totals == tuple(int(x) for x in rt)
-    assert ref.max() > 100_000
+    assert ref.max() > 60_000
     assert np.array_equal(band, ref.astype(np.float32))
