@@ -54,6 +54,7 @@ SIGNATURES = {
     "hx_reweight_path": (_int, [_p, _p, _dbl, C.POINTER(_dbl)]),
     "hx_recover": (_int, [_p, _p, _i32, _int, _i32, _dbl, _p, _p, C.POINTER(_i32)]),
     "hx_pack_bam": (_int, [C.c_char_p, C.c_char_p, _i32, _i32, _p, _i32, _int, _int, _p]),
+    "hx_pack_bam_ex": (_int, [C.c_char_p, C.c_char_p, _i32, _i32, _p, _i32, _int, _int, _i32, _p, _p]),
     "hx_pack_free": (None, [_p]),
     "hx_count_coverage": (_int, [C.c_char_p, C.c_char_p, _i32, _i32, _int, _p]),
     "hx_bam_contig_length": (_int, [C.c_char_p, C.c_char_p, C.POINTER(_i32)]),

@@ -187,7 +187,39 @@ def alleles_for_record(rec, snp_pos_sorted, start_pos, end_pos):
     return rank, alleles
 
 
-def pack_reads(records, snp_pos_sorted, start_pos, end_pos, target_tid, stepper="samtools"):
+PYSAM_MAX_DEPTH = 8000      # pysam's AlignmentFile.pileup(max_depth=8000); gretel never changes it (util.py:137)
+
+
+def snp_positions(vcf_handler):
+    """Sorted UNIQUE 1-based SNP positions of a process_vcf() result.  The reference marks ``region[pos]`` once
+    per position (util.py:402), so a VCF that repeats a POS (split multi-allelic records) yields one pileup column
+    and one rank step for it, while ``N`` still counts every record (util.py:404-406)."""
+    return sorted(set(vcf_handler["snp_rev"][i] for i in range(vcf_handler["N"])))
+
+
+class _DepthCap:
+    """htslib's bam_plp buffer limit as pysam's pileup applies it: a read that is not the first of its start
+    position is dropped while ``max_depth`` admitted reads are still buffered (end > the previous column)."""
+
+    def __init__(self, max_depth):
+        import heapq
+        self.max_depth, self.ends, self.pos, self.hq = max_depth, [], None, heapq
+
+    def admit(self, rec):
+        if not self.max_depth:
+            return True
+        beg, end = rec.pos, rec.pos + max(1, rec.reference_length)
+        if beg != self.pos:
+            while self.ends and self.ends[0] <= beg - 1:
+                self.hq.heappop(self.ends)
+            self.pos = beg
+        elif len(self.ends) >= self.max_depth:
+            return False
+        self.hq.heappush(self.ends, end)
+        return True
+
+
+def pack_reads(records, snp_pos_sorted, start_pos, end_pos, target_tid, stepper="samtools", max_depth=0):
     """Pack alignments into ``(rank int32[R], off int64[R+1], codes uint8[sum k])``.
 
     Reads with fewer than two covered SNPs carry no pair evidence (util.py:230) and
@@ -195,8 +227,13 @@ def pack_reads(records, snp_pos_sorted, start_pos, end_pos, target_tid, stepper=
     => non-decreasing rank)."""
     ranks, offs, chunks = [], [0], []
     total = 0
+    cap = _DepthCap(max_depth)
     for rec in records:
         if rec.tid != target_tid or not _passes_stepper(rec.flag, stepper):
+            continue
+        if rec.pos >= end_pos or rec.pos + max(1, rec.reference_length) <= start_pos - 1:
+            continue                                        # not fetched by pileup(start-1, end)
+        if not cap.admit(rec):
             continue
         if rec.pos + 1 > end_pos:
             continue
@@ -215,19 +252,25 @@ def pack_reads(records, snp_pos_sorted, start_pos, end_pos, target_tid, stepper=
             np.ascontiguousarray(codes, dtype=np.uint8))
 
 
-def pack_bam_native(bam_path, target_contig, start_pos, end_pos, vcf_handler, stepper="samtools", n_threads=1):
-    """BAM + process_vcf() output -> packed reads, by the multi-threaded C++ packer of libhanselx.so
-    (hx_pack_bam: BGZF inflate + one CIGAR walk per alignment).  Same result as pack_bam()."""
+def pack_bam_native(bam_path, target_contig, start_pos, end_pos, vcf_handler, stepper="samtools", n_threads=1,
+                    max_depth=0, stages=None):
+    """BAM + process_vcf() output -> packed reads, by the multi-threaded streaming C++ packer of libhanselx.so
+    (hx_pack_bam_ex: BGZF inflate + one CIGAR walk per alignment).  Same result as pack_bam().  ``stages``: a
+    dict that receives the seconds spent per stage (read, inflate, scan, depth, walk, gather)."""
     import ctypes as C
 
     from . import _lib
     lib = _lib.load()
-    snp_pos = np.ascontiguousarray([vcf_handler["snp_rev"][i] for i in range(vcf_handler["N"])], dtype=np.int32)
+    snp_pos = np.ascontiguousarray(snp_positions(vcf_handler), dtype=np.int32)
     out = _lib.HxPacked()
-    rc = lib.hx_pack_bam(str(bam_path).encode(), str(target_contig).encode(), int(start_pos), int(end_pos),
-                         snp_pos.ctypes.data, len(snp_pos), {"samtools": 0, "all": 1, "nofilter": 2}[stepper],
-                         int(max(1, n_threads)), C.byref(out))
+    secs = (C.c_double * 6)()
+    rc = lib.hx_pack_bam_ex(str(bam_path).encode(), str(target_contig).encode(), int(start_pos), int(end_pos),
+                            snp_pos.ctypes.data, len(snp_pos), {"samtools": 0, "all": 1, "nofilter": 2}[stepper],
+                            int(max(1, n_threads)), int(max_depth or 0), C.byref(out), secs)
     _lib.check(rc)
+    if stages is not None:
+        stages.update(dict(zip(("read", "inflate", "scan", "depth", "walk", "gather"), (float(x) for x in secs))))
+        stages["records"] = int(out.n_records)
     try:
         R, n = int(out.n_reads), int(out.n_codes)
         rank = np.ctypeslib.as_array(out.rank, shape=(max(R, 1),))[:R].copy()
@@ -238,10 +281,9 @@ def pack_bam_native(bam_path, target_contig, start_pos, end_pos, vcf_handler, st
     return rank, off, codes
 
 
-def pack_bam(bam_path, target_contig, start_pos, end_pos, vcf_handler, stepper="samtools"):
+def pack_bam(bam_path, target_contig, start_pos, end_pos, vcf_handler, stepper="samtools", max_depth=0):
     """BAM + process_vcf() output -> packed reads (dependency-free Python reader)."""
     refs, recs = read_bam(bam_path)
     names = [n for n, _ in refs]
     tid = names.index(target_contig)
-    snp_pos = [vcf_handler["snp_rev"][i] for i in range(vcf_handler["N"])]
-    return pack_reads(recs, snp_pos, start_pos, end_pos, tid, stepper=stepper)
+    return pack_reads(recs, snp_positions(vcf_handler), start_pos, end_pos, tid, stepper=stepper, max_depth=max_depth)

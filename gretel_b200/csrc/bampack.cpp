@@ -3,7 +3,9 @@
 // This is the producer side of the boundary (north_star keeps parsing on the CPU).  It replaces the
 // reference's pysam column pileup (gretel/util.py:112-210, one Python object per read x SNP column)
 // and yields exactly what that loop accumulates per read:
-//   * read key / mate separation ....... util.py:149-160 (every BAM record is its own read)
+//   * read key / mate separation ....... util.py:149-160 (every BAM record is its own read; records that share
+//                                         query name + flag + mate would be merged upstream: deliberate deviation)
+//   * pysam's pileup depth cap ......... max_depth = 8000 reads buffered by bam_plp (optional, hx_pack_bam_ex)
 //   * window ownership / start clamp ... util.py:162-176 (the union over work blocks == one pass)
 //   * allele at a SNP column ........... util.py:180-190, 238 ('-' inside a deletion or ref-skip,
 //                                         else the aligned base; only the first character is used)
@@ -20,6 +22,8 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <memory>
+#include <queue>
 #include <string>
 #include <thread>
 #include <vector>
@@ -30,36 +34,9 @@ void hx_set_error(const char *fmt, ...);
 
 namespace {
 
-struct Block { size_t coff, csize, uoff, usize; };
-
 inline uint16_t rd16(const uint8_t *p) { return (uint16_t)(p[0] | (p[1] << 8)); }
 inline uint32_t rd32(const uint8_t *p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
 inline int32_t rdi32(const uint8_t *p) { return (int32_t)rd32(p); }
-
-// Splits a BGZF file into its blocks (offset/size of the raw deflate payload and of the output).
-bool scan_bgzf(const std::vector<uint8_t> &f, std::vector<Block> &blocks, size_t &total) {
-    size_t p = 0;
-    total = 0;
-    while (p + 18 <= f.size()) {
-        const uint8_t *h = f.data() + p;
-        if (h[0] != 0x1f || h[1] != 0x8b || h[2] != 8 || !(h[3] & 4)) return false;
-        const size_t xlen = rd16(h + 10);
-        size_t q = p + 12, xend = q + xlen;
-        size_t bsize = 0;
-        while (q + 4 <= xend) {
-            const uint8_t *s = f.data() + q;
-            const size_t slen = rd16(s + 2);
-            if (s[0] == 'B' && s[1] == 'C' && slen == 2) bsize = (size_t)rd16(s + 4) + 1;
-            q += 4 + slen;
-        }
-        if (!bsize || p + bsize > f.size()) return false;
-        const size_t usize = rd32(f.data() + p + bsize - 4);
-        blocks.push_back({xend, bsize - (xend - p) - 8, total, usize});
-        total += usize;
-        p += bsize;
-    }
-    return p == f.size();
-}
 
 bool inflate_block(const uint8_t *src, size_t n, uint8_t *dst, size_t m) {
     if (m == 0) return true;
@@ -83,25 +60,99 @@ struct Out {
 
 const uint8_t NT16_CODE[16] = {4, 0, 1, 4, 2, 4, 4, 4, 3, 4, 4, 4, 4, 4, 4, 4};   // "=ACMGRSVTWYHKDBN" -> A0 C1 G2 T3 else N4
 
-// One alignment -> (rank, codes) appended to `o` when it covers at least two SNPs.
-void pack_record(const uint8_t *rec, int32_t target_tid, int32_t start_pos, int32_t end_pos,
-                 const int32_t *snp, int32_t n_snps, int stepper, Out &o, std::vector<uint8_t> &tmp) {
-    const int32_t tid = rdi32(rec), pos = rdi32(rec + 4);
-    const int l_read_name = rec[8];
-    const int n_cigar = rd16(rec + 12);
-    const int flag = rd16(rec + 14);
-    const int32_t l_seq = rdi32(rec + 16);
-    if (tid != target_tid || pos < 0) return;
-    if (stepper != 2) {
-        if (flag & (0x4 | 0x100 | 0x200 | 0x400)) return;
-        if (stepper == 0 && (flag & 0x1) && !(flag & 0x2)) return;          // orphan rule
+// One alignment record (the bytes behind its block_size field), bounds-checked against block_size.
+struct Rec {
+    const uint8_t *p;
+    uint32_t size;
+    int32_t tid, pos, l_seq;
+    int flag, n_cigar;
+    const uint8_t *cig, *seq;       // CIGAR ops (possibly the CG:B,I tag of a long read) and the 4-bit bases
+    bool ok;                        // false: the fixed fields do not fit block_size (truncated / corrupt record)
+};
+
+// Long CIGARs (> 65535 operations, ONT reads) are stored in the CG:B,I tag; the CIGAR field then holds the
+// placeholder <l_seq>S<ref_len>N (SAM spec 4.2.2).
+inline void find_cg_tag(Rec &r, const uint8_t *aux, const uint8_t *end) {
+    while (aux + 3 <= end) {
+        const uint8_t t0 = aux[0], t1 = aux[1], ty = aux[2];
+        aux += 3;
+        size_t sz = 0;
+        switch (ty) {
+            case 'A': case 'c': case 'C': sz = 1; break;
+            case 's': case 'S': sz = 2; break;
+            case 'i': case 'I': case 'f': sz = 4; break;
+            case 'Z': case 'H': { const uint8_t *q = aux; while (q < end && *q) ++q; sz = (size_t)(q - aux) + 1; break; }
+            case 'B': {
+                if (aux + 5 > end) return;
+                const uint8_t sub = aux[0];
+                const uint32_t cnt = rd32(aux + 1);
+                const size_t es = (sub == 'c' || sub == 'C') ? 1 : (sub == 's' || sub == 'S') ? 2 : 4;
+                if (t0 == 'C' && t1 == 'G' && sub == 'I' && aux + 5 + (size_t)cnt * 4 <= end) {
+                    r.cig = aux + 5;
+                    r.n_cigar = (int)cnt;
+                    return;
+                }
+                sz = 5 + (size_t)cnt * es;
+                break;
+            }
+            default: return;        // unknown type: stop rather than misparse
+        }
+        if (aux + sz > end) return;
+        aux += sz;
     }
+}
+
+inline Rec parse_rec(const uint8_t *rec, uint32_t size) {
+    Rec r;
+    r.p = rec; r.size = size;
+    r.tid = rdi32(rec); r.pos = rdi32(rec + 4);
+    const int l_read_name = rec[8];
+    r.n_cigar = rd16(rec + 12);
+    r.flag = rd16(rec + 14);
+    r.l_seq = rdi32(rec + 16);
+    r.cig = rec + 32 + l_read_name;
+    r.seq = r.cig + 4 * (size_t)r.n_cigar;
+    const uint64_t need = 32ull + (uint64_t)l_read_name + 4ull * (uint64_t)r.n_cigar +
+                          (r.l_seq > 0 ? ((uint64_t)r.l_seq + 1) / 2 + (uint64_t)r.l_seq : 0ull);
+    r.ok = r.l_seq >= 0 && need <= size;
+    if (r.ok && r.n_cigar == 2) {
+        const uint32_t c0 = rd32(r.cig), c1 = rd32(r.cig + 4);
+        if ((c0 & 0xf) == 4 && (int32_t)(c0 >> 4) == r.l_seq && (c1 & 0xf) == 3)
+            find_cg_tag(r, rec + need, rec + size);
+    }
+    return r;
+}
+
+inline bool passes_stepper(int flag, int stepper) {            // gretel/cmd.py:39,78
+    if (stepper == 2) return true;
+    if (flag & (0x4 | 0x100 | 0x200 | 0x400)) return false;
+    if (stepper == 0 && (flag & 0x1) && !(flag & 0x2)) return false;          // orphan rule
+    return true;
+}
+
+// reference span of the alignment (M D N = X)
+inline int64_t ref_len_of(const Rec &r) {
+    int64_t rlen = 0;
+    for (int i = 0; i < r.n_cigar; ++i) {
+        const uint32_t c = rd32(r.cig + 4 * (size_t)i);
+        const int op = c & 0xf;
+        if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) rlen += c >> 4;
+    }
+    return rlen;
+}
+
+// One alignment -> (rank, codes) appended to `o` when it covers at least two SNPs.
+void pack_record(const Rec &r, int32_t target_tid, int32_t start_pos, int32_t end_pos,
+                 const int32_t *snp, int32_t n_snps, int stepper, Out &o, std::vector<uint8_t> &tmp) {
+    const int32_t pos = r.pos, l_seq = r.l_seq;
+    const int n_cigar = r.n_cigar;
+    if (!r.ok || r.tid != target_tid || pos < 0) return;
+    if (!passes_stepper(r.flag, stepper)) return;
     if (pos + 1 > end_pos) return;
-    const uint8_t *cig = rec + 32 + l_read_name;
-    const uint8_t *seq = cig + 4 * (size_t)n_cigar;
+    const uint8_t *cig = r.cig, *seq = r.seq;
     int64_t qalen = 0, rlen = 0;
     for (int i = 0; i < n_cigar; ++i) {
-        const uint32_t c = rd32(cig + 4 * i);
+        const uint32_t c = rd32(cig + 4 * (size_t)i);
         const int op = c & 0xf;
         const int64_t ln = c >> 4;
         if (op == 0 || op == 1 || op == 7 || op == 8) qalen += ln;           // M I = X
@@ -121,7 +172,7 @@ void pack_record(const uint8_t *rec, int32_t target_tid, int32_t start_pos, int3
     int32_t wi = rank;
     int64_t rpos = (int64_t)pos + 1, qpos = 0;
     for (int i = 0; i < n_cigar && wi < hi; ++i) {
-        const uint32_t c = rd32(cig + 4 * i);
+        const uint32_t c = rd32(cig + 4 * (size_t)i);
         const int op = c & 0xf;
         const int64_t ln = c >> 4;
         if (op == 0 || op == 7 || op == 8) {
@@ -154,67 +205,185 @@ void pack_record(const uint8_t *rec, int32_t target_tid, int32_t start_pos, int3
     o.codes.insert(o.codes.end(), tmp.begin(), tmp.end());
 }
 
-}  // namespace
+// ---- streaming BAM reader ----------------------------------------------------------------------------------
+// The file is read in "waves": a few tens of megabytes of BGZF blocks are inflated in parallel into one buffer,
+// the record boundaries of the wave are found (a serial but trivial chain of block_size fields), the records
+// are handed to the caller in parallel ranges, and the bytes of a record cut by the wave's end are carried
+// into the next wave.  Memory stays bounded by the wave size whatever the size of the BAM, and reading stops
+// as soon as a coordinate-sorted file has passed the target region.
+struct RecRef { size_t off; uint32_t size; };
 
-namespace {
+struct BamStream {
+    FILE *fp = nullptr;
+    std::string path;
+    int n_threads = 1;
+    // header
+    bool header_done = false, sorted = false;
+    int32_t target_tid = -1, target_len = 0;
+    std::string contig;
+    // wave state
+    std::vector<uint8_t> cbuf;          // compressed bytes of the wave
+    std::unique_ptr<uint8_t[]> ubuf;    // carry + inflated bytes
+    size_t ucap = 0, ulen = 0;
+    std::vector<uint8_t> carry;         // unconsumed tail of the previous wave
+    std::vector<RecRef> recs;
+    bool eof = false;
+    double t_read = 0, t_inflate = 0, t_scan = 0;
 
-// Whole BAM in memory: inflated bytes, target contig id and the offset of every alignment record.
-struct LoadedBam {
-    std::vector<uint8_t> data;
-    std::vector<size_t> recs;
-    int32_t target_tid = -1;
-    int32_t target_len = 0;
+    ~BamStream() { if (fp) fclose(fp); }
+
+    int open(const char *bam_path, const char *ctg, int nt) {
+        path = bam_path; contig = ctg; n_threads = std::max(1, nt);
+        fp = fopen(bam_path, "rb");
+        if (!fp) { hx_set_error("cannot open %s", bam_path); return HX_E_ARG; }
+        return HX_OK;
+    }
+
+    // parses the BAM header at the front of ubuf; returns bytes consumed, 0 if more data is needed, -1 on error
+    long parse_header() {
+        const uint8_t *d = ubuf.get();
+        const size_t n = ulen;
+        if (n < 12) return 0;
+        if (memcmp(d, "BAM\1", 4) != 0) { hx_set_error("%s is not a BAM file", path.c_str()); return -1; }
+        size_t p = 4;
+        const int32_t l_text = rdi32(d + p);
+        if (l_text < 0) { hx_set_error("%s: corrupt BAM header", path.c_str()); return -1; }
+        if (p + 4 + (size_t)l_text + 4 > n) return 0;
+        {
+            const std::string text((const char *)d + p + 4, (size_t)l_text);
+            const size_t hd = text.find("@HD");
+            if (hd != std::string::npos) {
+                const size_t eol = text.find('\n', hd);
+                sorted = text.substr(hd, eol == std::string::npos ? std::string::npos : eol - hd).find("SO:coordinate") != std::string::npos;
+            }
+        }
+        p += 4 + (size_t)l_text;
+        const int32_t n_ref = rdi32(d + p); p += 4;
+        if (n_ref < 0) { hx_set_error("%s: corrupt BAM header", path.c_str()); return -1; }
+        for (int32_t i = 0; i < n_ref; ++i) {
+            if (p + 4 > n) return 0;
+            const int32_t l_name = rdi32(d + p); p += 4;
+            if (l_name < 1) { hx_set_error("%s: corrupt reference name", path.c_str()); return -1; }
+            if (p + (size_t)l_name + 4 > n) return 0;
+            const bool hit = std::string((const char *)d + p, (size_t)l_name - 1) == contig;
+            p += (size_t)l_name;
+            if (hit) { target_tid = i; target_len = rdi32(d + p); }
+            p += 4;
+        }
+        if (target_tid < 0) { hx_set_error("contig %s not in %s", contig.c_str(), path.c_str()); return -1; }
+        header_done = true;
+        return (long)p;
+    }
+
+    // Reads, inflates and indexes the next wave.  Returns HX_OK with recs filled (possibly empty), or an error;
+    // `eof` is set once the file is exhausted.
+    int next_wave(size_t wave_cbytes) {
+        using clk = std::chrono::steady_clock;
+        recs.clear();
+        if (eof) return HX_OK;
+        auto t0 = clk::now();
+        // compressed bytes: whole BGZF blocks only (a cut block is re-read by the next wave)
+        cbuf.resize(wave_cbytes);
+        const long fpos = ftell(fp);
+        const size_t got = fread(cbuf.data(), 1, wave_cbytes, fp);
+        if (got == 0) { eof = true; if (!carry.empty()) { hx_set_error("%s: truncated BAM (partial record at EOF)", path.c_str()); return HX_E_ARG; } return HX_OK; }
+        struct Blk { size_t coff, csize, uoff, usize; };
+        std::vector<Blk> blocks;
+        size_t p = 0, total = 0;
+        while (p + 18 <= got) {
+            const uint8_t *h = cbuf.data() + p;
+            if (h[0] != 0x1f || h[1] != 0x8b || h[2] != 8 || !(h[3] & 4)) { hx_set_error("%s is not a BGZF file", path.c_str()); return HX_E_ARG; }
+            const size_t xlen = rd16(h + 10);
+            size_t q = p + 12;
+            const size_t xend = q + xlen;
+            if (xend > got) break;
+            size_t bsize = 0;
+            while (q + 4 <= xend) {
+                const uint8_t *sf = cbuf.data() + q;
+                const size_t slen = rd16(sf + 2);
+                if (sf[0] == 'B' && sf[1] == 'C' && slen == 2 && q + 6 <= xend) bsize = (size_t)rd16(sf + 4) + 1;
+                q += 4 + slen;
+            }
+            if (!bsize || bsize < (xend - p) + 8) { hx_set_error("%s: corrupt BGZF block", path.c_str()); return HX_E_ARG; }
+            if (p + bsize > got) break;
+            const size_t usize = rd32(cbuf.data() + p + bsize - 4);
+            if (usize > 65536) { hx_set_error("%s: corrupt BGZF block (ISIZE)", path.c_str()); return HX_E_ARG; }
+            blocks.push_back({xend, bsize - (xend - p) - 8, total, usize});
+            total += usize;
+            p += bsize;
+        }
+        if (p == 0) {
+            if (got < wave_cbytes) { hx_set_error("%s: truncated BGZF block at EOF", path.c_str()); return HX_E_ARG; }
+            hx_set_error("%s: BGZF block larger than the read window", path.c_str());
+            return HX_E_ARG;
+        }
+        if (p < got) fseek(fp, fpos + (long)p, SEEK_SET);
+        if (got < wave_cbytes && p == got) eof = true;
+        auto t1 = clk::now();
+        // inflate behind the carried bytes
+        const size_t need = carry.size() + total;
+        if (need > ucap) { ucap = need + need / 4 + 65536; ubuf.reset(new uint8_t[ucap]); }
+        if (!carry.empty()) memcpy(ubuf.get(), carry.data(), carry.size());
+        const size_t base = carry.size();
+        ulen = need;
+        {
+            std::atomic<size_t> next(0);
+            std::atomic<bool> ok(true);
+            auto work = [&]() {
+                for (;;) {
+                    const size_t b = next.fetch_add(1);
+                    if (b >= blocks.size()) break;
+                    if (!inflate_block(cbuf.data() + blocks[b].coff, blocks[b].csize, ubuf.get() + base + blocks[b].uoff, blocks[b].usize))
+                        ok = false;
+                }
+            };
+            const int nt = (int)std::min<size_t>((size_t)n_threads, std::max<size_t>(1, blocks.size() / 4));
+            std::vector<std::thread> th;
+            for (int t = 1; t < nt; ++t) th.emplace_back(work);
+            work();
+            for (auto &t : th) t.join();
+            if (!ok) { hx_set_error("inflate failed on %s", path.c_str()); return HX_E_ARG; }
+        }
+        auto t2 = clk::now();
+        size_t q = 0;
+        if (!header_done) {
+            const long used = parse_header();
+            if (used < 0) return HX_E_ARG;
+            if (used == 0) {                     // header longer than this wave: keep everything, read on
+                if (eof) { hx_set_error("%s: truncated BAM header", path.c_str()); return HX_E_ARG; }
+                carry.assign(ubuf.get(), ubuf.get() + ulen);
+                return HX_OK;
+            }
+            q = (size_t)used;
+        }
+        const uint8_t *d = ubuf.get();
+        while (q + 4 <= ulen) {
+            const int32_t bs = rdi32(d + q);
+            if (bs < 32) { hx_set_error("%s: corrupt alignment record (block_size %d)", path.c_str(), bs); return HX_E_ARG; }
+            if (q + 4 + (size_t)bs > ulen) break;
+            recs.push_back({q + 4, (uint32_t)bs});
+            q += 4 + (size_t)bs;
+        }
+        carry.assign(d + q, d + ulen);
+        if (eof && !carry.empty()) { hx_set_error("%s: truncated BAM (partial record at EOF)", path.c_str()); return HX_E_ARG; }
+        auto t3 = clk::now();
+        t_read += std::chrono::duration<double>(t1 - t0).count();
+        t_inflate += std::chrono::duration<double>(t2 - t1).count();
+        t_scan += std::chrono::duration<double>(t3 - t2).count();
+        return HX_OK;
+    }
+
+    // a coordinate-sorted file has nothing more for [.., end_pos] on the target once its records are beyond it
+    bool past_region(int32_t end_pos) const {
+        if (!sorted || recs.empty()) return false;
+        const uint8_t *r = ubuf.get() + recs.back().off;
+        const int32_t tid = rdi32(r), pos = rdi32(r + 4);
+        if (tid < 0) return true;                                  // unmapped reads without a position come last
+        return tid > target_tid || (tid == target_tid && pos + 1 > end_pos);
+    }
 };
 
-int load_bam(const char *bam_path, const char *contig, int n_threads, LoadedBam &lb) {
-    FILE *fp = fopen(bam_path, "rb");
-    if (!fp) { hx_set_error("cannot open %s", bam_path); return HX_E_ARG; }
-    fseek(fp, 0, SEEK_END);
-    const long fsz = ftell(fp);
-    fseek(fp, 0, SEEK_SET);
-    std::vector<uint8_t> file((size_t)fsz);
-    if (fsz && fread(file.data(), 1, (size_t)fsz, fp) != (size_t)fsz) { fclose(fp); hx_set_error("short read on %s", bam_path); return HX_E_ARG; }
-    fclose(fp);
-    std::vector<Block> blocks;
-    size_t total = 0;
-    if (!scan_bgzf(file, blocks, total)) { hx_set_error("%s is not a BGZF file", bam_path); return HX_E_ARG; }
-    lb.data.resize(total);
-    std::atomic<size_t> next(0);
-    std::atomic<bool> ok(true);
-    auto work = [&]() {
-        for (;;) {
-            const size_t b = next.fetch_add(1);
-            if (b >= blocks.size()) break;
-            if (!inflate_block(file.data() + blocks[b].coff, blocks[b].csize, lb.data.data() + blocks[b].uoff, blocks[b].usize))
-                ok = false;
-        }
-    };
-    std::vector<std::thread> th;
-    for (int t = 1; t < n_threads; ++t) th.emplace_back(work);
-    work();
-    for (auto &t : th) t.join();
-    if (!ok) { hx_set_error("inflate failed on %s", bam_path); return HX_E_ARG; }
-    const uint8_t *d = lb.data.data();
-    if (total < 12 || memcmp(d, "BAM\1", 4) != 0) { hx_set_error("%s is not a BAM file", bam_path); return HX_E_ARG; }
-    size_t p = 4;
-    const int32_t l_text = rdi32(d + p); p += 4 + (size_t)l_text;
-    const int32_t n_ref = rdi32(d + p); p += 4;
-    for (int32_t i = 0; i < n_ref; ++i) {
-        const int32_t l_name = rdi32(d + p); p += 4;
-        const bool hit = std::string((const char *)d + p, (size_t)std::max(0, l_name - 1)) == contig;
-        p += (size_t)l_name;
-        if (hit) { lb.target_tid = i; lb.target_len = rdi32(d + p); }
-        p += 4;
-    }
-    if (lb.target_tid < 0) { hx_set_error("contig %s not in %s", contig, bam_path); return HX_E_ARG; }
-    while (p + 4 <= total) {
-        const int32_t bs = rdi32(d + p);
-        if (bs < 32 || p + 4 + (size_t)bs > total) break;
-        lb.recs.push_back(p + 4);
-        p += 4 + (size_t)bs;
-    }
-    return HX_OK;
-}
+constexpr size_t WAVE_CBYTES = (size_t)48 << 20;      // compressed bytes per wave (~150-250 MB inflated)
 
 }  // namespace
 
@@ -222,66 +391,128 @@ extern "C" {
 
 int hx_pack_bam(const char *bam_path, const char *contig, int32_t start_pos, int32_t end_pos,
                 const int32_t *snp_pos, int32_t n_snps, int stepper, int n_threads, hx_packed *out) {
-    if (!bam_path || !contig || !out || n_snps < 0 || (n_snps && !snp_pos) || stepper < 0 || stepper > 2) {
+    return hx_pack_bam_ex(bam_path, contig, start_pos, end_pos, snp_pos, n_snps, stepper, n_threads, 0, out, nullptr);
+}
+
+int hx_pack_bam_ex(const char *bam_path, const char *contig, int32_t start_pos, int32_t end_pos,
+                   const int32_t *snp_pos, int32_t n_snps, int stepper, int n_threads, int32_t max_depth,
+                   hx_packed *out, double stage_seconds[6]) {
+    if (!bam_path || !contig || !out || n_snps < 0 || (n_snps && !snp_pos) || stepper < 0 || stepper > 2 || max_depth < 0) {
         hx_set_error("hx_pack_bam: bad arguments");
         return HX_E_ARG;
     }
+    for (int32_t i = 1; i < n_snps; ++i)
+        if (snp_pos[i] <= snp_pos[i - 1]) { hx_set_error("hx_pack_bam: SNP positions must be strictly increasing"); return HX_E_ARG; }
     memset(out, 0, sizeof(*out));
     if (n_threads < 1) n_threads = 1;
-    const bool verbose = getenv("HX_PACK_VERBOSE") != nullptr;
-    auto t0 = std::chrono::steady_clock::now();
-    auto lap = [&](const char *what) {
-        if (!verbose) return;
-        auto t1 = std::chrono::steady_clock::now();
-        fprintf(stderr, "[hx_pack_bam] %-10s %.1f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
-        t0 = t1;
-    };
-    LoadedBam lb;
-    {
-        const int rc = load_bam(bam_path, contig, n_threads, lb);
+    using clk = std::chrono::steady_clock;
+    BamStream bs;
+    int rc = bs.open(bam_path, contig, n_threads);
+    if (rc) return rc;
+    std::vector<std::vector<Out>> waves;           // per wave, per thread range (BAM order is kept)
+    double t_walk = 0, t_depth = 0, t_gather = 0;
+    int64_t n_records = 0;
+    // pysam's pileup engine (bam_plp) buffers at most max_depth reads: a read that is not the first of its start
+    // position is dropped while max_depth reads are still live (gretel never changes pysam's default of 8000)
+    std::priority_queue<int64_t, std::vector<int64_t>, std::greater<int64_t>> live_ends;
+    int64_t depth_pos = -1;
+    std::vector<uint8_t> admit;
+    for (;;) {
+        rc = bs.next_wave(WAVE_CBYTES);
         if (rc) return rc;
+        const size_t nrec = bs.recs.size();
+        n_records += (int64_t)nrec;
+        const uint8_t *d = bs.ubuf.get();
+        if (nrec) {
+            auto t0 = clk::now();
+            const bool depth_on = max_depth > 0;
+            if (depth_on) {
+                admit.assign(nrec, 1);
+                for (size_t i = 0; i < nrec; ++i) {
+                    const Rec r = parse_rec(d + bs.recs[i].off, bs.recs[i].size);
+                    // only reads the pileup iterator fetches and its stepper lets through count: target contig,
+                    // overlapping [start_pos - 1, end_pos)
+                    if (!r.ok || r.tid != bs.target_tid || r.pos < 0 || !passes_stepper(r.flag, stepper)) continue;
+                    const int64_t beg = r.pos, end = (int64_t)r.pos + std::max<int64_t>(1, ref_len_of(r));
+                    if (beg >= end_pos || end <= (int64_t)start_pos - 1) continue;
+                    if (beg != depth_pos) {
+                        while (!live_ends.empty() && live_ends.top() <= beg - 1) live_ends.pop();
+                        depth_pos = beg;
+                    } else if ((int64_t)live_ends.size() >= max_depth) {
+                        admit[i] = 0;
+                        continue;
+                    }
+                    live_ends.push(end);
+                }
+            }
+            auto t1 = clk::now();
+            const int nt = (int)std::min<size_t>((size_t)n_threads, std::max<size_t>(1, nrec / 4096));
+            waves.emplace_back((size_t)nt);
+            std::vector<Out> &outs = waves.back();
+            auto work = [&](int t) {
+                std::vector<uint8_t> tmp;
+                const size_t a = nrec * (size_t)t / (size_t)nt, b = nrec * (size_t)(t + 1) / (size_t)nt;
+                for (size_t i = a; i < b; ++i) {
+                    if (depth_on && !admit[i]) continue;
+                    pack_record(parse_rec(d + bs.recs[i].off, bs.recs[i].size), bs.target_tid, start_pos, end_pos, snp_pos,
+                                n_snps, stepper, outs[(size_t)t], tmp);
+                }
+            };
+            std::vector<std::thread> th;
+            for (int t = 1; t < nt; ++t) th.emplace_back(work, t);
+            work(0);
+            for (auto &t : th) t.join();
+            auto t2 = clk::now();
+            t_depth += std::chrono::duration<double>(t1 - t0).count();
+            t_walk += std::chrono::duration<double>(t2 - t1).count();
+        }
+        if (bs.eof || (bs.header_done && bs.past_region(end_pos))) break;
     }
-    const std::vector<uint8_t> &data = lb.data;
-    const std::vector<size_t> &recs = lb.recs;
-    const int32_t target_tid = lb.target_tid;
-    const size_t total = data.size();
-    (void)total;
-    lap("index");
-    // parallel CIGAR walks over contiguous chunks of records (keeps BAM order)
-    const size_t nrec = recs.size();
-    const int nt = (int)std::min<size_t>((size_t)n_threads, std::max<size_t>(1, nrec / 4096));
-    std::vector<Out> outs((size_t)nt);
-    {
-        auto work = [&](int t) {
-            std::vector<uint8_t> tmp;
-            const size_t a = nrec * (size_t)t / (size_t)nt, b = nrec * (size_t)(t + 1) / (size_t)nt;
-            for (size_t i = a; i < b; ++i)
-                pack_record(data.data() + recs[i], target_tid, start_pos, end_pos, snp_pos, n_snps, stepper, outs[(size_t)t], tmp);
-        };
-        std::vector<std::thread> th;
-        for (int t = 1; t < nt; ++t) th.emplace_back(work, t);
-        work(0);
-        for (auto &t : th) t.join();
+    auto t0 = clk::now();
+    // gather: prefix the per-range sizes, then every range is copied into place by its own thread
+    std::vector<Out *> parts;
+    for (auto &w : waves) for (auto &o : w) parts.push_back(&o);
+    std::vector<int64_t> r0(parts.size() + 1, 0), c0(parts.size() + 1, 0);
+    for (size_t i = 0; i < parts.size(); ++i) {
+        r0[i + 1] = r0[i] + (int64_t)parts[i]->rank.size();
+        c0[i + 1] = c0[i] + (int64_t)parts[i]->codes.size();
     }
-    lap("walk");
-    int64_t R = 0, C = 0;
-    for (auto &o : outs) { R += (int64_t)o.rank.size(); C += (int64_t)o.codes.size(); }
+    const int64_t R = r0.back(), C = c0.back();
     out->rank = (int32_t *)malloc(sizeof(int32_t) * (size_t)std::max<int64_t>(R, 1));
     out->off = (int64_t *)malloc(sizeof(int64_t) * (size_t)(R + 1));
-    out->codes = (uint8_t *)malloc((size_t)std::max<int64_t>(C, 1));
+    out->codes = (uint8_t *)malloc((size_t)std::max<int64_t>(C, 1) + 16);
     if (!out->rank || !out->off || !out->codes) { hx_pack_free(out); return HX_E_NOMEM; }
-    int64_t r = 0, c = 0;
-    out->off[0] = 0;
-    for (auto &o : outs) {
-        if (!o.rank.empty()) memcpy(out->rank + r, o.rank.data(), sizeof(int32_t) * o.rank.size());
-        for (size_t i = 0; i < o.klen.size(); ++i) { out->off[r + 1] = out->off[r] + o.klen[i]; ++r; }
-        if (!o.codes.empty()) memcpy(out->codes + c, o.codes.data(), o.codes.size());
-        c += (int64_t)o.codes.size();
+    {
+        std::atomic<size_t> next(0);
+        auto work = [&]() {
+            for (;;) {
+                const size_t i = next.fetch_add(1);
+                if (i >= parts.size()) break;
+                const Out &o = *parts[i];
+                if (!o.rank.empty()) memcpy(out->rank + r0[i], o.rank.data(), sizeof(int32_t) * o.rank.size());
+                int64_t acc = c0[i];
+                for (size_t j = 0; j < o.klen.size(); ++j) { out->off[r0[i] + (int64_t)j] = acc; acc += o.klen[j]; }
+                if (!o.codes.empty()) memcpy(out->codes + c0[i], o.codes.data(), o.codes.size());
+            }
+        };
+        const int nt = (int)std::min<size_t>((size_t)n_threads, std::max<size_t>(1, parts.size()));
+        std::vector<std::thread> th;
+        for (int t = 1; t < nt; ++t) th.emplace_back(work);
+        work();
+        for (auto &t : th) t.join();
     }
-    lap("gather");
+    out->off[R] = C;
+    t_gather = std::chrono::duration<double>(clk::now() - t0).count();
     out->n_reads = R;
     out->n_codes = C;
-    out->n_records = (int64_t)nrec;
+    out->n_records = n_records;
+    if (stage_seconds) {
+        stage_seconds[0] = bs.t_read; stage_seconds[1] = bs.t_inflate; stage_seconds[2] = bs.t_scan;
+        stage_seconds[3] = t_depth; stage_seconds[4] = t_walk; stage_seconds[5] = t_gather;
+    }
+    if (getenv("HX_PACK_VERBOSE"))
+        fprintf(stderr, "[hx_pack_bam] read %.1f ms, inflate %.1f ms, scan %.1f ms, depth %.1f ms, walk %.1f ms, gather %.1f ms\n",
+                1e3 * bs.t_read, 1e3 * bs.t_inflate, 1e3 * bs.t_scan, 1e3 * t_depth, 1e3 * t_walk, 1e3 * t_gather);
     return HX_OK;
 }
 
@@ -291,64 +522,72 @@ int hx_count_coverage(const char *bam_path, const char *contig, int32_t start0, 
                       uint32_t *out) {
     if (!bam_path || !contig || !out || start0 < 0 || end0 < start0) { hx_set_error("hx_count_coverage: bad arguments"); return HX_E_ARG; }
     if (n_threads < 1) n_threads = 1;
-    LoadedBam lb;
-    int rc = load_bam(bam_path, contig, n_threads, lb);
+    BamStream bs;
+    int rc = bs.open(bam_path, contig, n_threads);
     if (rc) return rc;
     const int64_t len = (int64_t)end0 - start0;
     memset(out, 0, sizeof(uint32_t) * 4 * (size_t)len);
-    const size_t nrec = lb.recs.size();
-    const int nt = (int)std::min<size_t>((size_t)n_threads, std::max<size_t>(1, nrec / 4096));
-    std::vector<std::vector<uint32_t>> part((size_t)nt);
-    auto work = [&](int t) {
-        std::vector<uint32_t> &c = part[(size_t)t];
-        c.assign(4 * (size_t)len, 0u);
-        const size_t a = nrec * (size_t)t / (size_t)nt, b = nrec * (size_t)(t + 1) / (size_t)nt;
-        for (size_t i = a; i < b; ++i) {
-            const uint8_t *rec = lb.data.data() + lb.recs[i];
-            const int32_t tid = rdi32(rec), pos = rdi32(rec + 4);
-            if (tid != lb.target_tid || pos < 0) continue;
-            const int l_read_name = rec[8];
-            const int n_cigar = rd16(rec + 12);
-            const int32_t l_seq = rdi32(rec + 16);
-            const uint8_t *cig = rec + 32 + l_read_name;
-            const uint8_t *seq = cig + 4 * (size_t)n_cigar;
-            int64_t rpos = pos, qpos = 0;
-            for (int ci = 0; ci < n_cigar; ++ci) {
-                const uint32_t cv = rd32(cig + 4 * ci);
-                const int op = cv & 0xf;
-                const int64_t ln = cv >> 4;
-                if (op == 0 || op == 7 || op == 8) {
-                    for (int64_t j = 0; j < ln; ++j) {
-                        const int64_t r = rpos + j, q = qpos + j;
-                        if (r < start0 || r >= end0 || q >= l_seq) continue;
-                        const uint8_t bb = seq[q >> 1];
-                        const uint8_t code = NT16_CODE[(q & 1) ? (bb & 0xf) : (bb >> 4)];
-                        if (code < 4) c[(size_t)code * (size_t)len + (size_t)(r - start0)]++;
+    std::vector<std::vector<uint32_t>> part((size_t)n_threads);
+    for (;;) {
+        rc = bs.next_wave(WAVE_CBYTES);
+        if (rc) return rc;
+        const size_t nrec = bs.recs.size();
+        const uint8_t *d = bs.ubuf.get();
+        if (nrec) {
+            const int nt = (int)std::min<size_t>((size_t)n_threads, std::max<size_t>(1, nrec / 4096));
+            auto work = [&](int t) {
+                std::vector<uint32_t> &c = part[(size_t)t];
+                if (c.empty()) c.assign(4 * (size_t)len, 0u);
+                const size_t a = nrec * (size_t)t / (size_t)nt, b = nrec * (size_t)(t + 1) / (size_t)nt;
+                for (size_t i = a; i < b; ++i) {
+                    const Rec r = parse_rec(d + bs.recs[i].off, bs.recs[i].size);
+                    if (!r.ok || r.tid != bs.target_tid || r.pos < 0) continue;
+                    int64_t rpos = r.pos, qpos = 0;
+                    for (int ci = 0; ci < r.n_cigar; ++ci) {
+                        const uint32_t cv = rd32(r.cig + 4 * (size_t)ci);
+                        const int op = cv & 0xf;
+                        const int64_t ln = cv >> 4;
+                        if (op == 0 || op == 7 || op == 8) {
+                            for (int64_t j = 0; j < ln; ++j) {
+                                const int64_t rp = rpos + j, q = qpos + j;
+                                if (rp < start0 || rp >= end0 || q >= r.l_seq) continue;
+                                const uint8_t bb = r.seq[q >> 1];
+                                const uint8_t code = NT16_CODE[(q & 1) ? (bb & 0xf) : (bb >> 4)];
+                                if (code < 4) c[(size_t)code * (size_t)len + (size_t)(rp - start0)]++;
+                            }
+                            rpos += ln; qpos += ln;
+                        } else if (op == 2 || op == 3) {
+                            rpos += ln;
+                        } else if (op == 1 || op == 4) {
+                            qpos += ln;
+                        }
                     }
-                    rpos += ln; qpos += ln;
-                } else if (op == 2 || op == 3) {
-                    rpos += ln;
-                } else if (op == 1 || op == 4) {
-                    qpos += ln;
                 }
-            }
+            };
+            std::vector<std::thread> th;
+            for (int t = 1; t < nt; ++t) th.emplace_back(work, t);
+            work(0);
+            for (auto &t : th) t.join();
         }
-    };
-    std::vector<std::thread> th;
-    for (int t = 1; t < nt; ++t) th.emplace_back(work, t);
-    work(0);
-    for (auto &t : th) t.join();
-    for (int t = 0; t < nt; ++t)
-        for (size_t i = 0; i < 4 * (size_t)len; ++i) out[i] += part[(size_t)t][i];
+        if (bs.eof || (bs.header_done && bs.past_region(end0))) break;
+    }
+    for (auto &c : part)
+        if (!c.empty())
+            for (size_t i = 0; i < 4 * (size_t)len; ++i) out[i] += c[i];
     return HX_OK;
 }
 
 int hx_bam_contig_length(const char *bam_path, const char *contig, int32_t *length) {
     if (!bam_path || !contig || !length) { hx_set_error("hx_bam_contig_length: bad arguments"); return HX_E_ARG; }
-    LoadedBam lb;
-    int rc = load_bam(bam_path, contig, 1, lb);
+    BamStream bs;
+    int rc = bs.open(bam_path, contig, 1);
     if (rc) return rc;
-    *length = lb.target_len;
+    while (!bs.header_done) {                      // only the header is read: 1 MiB at a time
+        rc = bs.next_wave((size_t)1 << 20);
+        if (rc) return rc;
+        if (bs.eof && !bs.header_done) { hx_set_error("%s: truncated BAM header", bam_path); return HX_E_ARG; }
+    }
+    *length = bs.target_len;
     return HX_OK;
 }
 

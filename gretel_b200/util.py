@@ -222,20 +222,32 @@ def set_totals(hansel, slices, crumbs, covered, quiet=True):
 
 def load_from_bam(bam_path, target_contig, start_pos, end_pos, vcf_handler, use_end_sentinels=False,
                   n_threads=1, debug_reads=False, debug_pos=False, stepper="samtools", device=None,
-                  band_w=None):
+                  band_w=None, max_depth=bamio.PYSAM_MAX_DEPTH, stages=None):
     """gretel/util.py:33.  Same signature and return value; ``n_threads`` is accepted for
     compatibility (the reference's window sharding is replaced by one GPU kernel and the
     result is independent of it, cf. tests/test_test.py:35).  ``use_end_sentinels`` is an
-    experimental dead branch upstream (never passed, cmd.py:78) and is rejected here."""
+    experimental dead branch upstream (never passed, cmd.py:78) and is rejected here.  ``max_depth``: the
+    reference reads the BAM through pysam's pileup, whose buffer drops reads beyond 8000 per position
+    (bamio._DepthCap); the default reproduces that, ``max_depth=0`` keeps every read.  ``stages``: dict that
+    receives per-stage seconds of the packer and of the GPU ingestion."""
     if use_end_sentinels:
         raise NotImplementedError("use_end_sentinels is never enabled by the reference (cmd.py:28,78)")
     # n_threads (the reference's number of BAM iterators, cmd.py:31) drives the native packer's threads
+    import time
+    t0 = time.perf_counter()
     rank, off, codes = bamio.pack_bam_native(bam_path, target_contig, start_pos, end_pos, vcf_handler,
-                                             stepper=stepper, n_threads=n_threads)
+                                             stepper=stepper, n_threads=n_threads, max_depth=max_depth, stages=stages)
+    t1 = time.perf_counter()
     if band_w is None:
         # hold every ingested pair; at least N+1 for tiny regions so that the scalar API
         # (add/get_observation on arbitrary i<j) is band-resident like the reference's dense array
         band_w = band_width_for(off)
         if vcf_handler["N"] <= 256:
             band_w = max(band_w, vcf_handler["N"] + 1)
-    return load_from_packed(rank, off, codes, vcf_handler["N"], band_w=band_w, device=device, quiet=False)
+    h = load_from_packed(rank, off, codes, vcf_handler["N"], band_w=band_w, device=device, quiet=False,
+                         n_threads=max(1, n_threads))
+    if stages is not None:
+        stages["pack_total"] = t1 - t0
+        stages["gpu_ingest"] = time.perf_counter() - t1
+        stages["reads"] = int(len(rank))
+    return h

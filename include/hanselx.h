@@ -178,6 +178,14 @@ typedef struct {
 } hx_packed;
 int hx_pack_bam(const char *bam_path, const char *contig, int32_t start_pos, int32_t end_pos,
                 const int32_t *snp_pos, int32_t n_snps, int stepper, int n_threads, hx_packed *out);
+/* The same with pysam's pileup depth cap and stage timings.  max_depth > 0 reproduces bam_plp's buffer limit (the
+ * reference never changes pysam's default of 8000, gretel/util.py:137): a read that is not the first of its start
+ * position is dropped while max_depth reads are still buffered; 0 = keep every read.  stage_seconds (or NULL):
+ * { file read, BGZF inflate, record scan, depth filter, CIGAR walks, gather }.  The BAM is streamed in bounded
+ * waves of BGZF blocks and reading stops once a coordinate-sorted file has passed end_pos. */
+int hx_pack_bam_ex(const char *bam_path, const char *contig, int32_t start_pos, int32_t end_pos,
+                   const int32_t *snp_pos, int32_t n_snps, int stepper, int n_threads, int32_t max_depth,
+                   hx_packed *out, double stage_seconds[6]);
 void hx_pack_free(hx_packed *p);
 /* Packed reads (rank-sorted) -> the dense wire format of hx_ingest_host_dense, as one malloc'ed buffer whose
  * sections sit at the given byte offsets (rank_delta at 0): shipping it takes a single host->device copy.

@@ -14,19 +14,21 @@ def _bgzf_block(data):
             + comp + struct.pack("<II", zlib.crc32(data) & 0xffffffff, len(data)))
 
 
-def write_bam(path, refs, reads, block=40000):
-    """refs: [(name, length)]; reads: [(tid, pos0, flag, name, [(op_char, len)], seq)] in file order."""
+def write_bam(path, refs, reads, block=40000, aux=None):
+    """refs: [(name, length)]; reads: [(tid, pos0, flag, name, [(op_char, len)], seq)] in file order;
+    aux: optional list of raw aux-tag bytes per read."""
     text = "@HD\tVN:1.0\tSO:coordinate\n" + "".join("@SQ\tSN:%s\tLN:%d\n" % r for r in refs)
     out = bytearray(b"BAM\x01" + struct.pack("<i", len(text)) + text.encode() + struct.pack("<i", len(refs)))
     for name, ln in refs:
         out += struct.pack("<i", len(name) + 1) + name.encode() + b"\x00" + struct.pack("<i", ln)
-    for tid, pos, flag, name, cigar, seq in reads:
+    for ri, (tid, pos, flag, name, cigar, seq) in enumerate(reads):
         packed = bytearray((len(seq) + 1) // 2)
         for i, ch in enumerate(seq):
             packed[i >> 1] |= _NT16[ch] << (0 if i & 1 else 4)
         cig = b"".join(struct.pack("<I", (ln << 4) | _OPS[op]) for op, ln in cigar)
         body = (struct.pack("<iiBBHHHiiii", tid, pos, len(name) + 1, 42, 4680, len(cigar), flag, len(seq), -1, -1, 0)
-                + name.encode() + b"\x00" + cig + bytes(packed) + b"\xff" * len(seq))
+                + name.encode() + b"\x00" + cig + bytes(packed) + b"\xff" * len(seq)
+                + (aux[ri] if aux else b""))
         out += struct.pack("<i", len(body)) + body
     with open(path, "wb") as fh:
         for i in range(0, len(out), block):
