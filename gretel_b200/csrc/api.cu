@@ -392,6 +392,12 @@ int hx_ingest_host(hx_matrix *h, const int32_t *rank, const int64_t *off, const 
                    int64_t n_reads, int64_t totals[4]) {
     HX_CHECK_ARG(h && totals && n_reads >= 0);
     HX_CUDA(cudaSetDevice(h->device));
+    if (n_reads >= 200000 && rank && off && codes && !getenv("HX_NO_HOST_PIPELINE")) {
+        // large inputs: dense re-encoding on the host threads, pipelined with the copies and the pair expansion
+        const int rc = hx_ingest_host_pipelined(h, rank, off, codes, n_reads);
+        if (rc == HX_OK) return hx_ingest_totals(h, totals);
+        if (rc != HX_E_STATE) return rc;            // HX_E_STATE: not sorted by rank -> the packed arrays as they are
+    }
     if (n_reads > 0) {
         HX_CHECK_ARG(rank && off && codes);
         const int64_t n_codes = off[n_reads] - off[0];

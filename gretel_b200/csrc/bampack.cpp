@@ -361,6 +361,9 @@ struct BamStream {
             const int32_t bs = rdi32(d + q);
             if (bs < 32) { hx_set_error("%s: corrupt alignment record (block_size %d)", path.c_str(), bs); return HX_E_ARG; }
             if (q + 4 + (size_t)bs > ulen) break;
+            // the chain of block_size fields is serial and every step is a cache miss: fetch where the chain will
+            // be in 16 records if they are about this long
+            __builtin_prefetch(d + std::min(ulen - 1, q + 16 * (4 + (size_t)bs)));
             recs.push_back({q + 4, (uint32_t)bs});
             q += 4 + (size_t)bs;
         }
@@ -592,7 +595,147 @@ int hx_bam_contig_length(const char *bam_path, const char *contig, int32_t *leng
 }
 
 // ---- dense wire format encoder (CPU side of hx_ingest_host_dense; layout documented in wire.cu) ----------
+}  // extern "C"
+
+#include "dense_enc.h"
+
 static inline int64_t al16(int64_t x) { return (x + 15) & ~(int64_t)15; }
+
+static inline uint64_t ld64(const uint8_t *p) { uint64_t v; memcpy(&v, p, 8); return v; }
+
+template <class F>
+static void run_threads(int nt, F f) {
+    std::vector<std::thread> th;
+    for (int t = 1; t < nt; ++t) th.emplace_back(f, t);
+    f(0);
+    for (auto &x : th) x.join();
+}
+
+// Pass 1: validation, sizes and where every thread's list entries go.  Eight alleles per 64-bit operation.
+int hx_dense_plan(const int32_t *rank, const int64_t *off, const uint8_t *codes, int64_t n_reads, int n_threads,
+                  HxDensePlan *pl) {
+    HxDensePlan &P = *pl;
+    P.c0 = n_reads ? off[0] : 0;
+    P.n_codes = n_reads ? off[n_reads] - P.c0 : 0;
+    P.n_reads = n_reads;
+    if (P.n_codes < 0 || P.n_codes >= ((int64_t)1 << 32)) {
+        hx_set_error("hx_dense_encode: %lld alleles in one chunk (limit 2^32 - 1): split the reads", (long long)P.n_codes);
+        return HX_E_ARG;
+    }
+    const int nt = (int)std::max<int64_t>(1, std::min<int64_t>(std::min(n_threads, HX_DENSE_MAX_THREADS), 1 + n_reads / 65536));
+    P.nt = nt;
+    std::vector<int64_t> kmax((size_t)nt, 0);
+    std::vector<int> bad((size_t)nt, 0);
+    for (int t = 0; t < nt; ++t) { P.esc_at[t] = 0; P.exc_at[t] = 0; }
+    run_threads(nt, [&](int t) {
+        const int64_t a = n_reads * t / nt, b = n_reads * (t + 1) / nt;
+        int64_t ne = 0, km = 0;
+        int bd = 0;
+        for (int64_t r = a; r < b; ++r) {
+            const int64_t d = (int64_t)rank[r] - (r ? (int64_t)rank[r - 1] : 0), k = off[r + 1] - off[r];
+            if (d < 0) bd = 1;
+            if (k < 0 || k > 65535) bd = 2;
+            ne += d >= 255;
+            km = std::max(km, k);
+        }
+        int64_t nx = 0;
+        if (b > a && !bd) {
+            int64_t i = off[a], e = off[b];
+            uint64_t any = 0;
+            for (; i + 8 <= e; i += 8) {
+                const uint64_t x = ld64(codes + i);
+                any |= (x & 0xf8f8f8f8f8f8f8f8ull) | (x & (x >> 1) & (x >> 2) & 0x0101010101010101ull);   // > 6
+                nx += __builtin_popcountll(x & 0x0404040404040404ull);
+            }
+            for (; i < e; ++i) { if (codes[i] > 6) any = 1; nx += codes[i] >= 4; }
+            if (any) bd = 3;
+        }
+        P.esc_at[t] = ne; P.exc_at[t] = nx; kmax[(size_t)t] = km; bad[(size_t)t] = bd;
+    });
+    int64_t tot_esc = 0, tot_exc = 0, km = 0;
+    for (int t = 0; t < nt; ++t) {
+        if (bad[(size_t)t]) {
+            hx_set_error("hx_dense_encode: %s", bad[(size_t)t] == 1 ? "reads are not sorted by rank"
+                                               : bad[(size_t)t] == 2 ? "a read covers more than 65535 SNPs (or off[] decreases)"
+                                                                     : "allele code > 6");
+            return bad[(size_t)t] == 1 ? HX_E_STATE : HX_E_ARG;
+        }
+        const int64_t e = P.esc_at[t], x = P.exc_at[t];
+        P.esc_at[t] = tot_esc; P.exc_at[t] = tot_exc;       // exclusive prefix: where each thread writes its lists
+        tot_esc += e; tot_exc += x;
+        km = std::max(km, kmax[(size_t)t]);
+    }
+    P.n_esc = tot_esc; P.n_exc = tot_exc;
+    P.klen_bytes = km < 256 ? 1 : 2;
+    const int64_t n_words = (P.n_codes + 15) / 16;
+    P.o_klen = al16(n_reads);
+    P.o_codes2 = P.o_klen + al16(n_reads * P.klen_bytes);
+    P.o_exc = P.o_codes2 + al16(n_words * 4);
+    P.o_esc_idx = P.o_exc + al16(tot_exc * 4);
+    P.o_esc_delta = P.o_esc_idx + al16(tot_esc * 8);
+    P.bytes = P.o_esc_delta + al16(tot_esc * 4) + 16;
+    return HX_OK;
+}
+
+// Pass 2: every byte of the blob the device reads is written here (the blob need not be zeroed).
+void hx_dense_fill(const int32_t *rank, const int64_t *off, const uint8_t *codes, const HxDensePlan *pl, uint8_t *blob) {
+    const HxDensePlan &P = *pl;
+    const int nt = P.nt;
+    const int64_t n_reads = P.n_reads, n_codes = P.n_codes, c0 = P.c0;
+    const int kb = P.klen_bytes;
+    uint32_t *exc = (uint32_t *)(blob + P.o_exc);
+    int64_t *ei = (int64_t *)(blob + P.o_esc_idx);
+    int32_t *ed = (int32_t *)(blob + P.o_esc_delta);
+    uint8_t *c2 = blob + P.o_codes2;
+    run_threads(nt, [&](int t) {
+        const int64_t a = n_reads * t / nt, b = n_reads * (t + 1) / nt;
+        int64_t ne = P.esc_at[t];
+        for (int64_t r = a; r < b; ++r) {
+            const int64_t d = (int64_t)rank[r] - (r ? (int64_t)rank[r - 1] : 0), k = off[r + 1] - off[r];
+            blob[r] = (uint8_t)std::min<int64_t>(d, 255);
+            if (d >= 255) { ei[ne] = r; ed[ne] = (int32_t)d; ++ne; }
+            if (kb == 1) blob[P.o_klen + r] = (uint8_t)k; else ((uint16_t *)(blob + P.o_klen))[r] = (uint16_t)k;
+        }
+        if (b <= a) return;
+        // exception positions of this thread's reads
+        {
+            int64_t nx = P.exc_at[t];
+            int64_t i = off[a] - c0;
+            const int64_t e = off[b] - c0;
+            for (; i + 8 <= e; i += 8) {
+                uint64_t m = ld64(codes + c0 + i) & 0x0404040404040404ull;
+                while (m) {
+                    const int j = __builtin_ctzll(m) >> 3;
+                    exc[nx++] = (uint32_t)(i + j);
+                    m &= m - 1;
+                }
+            }
+            for (; i < e; ++i) if (codes[c0 + i] >= 4) exc[nx++] = (uint32_t)i;
+        }
+        // alleles [lo, hi) of the stream, rounded so that every output byte has exactly one writer
+        int64_t lo = off[a] - c0, hi = off[b] - c0;
+        lo = t == 0 ? 0 : (lo + 3) & ~(int64_t)3;
+        hi = t == nt - 1 ? n_codes : (hi + 3) & ~(int64_t)3;
+        hi = std::min(hi, n_codes);
+        int64_t i = lo;
+        for (; i + 8 <= hi; i += 8) {              // 8 alleles -> 16 bits (code & 3: N, -, _ store code - 4)
+            uint64_t x = ld64(codes + c0 + i) & 0x0303030303030303ull;
+            x = (x | (x >> 6)) & 0x000f000f000f000full;
+            x = (x | (x >> 12)) & 0x000000ff000000ffull;
+            x = (x | (x >> 24)) & 0xffffull;
+            const uint16_t v = (uint16_t)x;
+            memcpy(c2 + (i >> 2), &v, 2);
+        }
+        for (; i < hi; i += 4) {
+            uint8_t byte = 0;
+            const int64_t m = std::min<int64_t>(4, n_codes - i);
+            for (int64_t j = 0; j < m; ++j) byte |= (uint8_t)((codes[c0 + i + j] & 3) << (2 * j));
+            c2[i >> 2] = byte;
+        }
+    });
+}
+
+extern "C" {
 
 int hx_dense_encode(const int32_t *rank, const int64_t *off, const uint8_t *codes, int64_t n_reads, int n_threads,
                     hx_dense *out) {
@@ -601,112 +744,16 @@ int hx_dense_encode(const int32_t *rank, const int64_t *off, const uint8_t *code
         return HX_E_ARG;
     }
     memset(out, 0, sizeof(*out));
-    const int64_t c0 = n_reads ? off[0] : 0, n_codes = n_reads ? off[n_reads] - c0 : 0;
-    if (n_codes < 0 || n_codes >= ((int64_t)1 << 32)) {
-        hx_set_error("hx_dense_encode: %lld alleles in one chunk (limit 2^32 - 1): split the reads", (long long)n_codes);
-        return HX_E_ARG;
-    }
-    const int nt = (int)std::max<int64_t>(1, std::min<int64_t>(n_threads, 1 + n_reads / 65536));
-    // pass 1: per-thread maxima and counts over a contiguous range of reads (and of their alleles)
-    std::vector<int64_t> n_esc(nt, 0), n_exc(nt, 0), kmax(nt, 0);
-    std::vector<int> bad(nt, 0);
-    auto range = [&](int t, int64_t &a, int64_t &b) { a = n_reads * t / nt; b = n_reads * (t + 1) / nt; };
-    auto pass1 = [&](int t) {
-        int64_t a, b;
-        range(t, a, b);
-        for (int64_t r = a; r < b; ++r) {
-            const int64_t d = (int64_t)rank[r] - (r ? (int64_t)rank[r - 1] : 0), k = off[r + 1] - off[r];
-            if (d < 0 || k < 0 || k > 65535) bad[t] = d < 0 ? 1 : 2;
-            if (d >= 255) n_esc[t]++;
-            kmax[t] = std::max(kmax[t], k);
-        }
-        if (b > a && !bad[t])
-            for (int64_t i = off[a]; i < off[b]; ++i) {
-                if (codes[i] > 6) bad[t] = 3;
-                n_exc[t] += codes[i] >= 4;
-            }
-    };
-    {
-        std::vector<std::thread> th;
-        for (int t = 1; t < nt; ++t) th.emplace_back(pass1, t);
-        pass1(0);
-        for (auto &x : th) x.join();
-    }
-    int64_t tot_esc = 0, tot_exc = 0, km = 0;
-    for (int t = 0; t < nt; ++t) {
-        if (bad[t]) {
-            hx_set_error("hx_dense_encode: %s", bad[t] == 1 ? "reads are not sorted by rank"
-                                               : bad[t] == 2 ? "a read covers more than 65535 SNPs (or off[] decreases)"
-                                                             : "allele code > 6");
-            return HX_E_ARG;
-        }
-        const int64_t e = n_esc[t], x = n_exc[t];
-        n_esc[t] = tot_esc; n_exc[t] = tot_exc;       // exclusive prefix: where each thread writes its lists
-        tot_esc += e; tot_exc += x;
-        km = std::max(km, kmax[t]);
-    }
-    const int kb = km < 256 ? 1 : 2;
-    const int64_t n_words = (n_codes + 15) / 16;
-    const int64_t o_kl = al16(n_reads), o_c2 = o_kl + al16(n_reads * kb), o_ex = o_c2 + al16(n_words * 4);
-    const int64_t o_ei = o_ex + al16(tot_exc * 4), o_ed = o_ei + al16(tot_esc * 8), bytes = o_ed + al16(tot_esc * 4) + 16;
-    uint8_t *blob = (uint8_t *)calloc(1, (size_t)bytes);
-    if (!blob) { hx_set_error("hx_dense_encode: out of memory (%lld bytes)", (long long)bytes); return HX_E_NOMEM; }
-    uint32_t *exc = (uint32_t *)(blob + o_ex);
-    int64_t *ei = (int64_t *)(blob + o_ei);
-    int32_t *ed = (int32_t *)(blob + o_ed);
-    // pass 2: a thread's alleles start at off[a]-c0, which need not be a multiple of 4: boundaries move up to the
-    // next byte so that every output byte has exactly one writer
-    auto pass2 = [&](int t) {
-        int64_t a, b;
-        range(t, a, b);
-        int64_t ne = n_esc[t];
-        for (int64_t r = a; r < b; ++r) {
-            const int64_t d = (int64_t)rank[r] - (r ? (int64_t)rank[r - 1] : 0), k = off[r + 1] - off[r];
-            blob[r] = (uint8_t)std::min<int64_t>(d, 255);
-            if (d >= 255) { ei[ne] = r; ed[ne] = (int32_t)d; ++ne; }
-            if (kb == 1) blob[o_kl + r] = (uint8_t)k; else ((uint16_t *)(blob + o_kl))[r] = (uint16_t)k;
-        }
-        if (b <= a) return;
-        // alleles [lo, hi) of the stream, rounded so that every output byte has exactly one writer
-        int64_t lo = off[a] - c0, hi = off[b] - c0;
-        lo = t == 0 ? 0 : (lo + 3) & ~(int64_t)3;
-        hi = t == nt - 1 ? n_codes : (hi + 3) & ~(int64_t)3;
-        hi = std::min(hi, n_codes);
-        uint8_t *c2 = blob + o_c2;
-        for (int64_t i = lo; i < hi; i += 4) {
-            uint8_t byte = 0;
-            const int64_t m = std::min<int64_t>(4, n_codes - i);
-            for (int64_t j = 0; j < m; ++j) {
-                const uint8_t c = codes[c0 + i + j];
-                byte |= (uint8_t)((c >= 4 ? c - 4 : c) << (2 * j));
-            }
-            c2[i >> 2] = byte;
-        }
-    };
-    {
-        std::vector<std::thread> th;
-        for (int t = 1; t < nt; ++t) th.emplace_back(pass2, t);
-        pass2(0);
-        for (auto &x : th) x.join();
-    }
-    // exception positions: per-thread slots were sized by read ranges, so fill them by read ranges too
-    auto pass3 = [&](int t) {
-        int64_t a, b;
-        range(t, a, b);
-        if (b <= a) return;
-        int64_t nx = n_exc[t];
-        for (int64_t i = off[a] - c0; i < off[b] - c0; ++i)
-            if (codes[c0 + i] >= 4) exc[nx++] = (uint32_t)i;
-    };
-    {
-        std::vector<std::thread> th;
-        for (int t = 1; t < nt; ++t) th.emplace_back(pass3, t);
-        pass3(0);
-        for (auto &x : th) x.join();
-    }
-    out->blob = blob; out->blob_bytes = bytes; out->n_reads = n_reads; out->n_codes = n_codes;
-    out->n_exc = tot_exc; out->n_esc = tot_esc; out->klen_bytes = kb;
-    out->o_klen = o_kl; out->o_codes2 = o_c2; out->o_exc = o_ex; out->o_esc_idx = o_ei; out->o_esc_delta = o_ed;
+    HxDensePlan P;
+    int rc = hx_dense_plan(rank, off, codes, n_reads, n_threads, &P);
+    if (rc) return rc == HX_E_STATE ? HX_E_ARG : rc;
+    uint8_t *blob = (uint8_t *)calloc(1, (size_t)P.bytes);
+    if (!blob) { hx_set_error("hx_dense_encode: out of memory (%lld bytes)", (long long)P.bytes); return HX_E_NOMEM; }
+    hx_dense_fill(rank, off, codes, &P, blob);
+    out->blob = blob; out->blob_bytes = P.bytes; out->n_reads = n_reads; out->n_codes = P.n_codes;
+    out->n_exc = P.n_exc; out->n_esc = P.n_esc; out->klen_bytes = P.klen_bytes;
+    out->o_klen = P.o_klen; out->o_codes2 = P.o_codes2; out->o_exc = P.o_exc; out->o_esc_idx = P.o_esc_idx;
+    out->o_esc_delta = P.o_esc_delta;
     return HX_OK;
 }
 

@@ -61,6 +61,7 @@ struct hx_matrix {
     int64_t cap_klen, cap_codes4, cap_scan;
     hx_wire_set wire[HX_WIRE_SETS]; int wire_next;   // dense wire format: rotating staging sets
     cudaStream_t copy_stream, decode_stream; // host->device copies / decode kernels of the dense format
+    uint8_t *pin[2]; int64_t pin_cap[2]; cudaEvent_t pin_ev[2]; bool pin_busy[2];   // pinned encode buffers of hx_ingest_host
     // recovery scratch
     double *scnt;                    // (N+2)*8 per-site counts + total
     int32_t *vseen;                  // (N+2) valid symbols seen per site
@@ -152,6 +153,7 @@ int hx_ensure_counts_buffer(hx_matrix *h);
 // wire.cu
 void hx_wire_free(hx_matrix *h);
 void hx_wire_trace_dump();
+int hx_ingest_host_pipelined(hx_matrix *h, const int32_t *rank, const int64_t *off, const uint8_t *codes, int64_t n_reads);
 // ingest_long.cu
 int hx_launch_ingest_long(hx_matrix *h, const int32_t *d_rank, const int64_t *d_off,
                           const uint8_t *d_codes, int64_t n_reads, const int *sorted_flag);

@@ -13,7 +13,9 @@
 // sets and the decode on a third, so the copy and decode of chunk i+1 overlap the pair expansion of chunk i.
 #include <algorithm>
 #include <stdlib.h>
+#include <thread>
 
+#include "dense_enc.h"
 #include "hx_internal.cuh"
 
 namespace {
@@ -278,6 +280,11 @@ void hx_wire_free(hx_matrix *h) {
         if (w.decoded) cudaEventDestroy(w.decoded);
         w = hx_wire_set{};
     }
+    for (int s = 0; s < 2; ++s) {
+        if (h->pin_ev[s]) cudaEventDestroy(h->pin_ev[s]);
+        if (h->pin[s]) cudaFreeHost(h->pin[s]);
+        h->pin[s] = nullptr; h->pin_cap[s] = 0; h->pin_ev[s] = nullptr; h->pin_busy[s] = false;
+    }
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->decode_stream) cudaStreamDestroy(h->decode_stream);
     h->copy_stream = nullptr;
@@ -397,4 +404,58 @@ extern "C" int hx_ingest_host_dense(hx_matrix *h, const uint8_t *rank_delta, con
         HX_CUDA(cudaEventRecord(w.consumed, st));
     }
     return totals ? hx_ingest_totals(h, totals) : HX_OK;
+}
+
+
+// ---- host arrays -> matrix, pipelined -------------------------------------------------------------------------
+// hx_ingest_host for large rank-sorted inputs: the packed arrays are cut into a few chunks at read boundaries;
+// each chunk is encoded into the dense wire format by the host threads straight into one of two pinned buffers
+// and enqueued with hx_ingest_host_dense(totals = NULL), so the encoding of chunk i+1 runs while chunk i is
+// copied, decoded and pair-expanded.  HX_E_STATE = the reads are not sorted by rank (the caller ships them as
+// they are); nothing has been enqueued in that case.
+int hx_ingest_host_pipelined(hx_matrix *h, const int32_t *rank, const int64_t *off, const uint8_t *codes, int64_t n_reads) {
+    int nt = 0;
+    if (const char *e = getenv("HX_HOST_THREADS")) nt = atoi(e);
+    if (nt <= 0) nt = (int)std::min(32u, std::max(1u, std::thread::hardware_concurrency()));
+    const int64_t n_codes = off[n_reads] - off[0];
+    constexpr int64_t CHUNK_CODES = (int64_t)32 << 20;
+    int n_chunks = (int)std::max<int64_t>(3, (n_codes + CHUNK_CODES - 1) / CHUNK_CODES);
+    if ((int64_t)n_chunks > n_reads) n_chunks = (int)n_reads;
+    int64_t a = 0;
+    for (int c = 0; c < n_chunks; ++c) {
+        int64_t b = n_reads;
+        if (c + 1 < n_chunks) {
+            const int64_t target = off[0] + n_codes * (c + 1) / n_chunks;
+            b = std::lower_bound(off + a, off + n_reads, target) - off;
+            if (b <= a) continue;
+        }
+        HxDensePlan P;
+        int rc = hx_dense_plan(rank + a, off + a, codes, b - a, nt, &P);
+        if (rc == HX_E_STATE && c > 0) {           // sorted so far, not here: the rest goes as it is (still exact)
+            hx_set_error("hx_ingest_host: reads stop being sorted by rank inside the input");
+            return HX_E_ARG;
+        }
+        if (rc) return rc;
+        const int slot = c & 1;
+        if (h->pin_busy[slot]) { HX_CUDA(cudaEventSynchronize(h->pin_ev[slot])); h->pin_busy[slot] = false; }
+        if (P.bytes > h->pin_cap[slot]) {
+            if (h->pin[slot]) cudaFreeHost(h->pin[slot]);
+            h->pin[slot] = nullptr; h->pin_cap[slot] = 0;
+            const int64_t want = P.bytes + P.bytes / 4 + 4096;
+            HX_CUDA(cudaHostAlloc((void **)&h->pin[slot], (size_t)want, cudaHostAllocPortable));
+            h->pin_cap[slot] = want;
+        }
+        if (!h->pin_ev[slot]) HX_CUDA(cudaEventCreateWithFlags(&h->pin_ev[slot], cudaEventDisableTiming));
+        uint8_t *blob = h->pin[slot];
+        hx_dense_fill(rank + a, off + a, codes, &P, blob);
+        rc = hx_ingest_host_dense(h, blob, reinterpret_cast<const int64_t *>(blob + P.o_esc_idx),
+                                  reinterpret_cast<const int32_t *>(blob + P.o_esc_delta), P.n_esc, blob + P.o_klen,
+                                  P.klen_bytes, blob + P.o_codes2, reinterpret_cast<const uint32_t *>(blob + P.o_exc), P.n_exc,
+                                  b - a, P.n_codes, nullptr);
+        if (rc) return rc;
+        HX_CUDA(cudaEventRecord(h->pin_ev[slot], h->copy_stream));      // the slot is free again once its copy is done
+        h->pin_busy[slot] = true;
+        a = b;
+    }
+    return HX_OK;
 }

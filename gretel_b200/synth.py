@@ -137,3 +137,87 @@ def random_packed(rng, n_snps, n_reads, max_k, p_special=0.1, sort=True):
     special = rng.random(len(codes)) < p_special
     codes[special] = rng.integers(4, 7, size=int(special.sum())).astype(np.uint8)
     return ranks.astype(np.int32), off, codes
+
+
+def write_bam(path, d, w, contig="ctg", threads=8, level=1):
+    """Write the reads of a ``generate()`` result as a coordinate-sorted BAM (fixed-length 150M reads; vectorised,
+    so a million reads take seconds).  The reference base is 'A' everywhere; a read carries its packed alleles at
+    the SNP sites it covers ('-' cannot be expressed in a fixed-length all-match record and is written as 'N').
+    Returns ``(vcf_handler, keep)``: the dict process_vcf() would build for the region [1, genome_len] and the
+    mask of the reads that were written (reads clipped by the genome's ends are not)."""
+    import struct
+    import zlib
+    from concurrent.futures import ThreadPoolExecutor
+    if w.long_reads:
+        raise ValueError("write_bam: short-read workloads only")
+    sites, rank, off, codes = d["sites"], d["rank"].astype(np.int64), d["off"], d["codes"]
+    R, L, G = len(rank), int(w.read_len), int(w.genome_len)
+    k = np.diff(off)
+    # a read starts somewhere in (sites[rank-1], sites[rank]] and must cover exactly its k SNPs
+    last_site = sites[rank + k - 1]
+    nxt = np.where(rank + k < len(sites), sites[np.minimum(rank + k, len(sites) - 1)], G + L + 1)
+    lo = np.maximum(np.where(rank > 0, sites[np.maximum(rank - 1, 0)] + 1, 1), np.maximum(last_site - L + 1, 1))
+    hi = np.minimum(sites[rank], nxt - L)
+    # reads clipped by the ends of the genome cannot be full-length all-match records: they are left out
+    keep = (lo <= hi) & (lo + L - 1 <= G)
+    rank, k, start = rank[keep], k[keep], lo[keep]            # 1-based start
+    sel = np.repeat(keep, np.diff(off))
+    codes = codes[sel]
+    off = np.concatenate([[0], np.cumsum(k)])
+    R = len(rank)
+    order = np.argsort(start, kind="stable")
+    name_len = 10                                             # 9 characters + NUL
+    rec = 4 + 32 + name_len + 4 + (L + 1) // 2 + L
+    buf = np.zeros((R, rec), dtype=np.uint8)
+    def put32(col, vals):
+        buf[:, col:col + 4] = np.ascontiguousarray(vals, dtype="<i4").view(np.uint8).reshape(-1, 4)
+    put32(0, np.full(R, rec - 4))
+    put32(4, np.zeros(R))                                     # refID
+    put32(8, start - 1)                                       # pos (0-based)
+    buf[:, 12] = name_len
+    buf[:, 13] = 42                                           # mapq
+    buf[:, 14:16] = np.array([4680 & 0xff, 4680 >> 8], np.uint8)
+    buf[:, 16:18] = np.array([1, 0], np.uint8)                # n_cigar_op
+    buf[:, 18:20] = 0                                         # flag
+    put32(20, np.full(R, L))
+    put32(24, np.full(R, -1)); put32(28, np.full(R, -1)); put32(32, np.zeros(R))
+    ids = np.arange(R)
+    name = np.zeros((R, name_len), np.uint8)
+    name[:, 0] = ord("r")
+    for j in range(8):
+        name[:, 8 - j] = ord("0") + (ids // 10 ** j) % 10
+    buf[:, 36:36 + name_len] = name
+    buf[:, 36 + name_len:40 + name_len] = np.array([(L << 4) & 0xff, (L << 4) >> 8 & 0xff, 0, 0], np.uint8)
+    # bases: 'A' (1) everywhere, the packed alleles at the covered SNP sites
+    nt16 = np.array([1, 2, 4, 8, 15, 15, 15], np.uint8)       # A C G T N -(as N) _
+    bases = np.full((R, L + (L & 1)), 1, dtype=np.uint8)
+    rep = np.repeat(np.arange(R), k)
+    t = np.arange(len(codes)) - np.repeat(off[:-1], k)
+    col = sites[np.repeat(rank, k) + t] - start[rep]
+    bases[rep, col] = nt16[codes]
+    if L & 1:
+        bases[:, L] = 0
+    seq_at = 40 + name_len
+    buf[:, seq_at:seq_at + (L + 1) // 2] = (bases[:, 0::2] << 4) | bases[:, 1::2]
+    # base qualities: random (they dominate the size of a real BAM and the cost of inflating it)
+    buf[:, seq_at + (L + 1) // 2:] = np.random.default_rng(7).integers(2, 41, size=(R, L), dtype=np.uint8)
+    text = "@HD\tVN:1.0\tSO:coordinate\n@SQ\tSN:%s\tLN:%d\n" % (contig, G)
+    head = (b"BAM\x01" + struct.pack("<i", len(text)) + text.encode() + struct.pack("<i", 1)
+            + struct.pack("<i", len(contig) + 1) + contig.encode() + b"\x00" + struct.pack("<i", G))
+    payload = head + buf[order].tobytes()
+    def bgzf(chunk):
+        co = zlib.compressobj(level, zlib.DEFLATED, -15)
+        comp = co.compress(chunk) + co.flush()
+        return (b"\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff\x06\x00BC\x02\x00" + struct.pack("<H", len(comp) + 25)
+                + comp + struct.pack("<II", zlib.crc32(chunk) & 0xffffffff, len(chunk)))
+    blk = 65280
+    chunks = [payload[i:i + blk] for i in range(0, len(payload), blk)]
+    with ThreadPoolExecutor(max_workers=max(1, threads)) as ex, open(path, "wb") as fh:
+        for b in ex.map(bgzf, chunks, chunksize=64):
+            fh.write(b)
+        fh.write(bgzf(b""))
+    region = np.zeros(G + 1, dtype=int)
+    region[sites] = 1
+    vh = {"N": len(sites), "snp_fwd": {int(p): i for i, p in enumerate(sites)},
+          "snp_rev": {i: int(p) for i, p in enumerate(sites)}, "region": region}
+    return vh, keep

@@ -180,16 +180,15 @@ def load_from_packed(rank, off, codes, n_snps, band_w=None, device=None, hansel=
     """Packed reads -> Hansel (util.py:83 + 226-286 + 329-333).
 
     With ``finalize=False`` the integer counts stay pending so that partial matrices of
-    several GPUs can be summed first (see gretel_b200.dist).  ``wire``: "wide" ships the packed arrays as they
-    are; "dense" re-encodes rank-sorted reads into the dense wire format (native encoder) and feeds them in
-    chunks whose copies overlap the pair expansion; "auto" picks dense for large sorted inputs."""
+    several GPUs can be summed first (see gretel_b200.dist).  ``wire``: "auto" hands the packed arrays to
+    hx_ingest_host, which re-encodes large rank-sorted inputs into the dense wire format on the host threads,
+    chunk by chunk into pinned buffers, pipelined with the copies and the pair expansion (and ships anything
+    else as it is); "dense" does the same chunking from Python (hx_dense_encode + hx_ingest_host_dense)."""
     if hansel is None:
         if band_w is None:
             band_w = band_width_for(off)
         hansel = Hansel.init_matrix(REF_SYMBOLS, REF_UNSYMBOLS, n_snps, band_w=band_w, device=device)
     rank = np.asarray(rank)
-    if wire == "auto":
-        wire = "dense" if (len(rank) >= DENSE_MIN_READS and bool(np.all(rank[1:] >= rank[:-1]))) else "wide"
     if wire == "dense":
         off = np.asarray(off, dtype=np.int64)
         n_chunks = max(2, int((off[-1] - off[0]) // DENSE_CHUNK_CODES) + 1) if len(rank) > 1 else 1
