@@ -18,6 +18,10 @@
 #include <stdlib.h>
 #include <string.h>
 #include <zlib.h>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <atomic>
@@ -214,7 +218,9 @@ void pack_record(const Rec &r, int32_t target_tid, int32_t start_pos, int32_t en
 struct RecRef { size_t off; uint32_t size; };
 
 struct BamStream {
-    FILE *fp = nullptr;
+    int fd = -1;
+    const uint8_t *fmap = nullptr;      // the whole file, mapped: the inflate threads read the page cache directly
+    size_t fsize = 0, fpos = 0;
     std::string path;
     int n_threads = 1;
     // header
@@ -222,7 +228,6 @@ struct BamStream {
     int32_t target_tid = -1, target_len = 0;
     std::string contig;
     // wave state
-    std::vector<uint8_t> cbuf;          // compressed bytes of the wave
     std::unique_ptr<uint8_t[]> ubuf;    // carry + inflated bytes
     size_t ucap = 0, ulen = 0;
     std::vector<uint8_t> carry;         // unconsumed tail of the previous wave
@@ -230,12 +235,24 @@ struct BamStream {
     bool eof = false;
     double t_read = 0, t_inflate = 0, t_scan = 0;
 
-    ~BamStream() { if (fp) fclose(fp); }
+    ~BamStream() {
+        if (fmap && fsize) munmap(const_cast<uint8_t *>(fmap), fsize);
+        if (fd >= 0) close(fd);
+    }
 
     int open(const char *bam_path, const char *ctg, int nt) {
         path = bam_path; contig = ctg; n_threads = std::max(1, nt);
-        fp = fopen(bam_path, "rb");
-        if (!fp) { hx_set_error("cannot open %s", bam_path); return HX_E_ARG; }
+        fd = ::open(bam_path, O_RDONLY);
+        if (fd < 0) { hx_set_error("cannot open %s", bam_path); return HX_E_ARG; }
+        struct stat sb;
+        if (fstat(fd, &sb) != 0) { hx_set_error("cannot stat %s", bam_path); return HX_E_ARG; }
+        fsize = (size_t)sb.st_size;
+        if (fsize) {
+            void *m = mmap(nullptr, fsize, PROT_READ, MAP_PRIVATE, fd, 0);
+            if (m == MAP_FAILED) { hx_set_error("cannot map %s", bam_path); return HX_E_ARG; }
+            fmap = static_cast<const uint8_t *>(m);
+            madvise(m, fsize, MADV_SEQUENTIAL);
+        }
         return HX_OK;
     }
 
@@ -282,43 +299,38 @@ struct BamStream {
         recs.clear();
         if (eof) return HX_OK;
         auto t0 = clk::now();
-        // compressed bytes: whole BGZF blocks only (a cut block is re-read by the next wave)
-        cbuf.resize(wave_cbytes);
-        const long fpos = ftell(fp);
-        const size_t got = fread(cbuf.data(), 1, wave_cbytes, fp);
-        if (got == 0) { eof = true; if (!carry.empty()) { hx_set_error("%s: truncated BAM (partial record at EOF)", path.c_str()); return HX_E_ARG; } return HX_OK; }
+        // compressed bytes: the whole BGZF blocks that start within the next wave_cbytes of the file
+        if (fpos >= fsize) { eof = true; if (!carry.empty()) { hx_set_error("%s: truncated BAM (partial record at EOF)", path.c_str()); return HX_E_ARG; } return HX_OK; }
+        const uint8_t *cbase = fmap + fpos;
+        const size_t avail = fsize - fpos;
         struct Blk { size_t coff, csize, uoff, usize; };
         std::vector<Blk> blocks;
         size_t p = 0, total = 0;
-        while (p + 18 <= got) {
-            const uint8_t *h = cbuf.data() + p;
+        while (p < wave_cbytes && p + 18 <= avail) {
+            const uint8_t *h = cbase + p;
             if (h[0] != 0x1f || h[1] != 0x8b || h[2] != 8 || !(h[3] & 4)) { hx_set_error("%s is not a BGZF file", path.c_str()); return HX_E_ARG; }
             const size_t xlen = rd16(h + 10);
             size_t q = p + 12;
             const size_t xend = q + xlen;
-            if (xend > got) break;
+            if (xend > avail) { hx_set_error("%s: truncated BGZF block at EOF", path.c_str()); return HX_E_ARG; }
             size_t bsize = 0;
             while (q + 4 <= xend) {
-                const uint8_t *sf = cbuf.data() + q;
+                const uint8_t *sf = cbase + q;
                 const size_t slen = rd16(sf + 2);
                 if (sf[0] == 'B' && sf[1] == 'C' && slen == 2 && q + 6 <= xend) bsize = (size_t)rd16(sf + 4) + 1;
                 q += 4 + slen;
             }
             if (!bsize || bsize < (xend - p) + 8) { hx_set_error("%s: corrupt BGZF block", path.c_str()); return HX_E_ARG; }
-            if (p + bsize > got) break;
-            const size_t usize = rd32(cbuf.data() + p + bsize - 4);
+            if (p + bsize > avail) { hx_set_error("%s: truncated BGZF block at EOF", path.c_str()); return HX_E_ARG; }
+            const size_t usize = rd32(cbase + p + bsize - 4);
             if (usize > 65536) { hx_set_error("%s: corrupt BGZF block (ISIZE)", path.c_str()); return HX_E_ARG; }
             blocks.push_back({xend, bsize - (xend - p) - 8, total, usize});
             total += usize;
             p += bsize;
         }
-        if (p == 0) {
-            if (got < wave_cbytes) { hx_set_error("%s: truncated BGZF block at EOF", path.c_str()); return HX_E_ARG; }
-            hx_set_error("%s: BGZF block larger than the read window", path.c_str());
-            return HX_E_ARG;
-        }
-        if (p < got) fseek(fp, fpos + (long)p, SEEK_SET);
-        if (got < wave_cbytes && p == got) eof = true;
+        if (p == 0) { hx_set_error("%s: trailing bytes that are not a BGZF block", path.c_str()); return HX_E_ARG; }
+        fpos += p;
+        if (fpos >= fsize) eof = true;
         auto t1 = clk::now();
         // inflate behind the carried bytes
         const size_t need = carry.size() + total;
@@ -333,7 +345,7 @@ struct BamStream {
                 for (;;) {
                     const size_t b = next.fetch_add(1);
                     if (b >= blocks.size()) break;
-                    if (!inflate_block(cbuf.data() + blocks[b].coff, blocks[b].csize, ubuf.get() + base + blocks[b].uoff, blocks[b].usize))
+                    if (!inflate_block(cbase + blocks[b].coff, blocks[b].csize, ubuf.get() + base + blocks[b].uoff, blocks[b].usize))
                         ok = false;
                 }
             };
@@ -416,9 +428,11 @@ int hx_pack_bam_ex(const char *bam_path, const char *contig, int32_t start_pos, 
     double t_walk = 0, t_depth = 0, t_gather = 0;
     int64_t n_records = 0;
     // pysam's pileup engine (bam_plp) buffers at most max_depth reads: a read that is not the first of its start
-    // position is dropped while max_depth reads are still live (gretel never changes pysam's default of 8000)
-    std::priority_queue<int64_t, std::vector<int64_t>, std::greater<int64_t>> live_ends;
-    int64_t depth_pos = -1;
+    // position is dropped while max_depth reads are still live (gretel never changes pysam's default of 8000).
+    // Reads arrive sorted by start, so "live" = admitted - retired with the ends counted in a ring indexed by position.
+    std::vector<uint32_t> end_ring;
+    int64_t ring_mask = 0, depth_pos = -1, retired_upto = -1, live = 0;
+    std::vector<int64_t> rbeg, rend;
     std::vector<uint8_t> admit;
     for (;;) {
         rc = bs.next_wave(WAVE_CBYTES);
@@ -431,21 +445,61 @@ int hx_pack_bam_ex(const char *bam_path, const char *contig, int32_t start_pos, 
             const bool depth_on = max_depth > 0;
             if (depth_on) {
                 admit.assign(nrec, 1);
+                rbeg.resize(nrec); rend.resize(nrec);
+                // only reads the pileup iterator fetches and its stepper lets through count: target contig,
+                // overlapping [start_pos - 1, end_pos); their spans are extracted in parallel (end = -1: not counted)
+                {
+                    const int ntd = (int)std::min<size_t>((size_t)n_threads, std::max<size_t>(1, nrec / 4096));
+                    std::atomic<int64_t> span_max(0);
+                    auto spans = [&](int t) {
+                        int64_t mx = 0;
+                        const size_t a = nrec * (size_t)t / (size_t)ntd, b = nrec * (size_t)(t + 1) / (size_t)ntd;
+                        for (size_t i = a; i < b; ++i) {
+                            const Rec r = parse_rec(d + bs.recs[i].off, bs.recs[i].size);
+                            rend[i] = -1;
+                            if (!r.ok || r.tid != bs.target_tid || r.pos < 0 || !passes_stepper(r.flag, stepper)) continue;
+                            const int64_t beg = r.pos, end = (int64_t)r.pos + std::max<int64_t>(1, ref_len_of(r));
+                            if (beg >= end_pos || end <= (int64_t)start_pos - 1) continue;
+                            rbeg[i] = beg; rend[i] = end;
+                            mx = std::max(mx, end - beg);
+                        }
+                        int64_t cur = span_max.load();
+                        while (mx > cur && !span_max.compare_exchange_weak(cur, mx)) {}
+                    };
+                    std::vector<std::thread> th;
+                    for (int t = 1; t < ntd; ++t) th.emplace_back(spans, t);
+                    spans(0);
+                    for (auto &t : th) t.join();
+                    // the ring must hold every end that is still ahead of the sweep
+                    int64_t need = 2;
+                    while (need < span_max.load() + 2) need <<= 1;
+                    if (need > (int64_t)end_ring.size()) {
+                        std::vector<uint32_t> bigger((size_t)need, 0u);
+                        for (int64_t pos = retired_upto + 1; !end_ring.empty() && pos <= retired_upto + (int64_t)end_ring.size(); ++pos)
+                            bigger[(size_t)(pos & (need - 1))] = end_ring[(size_t)(pos & ring_mask)];
+                        end_ring.swap(bigger);
+                        ring_mask = need - 1;
+                    }
+                }
                 for (size_t i = 0; i < nrec; ++i) {
-                    const Rec r = parse_rec(d + bs.recs[i].off, bs.recs[i].size);
-                    // only reads the pileup iterator fetches and its stepper lets through count: target contig,
-                    // overlapping [start_pos - 1, end_pos)
-                    if (!r.ok || r.tid != bs.target_tid || r.pos < 0 || !passes_stepper(r.flag, stepper)) continue;
-                    const int64_t beg = r.pos, end = (int64_t)r.pos + std::max<int64_t>(1, ref_len_of(r));
-                    if (beg >= end_pos || end <= (int64_t)start_pos - 1) continue;
+                    if (rend[i] < 0) continue;
+                    const int64_t beg = rbeg[i];
                     if (beg != depth_pos) {
-                        while (!live_ends.empty() && live_ends.top() <= beg - 1) live_ends.pop();
+                        // the columns before the new start position have been emitted: reads ending there are gone
+                        const int64_t upto = beg - 1;
+                        if (live == 0) retired_upto = std::max(retired_upto, upto);
+                        for (; retired_upto < upto; ) {
+                            ++retired_upto;
+                            uint32_t &c = end_ring[(size_t)(retired_upto & ring_mask)];
+                            live -= c; c = 0;
+                        }
                         depth_pos = beg;
-                    } else if ((int64_t)live_ends.size() >= max_depth) {
+                    } else if (live >= max_depth) {
                         admit[i] = 0;
                         continue;
                     }
-                    live_ends.push(end);
+                    end_ring[(size_t)(rend[i] & ring_mask)]++;
+                    ++live;
                 }
             }
             auto t1 = clk::now();
@@ -611,9 +665,7 @@ static void run_threads(int nt, F f) {
     for (auto &x : th) x.join();
 }
 
-// Pass 1: validation, sizes and where every thread's list entries go.  Eight alleles per 64-bit operation.
-int hx_dense_plan(const int32_t *rank, const int64_t *off, const uint8_t *codes, int64_t n_reads, int n_threads,
-                  HxDensePlan *pl) {
+int hx_dense_begin(const int64_t *off, int64_t n_reads, int n_threads, int64_t kmax_hint, HxDensePlan *pl) {
     HxDensePlan &P = *pl;
     P.c0 = n_reads ? off[0] : 0;
     P.n_codes = n_reads ? off[n_reads] - P.c0 : 0;
@@ -624,115 +676,131 @@ int hx_dense_plan(const int32_t *rank, const int64_t *off, const uint8_t *codes,
     }
     const int nt = (int)std::max<int64_t>(1, std::min<int64_t>(std::min(n_threads, HX_DENSE_MAX_THREADS), 1 + n_reads / 65536));
     P.nt = nt;
-    std::vector<int64_t> kmax((size_t)nt, 0);
-    std::vector<int> bad((size_t)nt, 0);
-    for (int t = 0; t < nt; ++t) { P.esc_at[t] = 0; P.exc_at[t] = 0; }
-    run_threads(nt, [&](int t) {
-        const int64_t a = n_reads * t / nt, b = n_reads * (t + 1) / nt;
-        int64_t ne = 0, km = 0;
-        int bd = 0;
-        for (int64_t r = a; r < b; ++r) {
-            const int64_t d = (int64_t)rank[r] - (r ? (int64_t)rank[r - 1] : 0), k = off[r + 1] - off[r];
-            if (d < 0) bd = 1;
-            if (k < 0 || k > 65535) bd = 2;
-            ne += d >= 255;
-            km = std::max(km, k);
-        }
-        int64_t nx = 0;
-        if (b > a && !bd) {
-            int64_t i = off[a], e = off[b];
-            uint64_t any = 0;
-            for (; i + 8 <= e; i += 8) {
-                const uint64_t x = ld64(codes + i);
-                any |= (x & 0xf8f8f8f8f8f8f8f8ull) | (x & (x >> 1) & (x >> 2) & 0x0101010101010101ull);   // > 6
-                nx += __builtin_popcountll(x & 0x0404040404040404ull);
-            }
-            for (; i < e; ++i) { if (codes[i] > 6) any = 1; nx += codes[i] >= 4; }
-            if (any) bd = 3;
-        }
-        P.esc_at[t] = ne; P.exc_at[t] = nx; kmax[(size_t)t] = km; bad[(size_t)t] = bd;
-    });
-    int64_t tot_esc = 0, tot_exc = 0, km = 0;
-    for (int t = 0; t < nt; ++t) {
-        if (bad[(size_t)t]) {
-            hx_set_error("hx_dense_encode: %s", bad[(size_t)t] == 1 ? "reads are not sorted by rank"
-                                               : bad[(size_t)t] == 2 ? "a read covers more than 65535 SNPs (or off[] decreases)"
-                                                                     : "allele code > 6");
-            return bad[(size_t)t] == 1 ? HX_E_STATE : HX_E_ARG;
-        }
-        const int64_t e = P.esc_at[t], x = P.exc_at[t];
-        P.esc_at[t] = tot_esc; P.exc_at[t] = tot_exc;       // exclusive prefix: where each thread writes its lists
-        tot_esc += e; tot_exc += x;
-        km = std::max(km, kmax[(size_t)t]);
+    int64_t km = kmax_hint;
+    if (km <= 0) {
+        std::vector<int64_t> kmax((size_t)nt, 0);
+        run_threads(nt, [&](int t) {
+            int64_t m = 0;
+            for (int64_t r = n_reads * t / nt; r < n_reads * (t + 1) / nt; ++r) m = std::max(m, off[r + 1] - off[r]);
+            kmax[(size_t)t] = m;
+        });
+        for (int64_t m : kmax) km = std::max(km, m);
     }
-    P.n_esc = tot_esc; P.n_exc = tot_exc;
+    if (km > 65535) { hx_set_error("hx_dense_encode: a read covers more than 65535 SNPs"); return HX_E_ARG; }
     P.klen_bytes = km < 256 ? 1 : 2;
     const int64_t n_words = (P.n_codes + 15) / 16;
     P.o_klen = al16(n_reads);
     P.o_codes2 = P.o_klen + al16(n_reads * P.klen_bytes);
     P.o_exc = P.o_codes2 + al16(n_words * 4);
+    P.head_bytes = P.o_exc;
+    P.bytes = 0;
+    return HX_OK;
+}
+
+// The one pass over the reads.  Eight alleles per 64-bit operation; every byte of the fixed sections that the device
+// reads is written (the blob need not be zeroed).
+int hx_dense_pack(const int32_t *rank, const int64_t *off, const uint8_t *codes, HxDensePlan *pl, uint8_t *blob) {
+    HxDensePlan &P = *pl;
+    const int nt = P.nt;
+    const int64_t n_reads = P.n_reads, n_codes = P.n_codes, c0 = P.c0;
+    const int kb = P.klen_bytes;
+    const int64_t klim = kb == 1 ? 255 : 65535;
+    uint8_t *c2 = blob + P.o_codes2;
+    std::vector<int> bad((size_t)nt, 0);
+    run_threads(nt, [&](int t) {
+        const int64_t a = n_reads * t / nt, b = n_reads * (t + 1) / nt;
+        std::vector<uint32_t> &exc = P.exc[t];
+        std::vector<int64_t> &ei = P.esc_idx[t];
+        std::vector<int32_t> &ed = P.esc_delta[t];
+        exc.clear(); ei.clear(); ed.clear();
+        int bd = 0;
+        for (int64_t r = a; r < b; ++r) {
+            const int64_t d = (int64_t)rank[r] - (r ? (int64_t)rank[r - 1] : 0), k = off[r + 1] - off[r];
+            if (d < 0) bd = 1;
+            if (k < 0 || k > klim) bd = 2;
+            blob[r] = (uint8_t)std::min<int64_t>(d, 255);
+            if (d >= 255) { ei.push_back(r); ed.push_back((int32_t)d); }
+            if (kb == 1) blob[P.o_klen + r] = (uint8_t)k; else ((uint16_t *)(blob + P.o_klen))[r] = (uint16_t)k;
+        }
+        if (b <= a || bd) { bad[(size_t)t] = bd; return; }
+        // This thread lists the exceptions of its reads' alleles [xlo, xhi) and writes the output bytes of the
+        // alleles [lo, hi): the same range rounded so that every output byte has exactly one writer.
+        const int64_t xlo = off[a] - c0, xhi = off[b] - c0;
+        int64_t lo = t == 0 ? 0 : (xlo + 3) & ~(int64_t)3;
+        int64_t hi = t == nt - 1 ? n_codes : (xhi + 3) & ~(int64_t)3;
+        hi = std::min(hi, n_codes);
+        uint64_t any = 0;
+        auto note = [&](int64_t i, uint64_t x) {       // exceptions among the eight alleles at i, inside [xlo, xhi)
+            uint64_t m = x & 0x0404040404040404ull;
+            while (m) {
+                const int64_t j = i + (__builtin_ctzll(m) >> 3);
+                if (j >= xlo && j < xhi) exc.push_back((uint32_t)j);
+                m &= m - 1;
+            }
+        };
+        // head: the alleles of this thread's reads before its first output byte belong to the previous writer
+        for (int64_t i = xlo; i < std::min(lo, xhi); ++i) { const uint8_t c = codes[c0 + i]; if (c > 6) any = 1; if (c >= 4) exc.push_back((uint32_t)i); }
+        int64_t i = lo;
+        for (; i + 8 <= hi; i += 8) {              // 8 alleles -> 16 bits (code & 3: N, -, _ store code - 4)
+            const uint64_t x = ld64(codes + c0 + i);
+            any |= (x & 0xf8f8f8f8f8f8f8f8ull) | (x & (x >> 1) & (x >> 2) & 0x0101010101010101ull);   // a code > 6
+            if (x & 0x0404040404040404ull) note(i, x);
+            uint64_t y = x & 0x0303030303030303ull;
+            y = (y | (y >> 6)) & 0x000f000f000f000full;
+            y = (y | (y >> 12)) & 0x000000ff000000ffull;
+            y = (y | (y >> 24)) & 0xffffull;
+            const uint16_t v = (uint16_t)y;
+            memcpy(c2 + (i >> 2), &v, 2);
+        }
+        for (; i < hi; i += 4) {
+            uint8_t byte = 0;
+            const int64_t m = std::min<int64_t>(4, n_codes - i);
+            for (int64_t j = 0; j < m; ++j) {
+                const uint8_t c = codes[c0 + i + j];
+                if (c > 6) any = 1;
+                if (c >= 4 && i + j >= xlo && i + j < xhi) exc.push_back((uint32_t)(i + j));
+                byte |= (uint8_t)((c & 3) << (2 * j));
+            }
+            c2[i >> 2] = byte;
+        }
+        // (alleles in [hi, xhi) cannot exist: hi >= xhi by construction; alleles in [xhi, hi) are the next thread's
+        // reads, whose exceptions it lists itself in its head loop)
+        if (any) bd = 3;
+        bad[(size_t)t] = bd;
+    });
+    int64_t tot_esc = 0, tot_exc = 0;
+    for (int t = 0; t < nt; ++t) {
+        if (bad[(size_t)t]) {
+            hx_set_error("hx_dense_encode: %s", bad[(size_t)t] == 1 ? "reads are not sorted by rank"
+                                               : bad[(size_t)t] == 2 ? "a read covers more SNPs than announced (or off[] decreases)"
+                                                                     : "allele code > 6");
+            return bad[(size_t)t] == 1 ? HX_E_STATE : HX_E_ARG;
+        }
+        tot_esc += (int64_t)P.esc_idx[t].size();
+        tot_exc += (int64_t)P.exc[t].size();
+    }
+    P.n_esc = tot_esc; P.n_exc = tot_exc;
     P.o_esc_idx = P.o_exc + al16(tot_exc * 4);
     P.o_esc_delta = P.o_esc_idx + al16(tot_esc * 8);
     P.bytes = P.o_esc_delta + al16(tot_esc * 4) + 16;
     return HX_OK;
 }
 
-// Pass 2: every byte of the blob the device reads is written here (the blob need not be zeroed).
-void hx_dense_fill(const int32_t *rank, const int64_t *off, const uint8_t *codes, const HxDensePlan *pl, uint8_t *blob) {
+void hx_dense_finish(const HxDensePlan *pl, uint8_t *blob) {
     const HxDensePlan &P = *pl;
-    const int nt = P.nt;
-    const int64_t n_reads = P.n_reads, n_codes = P.n_codes, c0 = P.c0;
-    const int kb = P.klen_bytes;
     uint32_t *exc = (uint32_t *)(blob + P.o_exc);
     int64_t *ei = (int64_t *)(blob + P.o_esc_idx);
     int32_t *ed = (int32_t *)(blob + P.o_esc_delta);
-    uint8_t *c2 = blob + P.o_codes2;
-    run_threads(nt, [&](int t) {
-        const int64_t a = n_reads * t / nt, b = n_reads * (t + 1) / nt;
-        int64_t ne = P.esc_at[t];
-        for (int64_t r = a; r < b; ++r) {
-            const int64_t d = (int64_t)rank[r] - (r ? (int64_t)rank[r - 1] : 0), k = off[r + 1] - off[r];
-            blob[r] = (uint8_t)std::min<int64_t>(d, 255);
-            if (d >= 255) { ei[ne] = r; ed[ne] = (int32_t)d; ++ne; }
-            if (kb == 1) blob[P.o_klen + r] = (uint8_t)k; else ((uint16_t *)(blob + P.o_klen))[r] = (uint16_t)k;
+    for (int t = 0; t < P.nt; ++t) {
+        if (!P.exc[t].empty()) memcpy(exc, P.exc[t].data(), 4 * P.exc[t].size());
+        exc += P.exc[t].size();
+        if (!P.esc_idx[t].empty()) {
+            memcpy(ei, P.esc_idx[t].data(), 8 * P.esc_idx[t].size());
+            memcpy(ed, P.esc_delta[t].data(), 4 * P.esc_delta[t].size());
         }
-        if (b <= a) return;
-        // exception positions of this thread's reads
-        {
-            int64_t nx = P.exc_at[t];
-            int64_t i = off[a] - c0;
-            const int64_t e = off[b] - c0;
-            for (; i + 8 <= e; i += 8) {
-                uint64_t m = ld64(codes + c0 + i) & 0x0404040404040404ull;
-                while (m) {
-                    const int j = __builtin_ctzll(m) >> 3;
-                    exc[nx++] = (uint32_t)(i + j);
-                    m &= m - 1;
-                }
-            }
-            for (; i < e; ++i) if (codes[c0 + i] >= 4) exc[nx++] = (uint32_t)i;
-        }
-        // alleles [lo, hi) of the stream, rounded so that every output byte has exactly one writer
-        int64_t lo = off[a] - c0, hi = off[b] - c0;
-        lo = t == 0 ? 0 : (lo + 3) & ~(int64_t)3;
-        hi = t == nt - 1 ? n_codes : (hi + 3) & ~(int64_t)3;
-        hi = std::min(hi, n_codes);
-        int64_t i = lo;
-        for (; i + 8 <= hi; i += 8) {              // 8 alleles -> 16 bits (code & 3: N, -, _ store code - 4)
-            uint64_t x = ld64(codes + c0 + i) & 0x0303030303030303ull;
-            x = (x | (x >> 6)) & 0x000f000f000f000full;
-            x = (x | (x >> 12)) & 0x000000ff000000ffull;
-            x = (x | (x >> 24)) & 0xffffull;
-            const uint16_t v = (uint16_t)x;
-            memcpy(c2 + (i >> 2), &v, 2);
-        }
-        for (; i < hi; i += 4) {
-            uint8_t byte = 0;
-            const int64_t m = std::min<int64_t>(4, n_codes - i);
-            for (int64_t j = 0; j < m; ++j) byte |= (uint8_t)((codes[c0 + i + j] & 3) << (2 * j));
-            c2[i >> 2] = byte;
-        }
-    });
+        ei += P.esc_idx[t].size();
+        ed += P.esc_delta[t].size();
+    }
 }
 
 extern "C" {
@@ -745,11 +813,15 @@ int hx_dense_encode(const int32_t *rank, const int64_t *off, const uint8_t *code
     }
     memset(out, 0, sizeof(*out));
     HxDensePlan P;
-    int rc = hx_dense_plan(rank, off, codes, n_reads, n_threads, &P);
+    int rc = hx_dense_begin(off, n_reads, n_threads, 0, &P);
+    if (rc) return rc;
+    std::vector<uint8_t> head((size_t)P.head_bytes + 16, 0);
+    rc = hx_dense_pack(rank, off, codes, &P, head.data());
     if (rc) return rc == HX_E_STATE ? HX_E_ARG : rc;
     uint8_t *blob = (uint8_t *)calloc(1, (size_t)P.bytes);
     if (!blob) { hx_set_error("hx_dense_encode: out of memory (%lld bytes)", (long long)P.bytes); return HX_E_NOMEM; }
-    hx_dense_fill(rank, off, codes, &P, blob);
+    memcpy(blob, head.data(), (size_t)P.head_bytes);
+    hx_dense_finish(&P, blob);
     out->blob = blob; out->blob_bytes = P.bytes; out->n_reads = n_reads; out->n_codes = P.n_codes;
     out->n_exc = P.n_exc; out->n_esc = P.n_esc; out->klen_bytes = P.klen_bytes;
     out->o_klen = P.o_klen; out->o_codes2 = P.o_codes2; out->o_exc = P.o_exc; out->o_esc_idx = P.o_esc_idx;

@@ -422,6 +422,7 @@ int hx_ingest_host_pipelined(hx_matrix *h, const int32_t *rank, const int64_t *o
     int n_chunks = (int)std::max<int64_t>(3, (n_codes + CHUNK_CODES - 1) / CHUNK_CODES);
     if ((int64_t)n_chunks > n_reads) n_chunks = (int)n_reads;
     int64_t a = 0;
+    static thread_local HxDensePlan plan;             // keeps its list buffers between chunks and calls
     for (int c = 0; c < n_chunks; ++c) {
         int64_t b = n_reads;
         if (c + 1 < n_chunks) {
@@ -429,25 +430,35 @@ int hx_ingest_host_pipelined(hx_matrix *h, const int32_t *rank, const int64_t *o
             b = std::lower_bound(off + a, off + n_reads, target) - off;
             if (b <= a) continue;
         }
-        HxDensePlan P;
-        int rc = hx_dense_plan(rank + a, off + a, codes, b - a, nt, &P);
-        if (rc == HX_E_STATE && c > 0) {           // sorted so far, not here: the rest goes as it is (still exact)
+        HxDensePlan &P = plan;
+        int rc = hx_dense_begin(off + a, b - a, nt, (int64_t)h->W + 1, &P);
+        if (rc) return rc;
+        const int slot = c & 1;
+        if (h->pin_busy[slot]) { HX_CUDA(cudaEventSynchronize(h->pin_ev[slot])); h->pin_busy[slot] = false; }
+        auto ensure_pin = [&](int64_t bytes, int64_t keep) -> int {
+            if (bytes <= h->pin_cap[slot]) return HX_OK;
+            const int64_t want = bytes + bytes / 8 + ((int64_t)1 << 20);
+            uint8_t *np = nullptr;
+            HX_CUDA(cudaHostAlloc((void **)&np, (size_t)want, cudaHostAllocPortable));
+            if (keep > 0) memcpy(np, h->pin[slot], (size_t)keep);
+            if (h->pin[slot]) cudaFreeHost(h->pin[slot]);
+            h->pin[slot] = np;
+            h->pin_cap[slot] = want;
+            return HX_OK;
+        };
+        rc = ensure_pin(P.head_bytes + 16, 0);
+        if (rc) return rc;
+        if (!h->pin_ev[slot]) HX_CUDA(cudaEventCreateWithFlags(&h->pin_ev[slot], cudaEventDisableTiming));
+        rc = hx_dense_pack(rank + a, off + a, codes, &P, h->pin[slot]);
+        if (rc == HX_E_STATE && c > 0) {           // sorted so far, not here: chunks already went out
             hx_set_error("hx_ingest_host: reads stop being sorted by rank inside the input");
             return HX_E_ARG;
         }
         if (rc) return rc;
-        const int slot = c & 1;
-        if (h->pin_busy[slot]) { HX_CUDA(cudaEventSynchronize(h->pin_ev[slot])); h->pin_busy[slot] = false; }
-        if (P.bytes > h->pin_cap[slot]) {
-            if (h->pin[slot]) cudaFreeHost(h->pin[slot]);
-            h->pin[slot] = nullptr; h->pin_cap[slot] = 0;
-            const int64_t want = P.bytes + P.bytes / 4 + 4096;
-            HX_CUDA(cudaHostAlloc((void **)&h->pin[slot], (size_t)want, cudaHostAllocPortable));
-            h->pin_cap[slot] = want;
-        }
-        if (!h->pin_ev[slot]) HX_CUDA(cudaEventCreateWithFlags(&h->pin_ev[slot], cudaEventDisableTiming));
+        rc = ensure_pin(P.bytes, P.head_bytes);
+        if (rc) return rc;
         uint8_t *blob = h->pin[slot];
-        hx_dense_fill(rank + a, off + a, codes, &P, blob);
+        hx_dense_finish(&P, blob);
         rc = hx_ingest_host_dense(h, blob, reinterpret_cast<const int64_t *>(blob + P.o_esc_idx),
                                   reinterpret_cast<const int32_t *>(blob + P.o_esc_delta), P.n_esc, blob + P.o_klen,
                                   P.klen_bytes, blob + P.o_codes2, reinterpret_cast<const uint32_t *>(blob + P.o_exc), P.n_exc,

@@ -20,7 +20,8 @@ def _run(*args):
 
 
 def test_bench_line_contract():
-    j = _run("--reads", "200000", "--steps", "3", "--warmup", "3", "--recover-paths", "1", "--ref-sample", "4000")
+    j = _run("--reads", "200000", "--steps", "3", "--warmup", "3", "--recover-paths", "1", "--ref-sample", "4000",
+             "--bam-reads", "50000")
     for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
                 "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "roofline", "cpu_baseline", "clocks"):
         assert key in j, key
@@ -33,6 +34,10 @@ def test_bench_line_contract():
     c = j["cpu_baseline"]
     assert c["kind"] == "port" and c["cores"] >= 1 and c["value"] > 0 and c["sample"]
     assert j["recovery"]["haplotypes"] >= 0
+    assert j["parity_probe"]["ok"] is True and j["parity_probe"]["rows_equal"] and j["parity_probe"]["band_sum"] > 0
+    b = j["e2e_bam"]
+    assert b["reads_per_s"] > 0 and b["same_totals_as_packed_arrays"] and 0 < b["gpu_share"] < 1
+    assert set(b["stage_seconds"]) >= {"read", "inflate", "scan", "walk", "gather", "gpu_ingest"}
 
 
 def test_reference_arm_contract():
