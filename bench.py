@@ -13,10 +13,10 @@ same metagenome (different reads, same strains/sites).
 
 `value`   : observations/s with the packed reads already resident in HBM.
 `e2e`     : the same metric from the north_star boundary: the packed (rank, off, codes) arrays in pinned HOST
-            memory go through the public call (Hansel.ingest_packed -> hx_ingest_host), which re-encodes them
-            into the dense wire format on the host threads (inside the clock), ships them in pipelined chunks,
-            expands, folds into the working matrix and returns the totals - a new matrix every step.
-            `e2e.preencoded` is the device-side limit of that pipeline: the same chunks encoded before the clock.
+            memory go through the public call (Hansel.ingest_packed -> hx_ingest_host), which
+            copies them in a few chunks (each expanded while the next is in flight), folds into the working matrix
+            and returns the totals - a new matrix every step.  `e2e.other_paths`: the dense wire format with the
+            host-side encoder inside the clock, and with the chunks encoded before the clock (device-side limit).
 `e2e_bam` : a synthetic coordinate-sorted BAM of the same reads (bounded sample) through util.load_from_bam:
             reads/s with the per-stage seconds (file read, inflate, record scan, depth cap, CIGAR walks, gather,
             GPU ingestion).
@@ -287,7 +287,10 @@ def run_ours(args):
             _keep.append(pinned)
             dense_chunks.append(c.rebased(pinned.numpy()))
         dense_h2d = sum(c.nbytes for c in dense_chunks)
-        h2d_bytes = dense_h2d                 # what crosses PCIe per step either way (the library encodes the same chunks)
+        if args.e2e_format == "dense":
+            h2d_bytes = dense_h2d
+        else:                                 # the packed arrays cross PCIe as they are
+            h2d_bytes = p_rank.numel() * 4 + p_off.numel() * 8 + p_codes.numel()
 
     h = Hansel.init_matrix(REF_SYMBOLS, REF_UNSYMBOLS, N, band_w=W, device=local_rank)
     h.set_ingest_kernel(args.kernel)
@@ -400,12 +403,12 @@ def run_ours(args):
         hh.set_ingest_kernel(args.kernel)
         if fmt == "auto":                  # the north_star boundary: packed arrays in, the library does the rest
             hh.ingest_packed(p_rank.numpy(), p_off.numpy(), p_codes.numpy())
-        elif fmt == "wide":
-            os.environ["HX_NO_HOST_PIPELINE"] = "1"
+        elif fmt in ("encoded", "wide"):   # force the host-side dense encoder / one plain copy of the packed arrays
+            os.environ["HX_HOST_PIPELINE"] = "dense" if fmt == "encoded" else "off"
             try:
                 hh.ingest_packed(p_rank.numpy(), p_off.numpy(), p_codes.numpy())
             finally:
-                del os.environ["HX_NO_HOST_PIPELINE"]
+                del os.environ["HX_HOST_PIPELINE"]
         elif fmt == "dense":
             for c in dense_chunks:
                 hh.ingest_packed_dense(c, wait=False)
@@ -442,8 +445,13 @@ def run_ours(args):
     e2e_pre = None
     if args.e2e_format == "auto" and dense_chunks:
         v2, s2 = time_e2e("dense", e2e_steps)
-        e2e_pre = {"value": v2, "unit": UNIT, "ms_per_step": 1e3 * s2, "h2d_bytes_per_step": int(dense_h2d),
-                   "what": "the same pipeline with the dense chunks encoded BEFORE the clock (device-side limit; not the headline)"}
+        v3, s3 = time_e2e("encoded", e2e_steps)
+        e2e_pre = {"preencoded_dense": {"value": v2, "unit": UNIT, "ms_per_step": 1e3 * s2, "h2d_bytes_per_step": int(dense_h2d),
+                                        "what": "dense chunks encoded BEFORE the clock (device-side limit of the pipeline; not "
+                                                "the headline)"},
+                   "host_encoded_dense": {"value": v3, "unit": UNIT, "ms_per_step": 1e3 * s3, "h2d_bytes_per_step": int(dense_h2d),
+                                          "what": "HX_HOST_PIPELINE=dense: the same packed host arrays re-encoded by the host "
+                                                  "threads inside the clock, pipelined with copies and expansion"}}
     clocks = sampler.stop() if rank == 0 else None
 
     if rank != 0:
@@ -628,11 +636,12 @@ def run_ours(args):
                     "wire_format": args.e2e_format, "host_threads": int(os.environ.get("HX_HOST_THREADS", "0")),
                     "host_bytes_read_per_step": int(p_rank.numel() * 4 + p_off.numel() * 8 + p_codes.numel()),
                     "api": {"auto": "Hansel.init_matrix + Hansel.ingest_packed(rank, off, codes in pinned host memory) -> "
-                                    "hx_ingest_host: dense encoding on the host threads INSIDE the clock, pipelined chunks "
-                                    "[+ all-reduce] + finalize + totals, a new matrix every step",
+                                    "hx_ingest_host: the packed arrays copied in 4 chunks, each expanded while the next "
+                                    "is in flight [+ all-reduce] + finalize + totals, a new matrix every step",
+                            "encoded": "the same with HX_HOST_PIPELINE=dense (host threads re-encode inside the clock)",
                             "dense": "pre-encoded dense chunks (encoding outside the clock) + finalize + totals",
-                            "compact": "ingest_packed_compact", "wide": "hx_ingest_host without the host pipeline"}[args.e2e_format],
-                    "preencoded": e2e_pre},
+                            "compact": "ingest_packed_compact", "wide": "hx_ingest_host, one plain copy"}[args.e2e_format],
+                    "other_paths": e2e_pre},
             "e2e_bam": e2e_bam,
             "gpu_launches": int(launches), "parity_probe": parity_probe, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
             "observations_per_step": int(n_obs_global), "wall_s_timed_region": wall_s,
@@ -661,10 +670,10 @@ def main():
                          "NVLink peer memory + all-gather of the owned rows")
     ap.add_argument("--segments", type=int, default=1,
                     help="N>1: ingest in this many launches, all-reducing finished band rows behind the next one")
-    ap.add_argument("--e2e-format", default="auto", choices=["auto", "dense", "compact", "wide"],
-                    help="e2e leg: auto = packed (rank, off, codes) host arrays through hx_ingest_host (host-side dense "
-                         "encoding inside the clock; the headline); dense = chunks pre-encoded before the clock; "
-                         "compact = int32 ranks + uint16 counts + nibble codes; wide = the packed arrays copied as they are")
+    ap.add_argument("--e2e-format", default="auto", choices=["auto", "encoded", "dense", "compact", "wide"],
+                    help="e2e leg: auto = packed (rank, off, codes) host arrays through hx_ingest_host (the headline); "
+                         "encoded = the same with the host-side dense encoder forced; dense = chunks pre-encoded before "
+                         "the clock; compact = int32 ranks + uint16 counts + nibble codes; wide = one plain copy")
     ap.add_argument("--e2e-chunks", type=int, default=4,
                     help="dense format: chunks per step (copy of chunk i+1 overlaps the expansion of chunk i)")
     ap.add_argument("--bam-reads", type=int, default=1_000_000,

@@ -84,6 +84,7 @@ struct hx_matrix {
     int ingest_kernel;
     void *lr_scratch;                // long-read ingestion scratch (ingest_long.cu)
     cudaEvent_t ev0, ev1;
+    cudaEvent_t host_ev;             // orders the chunked host->device copies of hx_ingest_host
     bool ev_rec;                     // ev0/ev1 have been recorded at least once
     float last_ms[3];
     int64_t launches;

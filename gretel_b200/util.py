@@ -181,9 +181,10 @@ def load_from_packed(rank, off, codes, n_snps, band_w=None, device=None, hansel=
 
     With ``finalize=False`` the integer counts stay pending so that partial matrices of
     several GPUs can be summed first (see gretel_b200.dist).  ``wire``: "auto" hands the packed arrays to
-    hx_ingest_host, which re-encodes large rank-sorted inputs into the dense wire format on the host threads,
-    chunk by chunk into pinned buffers, pipelined with the copies and the pair expansion (and ships anything
-    else as it is); "dense" does the same chunking from Python (hx_dense_encode + hx_ingest_host_dense)."""
+    hx_ingest_host (large inputs go in a few chunks, each expanded while the next is copied; with
+    HX_HOST_PIPELINE=dense the host threads re-encode them into the dense wire format first, which pays on hosts
+    with many cores); "dense" does that re-encoding chunk by chunk from Python (hx_dense_encode +
+    hx_ingest_host_dense)."""
     if hansel is None:
         if band_w is None:
             band_w = band_width_for(off)

@@ -291,17 +291,35 @@ def test_packed_exchange_format_single_gpu(c_oracle):
     assert np.array_equal(h2.band(), ref.astype(np.float32))
 
 
-def test_load_from_packed_picks_dense_for_large_sorted_input():
-    """util.load_from_packed(wire="auto"): native encoder + chunked overlapped ingestion == the wide path."""
+def test_load_from_packed_host_paths_agree(monkeypatch):
+    """util.load_from_packed from host arrays: the chunked copy of the packed arrays (default), the host-side dense
+    encoder pipelined in C (HX_HOST_PIPELINE=dense), the Python-driven dense chunks and one plain copy all give
+    the same matrix."""
     from gretel_b200 import util
     d = synth.generate(synth.scaled(synth.WORKLOADS["metagenome"], 250_000))
     N, W = d["n_snps"], d["max_k"] - 1
     assert len(d["rank"]) >= util.DENSE_MIN_READS
-    a = util.load_from_packed(d["rank"], d["off"], d["codes"], N, band_w=W, wire="wide")
+    a = util.load_from_packed(d["rank"], d["off"], d["codes"], N, band_w=W)
+    ref = a.band()
+    monkeypatch.setenv("HX_HOST_PIPELINE", "dense")
     b = util.load_from_packed(d["rank"], d["off"], d["codes"], N, band_w=W)
-    assert (a.n_slices, a.n_crumbs, a.L) == (b.n_slices, b.n_crumbs, b.L)
-    assert np.array_equal(a.band(), b.band())
     assert b.launch_count() > a.launch_count()              # the decode kernels ran
+    monkeypatch.setenv("HX_HOST_PIPELINE", "off")
+    c = util.load_from_packed(d["rank"], d["off"], d["codes"], N, band_w=W)
+    monkeypatch.delenv("HX_HOST_PIPELINE")
+    e = util.load_from_packed(d["rank"], d["off"], d["codes"], N, band_w=W, wire="dense")
+    for x in (b, c, e):
+        assert (a.n_slices, a.n_crumbs, a.L) == (x.n_slices, x.n_crumbs, x.L)
+        assert np.array_equal(ref, x.band())
+    # unsorted input cannot be dense-encoded: the library notices and ships it as it is
+    perm = np.random.default_rng(0).permutation(len(d["rank"]))
+    k = np.diff(d["off"])
+    off2 = np.concatenate([[0], np.cumsum(k[perm])]).astype(np.int64)
+    idx = np.repeat(d["off"][:-1][perm], k[perm]) + (np.arange(int(off2[-1])) - np.repeat(off2[:-1], k[perm]))
+    monkeypatch.setenv("HX_HOST_PIPELINE", "dense")
+    u = util.load_from_packed(d["rank"][perm], off2, d["codes"][idx], N, band_w=W)
+    assert (a.n_slices, a.n_crumbs, a.L) == (u.n_slices, u.n_crumbs, u.L)
+    assert np.array_equal(ref, u.band())
 
 
 def test_dense_wire_format_rejects_bad_input():
