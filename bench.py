@@ -116,6 +116,11 @@ class ClockSampler:
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
+def gdist_bounds(off, world):
+    from gretel_b200 import dist as gdist
+    return gdist.shard_bounds(off, world)
+
+
 def workload_config(args, k_mean=None, n_reads=None):
     w = synth.WORKLOADS[args.workload]
     cfg = {"workload": "BASELINE.json configs[%d] %s: %d SNPs, %d x %s reads per GPU%s" % (
@@ -247,7 +252,21 @@ def run_ours(args):
     if args.reads:
         w = synth.scaled(w, args.reads)
     t0 = time.time()
-    d = synth.generate(w, shard=rank)
+    strong = args.scaling == "strong" and world > 1
+    if strong:
+        # BASELINE.json configs[2] as named: ONE read set, cut into contiguous chunks of the rank-sorted reads
+        # balanced by pair count; every rank generates the same reads and keeps its chunk
+        full = synth.generate(w, shard=0)
+        bnd = gdist_bounds(full["off"], world)
+        lo_r, hi_r = int(bnd[rank]), int(bnd[rank + 1])
+        o0 = int(full["off"][lo_r])
+        d = dict(full)
+        d["rank"] = full["rank"][lo_r:hi_r].copy()
+        d["off"] = (full["off"][lo_r:hi_r + 1] - o0).copy()
+        d["codes"] = full["codes"][o0:int(full["off"][hi_r])].copy()
+        del full
+    else:
+        d = synth.generate(w, shard=rank)
     gen_s = time.time() - t0
     N = w.n_snps
     k = np.diff(d["off"])
@@ -299,6 +318,9 @@ def run_ours(args):
 
     pipe = None
     fused = None
+    seam = None
+    if strong and args.exchange in ("allreduce", "seam"):
+        seam = gdist.SeamExchange(h, int(d["rank"][-1]) if R else -1)
     if world > 1 and args.exchange == "fused":
         fused = gdist.FusedExchange(h)
     elif world > 1 and args.segments > 1:
@@ -315,7 +337,9 @@ def run_ours(args):
             pipe.run(t_rank.data_ptr(), t_off.data_ptr(), t_codes.data_ptr())
             return
         h.ingest_device(t_rank.data_ptr(), t_off.data_ptr(), t_codes.data_ptr(), R)
-        if world > 1:
+        if seam is not None:
+            gdist.seam_exchange_counts(h, None, plan=seam)
+        elif world > 1:
             if args.exchange == "reduce":
                 gdist.reduce_counts(h, dst=0)
             elif args.exchange == "packed":
@@ -379,7 +403,7 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(rows_exp, op=dist.ReduceOp.SUM)
     pt = h.ingest_totals()
-    holder = rank == 0 or args.exchange != "reduce"          # "reduce" leaves the sums on rank 0 only
+    holder = rank == 0 or (args.exchange != "reduce" and seam is None)   # "reduce" / the seam exchange leave the sums on rank 0
     rows_ok = bool(torch.equal(rows_exp, rows_got)) if holder else True
     sum_ok = int(rows_got.sum().item()) == int(pt[1]) + int(pt[3]) if holder else True
     pok = torch.tensor([int(rows_ok and sum_ok)], device=dev)
@@ -387,7 +411,7 @@ def run_ours(args):
         dist.all_reduce(pok, op=dist.ReduceOp.MIN)
     parity_probe = {"ok": bool(pok.item()), "rows_equal": rows_ok, "sum_equals_crumbs_plus_sentinels": sum_ok,
                     "rows": N + 2, "band_sum": int(rows_got.sum().item()), "n_crumbs": int(pt[1]),
-                    "sentinel_increments": int(pt[3]), "ranks_checked": world if args.exchange != "reduce" else 1,
+                    "sentinel_increments": int(pt[3]), "ranks_checked": world if (args.exchange != "reduce" and seam is None) else 1,
                     "how": "hx_probe_expected_rows (one thread per read, independent of the ingestion kernels) "
                            "summed over ranks vs hx_counts_row_sums of the exchanged counts"}
 
@@ -414,7 +438,9 @@ def run_ours(args):
                 hh.ingest_packed_dense(c, wait=False)
         else:
             hh.ingest_packed_compact(p_rank.numpy(), p_klen.numpy(), p_codes4.numpy(), n_codes)
-        if world > 1:
+        if seam is not None:
+            gdist.seam_exchange_counts(hh, None, plan=seam)
+        elif world > 1:
             (gdist.allreduce_counts_packed if args.exchange == "packed" else gdist.allreduce_counts)(hh)
         hh.finalize()                      # enqueue the fold into the float matrix, then one wait for everything
         s, c, v, _ = hh.ingest_totals()
@@ -629,8 +655,11 @@ def run_ours(args):
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-            "config": workload_config(args, k_mean, R),
+            "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "config": dict(workload_config(args, k_mean, R), **({"reads_total": int(args.reads or w.n_reads),
+                                                                 "reads_per_gpu": "one read set cut into %d contiguous chunks balanced by pair count" % world} if strong else {})),
+            "exchange_detail": ({"kind": "seam" if not seam.fallback else "allreduce (seam fallback)",
+                                 "bytes_on_wire": seam.bytes_on_wire(), "own_rows": [seam.own_lo, seam.own_hi]} if seam is not None else None),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes),
                     "d2h_bytes_per_step": 32 + 4, "steps": e2e_steps, "ms_per_step": 1e3 * e2e_step_s,
                     "wire_format": args.e2e_format, "host_threads": int(os.environ.get("HX_HOST_THREADS", "0")),
@@ -663,7 +692,10 @@ def main():
     ap.add_argument("--workload", default="metagenome", choices=sorted(synth.WORKLOADS))
     ap.add_argument("--reads", type=int, default=0, help="reads per GPU (default: the workload's full size)")
     ap.add_argument("--kernel", type=int, default=0, help="ingestion kernel: 0 auto, 1 generic, 2 bit-sliced")
-    ap.add_argument("--exchange", default="allreduce", choices=["allreduce", "packed", "reduce", "fused"],
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N>1: weak = every GPU ingests its own full-size read set of the same region (default, what the "
+                         "driver's scaling run uses); strong = ONE read set cut into contiguous chunks, seam-only exchange")
+    ap.add_argument("--exchange", default="allreduce", choices=["allreduce", "packed", "reduce", "fused", "seam"],
                     help="N>1: NCCL all-reduce of the partial matrices (default, as north_star names it); the same "
                          "all-reduce over counts packed into uint16 lanes (half the bytes); reduce onto "
                          "rank 0 only (recovery runs there); or counts added straight into the owning GPU over "

@@ -94,6 +94,105 @@ def allreduce_counts(hansel, group=None):
             dist.all_reduce(totals, op=dist.ReduceOp.SUM, group=group)
 
 
+class SeamExchange:
+    """Strong scaling: the rank-sorted reads are cut into ``world`` contiguous chunks (shard_bounds), so the partial
+    matrices of neighbouring GPUs overlap only in the band rows their boundary reads share (a read of rank r
+    touches rows r+2 .. r+k): the "seam" of at most W+1 rows behind the last rank of a chunk.  Instead of
+    all-reducing the whole band, GPU g sends its seam rows to GPU g+1, which adds them; then every GPU holds
+    the final values of the rows it owns ([first rank of its chunk + 2, last rank + 2), rank 0 from row 0, the last
+    GPU to row N+1) and sends them to ``dst`` (recovery runs on one GPU).  Bytes on the wire: (world-1) seams of
+    (W+1)*W*196 B plus each row once, instead of 2x the whole band per GPU.
+
+    ``last_rank``: the rank value of this GPU's last read (-1 if it has no reads).  Falls back to the plain
+    all-reduce (``fallback`` is True) when some chunk spans fewer ranks than a read, i.e. when rows would be shared
+    by more than two neighbours."""
+
+    def __init__(self, hansel, last_rank, group=None, dst=0, tensor_ops=None):
+        import torch
+        import torch.distributed as dist
+        self.h, self.group, self.dist, self.torch, self.dst = hansel, group, dist, torch, dst
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        N, W = hansel.n_snps, hansel.band_w
+        dev = tensor_ops["device"] if tensor_ops else torch.device("cuda", hansel.device)
+        t = torch.tensor([int(last_rank)], device=dev, dtype=torch.int64)
+        allr = [torch.zeros(1, device=dev, dtype=torch.int64) for _ in range(self.world)]
+        dist.all_gather(allr, t, group=group)
+        last = [int(x.item()) for x in allr]
+        for g in range(1, self.world):                       # a GPU without reads ends where its predecessor ended
+            if last[g] < 0:
+                last[g] = last[g - 1]
+        if last[0] < 0:
+            last[0] = 0
+        self.last = last
+        # rows owned by GPU g: [own_lo[g], own_hi[g]); seam sent by g to g+1: [own_hi[g], seam_hi[g])
+        self.own_lo = [0] + [min(last[g - 1] + 2, N + 2) for g in range(1, self.world)]
+        self.own_hi = [min(last[g] + 2, N + 2) for g in range(self.world - 1)] + [N + 2]
+        self.seam_hi = [min(self.own_hi[g] + W + 1, N + 2) for g in range(self.world)]
+        # exact only while a seam ends inside the next GPU's own rows (chunks at least a read wide)
+        # (also: rank-0 reads in two chunks share the start sentinel's row 1; a chunk without reads would have to
+        # forward its predecessor's seam)
+        self.fallback = any(self.seam_hi[g] > self.own_hi[g + 1] and g + 1 < self.world - 1 for g in range(self.world - 1)) \
+            or any(self.own_hi[g] <= self.own_lo[g] for g in range(self.world)) \
+            or any(last[g] == 0 for g in range(self.world - 1))
+        self.row = W * 49
+
+    def run(self, counts, totals):
+        """``counts``: this GPU's partial band as an int32 tensor [(N+2)*W*49]; ``totals``: int64[4].  Enqueues the
+        exchange on the current stream; afterwards ``dst`` holds the complete band, every rank the global totals."""
+        dist, g, w, row = self.dist, self.rank, self.world, self.row
+        dist.all_reduce(totals, op=dist.ReduceOp.SUM, group=self.group)
+        if self.fallback:
+            dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=self.group)
+            return
+        ops = []
+        recv_buf = None
+        if g + 1 < w and self.seam_hi[g] > self.own_hi[g]:
+            ops.append(dist.P2POp(dist.isend, counts[self.own_hi[g] * row:self.seam_hi[g] * row], g + 1, group=self.group))
+        if g > 0 and self.seam_hi[g - 1] > self.own_hi[g - 1]:
+            recv_buf = self.torch.empty((self.seam_hi[g - 1] - self.own_hi[g - 1]) * row, dtype=counts.dtype, device=counts.device)
+            ops.append(dist.P2POp(dist.irecv, recv_buf, g - 1, group=self.group))
+        if ops:
+            for r in dist.batch_isend_irecv(ops):
+                r.wait()
+        if recv_buf is not None:
+            counts[self.own_hi[g - 1] * row:self.seam_hi[g - 1] * row] += recv_buf
+        # owned rows -> dst
+        ops = []
+        if g == self.dst:
+            for src in range(w):
+                if src != g and self.own_hi[src] > self.own_lo[src]:
+                    ops.append(dist.P2POp(dist.irecv, counts[self.own_lo[src] * row:self.own_hi[src] * row], src, group=self.group))
+        elif self.own_hi[g] > self.own_lo[g]:
+            ops.append(dist.P2POp(dist.isend, counts[self.own_lo[g] * row:self.own_hi[g] * row], self.dst, group=self.group))
+        if ops:
+            for r in dist.batch_isend_irecv(ops):
+                r.wait()
+
+    def bytes_on_wire(self):
+        if self.fallback:
+            return None
+        seams = sum((self.seam_hi[g] - self.own_hi[g]) for g in range(self.world - 1)) * self.row * 4
+        rows = sum((self.own_hi[g] - self.own_lo[g]) for g in range(self.world) if g != self.dst) * self.row * 4
+        return seams + rows
+
+
+def seam_exchange_counts(hansel, last_rank, group=None, dst=0, plan=None):
+    """Run the seam exchange on the pending integer counts of ``hansel`` (device tensors over the C-ABI buffers)."""
+    import torch
+    cptr, cn, tptr, tn = hansel.counts_buffer()
+    dev = torch.device("cuda", hansel.device)
+    with torch.cuda.device(dev):
+        s = torch.cuda.ExternalStream(hansel.stream, device=dev)
+        with torch.cuda.stream(s):
+            counts = torch.as_tensor(_DevBuf(cptr, cn, "<i4"), device=dev)
+            totals = torch.as_tensor(_DevBuf(tptr, tn, "<i8"), device=dev)
+            if plan is None:
+                plan = SeamExchange(hansel, last_rank, group=group, dst=dst)
+            plan.run(counts, totals)
+    return plan
+
+
 class PipelinedIngest:
     """Ingestion of device-resident, rank-sorted reads in ``segments`` launches with the
     all-reduce of the finished band rows overlapped with the next launch.
