@@ -150,6 +150,9 @@ void free_all(hx_matrix *h) {
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->host_ev) cudaEventDestroy(h->host_ev);
+    if (h->sum_stream) { cudaStreamSynchronize(h->sum_stream); cudaStreamDestroy(h->sum_stream); }
+    for (int b = 0; b < 2; ++b) if (h->sum_done[b]) cudaEventDestroy(h->sum_done[b]);
+    if (h->site_ready) cudaEventDestroy(h->site_ready);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     free(h);
 }
@@ -221,6 +224,7 @@ int reset_parked(hx_matrix *h) {
     h->launches = 0;
     h->ingest_kernel = 0;
     h->wire_next = 0;
+    h->sum_busy[0] = h->sum_busy[1] = false;
     h->last_ms[0] = h->last_ms[1] = h->last_ms[2] = 0.0f;
     return HX_OK;
 }
@@ -273,7 +277,7 @@ int hx_create(int32_t n_snps, int32_t band_w, int32_t device, hx_matrix **out) {
     HX_TRY(hx_fill_async(h->d_err, 0, sizeof(int), h->stream));
     HX_TRY(cudaMallocAsync((void **)&h->scnt, sizeof(double) * 8 * ((size_t)n_snps + 2), h->stream));
     HX_TRY(cudaMallocAsync((void **)&h->vseen, sizeof(int32_t) * ((size_t)n_snps + 2), h->stream));
-    HX_TRY(cudaMallocAsync((void **)&h->d_site, sizeof(double) * 3 * ((size_t)n_snps + 2), h->stream));
+    HX_TRY(cudaMallocAsync((void **)&h->d_site, sizeof(double) * 6 * ((size_t)n_snps + 2), h->stream));
     HX_TRY(cudaMallocAsync((void **)&h->d_flags, 8 * sizeof(int), h->stream));
     HX_TRY(hx_fill_async(h->d_flags, 0, 8 * sizeof(int), h->stream));
     HX_TRY(cudaMallocAsync((void **)&h->d_misc, 32 * sizeof(double), h->stream));

@@ -32,9 +32,14 @@
 #include <thread>
 #include <vector>
 
+#include <cuda_runtime.h>
+
 #include "hanselx.h"
 
 void hx_set_error(const char *fmt, ...);
+int hx_launch_coverage(const int32_t *d_seg_start, const int64_t *d_seg_nib, const int32_t *d_seg_len,
+                       const uint8_t *d_seq4, int64_t n_seg, int32_t start0, int32_t len, uint32_t *d_counts,
+                       cudaStream_t stream);
 
 namespace {
 
@@ -632,6 +637,136 @@ int hx_count_coverage(const char *bam_path, const char *contig, int32_t start0, 
         if (!c.empty())
             for (size_t i = 0; i < 4 * (size_t)len; ++i) out[i] += c[i];
     return HX_OK;
+}
+
+/* The same counts with the histogram on the GPU (coverage.cu): the CPU decodes the BAM wave by wave into aligned
+ * segments + the BAM's own 4-bit bases, the device counts them.  out[4*(end0-start0)] on the host. */
+int hx_count_coverage_gpu(const char *bam_path, const char *contig, int32_t start0, int32_t end0, int n_threads,
+                          int32_t device, uint32_t *out) {
+    if (!bam_path || !contig || !out || start0 < 0 || end0 < start0) { hx_set_error("hx_count_coverage_gpu: bad arguments"); return HX_E_ARG; }
+    if (n_threads < 1) n_threads = 1;
+    const int64_t len = (int64_t)end0 - start0;
+    if (len == 0) return HX_OK;
+    BamStream bs;
+    int rc = bs.open(bam_path, contig, n_threads);
+    if (rc) return rc;
+#define COV_CUDA(call)                                                                                    \
+    do {                                                                                                  \
+        cudaError_t e__ = (call);                                                                         \
+        if (e__ != cudaSuccess) {                                                                         \
+            hx_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__));           \
+            for (void *p__ : dev_bufs) if (p__) cudaFree(p__);                                            \
+            if (st) cudaStreamDestroy(st);                                                                \
+            return HX_E_CUDA;                                                                             \
+        }                                                                                                 \
+    } while (0)
+    cudaStream_t st = nullptr;
+    uint32_t *d_counts = nullptr;
+    int32_t *d_start = nullptr, *d_len = nullptr;
+    int64_t *d_nib = nullptr;
+    uint8_t *d_seq = nullptr;
+    size_t cap_seg = 0, cap_seq = 0;
+    std::vector<void *> dev_bufs;
+    COV_CUDA(cudaSetDevice(device));
+    COV_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    COV_CUDA(cudaMalloc((void **)&d_counts, sizeof(uint32_t) * 4 * (size_t)len));
+    dev_bufs.push_back(d_counts);
+    COV_CUDA(cudaMemsetAsync(d_counts, 0, sizeof(uint32_t) * 4 * (size_t)len, st));
+    struct Part { std::vector<int32_t> start, len; std::vector<int64_t> nib; std::vector<uint8_t> seq; };
+    std::vector<int32_t> h_start, h_len;
+    std::vector<int64_t> h_nib;
+    std::vector<uint8_t> h_seq;
+    for (;;) {
+        rc = bs.next_wave(WAVE_CBYTES / 4);
+        if (rc) break;
+        const size_t nrec = bs.recs.size();
+        const uint8_t *d = bs.ubuf.get();
+        if (nrec) {
+            const int nt = (int)std::min<size_t>((size_t)n_threads, std::max<size_t>(1, nrec / 4096));
+            std::vector<Part> parts((size_t)nt);
+            auto work = [&](int t) {
+                Part &P = parts[(size_t)t];
+                const size_t a = nrec * (size_t)t / (size_t)nt, b = nrec * (size_t)(t + 1) / (size_t)nt;
+                for (size_t i = a; i < b; ++i) {
+                    const Rec r = parse_rec(d + bs.recs[i].off, bs.recs[i].size);
+                    if (!r.ok || r.tid != bs.target_tid || r.pos < 0 || r.l_seq <= 0) continue;
+                    const int64_t seq_nib0 = 2 * (int64_t)P.seq.size();
+                    bool used = false;
+                    int64_t rpos = r.pos, qpos = 0;
+                    for (int ci = 0; ci < r.n_cigar; ++ci) {
+                        const uint32_t cv = rd32(r.cig + 4 * (size_t)ci);
+                        const int op = cv & 0xf;
+                        const int64_t ln = cv >> 4;
+                        if (op == 0 || op == 7 || op == 8) {
+                            const int64_t usable = std::min<int64_t>(ln, (int64_t)r.l_seq - qpos);
+                            if (usable > 0 && rpos < end0 && rpos + usable > start0) {
+                                P.start.push_back((int32_t)rpos);
+                                P.len.push_back((int32_t)usable);
+                                P.nib.push_back(seq_nib0 + qpos);
+                                used = true;
+                            }
+                            rpos += ln; qpos += ln;
+                        } else if (op == 2 || op == 3) {
+                            rpos += ln;
+                        } else if (op == 1 || op == 4) {
+                            qpos += ln;
+                        }
+                    }
+                    if (used) P.seq.insert(P.seq.end(), r.seq, r.seq + ((size_t)r.l_seq + 1) / 2);
+                    else { /* nothing shipped for this record */ }
+                }
+            };
+            std::vector<std::thread> th;
+            for (int t = 1; t < nt; ++t) th.emplace_back(work, t);
+            work(0);
+            for (auto &t : th) t.join();
+            // gather (the nibble offsets of a part are relative to its own bases)
+            h_start.clear(); h_len.clear(); h_nib.clear(); h_seq.clear();
+            for (auto &P : parts) {
+                const int64_t shift = 2 * (int64_t)h_seq.size();
+                h_start.insert(h_start.end(), P.start.begin(), P.start.end());
+                h_len.insert(h_len.end(), P.len.begin(), P.len.end());
+                for (int64_t v : P.nib) h_nib.push_back(v + shift);
+                h_seq.insert(h_seq.end(), P.seq.begin(), P.seq.end());
+            }
+            const size_t ns = h_start.size();
+            if (ns) {
+                COV_CUDA(cudaStreamSynchronize(st));               // the previous wave's kernel has read its buffers
+                if (ns > cap_seg) {
+                    for (void *p : {(void *)d_start, (void *)d_len, (void *)d_nib}) if (p) cudaFree(p);
+                    dev_bufs.resize(1);
+                    if (d_seq) dev_bufs.push_back(d_seq);
+                    cap_seg = ns + ns / 4;
+                    d_start = nullptr; d_len = nullptr; d_nib = nullptr;
+                    COV_CUDA(cudaMalloc((void **)&d_start, 4 * cap_seg)); dev_bufs.push_back(d_start);
+                    COV_CUDA(cudaMalloc((void **)&d_len, 4 * cap_seg)); dev_bufs.push_back(d_len);
+                    COV_CUDA(cudaMalloc((void **)&d_nib, 8 * cap_seg)); dev_bufs.push_back(d_nib);
+                }
+                if (h_seq.size() + 16 > cap_seq) {
+                    if (d_seq) { cudaFree(d_seq); dev_bufs.erase(std::find(dev_bufs.begin(), dev_bufs.end(), (void *)d_seq)); }
+                    cap_seq = h_seq.size() + h_seq.size() / 4 + 16;
+                    d_seq = nullptr;
+                    COV_CUDA(cudaMalloc((void **)&d_seq, cap_seq)); dev_bufs.push_back(d_seq);
+                }
+                COV_CUDA(cudaMemcpyAsync(d_start, h_start.data(), 4 * ns, cudaMemcpyHostToDevice, st));
+                COV_CUDA(cudaMemcpyAsync(d_len, h_len.data(), 4 * ns, cudaMemcpyHostToDevice, st));
+                COV_CUDA(cudaMemcpyAsync(d_nib, h_nib.data(), 8 * ns, cudaMemcpyHostToDevice, st));
+                COV_CUDA(cudaMemcpyAsync(d_seq, h_seq.data(), h_seq.size(), cudaMemcpyHostToDevice, st));
+                rc = hx_launch_coverage(d_start, d_nib, d_len, d_seq, (int64_t)ns, start0, (int32_t)len, d_counts, st);
+                if (rc) break;
+                COV_CUDA(cudaStreamSynchronize(st));               // the host vectors are reused by the next wave
+            }
+        }
+        if (bs.eof || (bs.header_done && bs.past_region(end0))) break;
+    }
+    if (!rc) {
+        COV_CUDA(cudaMemcpyAsync(out, d_counts, sizeof(uint32_t) * 4 * (size_t)len, cudaMemcpyDeviceToHost, st));
+        COV_CUDA(cudaStreamSynchronize(st));
+    }
+    for (void *p : dev_bufs) if (p) cudaFree(p);
+    cudaStreamDestroy(st);
+#undef COV_CUDA
+    return rc;
 }
 
 int hx_bam_contig_length(const char *bam_path, const char *contig, int32_t *length) {

@@ -70,7 +70,10 @@ struct hx_matrix {
     int64_t cap_path;
     double *d_stats;                 // per-iteration stats
     int64_t cap_stats;
-    double *d_site;                  // 3*(N+2) per-site log10 marginal (cur), (orig), marginal
+    double *d_site;                  // 2 x 3*(N+2) per-site log10 marginal (cur), (orig), marginal (alternating haplotypes)
+    cudaStream_t sum_stream;         // the ordered log10 sums of a haplotype run here, off the critical path
+    cudaEvent_t sum_done[2], site_ready;
+    bool sum_busy[2];
     double *d_terms;                 // walk tables: (N+2)*Lw*49 log10 lookback terms + (N+2)*8 log10 marginals
     int64_t cap_terms;
     double *d_partials;              // block partials of the reweight reduction

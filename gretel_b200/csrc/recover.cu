@@ -590,28 +590,50 @@ __global__ void k_path_stats(const double *__restrict__ scnt_cur, const double *
     site[2 * stride + snp] = m;
 }
 
-// Three threads each run one strictly ordered accumulation (same order as gretel.py:185-189) out of shared
-// memory while warps 2..7 stage the next block of per-site values, so the ordered adds never wait on HBM.
+// The minimum marginal is what the reweighting needs (ratio = max(min, min_remove), cmd.py:157-160): a parallel
+// reduction on the main stream.  The two log10 sums are only reported; they are strictly ordered chains (same order
+// as gretel.py:185-186) and run on a side stream while the reweighting and the next haplotype's tables proceed.
+__global__ void __launch_bounds__(1024)
+k_path_min(const double *__restrict__ site, int N, double min_remove, double *__restrict__ stats,
+           const int *__restrict__ flagsd) {
+    __shared__ double sh[32];
+    if (flagsd[1]) { if (threadIdx.x == 0) stats[5] = 0.0; return; }
+    const double *m = site + 2 * ((int64_t)N + 2);
+    double acc = INFINITY;
+    for (int x = 1 + threadIdx.x; x <= N; x += 1024) { const double v = m[x]; acc = v < acc ? v : acc; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { const double v = __shfl_xor_sync(0xffffffffu, acc, o); acc = v < acc ? v : acc; }
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 32; ++w) acc = sh[w] < acc ? sh[w] : acc;
+        stats[2] = acc;                                        // min marginal
+        stats[3] = acc < min_remove ? min_remove : acc;        // cmd.py:157-160
+        stats[5] = 1.0;                                        // iteration completed
+    }
+}
+
+// Two threads each run one strictly ordered accumulation out of shared memory while warps 2..7 stage the next
+// block of per-site values, so the ordered adds never wait on HBM.
 constexpr int HX_SUM_CH = 896;
 
 __global__ void __launch_bounds__(256)
-k_path_sum(const double *__restrict__ site, int N, double min_remove, double *__restrict__ stats,
-           const int *__restrict__ flagsd) {
-    __shared__ double buf[2][3][HX_SUM_CH];
+k_path_sum(const double *__restrict__ site, int N, double *__restrict__ stats) {
+    __shared__ double buf[2][2][HX_SUM_CH];
     const int tid = threadIdx.x;
-    if (flagsd[1]) { if (tid == 0) stats[5] = 0.0; return; }
+    if (stats[5] != 1.0) return;                               // the walk found a hole (k_path_min): nothing to sum
     const int64_t stride = (int64_t)N + 2;
     const int nch = (N + HX_SUM_CH - 1) / HX_SUM_CH;
     auto stage = [&](int c, int t0, int nt) {
         const int base = 1 + c * HX_SUM_CH;
         const int n = min(HX_SUM_CH, N - base + 1);
-        for (int a = 0; a < 3; ++a)
+        for (int a = 0; a < 2; ++a)
             for (int x = t0; x < n; x += nt) buf[c & 1][a][x] = site[a * stride + base + x];
     };
     stage(0, tid, 256);
     __syncthreads();
-    const int role = tid < 2 ? tid : (tid == 32 ? 2 : -1);     // two ordered sums in warp 0, the min in warp 1
-    double acc = role == 2 ? INFINITY : 0.0;
+    const int role = tid < 2 ? tid : -1;                       // two ordered sums in warp 0
+    double acc = 0.0;
     for (int c = 0; c < nch; ++c) {
         if (tid >= 64) {
             if (c + 1 < nch) stage(c + 1, tid - 64, 192);
@@ -623,27 +645,14 @@ k_path_sum(const double *__restrict__ site, int N, double min_remove, double *__
                 double v[8];
 #pragma unroll
                 for (int q = 0; q < 8; ++q) v[q] = p[x + q];
-                if (role < 2) {
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) acc += v[q];
-                } else {
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) acc = v[q] < acc ? v[q] : acc;
-                }
+                for (int q = 0; q < 8; ++q) acc += v[q];
             }
-            for (; x < n; ++x) {
-                if (role < 2) acc += p[x];
-                else acc = p[x] < acc ? p[x] : acc;
-            }
+            for (; x < n; ++x) acc += p[x];
         }
         __syncthreads();
     }
-    if (role >= 0 && role < 2) stats[role] = acc;              // hp_current, hp_original
-    else if (role == 2) {
-        stats[2] = acc;                                        // min marginal
-        stats[3] = acc < min_remove ? min_remove : acc;        // cmd.py:157-160
-        stats[5] = 1.0;                                        // iteration completed
-    }
+    if (role >= 0) stats[role] = acc;                          // hp_current, hp_original
 }
 
 // ---- reweight ---------------------------------------------------------------------------
@@ -743,8 +752,15 @@ int launch_reweight(hx_matrix *h, const uint8_t *d_path, const double *d_ratio, 
     return HX_OK;
 }
 
+// the ordered sums of every haplotype enqueued so far are done before anything later on the main stream
+int join_sums(hx_matrix *cur) {
+    for (int b = 0; b < 2; ++b)
+        if (cur->sum_busy[b]) { HX_CUDA(cudaStreamWaitEvent(cur->stream, cur->sum_done[b], 0)); cur->sum_busy[b] = false; }
+    return HX_OK;
+}
+
 int launch_generate(hx_matrix *cur, hx_matrix *orig, int L, int flags, uint8_t *d_path,
-                    double *d_stats, double min_remove) {
+                    double *d_stats, double min_remove, int it = 0) {
     int rc = hx_ensure_counts(cur);
     if (rc) return rc;
     rc = hx_ensure_counts(orig);
@@ -800,10 +816,23 @@ int launch_generate(hx_matrix *cur, hx_matrix *orig, int L, int flags, uint8_t *
                                                      cur->d_flags);
     }
     cur->launches += 2;
-    k_path_stats<<<(N + 255) / 256, 256, 0, cur->stream>>>(cur->scnt, orig->scnt, N, d_path, cur->d_site,
-                                                           cur->d_flags);
-    k_path_sum<<<1, 256, 0, cur->stream>>>(cur->d_site, N, min_remove, d_stats, cur->d_flags);
-    cur->launches += 3;
+    // per-site values of this haplotype: two alternating buffers, so that the ordered sums of haplotype `it` (side
+    // stream) may still be running while haplotype it+1 is walked
+    double *site = cur->d_site + (size_t)(it & 1) * 3 * ((size_t)N + 2);
+    if (!cur->sum_stream) {
+        HX_CUDA(cudaStreamCreateWithFlags(&cur->sum_stream, cudaStreamNonBlocking));
+        for (int b = 0; b < 2; ++b) HX_CUDA(cudaEventCreateWithFlags(&cur->sum_done[b], cudaEventDisableTiming));
+        HX_CUDA(cudaEventCreateWithFlags(&cur->site_ready, cudaEventDisableTiming));
+    }
+    if (cur->sum_busy[it & 1]) HX_CUDA(cudaStreamWaitEvent(cur->stream, cur->sum_done[it & 1], 0));
+    k_path_stats<<<(N + 255) / 256, 256, 0, cur->stream>>>(cur->scnt, orig->scnt, N, d_path, site, cur->d_flags);
+    k_path_min<<<1, 1024, 0, cur->stream>>>(site, N, min_remove, d_stats, cur->d_flags);
+    HX_CUDA(cudaEventRecord(cur->site_ready, cur->stream));
+    HX_CUDA(cudaStreamWaitEvent(cur->sum_stream, cur->site_ready, 0));
+    k_path_sum<<<1, 256, 0, cur->sum_stream>>>(site, N, d_stats);
+    HX_CUDA(cudaEventRecord(cur->sum_done[it & 1], cur->sum_stream));
+    cur->sum_busy[it & 1] = true;
+    cur->launches += 4;
     HX_CUDA(cudaGetLastError());
     return HX_OK;
 }
@@ -884,7 +913,11 @@ int hx_generate_path(hx_matrix *cur, hx_matrix *orig, int32_t L, int flags, uint
     }
     HX_CUDA(cudaMemsetAsync(cur->d_flags, 0, 3 * sizeof(int), cur->stream));
     HX_CUDA(cudaEventRecord(cur->ev0, cur->stream));
+    // (the single-haplotype entry point: stats[5] must start at 0 for the hole test of the ordered sums)
+    HX_CUDA(cudaMemsetAsync(cur->d_stats, 0, 8 * sizeof(double), cur->stream));
     rc = launch_generate(cur, orig, L, flags, cur->d_path, cur->d_stats, 0.0);
+    if (rc) return rc;
+    rc = join_sums(cur);
     if (rc) return rc;
     HX_CUDA(cudaEventRecord(cur->ev1, cur->stream));
     cur->ev_rec = true;
@@ -945,11 +978,13 @@ int hx_recover(hx_matrix *cur, hx_matrix *orig, int32_t L, int flags, int32_t ma
     for (int it = 0; it < max_paths; ++it) {
         uint8_t *dp = cur->d_path + (size_t)it * (N + 1);
         double *ds = cur->d_stats + (size_t)it * 8;
-        rc = launch_generate(cur, orig, L, flags, dp, ds, min_remove);
+        rc = launch_generate(cur, orig, L, flags, dp, ds, min_remove, it);
         if (rc) return rc;
         rc = launch_reweight(cur, dp, ds + 3, 0.0, ds + 4);
         if (rc) return rc;
     }
+    rc = join_sums(cur);
+    if (rc) return rc;
     HX_CUDA(cudaEventRecord(cur->ev1, cur->stream));
     cur->ev_rec = true;
     double *hs = (double *)malloc(sizeof(double) * 8 * (size_t)max_paths);

@@ -17,12 +17,18 @@ import numpy as np
 from . import _lib
 
 
-def count_coverage(bam, contig, start0, end0, n_threads=1):
-    """uint32 [4][end0-start0] counts of A,C,G,T (0-based half-open interval)."""
+def count_coverage(bam, contig, start0, end0, n_threads=1, device=0):
+    """uint32 [4][end0-start0] counts of A,C,G,T (0-based half-open interval).  The BAM is decoded on the CPU, the
+    per-position histogram runs on GPU ``device`` (hx_count_coverage_gpu); ``device=None`` counts on the CPU
+    (hx_count_coverage: the checker of the GPU kernel in the tests, and what a CPU-only box can run)."""
     lib = _lib.load()
     out = np.zeros((4, max(0, end0 - start0)), dtype=np.uint32)
-    _lib.check(lib.hx_count_coverage(str(bam).encode(), str(contig).encode(), int(start0), int(end0),
-                                     int(max(1, n_threads)), out.ctypes.data))
+    if device is None:
+        _lib.check(lib.hx_count_coverage(str(bam).encode(), str(contig).encode(), int(start0), int(end0),
+                                         int(max(1, n_threads)), out.ctypes.data))
+    else:
+        _lib.check(lib.hx_count_coverage_gpu(str(bam).encode(), str(contig).encode(), int(start0), int(end0),
+                                             int(max(1, n_threads)), int(device), out.ctypes.data))
     return out
 
 
@@ -47,11 +53,13 @@ def main(argv=None, out=sys.stdout):
     p.add_argument("-e", type=int)
     p.add_argument("--depth", type=int, default=0)
     p.add_argument("-@", "--threads", type=int, default=1)
+    p.add_argument("--device", type=int, default=0, help="GPU that counts the bases (default 0)")
+    p.add_argument("--cpu", action="store_true", help="count on the CPU instead")
     a = p.parse_args(argv)
     if not a.e:
         a.e = contig_length(a.bam, a.contig)
     s0 = a.s - 1
-    counts = count_coverage(a.bam, a.contig, s0, a.e, n_threads=a.threads)
+    counts = count_coverage(a.bam, a.contig, s0, a.e, n_threads=a.threads, device=None if a.cpu else a.device)
     out.write("##fileformat=VCFv4.2\n")
     for i in call_sites(counts, a.depth):
         out.write("\t".join([a.contig, str(int(i) + 1 + s0), ".", "A", "C,T,G", "0", ".", "INFO"]) + "\n")

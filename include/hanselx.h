@@ -203,6 +203,10 @@ void hx_dense_free(hx_dense *d);
  * what gretel/snpper.py:30 asks pysam.count_coverage for.  out[4*(end0-start0)], A row first. */
 int hx_count_coverage(const char *bam_path, const char *contig, int32_t start0, int32_t end0, int n_threads,
                       uint32_t *out);
+/* The same with the histogram on the GPU: the CPU decodes the BAM into aligned segments and 4-bit bases, a
+ * shared-memory-privatised histogram kernel counts them (gretel/snpper.py:29-41).  out on the host. */
+int hx_count_coverage_gpu(const char *bam_path, const char *contig, int32_t start0, int32_t end0, int n_threads,
+                          int32_t device, uint32_t *out);
 int hx_bam_contig_length(const char *bam_path, const char *contig, int32_t *length);
 
 /* ---- parity probe (bench.py parity_probe, multi-GPU tests) ------------------------ */

@@ -114,10 +114,10 @@ def test_snpper_matches_python(tmp_path, golden_dir):
     for (s0, e0) in ((0, 3000), (400, 1900)):
         exp = _py_coverage(path, "ctgA", s0, e0)
         for th in (1, 3):
-            assert np.array_equal(snpper.count_coverage(path, "ctgA", s0, e0, n_threads=th), exp)
+            assert np.array_equal(snpper.count_coverage(path, "ctgA", s0, e0, n_threads=th, device=None), exp)
     assert snpper.contig_length(path, "ctgB") == 3000
     buf = io.StringIO()
-    assert snpper.main(["--bam", path, "--contig", "ctgA", "-s", "401", "-e", "1900", "--depth", "2"], out=buf) == 0
+    assert snpper.main(["--bam", path, "--contig", "ctgA", "-s", "401", "-e", "1900", "--depth", "2", "--cpu"], out=buf) == 0
     lines = buf.getvalue().strip().split("\n")
     assert lines[0] == "##fileformat=VCFv4.2"
     exp = _py_coverage(path, "ctgA", 400, 1900)
@@ -125,6 +125,32 @@ def test_snpper_matches_python(tmp_path, golden_dir):
     assert [int(l.split("\t")[1]) for l in lines[1:]] == sites and len(sites) > 10
     assert lines[1].split("\t")[3:] == ["A", "C,T,G", "0", ".", "INFO"]
     # the reference's toy BAM: reads 1-4 disagree at positions 1 and 2 of 'hoot' (A, C, T, T)
+    buf = io.StringIO()
+    snpper.main(["--bam", os.path.join(golden_dir, "ref_test.bam"), "--contig", "hoot", "--cpu"], out=buf)
+    assert [int(l.split("\t")[1]) for l in buf.getvalue().strip().split("\n")[1:]] == [1, 2, 10]
+
+
+@pytest.mark.gpu
+def test_snpper_gpu_histogram(tmp_path, golden_dir):
+    """gretel-snpper with the per-position histogram on the GPU (hx_count_coverage_gpu, coverage.cu): equal to the
+    CPU counts on random BAMs (indels, clips, skips, several threads, sub-regions), on a deep synthetic BAM, and the
+    reference's toy BAM gives the reference's sites (gretel/snpper.py:29-41)."""
+    import io
+    from gretel_b200 import snpper, synth
+    rng = np.random.default_rng(19)
+    path = str(tmp_path / "g.bam")
+    _random_bam(path, rng, 4000)
+    for (s0, e0) in ((0, 3000), (400, 1900), (2999, 3000)):
+        exp = _py_coverage(path, "ctgA", s0, e0)
+        for th in (1, 4):
+            assert np.array_equal(snpper.count_coverage(path, "ctgA", s0, e0, n_threads=th, device=0), exp)
+    w = synth.scaled(synth.WORKLOADS["metagenome"], 200_000)
+    d = synth.generate(w)
+    deep = str(tmp_path / "deep.bam")
+    synth.write_bam(deep, d, w)
+    cpu = snpper.count_coverage(deep, "ctg", 0, w.genome_len, n_threads=4, device=None)
+    gpu = snpper.count_coverage(deep, "ctg", 0, w.genome_len, n_threads=4, device=0)
+    assert np.array_equal(cpu, gpu) and int(gpu.sum()) > 25_000_000
     buf = io.StringIO()
     snpper.main(["--bam", os.path.join(golden_dir, "ref_test.bam"), "--contig", "hoot"], out=buf)
     assert [int(l.split("\t")[1]) for l in buf.getvalue().strip().split("\n")[1:]] == [1, 2, 10]
