@@ -143,6 +143,7 @@ void free_all(hx_matrix *h) {
     if (h->d_terms) cudaFreeAsync(h->d_terms, h->stream);
     if (h->d_flags) cudaFreeAsync(h->d_flags, h->stream);
     if (h->d_run_end) cudaFreeAsync(h->d_run_end, h->stream);
+    if (h->d_run_list) cudaFreeAsync(h->d_run_list, h->stream);
     if (h->d_misc) cudaFreeAsync(h->d_misc, h->stream);
     if (h->d_pack) cudaFreeAsync(h->d_pack, h->stream);
     if (h->stream) cudaStreamSynchronize(h->stream);
@@ -282,6 +283,7 @@ int hx_create(int32_t n_snps, int32_t band_w, int32_t device, hx_matrix **out) {
     HX_TRY(hx_fill_async(h->d_flags, 0, 8 * sizeof(int), h->stream));
     HX_TRY(cudaMallocAsync((void **)&h->d_misc, 32 * sizeof(double), h->stream));
     HX_TRY(cudaMallocAsync((void **)&h->d_run_end, sizeof(int64_t) * ((size_t)n_snps + 2), h->stream));
+    HX_TRY(cudaMallocAsync((void **)&h->d_run_list, sizeof(int64_t) * (((size_t)n_snps + 3) / 2 + (size_t)n_snps + 2 + 2), h->stream));
     h->h_pinned = calloc(1, 256);     // scalars come back through pageable memory: a pinned allocation per
                                       // matrix costs more (cudaMallocHost/cudaFreeHost) than it saves
     if (!h->h_pinned) { free_all(h); return HX_E_NOMEM; }

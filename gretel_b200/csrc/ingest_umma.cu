@@ -24,8 +24,11 @@
 
 namespace {
 
+#ifndef UM_EXP_WARPS_N
+#define UM_EXP_WARPS_N 24
+#endif
 constexpr int UM_RD_WARPS = 8;               // readout warps: two per TMEM lane quarter (warp id % 4)
-constexpr int UM_EXP_WARPS = 24;             // expander warps 8..31
+constexpr int UM_EXP_WARPS = UM_EXP_WARPS_N; // expander warps 8..
 constexpr int UM_THREADS = (UM_RD_WARPS + UM_EXP_WARPS) * 32;
 constexpr int UM_NACC = 4;                   // accumulator stages (runs in flight)
 constexpr int UM_TMEM_COLS = 128 * UM_NACC;  // 128 int32 columns each
@@ -108,58 +111,93 @@ __device__ __forceinline__ void um_st16_zero(uint32_t taddr) {
 __device__ __forceinline__ void um_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void um_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// The schedule, walked identically by every warp: runs of reads that share a rank (run_end[r] = index after the
-// last read of rank r, -1 for ranks without reads), clipped to the CTA's slice [lo, hi).
+// The schedule, walked identically by every warp: the runs of reads that share a rank, as a compact list in rank
+// order (k_run_list below: run_rank[j], run_stop[j] = index after the run's last read), clipped to the CTA's slice
+// [lo, hi).  The next entry is requested while the current run is being processed.
 struct UmWalk {
-    const int64_t *run_end;
-    int64_t hi, cur, wval;
-    int N, wbase;
+    const int32_t *run_rank;
+    const int64_t *run_stop;
+    int64_t hi, cur, p_stop;
+    int n_runs, j, p_rank;
     // the current run
     int64_t start, n;
     int r;
     unsigned ri;
 
-    __device__ __forceinline__ void init(const int64_t *re, int64_t lo_, int64_t hi_, int N_, int r0) {
-        run_end = re; hi = hi_; cur = lo_; N = N_; r = r0; ri = 0u - 1u;
-        wbase = r0 < 0 ? 0 : r0;
-        load_window();
+    __device__ __forceinline__ void fetch() {
+        if (j < n_runs) { p_rank = run_rank[j]; p_stop = run_stop[j]; }
     }
-    __device__ __forceinline__ void load_window() {
-        const int i = wbase + (int)(threadIdx.x & 31);
-        wval = i <= N ? run_end[i] : -1;
+    __device__ __forceinline__ void init(const int32_t *rr, const int64_t *rs, int n_runs_, int64_t lo_, int64_t hi_) {
+        run_rank = rr; run_stop = rs; n_runs = n_runs_; hi = hi_; cur = lo_; ri = 0u - 1u; r = 0; start = lo_; n = 0;
+        int a = 0, b = n_runs_;                                 // first run that ends behind lo
+        while (a < b) {
+            const int m = (a + b) >> 1;
+            if (run_stop[m] > lo_) b = m; else a = m + 1;
+        }
+        j = a;
+        p_rank = 0; p_stop = 0;
+        fetch();
     }
     __device__ __forceinline__ bool next_run() {
-        if (cur >= hi) return false;
-        for (;;) {
-            const unsigned m = __ballot_sync(0xffffffffu, wval > cur);
-            if (m) {
-                const int l = __ffs(m) - 1;
-                r = wbase + l;
-                const int64_t e = __shfl_sync(0xffffffffu, wval, l);
-                const int64_t run_hi = e < hi ? e : hi;
-                start = cur;
-                n = run_hi - cur;
-                cur = run_hi;
-                ++ri;
-                return true;
-            }
-            wbase += 32;
-            if (wbase > N) { cur = hi; return false; }          // reads with ranks outside [0,N]: flagged by the pre-pass
-            load_window();
+        while (cur < hi && j < n_runs) {
+            const int64_t stop = p_stop;
+            r = p_rank;
+            ++j;
+            fetch();
+            if (stop <= cur) continue;
+            const int64_t run_hi = stop < hi ? stop : hi;
+            start = cur;
+            n = run_hi - cur;
+            cur = run_hi;
+            ++ri;
+            return true;
         }
+        cur = hi;                                               // reads with ranks outside [0,N]: flagged by the pre-pass
+        return false;
     }
 };
 
-// lane = read: the aligned words holding its allele bytes (CH+1 of them cover 4*CH sites at any alignment).
+// run_end[0..N] (-1 = no reads of that rank) -> the compact run list, in rank order.  One CTA: N is small.
+__global__ void __launch_bounds__(1024)
+k_run_list(const int64_t *__restrict__ run_end, int N, int32_t *__restrict__ run_rank, int64_t *__restrict__ run_stop,
+           int *__restrict__ n_runs) {
+    __shared__ int s_warp[32];
+    __shared__ int s_base;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_base = 0;
+    __syncthreads();
+    for (int i0 = 0; i0 <= N; i0 += 1024) {
+        const int i = i0 + (int)threadIdx.x;
+        const int64_t e = i <= N ? run_end[i] : -1;
+        const unsigned m = __ballot_sync(0xffffffffu, e >= 0);
+        if (lane == 0) s_warp[warp] = __popc(m);
+        __syncthreads();
+        int before = s_base;
+        for (int w = 0; w < warp; ++w) before += s_warp[w];
+        if (e >= 0) {
+            const int pos = before + __popc(m & ((1u << lane) - 1u));
+            run_rank[pos] = i;
+            run_stop[pos] = e;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) { int t = 0; for (int w = 0; w < 32; ++w) t += s_warp[w]; s_base += t; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *n_runs = s_base;
+}
+
+// lane = read: the aligned words holding its allele bytes.  The number of words is warp-uniform (what the widest
+// read of the group needs at the worst alignment): a narrower read loads a few bytes of its successors, which the
+// expansion masks; the packed codes are padded, so the loads stay in bounds.
 template <int CH>
-__device__ __forceinline__ void um_load_read(const uint8_t *__restrict__ codes, int64_t o, int kb, int kg,
+__device__ __forceinline__ void um_load_read(const uint8_t *__restrict__ codes, int64_t o, int kg,
                                              uint32_t (&wd)[CH + 1], unsigned &mis) {
     const uint8_t *__restrict__ c = codes + o;
     mis = (unsigned)(reinterpret_cast<uintptr_t>(c) & 3u);
     const uint32_t *__restrict__ cw = reinterpret_cast<const uint32_t *>(c - mis);
-    const int nw = kb ? (int)((mis + kb + 3) >> 2) : 0;
+    const int nwg = (kg + 6) >> 2;                                  // ceil((3 + kg) / 4) words
 #pragma unroll
-    for (int w = 0; w <= CH; ++w) wd[w] = (w < nw && (w == 0 || 4 * (w - 1) < kg)) ? __ldg(cw + w) : 0u;
+    for (int w = 0; w <= CH; ++w) wd[w] = w < nwg ? __ldg(cw + w) : 0u;
 }
 
 // ... and their expansion into the one-hot operand row (CH chunks of four sites, one 16-byte store each).
@@ -181,9 +219,9 @@ __device__ __forceinline__ void um_expand_read(const uint32_t (&wd)[CH + 1], uns
             const uint32_t x = (xx & ~inval) | (0x04040404u & inval);   // past the end -> 'N' -> no column
             if (ch == 0) x0 = x;
             const uint32_t y = x << 3;                            // byte j = 8 * code of site 4ch+j
-            o0 = um_shl(1u, y & 0xffu);
-            o1 = um_shl(1u, (y >> 8) & 0xffu);
-            o2 = um_shl(1u, (y >> 16) & 0xffu);
+            o0 = um_shl(1u, __byte_perm(y, 0u, 0x4440u));
+            o1 = um_shl(1u, __byte_perm(y, 0u, 0x4441u));
+            o2 = um_shl(1u, __byte_perm(y, 0u, 0x4442u));
             o3 = um_shl(1u, y >> 24);
         }
         asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(rowaddr + (uint32_t)ch * 128u), "r"(o0), "r"(o1),
@@ -196,7 +234,8 @@ template <int CH, bool FUSED>
 __global__ void __launch_bounds__(UM_THREADS, 1)
 k1_umma(const int32_t *__restrict__ rank, const int64_t *__restrict__ off, const uint8_t *__restrict__ codes,
         int64_t n_reads, int N, int W, int kmax, const HxCnt cnt_in, unsigned long long *__restrict__ totals,
-        int *__restrict__ err, const int *__restrict__ sorted_flag, const int64_t *__restrict__ run_end) {
+        int *__restrict__ err, const int *__restrict__ sorted_flag, const int32_t *__restrict__ run_rank,
+        const int64_t *__restrict__ run_stop, const int *__restrict__ n_runs_ptr) {
     extern __shared__ __align__(1024) uint8_t um_smem[];
     UM_T(k_begin);
     HxCnt cnt = cnt_in;                              // single-GPU build: the peer path folds away
@@ -262,7 +301,7 @@ k1_umma(const int32_t *__restrict__ rank, const int64_t *__restrict__ off, const
 #endif
 
     UmWalk wk;
-    wk.init(run_end, lo, hi, N, rank[lo]);
+    wk.init(run_rank, run_stop, *n_runs_ptr, lo, hi);
     UM_T(k_roles);
 
     if (warp >= UM_RD_WARPS) {
@@ -275,16 +314,21 @@ k1_umma(const int32_t *__restrict__ rank, const int64_t *__restrict__ off, const
         const uint32_t slot_addr = x_saddr + (uint32_t)e * SLOTB;
         const uint32_t slot_bar = ws_smem_u32(&s_slot[e]);
         const uint64_t desc = um_desc(slot_addr, LBO);
+        const uint32_t idesc0 = um_idesc(0);
+        const uint32_t accfull_addr = ws_smem_u32(&s_acc_full[0]);
         const uint32_t rowaddr = slot_addr + (uint32_t)(lane >> 3) * LBO + (uint32_t)(lane & 7) * 16u;
-        constexpr int64_t PF_READS = 2048;                      // L2 prefetch distance in reads
+#ifndef UM_PF_READS
+#define UM_PF_READS 2048
+#endif
+        constexpr int64_t PF_READS = UM_PF_READS;               // L2 prefetch distance in reads
         int gmod = 0;                                            // groups dealt so far, modulo the expander count
         unsigned njobs = 0;
         int jg = 0, cur_ng = 0;
-        struct Job { int64_t start, n; int r, g; unsigned ri; bool valid; };
+        struct Job { int64_t start; int n, r, g; unsigned ri; bool valid; };
         auto next_job = [&]() -> Job {
             for (;;) {
                 if (jg < cur_ng) {
-                    Job j{wk.start, wk.n, wk.r, jg, wk.ri, true};
+                    Job j{wk.start, (int)wk.n, wk.r, jg, wk.ri, true};
                     jg += UM_EXP_WARPS;
                     return j;
                 }
@@ -308,27 +352,31 @@ k1_umma(const int32_t *__restrict__ rank, const int64_t *__restrict__ off, const
             }
         };
         auto load_off = [&](const Job &j, int64_t &o, int64_t &o1) {
-            const int64_t idx = (int64_t)j.g * 32 + lane;
+            const int idx = j.g * 32 + lane;
             o = 0; o1 = 0;
-            if (j.valid && idx < j.n) { o = off[j.start + idx]; o1 = off[j.start + idx + 1]; }
+            if (j.valid && idx < j.n) { const int64_t *p = off + j.start + idx; o = p[0]; o1 = p[1]; }
         };
+        const uint32_t runs_addr = ws_smem_u32(&s_runs_read);
         Job cur = next_job();
         int64_t o, o1;
         load_off(cur, o, o1);
         while (cur.valid) {
             UM_T(tA);
+#ifndef UM_NO_LOOKAHEAD
             const Job nxt = next_job();
             int64_t on, o1n;
             load_off(nxt, on, o1n);                             // in flight while this job is expanded
+#endif
             const int r = cur.r;
             const int s = cur.ri % UM_NACC;
+            // SNPs on my read: 0 for a lane past the run's end or a read with fewer than two; a read that leaves
+            // [0, N] or is wider than the band is an error (the same test as the other kernels)
+            const uint64_t kd = (uint64_t)(o1 - o);
+            const int klim = min(W + 1, N - r);                     // warp-uniform
             int kb = 0;
-            {
-                const int64_t k64 = o1 - o;
-                if (k64 >= 2) {
-                    if (r < 0 || (int64_t)r + k64 > N || k64 - 1 > W) errbits |= 1;
-                    else kb = (int)k64;
-                }
+            if (kd >= 2) {
+                if (r < 0 || kd > (uint64_t)(klim < 0 ? 0 : klim)) errbits |= 1;
+                else kb = (int)kd;
             }
             n_slices += kb >= 2;
             n_codes += kb;
@@ -336,13 +384,13 @@ k1_umma(const int32_t *__restrict__ rank, const int64_t *__restrict__ off, const
             UM_T(tC);
             uint32_t wd[CH + 1];
             unsigned mis;
-            um_load_read<CH>(codes, o, kb, kg, wd, mis);
+            um_load_read<CH>(codes, o, kg, wd, mis);
             UM_T(tD);
             // the run's accumulator stage: run ri-NACC must have been read out (and the stage zeroed) before anything
             // of run ri is added; the previous MMA of this warp must have read the slot before it is rewritten
             if (cur.ri >= (unsigned)UM_NACC) {
                 const unsigned need = cur.ri - UM_NACC + 1;
-                while (um_ld_acquire(ws_smem_u32(&s_runs_read)) < need) __nanosleep(200);
+                while (um_ld_acquire(runs_addr) < need) __nanosleep(200);
             }
             ws_mbar_wait(slot_bar, (njobs & 1) ^ 1);
             um_fence_after();
@@ -353,27 +401,30 @@ k1_umma(const int32_t *__restrict__ rank, const int64_t *__restrict__ off, const
             __syncwarp();
             if (lane == 0) {
                 if (kg >= 2) {
+                    const int c4 = (kg + 3) >> 2;                   // chunks of four sites the group reaches
                     atomicMax(&s_runkg[s], kg);
-                    __threadfence_block();
-                    um_mma(tmem_base + (uint32_t)s * 128u, desc, um_idesc(16 * ((kg + 3) >> 2)), 1u);
+                    asm volatile("fence.acq_rel.cta;" ::: "memory");
+                    um_mma(tmem_base + (uint32_t)s * 128u, desc, idesc0 | ((uint32_t)c4 << 18), 1u);
                 }
                 um_commit(slot_bar);
-                um_commit(ws_smem_u32(&s_acc_full[s]));
+                um_commit(accfull_addr + 8u * (uint32_t)s);
             }
             ++njobs;
             UM_T(tG);
-            if (kb >= 2) {
-                const uint8_t *__restrict__ c = codes + o;
-                const unsigned a0 = x0 & 0xffu;
-                if (r == 0 && sym_valid_from(a0)) {            // util.py:262-266
-                    atomicAdd(cnt.cell(W, 0, 1) + HX_SYM_GAP * HX_NSYM + a0, 1u);
-                    n_sent++;
-                }
-                if (r + kb == N && !(kb == 2 && r == 0)) {     // util.py:271-275
-                    const unsigned ap = c[kb - 2], bl = c[kb - 1];
-                    if (sym_valid_from(ap) && bl <= 6) {
-                        atomicAdd(cnt.cell(W, N, N + 1) + bl * HX_NSYM + HX_SYM_GAP, 1u);
+            if (r == 0 || r + kg >= N) {                            // warp-uniform: runs at the ends of the region
+                if (kb >= 2) {
+                    const uint8_t *__restrict__ c = codes + o;
+                    const unsigned a0 = x0 & 0xffu;
+                    if (r == 0 && sym_valid_from(a0)) {            // util.py:262-266
+                        atomicAdd(cnt.cell(W, 0, 1) + HX_SYM_GAP * HX_NSYM + a0, 1u);
                         n_sent++;
+                    }
+                    if (r + kb == N && !(kb == 2 && r == 0)) {     // util.py:271-275
+                        const unsigned ap = c[kb - 2], bl = c[kb - 1];
+                        if (sym_valid_from(ap) && bl <= 6) {
+                            atomicAdd(cnt.cell(W, N, N + 1) + bl * HX_NSYM + HX_SYM_GAP, 1u);
+                            n_sent++;
+                        }
                     }
                 }
             }
@@ -388,7 +439,12 @@ k1_umma(const int32_t *__restrict__ rank, const int64_t *__restrict__ off, const
             }
             UM_T(tH);
             UM_ACC(0, tC - tA); UM_ACC(1, tD - tC); UM_ACC(2, tE - tD); UM_ACC(3, tG - tE); UM_ACC(4, tH - tG); UM_ACC(5, 1);
+#ifndef UM_NO_LOOKAHEAD
             cur = nxt; o = on; o1 = o1n;
+#else
+            cur = next_job();
+            load_off(cur, o, o1);
+#endif
         }
 #ifdef UM_PROFILE
         if (lane == 0) for (int i = 0; i < 6; ++i) atomicAdd(&um_prof[i], prof_acc[i]);
@@ -401,6 +457,10 @@ k1_umma(const int32_t *__restrict__ rank, const int64_t *__restrict__ off, const
         const int q = warp & 3, half = warp >> 2;
         const int m = q * 32 + lane, t1 = m >> 2, a = m & 3;
         const int per_row = cells * 16;
+        // where this thread's tile words (tid and tid + 256 of a row of cells x 16 counters) live in a band row
+        auto word_off = [](int w) { return (w >> 4) * HX_CELL + ((w & 15) >> 2) * HX_NSYM + (w & 3); };
+        const int goff0 = word_off(threadIdx.x), goff1 = word_off(threadIdx.x + npt);
+        static_assert(UM_RD_WARPS * 32 * 2 >= 31 * 16, "two tile words per readout thread cover a band row");
         int64_t flushed_upto = (int64_t)rank[lo] + 1;
         while (wk.next_run()) {
             const int r = wk.r;
@@ -415,11 +475,11 @@ k1_umma(const int32_t *__restrict__ rank, const int64_t *__restrict__ off, const
                 int row = (int)((flushed_upto + 1) % rows);
                 for (int64_t pj = flushed_upto + 1; pj <= lastrow; ++pj) {
                     uint32_t *base = tile32 + (size_t)row * per_row;
-                    for (int w = threadIdx.x; w < per_row; w += npt) {
+                    uint32_t *grow = cnt.cell(W, pj - 1, pj);        // cell d = 1 of band row pj; cell d is 49*(d-1) further
+                    for (int w = threadIdx.x, k2 = 0; w < per_row; w += npt, ++k2) {
                         const uint32_t v = base[w];
                         if (v) {
-                            const int d = (w >> 4) + 1, ab = w & 15;
-                            atomicAdd(cnt.cell(W, pj - d, pj) + (ab >> 2) * HX_NSYM + (ab & 3), v);
+                            atomicAdd(grow + (k2 ? goff1 : goff0), v);
                             base[w] = 0;
                             sum += v;
                         }
@@ -553,13 +613,18 @@ int hx_launch_ingest_umma(hx_matrix *h, const int32_t *d_rank, const int64_t *d_
     int64_t grid = sms;
     const int64_t max_useful = (n_reads + 255) / 256;          // no thinner than 256 reads per CTA
     if (grid > max_useful) grid = max_useful;
+    int32_t *run_rank = reinterpret_cast<int32_t *>(h->d_run_list);
+    int64_t *run_stop = reinterpret_cast<int64_t *>(h->d_run_list) + (((size_t)h->N + 2 + 1) / 2);
+    int *n_runs = reinterpret_cast<int *>(run_stop + (size_t)h->N + 2);
+    k_run_list<<<1, 1024, 0, h->stream>>>(run_end, h->N, run_rank, run_stop, n_runs);
+    h->launches++;
 #define HX_UM_LAUNCH(CH_)                                                                                       \
     do {                                                                                                        \
         auto kern = fused ? k1_umma<CH_, true> : k1_umma<CH_, false>;                                           \
         HX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));            \
         kern<<<(unsigned)grid, UM_THREADS, smem, h->stream>>>(d_rank, d_off, d_codes, n_reads, h->N, h->W, kmax, \
                                                               hx_cnt_ref(h), h->d_totals, h->d_err, sorted_flag, \
-                                                              run_end);                                         \
+                                                              run_rank, run_stop, n_runs);                      \
     } while (0)
     if (kmax <= 16) HX_UM_LAUNCH(4);
     else HX_UM_LAUNCH(8);

@@ -1,5 +1,6 @@
 """One ingestion launch for ncu (scratch)."""
 import sys, os
+os.environ["HX_HOST_PIPELINE"] = "off"
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from gretel_b200 import synth
 from gretel_b200.hansel import Hansel, REF_SYMBOLS, REF_UNSYMBOLS

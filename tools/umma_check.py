@@ -1,5 +1,6 @@
 """Quick parity + timing check of the tensor-core ingestion kernel (kernel 6) against the C oracle."""
-import sys, time
+import os, sys, time
+os.environ["HX_HOST_PIPELINE"] = "off"      # one launch per ingest_packed: kernel_ms is the whole ingestion
 import numpy as np
 sys.path.insert(0, ".")
 from gretel_b200 import synth

@@ -1,5 +1,6 @@
 """Per-role cycle accounting of the tensor-core ingestion kernel (build with HX_NVCC_DEFS=-DUM_PROFILE)."""
-import ctypes as C, sys
+import ctypes as C, os, sys
+os.environ["HX_HOST_PIPELINE"] = "off"
 import numpy as np
 sys.path.insert(0, ".")
 from gretel_b200 import synth, _lib
