@@ -242,8 +242,11 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device; there is no CPU fallback")
     torch.cuda.set_device(local_rank)
     dist = None
+    overlap = world > 1 and args.overlap_steps and args.exchange == "allreduce" and args.scaling == "weak" and args.segments <= 1
     if world > 1:
         import torch.distributed as dist
+        if overlap:
+            os.environ.setdefault("NCCL_MAX_CTAS", str(args.comm_sms))   # the collective shares the GPU with the next step's kernel
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     from gretel_b200 import dist as gdist, util
     from gretel_b200.hansel import Hansel, REF_SYMBOLS, REF_UNSYMBOLS
@@ -352,8 +355,28 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # N > 1, weak scaling: consecutive steps are independent ingestion jobs, so the all-reduce of step i is put behind
+    # the pair expansion of step i+1 (two matrices take turns, a few SMs are left to NCCL).  Every step still zeroes,
+    # expands and all-reduces its own matrix, and all K all-reduces end inside the timed region.
+    ov = None
+    if overlap:
+        h2 = Hansel.init_matrix(REF_SYMBOLS, REF_UNSYMBOLS, N, band_w=W, device=local_rank)
+        h2.set_ingest_kernel(args.kernel)
+        h2.counts_buffer()
+        ov = gdist.OverlappedAllreduce([h, h2], free_sms=args.comm_sms)
+        stream = ov.main
+
+    def ov_ingest(hh):
+        hh.reset_counts()
+        hh.ingest_device(t_rank.data_ptr(), t_off.data_ptr(), t_codes.data_ptr(), R)
+
     for _ in range(max(args.warmup, 3)):
-        step()
+        if ov is not None:
+            ov.step(ov_ingest)
+        else:
+            step()
+    if ov is not None:
+        ov.drain()
     barrier()
     totals = h.ingest_totals()
     n_obs_global = totals[1]               # crumbs of ALL ranks (totals are all-reduced too)
@@ -366,17 +389,41 @@ def run_ours(args):
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
     t_wall0 = time.perf_counter()
-    with torch.cuda.stream(stream):
-        for i in range(args.steps):
-            ev[i][0].record(stream)
-            step()
-            ev[i][1].record(stream)
-    barrier()
-    wall_s = time.perf_counter() - t_wall0
-    sampler.region(False)
-    launches = h.launch_count() - launches0
-    step_ms = [a.elapsed_time(b) for a, b in ev]
-    total_ms = float(sum(step_ms))
+    if ov is not None:
+        launches0 += h2.launch_count()
+        with torch.cuda.stream(stream):
+            ev[0][0].record(stream)
+            for i in range(args.steps):
+                ov.step(ov_ingest)
+            ov.drain()
+            ev[0][1].record(stream)
+        barrier()
+        wall_s = time.perf_counter() - t_wall0
+        sampler.region(False)
+        launches = h.launch_count() + h2.launch_count() - launches0
+        total_ms = float(ev[0][0].elapsed_time(ev[0][1]))
+        # the same K steps one after the other (the all-reduce fully exposed), for comparison
+        barrier()
+        with torch.cuda.stream(stream):
+            ev[1 % len(ev)][0].record(stream)
+            for i in range(args.steps):
+                step()
+            ev[1 % len(ev)][1].record(stream)
+        barrier()
+        serial_ms = float(ev[1 % len(ev)][0].elapsed_time(ev[1 % len(ev)][1]))
+    else:
+        with torch.cuda.stream(stream):
+            for i in range(args.steps):
+                ev[i][0].record(stream)
+                step()
+                ev[i][1].record(stream)
+        barrier()
+        wall_s = time.perf_counter() - t_wall0
+        sampler.region(False)
+        launches = h.launch_count() - launches0
+        step_ms = [a.elapsed_time(b) for a, b in ev]
+        total_ms = float(sum(step_ms))
+        serial_ms = None
     # kernel-only duration (events inside the library, on the launching stream) for the roofline
     for _ in range(3):
         h.reset_counts()
@@ -388,6 +435,10 @@ def run_ours(args):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         total_ms = float(tt.item())
     value = n_obs_global * args.steps / (total_ms * 1e-3)
+    if serial_ms is not None and world > 1:
+        tt = torch.tensor([serial_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        serial_ms = float(tt.item())
 
     # ---- parity probe: one more complete step (ingestion + exchange), then an independent recount of what
     # every band row must hold (hx_probe_expected_rows, summed over ranks) against the row sums of the
@@ -658,6 +709,11 @@ def run_ours(args):
             "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
             "config": dict(workload_config(args, k_mean, R), **({"reads_total": int(args.reads or w.n_reads),
                                                                  "reads_per_gpu": "one read set cut into %d contiguous chunks balanced by pair count" % world} if strong else {})),
+            "step_overlap": ({"on": True, "comm_sms": args.comm_sms,
+                              "what": "the all-reduce of step i runs on a second stream beside the pair expansion of step i+1 "
+                                      "(two matrices take turns; the ingestion kernel leaves comm_sms SMs to NCCL)",
+                              "value_without_overlap": n_obs_global * args.steps / (serial_ms * 1e-3),
+                              "ms_per_step_without_overlap": serial_ms / args.steps} if ov is not None else None),
             "exchange_detail": ({"kind": "seam" if not seam.fallback else "allreduce (seam fallback)",
                                  "bytes_on_wire": seam.bytes_on_wire(), "own_rows": [seam.own_lo, seam.own_hi]} if seam is not None else None),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes),
@@ -700,6 +756,10 @@ def main():
                          "all-reduce over counts packed into uint16 lanes (half the bytes); reduce onto "
                          "rank 0 only (recovery runs there); or counts added straight into the owning GPU over "
                          "NVLink peer memory + all-gather of the owned rows")
+    ap.add_argument("--overlap-steps", action="store_true", default=True,
+                    help="N>1, weak scaling: put the all-reduce of step i behind the pair expansion of step i+1 (default)")
+    ap.add_argument("--no-overlap-steps", dest="overlap_steps", action="store_false")
+    ap.add_argument("--comm-sms", type=int, default=8, help="SMs left to NCCL when steps overlap")
     ap.add_argument("--segments", type=int, default=1,
                     help="N>1: ingest in this many launches, all-reducing finished band rows behind the next one")
     ap.add_argument("--e2e-format", default="auto", choices=["auto", "encoded", "dense", "compact", "wide"],

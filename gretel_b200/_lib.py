@@ -36,6 +36,7 @@ SIGNATURES = {
     "hx_ingest_host_dense": (_int, [_p, _p, _p, _p, _i64, _p, _i32, _p, _p, _i64, _i64, _i64, _p]),
     "hx_ingest_device": (_int, [_p, _p, _p, _p, _i64]),
     "hx_set_ingest_kernel": (_int, [_p, _int]),
+    "hx_set_ingest_sms": (_int, [_p, _int]),
     "hx_ingest_totals": (_int, [_p, _p]),
     "hx_counts_buffer": (_int, [_p, _pp, C.POINTER(_i64), _pp, C.POINTER(_i64)]),
     "hx_counts_ipc_export": (_int, [_p, _i32, _p]),

@@ -224,6 +224,7 @@ int reset_parked(hx_matrix *h) {
     h->ev_rec = false;
     h->launches = 0;
     h->ingest_kernel = 0;
+    h->ingest_sms = 0;
     h->wire_next = 0;
     h->sum_busy[0] = h->sum_busy[1] = false;
     h->last_ms[0] = h->last_ms[1] = h->last_ms[2] = 0.0f;
@@ -362,6 +363,12 @@ extern "C" {
 int hx_set_ingest_kernel(hx_matrix *h, int which) {
     HX_CHECK_ARG(h && which >= 0 && which <= 6);
     h->ingest_kernel = which;
+    return HX_OK;
+}
+
+int hx_set_ingest_sms(hx_matrix *h, int n_sms) {
+    HX_CHECK_ARG(h && n_sms >= 0);
+    h->ingest_sms = n_sms;
     return HX_OK;
 }
 

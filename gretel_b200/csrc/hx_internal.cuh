@@ -86,6 +86,7 @@ struct hx_matrix {
     int64_t cap_pack;
     void *h_pinned;                  // small host buffer for D2H of scalars
     int ingest_kernel;
+    int ingest_sms;                  // SMs the persistent ingestion kernels may use (0 = all)
     void *lr_scratch;                // long-read ingestion scratch (ingest_long.cu)
     cudaEvent_t ev0, ev1;
     cudaEvent_t host_ev;             // orders the chunked host->device copies of hx_ingest_host

@@ -758,6 +758,7 @@ static int launch_ingest(hx_matrix *h, const int32_t *d_rank, const int64_t *d_o
     if (!presorted) run_end = h->d_run_end;
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+    if (h->ingest_sms > 0 && h->ingest_sms < sms) sms = h->ingest_sms;
     const int *sorted_flag = presorted ? ok : h->d_flags + 4;
     constexpr int GBLOCK = 256;
     const int64_t gwant = (n_reads + (GBLOCK / 32) - 1) / (GBLOCK / 32);

@@ -607,6 +607,7 @@ int hx_launch_ingest_umma(hx_matrix *h, const int32_t *d_rank, const int64_t *d_
                           int64_t n_reads, const int64_t *run_end, const int *sorted_flag) {
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+    if (h->ingest_sms > 0 && h->ingest_sms < sms) sms = h->ingest_sms;
     const int kmax = h->W + 1;
     const bool fused = h->peer_world > 1;
     const size_t smem = UmLayout{kmax}.bytes();

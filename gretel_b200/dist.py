@@ -94,6 +94,61 @@ def allreduce_counts(hansel, group=None):
             dist.all_reduce(totals, op=dist.ReduceOp.SUM, group=group)
 
 
+class OverlappedAllreduce:
+    """Back-to-back ingestion jobs (one matrix per region / sample): the all-reduce of job i runs on a
+    communication stream while the pair expansion of job i+1 runs on the compute stream, with two matrices taking
+    turns.  Every job still does all of its work (zero, expand, sum across GPUs); only the exposure of the
+    collective changes.  The ingestion kernels are persistent (one CTA per SM), so a few SMs are left to NCCL
+    (``free_sms``)."""
+
+    def __init__(self, hansels, group=None, free_sms=8):
+        import torch
+        import torch.distributed as dist
+        self.hs, self.group, self.dist, self.torch = list(hansels), group, dist, torch
+        assert len(self.hs) == 2
+        dev = torch.device("cuda", self.hs[0].device)
+        self.dev = dev
+        self.main = torch.cuda.Stream(device=dev)
+        self.comm = torch.cuda.Stream(device=dev)
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        self.bufs = []
+        for h in self.hs:
+            h.sync()
+            h.set_stream(self.main.cuda_stream)
+            h.set_ingest_sms(max(1, sms - free_sms))
+            cptr, cn, tptr, tn = h.counts_buffer()
+            self.bufs.append((torch.as_tensor(_DevBuf(cptr, cn, "<i4"), device=dev),
+                              torch.as_tensor(_DevBuf(tptr, tn, "<i8"), device=dev)))
+        self.ingested = [torch.cuda.Event() for _ in range(2)]
+        self.reduced = [torch.cuda.Event() for _ in range(2)]
+        self.used = [False, False]
+        self.i = 0
+
+    def step(self, ingest):
+        """``ingest(h)`` enqueues one job's reset + pair expansion on matrix ``h`` (its stream is ``self.main``)."""
+        b = self.i & 1
+        h = self.hs[b]
+        if self.used[b]:
+            self.main.wait_event(self.reduced[b])            # the matrix's previous job has been summed and consumed
+        ingest(h)
+        self.ingested[b].record(self.main)
+        self.comm.wait_event(self.ingested[b])
+        counts, totals = self.bufs[b]
+        with self.torch.cuda.stream(self.comm):
+            self.dist.all_reduce(counts, op=self.dist.ReduceOp.SUM, group=self.group)
+            self.dist.all_reduce(totals, op=self.dist.ReduceOp.SUM, group=self.group)
+            self.reduced[b].record(self.comm)
+        self.used[b] = True
+        self.i += 1
+        return h
+
+    def drain(self):
+        """Order the compute stream behind every outstanding all-reduce."""
+        for b in range(2):
+            if self.used[b]:
+                self.main.wait_event(self.reduced[b])
+
+
 class SeamExchange:
     """Strong scaling: the rank-sorted reads are cut into ``world`` contiguous chunks (shard_bounds), so the partial
     matrices of neighbouring GPUs overlap only in the band rows their boundary reads share (a read of rank r

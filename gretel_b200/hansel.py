@@ -177,6 +177,14 @@ class Hansel:
     def set_ingest_kernel(self, which):
         _lib.check(self._lib.hx_set_ingest_kernel(self._h, int(which)))
 
+    def set_ingest_sms(self, n_sms):
+        """Leave SMs free for a collective running beside the next batch's pair expansion (0 = use all)."""
+        _lib.check(self._lib.hx_set_ingest_sms(self._h, int(n_sms)))
+
+    def set_stream(self, stream_ptr):
+        """Order all work of this matrix on an existing CUDA stream (cudaStream_t as int)."""
+        _lib.check(self._lib.hx_set_stream(self._h, stream_ptr))
+
     def counts_buffer(self):
         """(device ptr, n uint32, device ptr, n int64) of the partial counts and totals."""
         a, b = C.c_void_p(), C.c_void_p()

@@ -99,6 +99,9 @@ int hx_ingest_device(hx_matrix *h, const int32_t *d_rank, const int64_t *d_off,
  * 6 = tensor-core kernel (int8 tcgen05.mma over one-hot allele rows; rank-sorted reads of <= 32 SNPs; what
  * auto picks for such reads). */
 int hx_set_ingest_kernel(hx_matrix *h, int which);
+/* Limit the persistent ingestion kernels to n_sms SMs (0 = all of them): leaves room for a collective that runs
+ * beside the pair expansion of the next batch (bench.py --overlap-steps). */
+int hx_set_ingest_sms(hx_matrix *h, int n_sms);
 int hx_ingest_totals(hx_matrix *h, int64_t totals[4]);               /* synchronises */
 /* Partial-matrix exchange across GPUs (the reference's fork-shared matrix,
  * util.py:303-326): device pointer + length of the uint32 counts and of the int64
