@@ -759,7 +759,7 @@ def main():
     ap.add_argument("--overlap-steps", action="store_true", default=True,
                     help="N>1, weak scaling: put the all-reduce of step i behind the pair expansion of step i+1 (default)")
     ap.add_argument("--no-overlap-steps", dest="overlap_steps", action="store_false")
-    ap.add_argument("--comm-sms", type=int, default=8, help="SMs left to NCCL when steps overlap")
+    ap.add_argument("--comm-sms", type=int, default=16, help="SMs left to NCCL when steps overlap")
     ap.add_argument("--segments", type=int, default=1,
                     help="N>1: ingest in this many launches, all-reducing finished band rows behind the next one")
     ap.add_argument("--e2e-format", default="auto", choices=["auto", "encoded", "dense", "compact", "wide"],
