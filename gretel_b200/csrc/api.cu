@@ -58,6 +58,20 @@ __global__ void k_fold_counts(const uint32_t *__restrict__ cnt, float *__restric
 
 __global__ void k_add_one(float *p, float amount) { *p += amount; }
 
+// counts (16-byte aligned allocation, size in bytes), totals[8] and the error word in one launch
+__global__ void k_reset_counts(uint4 *__restrict__ cnt, size_t bytes, unsigned long long *__restrict__ totals,
+                               int *__restrict__ err) {
+    const size_t n16 = bytes / 16;
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) cnt[i] = z;
+    if (blockIdx.x == 0) {
+        uint8_t *tail = reinterpret_cast<uint8_t *>(cnt) + n16 * 16;
+        for (size_t i = threadIdx.x; i < bytes - n16 * 16; i += blockDim.x) tail[i] = 0;
+        if (threadIdx.x < 8) totals[threadIdx.x] = 0;
+        if (threadIdx.x == 8) *err = 0;
+    }
+}
+
 // ---- packed exchange: the 49 uint32 counts of a site pair travel as 49 x uint16 in 25 words.  Summing the
 // words as uint32 across GPUs is exact as long as no 16-bit lane carries, i.e. every count <= 65535/world on
 // every rank; the pack kernel raises a flag word otherwise and the caller falls back to the plain exchange.
@@ -641,9 +655,18 @@ int hx_counts_ipc_close(hx_matrix *h) {
 int hx_reset_counts(hx_matrix *h) {
     HX_CHECK_ARG(h);
     HX_CUDA(cudaSetDevice(h->device));
-    if (h->cnt) HX_CUDA(hx_fill_async(h->cnt, 0, sizeof(uint32_t) * (size_t)h->cnt_elems, h->stream));
-    HX_CUDA(hx_fill_async(h->d_totals, 0, 8 * sizeof(unsigned long long), h->stream));
-    HX_CUDA(hx_fill_async(h->d_err, 0, sizeof(int), h->stream));
+    // one launch: the counts, the eight totals and the error word
+    if (h->cnt) {
+        const size_t n16 = (sizeof(uint32_t) * (size_t)h->cnt_elems + 15) / 16;
+        const size_t want = (n16 + 255) / 256;
+        const unsigned grid = (unsigned)(want < 1 ? 1 : (want > 148 * 16 ? 148 * 16 : want));
+        k_reset_counts<<<grid, 256, 0, h->stream>>>(reinterpret_cast<uint4 *>(h->cnt), sizeof(uint32_t) * (size_t)h->cnt_elems,
+                                                    h->d_totals, h->d_err);
+        HX_CUDA(cudaGetLastError());
+    } else {
+        HX_CUDA(hx_fill_async(h->d_totals, 0, 8 * sizeof(unsigned long long), h->stream));
+        HX_CUDA(hx_fill_async(h->d_err, 0, sizeof(int), h->stream));
+    }
     return HX_OK;
 }
 

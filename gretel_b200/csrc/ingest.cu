@@ -98,6 +98,13 @@ k1_pairs_red(const int32_t *__restrict__ rank, const int64_t *__restrict__ off,
     flush_totals(t_slices, t_crumbs, t_cov, t_sent, totals);
 }
 
+// One launch instead of two fills: the "sorted" flag starts at 1, run_end at -1 (= no reads of that rank).
+__global__ void k_prepass_init(int *__restrict__ flag, int64_t *__restrict__ run_end, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) *flag = 1;
+    if (i < n) run_end[i] = -1;
+}
+
 // Pre-pass over the rank array: clears *flag when the reads are not rank-sorted and records
 // where the run of reads of each rank ends (exclusive), so the main kernel never searches.
 __global__ void k_prepass(const int32_t *__restrict__ rank, int64_t n_reads, int N, int *__restrict__ flag,
@@ -798,8 +805,8 @@ static int launch_ingest(hx_matrix *h, const int32_t *d_rank, const int64_t *d_o
         h->launches++;
     } else {
         if (!presorted) {
-            HX_CUDA(hx_fill_async(h->d_flags + 4, 1, sizeof(int), h->stream));     // non-zero = sorted
-            if (use_umma) HX_CUDA(hx_fill_async(run_end, 0xff, sizeof(int64_t) * ((size_t)h->N + 2), h->stream));   // -1 = no reads
+            // flag: non-zero = sorted; run_end: -1 = no reads of that rank (the tensor-core kernel walks it)
+            k_prepass_init<<<(unsigned)((h->N + 2 + 255) / 256), 256, 0, h->stream>>>(h->d_flags + 4, run_end, use_umma ? h->N + 2 : 0);
             k_prepass<<<(unsigned)((n_reads + 255) / 256), 256, 0, h->stream>>>(d_rank, n_reads, h->N, h->d_flags + 4,
                                                                                 run_end, h->d_err);
             h->launches += 2;

@@ -157,33 +157,41 @@ struct UmWalk {
     }
 };
 
-// run_end[0..N] (-1 = no reads of that rank) -> the compact run list, in rank order.  One CTA: N is small.
+// run_end[0..N] (-1 = no reads of that rank) -> the compact run list, in rank order.  One CTA: every thread takes a
+// contiguous piece of the ranks, the piece counts are scanned over the block, then the pieces are written in place.
 __global__ void __launch_bounds__(1024)
 k_run_list(const int64_t *__restrict__ run_end, int N, int32_t *__restrict__ run_rank, int64_t *__restrict__ run_stop,
            int *__restrict__ n_runs) {
     __shared__ int s_warp[32];
-    __shared__ int s_base;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) s_base = 0;
-    __syncthreads();
-    for (int i0 = 0; i0 <= N; i0 += 1024) {
-        const int i = i0 + (int)threadIdx.x;
-        const int64_t e = i <= N ? run_end[i] : -1;
-        const unsigned m = __ballot_sync(0xffffffffu, e >= 0);
-        if (lane == 0) s_warp[warp] = __popc(m);
-        __syncthreads();
-        int before = s_base;
-        for (int w = 0; w < warp; ++w) before += s_warp[w];
-        if (e >= 0) {
-            const int pos = before + __popc(m & ((1u << lane) - 1u));
-            run_rank[pos] = i;
-            run_stop[pos] = e;
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) { int t = 0; for (int w = 0; w < 32; ++w) t += s_warp[w]; s_base += t; }
-        __syncthreads();
+    const int per = (N + 1 + 1023) / 1024;
+    const int i0 = (int)threadIdx.x * per, i1 = min(i0 + per, N + 1);
+    int mine = 0;
+    for (int i = i0; i < i1; ++i) mine += run_end[i] >= 0;
+    int incl = mine;                                           // inclusive scan over the warp, then over the warps
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
     }
-    if (threadIdx.x == 0) *n_runs = s_base;
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        int w = s_warp[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= o) w += v;
+        }
+        s_warp[lane] = w;                                      // inclusive over the warps
+    }
+    __syncthreads();
+    int pos = incl - mine + (warp ? s_warp[warp - 1] : 0);
+    for (int i = i0; i < i1; ++i) {
+        const int64_t e = run_end[i];
+        if (e >= 0) { run_rank[pos] = i; run_stop[pos] = e; ++pos; }
+    }
+    if (threadIdx.x == 1023) *n_runs = s_warp[31];
 }
 
 // lane = read: the aligned words holding its allele bytes.  The number of words is warp-uniform (what the widest
