@@ -415,11 +415,11 @@ int hx_launch_ingest_long(hx_matrix *h, const int32_t *d_rank, const int64_t *d_
     k_scan_apply<int32_t, 1, ITEMS, false><<<(unsigned)nblk, 256, 0, st>>>(s->g_hi, ng, s->part32, s->g_hipm);
     h->launches += 8;
     HX_CUDA(cudaGetLastError());
-    // the plane buffer is sized by the scan total: one small D2H (this path is not latency critical)
-    int64_t total_sites = 0;
-    HX_CUDA(cudaMemcpyAsync(&total_sites, s->d_total, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-    HX_CUDA(cudaStreamSynchronize(st));
-    if ((rc = grow(&s->planes, &s->cap_planes, 2 * total_sites + 2, st))) return rc;
+    // The plane buffer is sized by a bound instead of the scan total (no device->host round trip, so chunks of long
+    // reads can overlap their copies like the short ones): a group's frame spans the ranks of its 32 rank-sorted
+    // reads plus one read, and the rank ranges of consecutive groups do not overlap.
+    const int64_t total_sites_bound = (int64_t)N + 1 + ng * ((int64_t)W + 1);
+    if ((rc = grow(&s->planes, &s->cap_planes, 2 * total_sites_bound + 2, st))) return rc;
 
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
