@@ -26,6 +26,7 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <future>
 #include <memory>
 #include <queue>
 #include <string>
@@ -222,6 +223,13 @@ void pack_record(const Rec &r, int32_t target_tid, int32_t start_pos, int32_t en
 // as soon as a coordinate-sorted file has passed the target region.
 struct RecRef { size_t off; uint32_t size; };
 
+// one wave: the inflated bytes (behind the bytes carried over from the previous wave) and its records
+struct Wave {
+    std::unique_ptr<uint8_t[]> ubuf;
+    size_t ucap = 0, ulen = 0;
+    std::vector<RecRef> recs;
+};
+
 struct BamStream {
     int fd = -1;
     const uint8_t *fmap = nullptr;      // the whole file, mapped: the inflate threads read the page cache directly
@@ -233,10 +241,10 @@ struct BamStream {
     int32_t target_tid = -1, target_len = 0;
     std::string contig;
     // wave state
-    std::unique_ptr<uint8_t[]> ubuf;    // carry + inflated bytes
-    size_t ucap = 0, ulen = 0;
+    Wave own;                           // the wave of the single-buffer interface below
+    std::unique_ptr<uint8_t[]> &ubuf = own.ubuf;
+    std::vector<RecRef> &recs = own.recs;
     std::vector<uint8_t> carry;         // unconsumed tail of the previous wave
-    std::vector<RecRef> recs;
     bool eof = false;
     double t_read = 0, t_inflate = 0, t_scan = 0;
 
@@ -262,9 +270,9 @@ struct BamStream {
     }
 
     // parses the BAM header at the front of ubuf; returns bytes consumed, 0 if more data is needed, -1 on error
-    long parse_header() {
-        const uint8_t *d = ubuf.get();
-        const size_t n = ulen;
+    long parse_header(const Wave &w) {
+        const uint8_t *d = w.ubuf.get();
+        const size_t n = w.ulen;
         if (n < 12) return 0;
         if (memcmp(d, "BAM\1", 4) != 0) { hx_set_error("%s is not a BAM file", path.c_str()); return -1; }
         size_t p = 4;
@@ -299,8 +307,13 @@ struct BamStream {
 
     // Reads, inflates and indexes the next wave.  Returns HX_OK with recs filled (possibly empty), or an error;
     // `eof` is set once the file is exhausted.
-    int next_wave(size_t wave_cbytes) {
+    int next_wave(size_t wave_cbytes) { return next_wave(own, wave_cbytes); }
+
+    int next_wave(Wave &w, size_t wave_cbytes) {
         using clk = std::chrono::steady_clock;
+        std::unique_ptr<uint8_t[]> &ubuf = w.ubuf;
+        std::vector<RecRef> &recs = w.recs;
+        size_t &ucap = w.ucap, &ulen = w.ulen;
         recs.clear();
         if (eof) return HX_OK;
         auto t0 = clk::now();
@@ -364,7 +377,7 @@ struct BamStream {
         auto t2 = clk::now();
         size_t q = 0;
         if (!header_done) {
-            const long used = parse_header();
+            const long used = parse_header(w);
             if (used < 0) return HX_E_ARG;
             if (used == 0) {                     // header longer than this wave: keep everything, read on
                 if (eof) { hx_set_error("%s: truncated BAM header", path.c_str()); return HX_E_ARG; }
@@ -394,9 +407,10 @@ struct BamStream {
     }
 
     // a coordinate-sorted file has nothing more for [.., end_pos] on the target once its records are beyond it
-    bool past_region(int32_t end_pos) const {
-        if (!sorted || recs.empty()) return false;
-        const uint8_t *r = ubuf.get() + recs.back().off;
+    bool past_region(int32_t end_pos) const { return past_region(own, end_pos); }
+    bool past_region(const Wave &w, int32_t end_pos) const {
+        if (!sorted || w.recs.empty()) return false;
+        const uint8_t *r = w.ubuf.get() + w.recs.back().off;
         const int32_t tid = rdi32(r), pos = rdi32(r + 4);
         if (tid < 0) return true;                                  // unmapped reads without a position come last
         return tid > target_tid || (tid == target_tid && pos + 1 > end_pos);
@@ -439,12 +453,21 @@ int hx_pack_bam_ex(const char *bam_path, const char *contig, int32_t start_pos, 
     int64_t ring_mask = 0, depth_pos = -1, retired_upto = -1, live = 0;
     std::vector<int64_t> rbeg, rend;
     std::vector<uint8_t> admit;
-    for (;;) {
-        rc = bs.next_wave(WAVE_CBYTES);
+    // two waves take turns: while this thread filters and walks wave i, a helper reads, inflates and indexes wave i+1
+    // (the serial parts of either side - the record scan, the depth cap - hide behind the other side's parallel work)
+    Wave wv[2];
+    constexpr size_t PACK_WAVE = (size_t)16 << 20;
+    std::future<int> next = std::async(std::launch::async, [&]() { return bs.next_wave(wv[0], PACK_WAVE); });
+    for (int wi = 0;; ++wi) {
+        rc = next.get();
         if (rc) return rc;
-        const size_t nrec = bs.recs.size();
+        Wave &cw = wv[wi & 1];
+        const bool more = !(bs.eof || (bs.header_done && bs.past_region(cw, end_pos)));
+        if (more) next = std::async(std::launch::async, [&, wi]() { return bs.next_wave(wv[(wi + 1) & 1], PACK_WAVE); });
+        const size_t nrec = cw.recs.size();
         n_records += (int64_t)nrec;
-        const uint8_t *d = bs.ubuf.get();
+        const uint8_t *d = cw.ubuf.get();
+        const std::vector<RecRef> &recs = cw.recs;
         if (nrec) {
             auto t0 = clk::now();
             const bool depth_on = max_depth > 0;
@@ -460,7 +483,7 @@ int hx_pack_bam_ex(const char *bam_path, const char *contig, int32_t start_pos, 
                         int64_t mx = 0;
                         const size_t a = nrec * (size_t)t / (size_t)ntd, b = nrec * (size_t)(t + 1) / (size_t)ntd;
                         for (size_t i = a; i < b; ++i) {
-                            const Rec r = parse_rec(d + bs.recs[i].off, bs.recs[i].size);
+                            const Rec r = parse_rec(d + recs[i].off, recs[i].size);
                             rend[i] = -1;
                             if (!r.ok || r.tid != bs.target_tid || r.pos < 0 || !passes_stepper(r.flag, stepper)) continue;
                             const int64_t beg = r.pos, end = (int64_t)r.pos + std::max<int64_t>(1, ref_len_of(r));
@@ -516,7 +539,7 @@ int hx_pack_bam_ex(const char *bam_path, const char *contig, int32_t start_pos, 
                 const size_t a = nrec * (size_t)t / (size_t)nt, b = nrec * (size_t)(t + 1) / (size_t)nt;
                 for (size_t i = a; i < b; ++i) {
                     if (depth_on && !admit[i]) continue;
-                    pack_record(parse_rec(d + bs.recs[i].off, bs.recs[i].size), bs.target_tid, start_pos, end_pos, snp_pos,
+                    pack_record(parse_rec(d + recs[i].off, recs[i].size), bs.target_tid, start_pos, end_pos, snp_pos,
                                 n_snps, stepper, outs[(size_t)t], tmp);
                 }
             };
@@ -528,7 +551,7 @@ int hx_pack_bam_ex(const char *bam_path, const char *contig, int32_t start_pos, 
             t_depth += std::chrono::duration<double>(t1 - t0).count();
             t_walk += std::chrono::duration<double>(t2 - t1).count();
         }
-        if (bs.eof || (bs.header_done && bs.past_region(end_pos))) break;
+        if (!more) break;
     }
     auto t0 = clk::now();
     // gather: prefix the per-range sizes, then every range is copied into place by its own thread
