@@ -154,6 +154,7 @@ void free_all(hx_matrix *h) {
     if (h->d_stats) cudaFreeAsync(h->d_stats, h->stream);
     if (h->d_site) cudaFreeAsync(h->d_site, h->stream);
     if (h->d_partials) cudaFreeAsync(h->d_partials, h->stream);
+    if (h->d_spec) cudaFreeAsync(h->d_spec, h->stream);
     if (h->d_terms) cudaFreeAsync(h->d_terms, h->stream);
     if (h->d_flags) cudaFreeAsync(h->d_flags, h->stream);
     if (h->d_run_end) cudaFreeAsync(h->d_run_end, h->stream);

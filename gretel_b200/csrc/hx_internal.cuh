@@ -76,6 +76,8 @@ struct hx_matrix {
     bool sum_busy[2];
     double *d_terms;                 // walk tables: (N+2)*Lw*49 log10 lookback terms + (N+2)*8 log10 marginals
     int64_t cap_terms;
+    uint8_t *d_spec;                 // speculative block paths, majority-allele guess and block flags of the walk
+    int64_t cap_spec;
     double *d_partials;              // block partials of the reweight reduction
     int64_t cap_partials;
     int *d_flags;                    // [0] hole site / abort flag, [1..] misc

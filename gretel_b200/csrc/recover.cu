@@ -171,15 +171,18 @@ __global__ void k_walk_terms(const float *__restrict__ band, const int32_t *__re
 }
 
 __global__ void k_walk_logm(const double *__restrict__ scnt, int N, int flags, double *__restrict__ logm,
-                            int32_t *__restrict__ logmq) {
+                            int32_t *__restrict__ logmq, uint8_t *__restrict__ guess) {
     const int snp = blockIdx.x * blockDim.x + threadIdx.x;
     if (snp > N) return;
     const double total = scnt[(int64_t)snp * 8 + 7];
     const bool skip_unsym = !(flags & HX_F_KEEP_UNSYMBOLS);
     unsigned mask = 0;
+    double gbest = -1.0;
+    int gsym = snp == 0 ? HX_SYM_GAP : 0;                   // the majority allele: where a speculative block starts from
     for (int s = 0; s < HX_NSYM; ++s) {
         const double c = scnt[(int64_t)snp * 8 + s];
         const bool cand = c > 0 && !(skip_unsym && (s == HX_SYM_N || s == HX_SYM_GAP));
+        if (cand && snp > 0 && c > gbest) { gbest = c; gsym = s; }
         const double lm = cand ? log10(c / total) : 0.0;
         logm[(int64_t)snp * 8 + s] = lm;
         if (logmq) logmq[(int64_t)snp * 8 + s] = cand ? __double2int_rn(lm * HX_QSCALE) : HX_QSUNK;
@@ -187,6 +190,7 @@ __global__ void k_walk_logm(const double *__restrict__ scnt, int N, int flags, d
     }
     logm[(int64_t)snp * 8 + 7] = (double)mask;
     if (logmq) logmq[(int64_t)snp * 8 + 7] = HX_QSUNK;
+    if (guess) guess[snp] = (uint8_t)gsym;
 }
 
 // ---- TMA / mbarrier helpers (1-D bulk copies of the walk tables into shared memory) -------
@@ -344,50 +348,37 @@ k_walk_tables(const double *__restrict__ terms, const double *__restrict__ logm,
     if (lane == 0) flagsd[0] = 0;
 }
 
-// Quantised walk (L <= 32, all lookbacks inside the band).  The log terms are kept as 2^-20 fixed point, so a
-// candidate's log weight is an exact integer sum in any order.  Lane = (lookback group g = lane/8, candidate
-// q = lane%8).  Only the lookback-1 term depends on the symbol chosen at the previous site, so the walk is
-// software-pipelined: while site s is being decided, every lane already sums the lookback >= 2 terms of site
-// s+1 for its (g,q) (their history is known; rows 1+g, 5+g, ... of the table, NIT per lane) and two shuffles fold
-// the four groups.  The serial chain per site is one shared-memory load, an add, a warp max (REDUX), a ballot
-// and a find-first-set.  A candidate wins outright only if it leads by more than 1.6e-4 in log10 weight (ten
-// times the worst-case quantisation error of 33 terms); otherwise - and whenever 10**x could under/overflow,
-// or a term did not fit the fixed-point range - the site is re-evaluated exactly, in the reference's order,
-// from the float64 tables (gretel.py:166-174 semantics, first max wins a tie).
-// History: h[t] byte b = 32 * symbol chosen 4t+b+1 sites back (byte granular so one PRMT yields a row offset).
 __device__ __forceinline__ int lds32(uint32_t addr) {
     int v;
     asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr));
     return v;
 }
 
+// The walk over sites [s_begin, s_end] given the symbols chosen before s_begin (hsrc[site]; site 0 = '_').  One warp.
+// Decided symbols go to out[snp - s_begin].  Returns 0, or the site without a candidate (gretel.py:176-180).
 template <int NIT>
-__global__ void __launch_bounds__(32)
-k_walk_q(const int32_t *__restrict__ termsq, const int32_t *__restrict__ logmq, const double *__restrict__ terms,
-         const double *__restrict__ logm, int N, int L, int C, uint8_t *__restrict__ path,
-         int *__restrict__ flagsd) {
-    extern __shared__ __align__(128) unsigned char smraw[];
-    __shared__ __align__(8) unsigned long long bars[3];
+__device__ __forceinline__ int walk_q_range(const int32_t *__restrict__ termsq, const int32_t *__restrict__ logmq,
+                                            const double *__restrict__ terms, const double *__restrict__ logm,
+                                            int L, int C, int s_begin, int s_end, const uint8_t *hsrc,
+                                            uint8_t *out, bool force_exact, unsigned char *smraw,
+                                            unsigned long long *bars, uint32_t &bar_uses) {
     constexpr int Lq = 4 * NIT + 1;
     constexpr uint32_t site_t_bytes = (uint32_t)Lq * 224u;             // int32 terms of one site
-    const int lane = threadIdx.x;
-    if (flagsd[1]) return;
-    const bool force_exact = flagsd[2] != 0;
+    const int lane = threadIdx.x & 31;
     const uint32_t chunk_t_bytes = (uint32_t)C * site_t_bytes;
     const uint32_t sm_terms = smem_u32(smraw);                                   // [3][C][Lq][7][8] int32
     const uint32_t sm_logm = sm_terms + 3u * chunk_t_bytes;                      // [3][C][8] int32
-    const int nchunks = (N + C - 1) / C;
-    if (lane == 0) {
-        path[0] = HX_SYM_GAP;
-        for (int b = 0; b < 3; ++b) mbar_init(smem_u32(&bars[b]), 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncwarp();
+    const int n_sites = s_end - s_begin + 1;
+    const int nchunks = (n_sites + C - 1) / C;
+    // the three mbarriers are reused by consecutive ranges of one CTA: a buffer's phase is counted over all uses
+    const uint32_t use0 = bar_uses;
+    auto parity_of = [&](int k) { return (uint32_t)(((use0 + (uint32_t)k) / 3u) & 1u); };
+    auto buf_of = [&](int k) { return (int)((use0 + (uint32_t)k) % 3u); };
     auto issue = [&](int k) {
         if (k >= nchunks) return;
-        const int b = k % 3;
-        const int first = 1 + k * C;
-        const int ns = min(C, N - first + 1);
+        const int b = buf_of(k);
+        const int first = s_begin + k * C;
+        const int ns = min(C, s_end - first + 1);
         const uint32_t bar = smem_u32(&bars[b]);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         mbar_expect_tx(bar, (uint32_t)ns * (site_t_bytes + 32u));
@@ -395,34 +386,57 @@ k_walk_q(const int32_t *__restrict__ termsq, const int32_t *__restrict__ logmq, 
                  (uint32_t)ns * site_t_bytes, bar);
         bulk_g2s(sm_logm + (uint32_t)b * C * 32u, logmq + (int64_t)first * 8, (uint32_t)ns * 32u, bar);
     };
+    __syncwarp();
     if (lane == 0) { issue(0); issue(1); }
+    bar_uses += (uint32_t)nchunks;
     const uint32_t q4 = 4u * (uint32_t)(lane & 7);
     const uint32_t g = (uint32_t)lane >> 3;
     const uint32_t look_off = (1u + g) * 224u + q4;         // this lane's first look-ahead row, its candidate slot
     const uint32_t psel = 0x4440u | g;                      // PRMT selector: byte g of a history word
+    // history relative to s_begin - 1: h[t] byte b = 32 * symbol at site (s_begin - 1) - (4t + b + 1); 0 before the start
     uint32_t h[NIT + 1];
 #pragma unroll
-    for (int t = 0; t <= NIT; ++t) h[t] = 0;
-    h[0] = HX_SYM_GAP * 32u;
-    uint32_t prev32 = HX_SYM_GAP * 32u;                     // 32 * symbol at the previous site
+    for (int t = 0; t <= NIT; ++t) {
+        uint32_t w = 0;
+#pragma unroll
+        for (int bb = 0; bb < 4; ++bb) {
+            const int site = s_begin - 1 - (4 * t + bb + 1);
+            const uint32_t sym = site >= 0 ? (uint32_t)hsrc[site] : 0u;
+            w |= (sym << 5) << (8 * bb);
+        }
+        h[t] = w;
+    }
     unsigned mine = 0;                                      // lane's slot of the 32-site output block
     const int margin_q = 168;                               // 1.6e-4 * 2^20
     const int floor_q = -300 * 1048576;                     // 10**x must stay representable
-#ifdef HX_WALK_STATS
-    int n_exact = 0;
-#endif
-    mbar_wait(smem_u32(&bars[0]), 0u);
-    int R = lds32(sm_logm + q4);                            // site 1 has only lookback 1
+    mbar_wait(smem_u32(&bars[buf_of(0)]), parity_of(0));
+    // lookback >= 2 terms of the first site (rows past the start of the region are zero), then its log marginal
+    int R;
+    {
+        const uint32_t site0 = sm_terms + (uint32_t)buf_of(0) * chunk_t_bytes;
+        int acc = 0;
+#pragma unroll
+        for (int t = 0; t < NIT; ++t)
+            acc += lds32(site0 + look_off + (uint32_t)t * 896u + __byte_perm(h[t], 0u, psel));
+        acc += __shfl_xor_sync(0xffffffffu, acc, 8);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+        R = acc + lds32(sm_logm + (uint32_t)buf_of(0) * C * 32u + q4);
+    }
+    // ... and the history relative to s_begin: shift in the symbol at s_begin - 1
+    uint32_t prev32 = (uint32_t)hsrc[s_begin - 1] << 5;
+#pragma unroll
+    for (int t = NIT; t >= 1; --t) h[t] = __funnelshift_l(h[t - 1], h[t], 8);
+    h[0] = (h[0] << 8) | prev32;
     for (int k = 0; k < nchunks; ++k) {
         __syncwarp();
         if (lane == 0) issue(k + 2);
-        if (k + 1 < nchunks) mbar_wait(smem_u32(&bars[(k + 1) % 3]), (uint32_t)(((k + 1) / 3) & 1));
-        const int first = 1 + k * C;
-        const int ns = min(C, N - first + 1);
-        const uint32_t ct_n = sm_terms + (uint32_t)((k + 1) % 3) * chunk_t_bytes;
-        const uint32_t cl_n = sm_logm + (uint32_t)((k + 1) % 3) * C * 32u;
-        uint32_t csite = sm_terms + (uint32_t)(k % 3) * chunk_t_bytes;     // current site's table
-        uint32_t clm = sm_logm + (uint32_t)(k % 3) * C * 32u;
+        if (k + 1 < nchunks) mbar_wait(smem_u32(&bars[buf_of(k + 1)]), parity_of(k + 1));
+        const int first = s_begin + k * C;
+        const int ns = min(C, s_end - first + 1);
+        const uint32_t ct_n = sm_terms + (uint32_t)buf_of(k + 1) * chunk_t_bytes;
+        const uint32_t cl_n = sm_logm + (uint32_t)buf_of(k + 1) * C * 32u;
+        uint32_t csite = sm_terms + (uint32_t)buf_of(k) * chunk_t_bytes;     // current site's table
+        uint32_t clm = sm_logm + (uint32_t)buf_of(k) * C * 32u;
         for (int j = 0; j < ns; ++j) {
             const int snp = first + j;
             // ---- look ahead: lookback >= 2 terms of site snp+1 (independent of this site's choice).  After the
@@ -446,15 +460,12 @@ k_walk_q(const int32_t *__restrict__ termsq, const int32_t *__restrict__ logmq, 
                 const unsigned cmask = (unsigned)logm[(int64_t)snp * 8 + 7];
                 if (cmask == 0) next = -1;
                 else {
-#ifdef HX_WALK_STATS
-                    ++n_exact;
-#endif
                     // exact evaluation from the float64 tables in the reference's order (lane = candidate)
                     const int lmax = L < snp ? L : snp;
-                    const int s = lane < HX_NSYM ? lane : 0;
+                    const int sy = lane < HX_NSYM ? lane : 0;
                     const bool cand = lane < HX_NSYM && ((cmask >> lane) & 1u);
-                    const double *base = terms + ((int64_t)snp * L) * 56 + s;
-                    double lw = logm[(int64_t)snp * 8 + s];
+                    const double *base = terms + ((int64_t)snp * L) * 56 + sy;
+                    double lw = logm[(int64_t)snp * 8 + sy];
 #pragma unroll
                     for (int l = 1; l <= 4 * NIT + 1; ++l) {
                         if (l <= lmax) {
@@ -467,30 +478,140 @@ k_walk_q(const int32_t *__restrict__ termsq, const int32_t *__restrict__ logmq, 
                     next = normalise_and_pick(ws, cmask, &wn, &tw);
                 }
                 if (next < 0) {                          // gretel.py:176-180
-                    if (lane == 0) { flagsd[0] = snp; flagsd[1] = 1; }
                     for (int k2 = k + 1; k2 <= k + 2 && k2 < nchunks; ++k2)
-                        mbar_wait(smem_u32(&bars[k2 % 3]), (uint32_t)((k2 / 3) & 1));
-                    return;
+                        mbar_wait(smem_u32(&bars[buf_of(k2)]), parity_of(k2));
+                    return snp;
                 }
             }
             prev32 = (uint32_t)next << 5;
 #pragma unroll
             for (int t = NIT; t >= 1; --t) h[t] = __funnelshift_l(h[t - 1], h[t], 8);
             h[0] = (h[0] << 8) | prev32;
-            mine = lane == ((snp - 1) & 31) ? (unsigned)next : mine;
-            if (((snp - 1) & 31) == 31 || snp == N) {    // a block of 32 sites (or the tail) is complete
-                const int at = ((snp - 1) & ~31) + 1 + lane;
-                if (at <= snp) path[at] = (uint8_t)mine;
+            const int rel = snp - s_begin;
+            mine = lane == (rel & 31) ? (unsigned)next : mine;
+            if ((rel & 31) == 31 || snp == s_end) {      // a block of 32 sites (or the tail) is complete
+                const int at = (rel & ~31) + lane;
+                if (at <= rel) out[at] = (uint8_t)mine;
             }
             R = Rn;
             csite = nsite;
             clm = nlm;
         }
     }
-#ifdef HX_WALK_STATS
-    if (lane == 0) printf("k_walk_q: N=%d L=%d exact sites=%d\n", N, L, n_exact);
-#endif
-    if (lane == 0) flagsd[0] = 0;
+    __syncwarp();
+    return 0;
+}
+
+// Quantised walk (L <= 32, all lookbacks inside the band).  The log terms are kept as 2^-20 fixed point, so a
+// candidate's log weight is an exact integer sum in any order.  Lane = (lookback group g = lane/8, candidate
+// q = lane%8).  Only the lookback-1 term depends on the symbol chosen at the previous site, so the walk is
+// software-pipelined: while site s is being decided, every lane already sums the lookback >= 2 terms of site
+// s+1 for its (g,q) (their history is known; rows 1+g, 5+g, ... of the table, NIT per lane) and two shuffles fold
+// the four groups.  The serial chain per site is one shared-memory load, an add, a warp max (REDUX), a ballot
+// and a find-first-set.  A candidate wins outright only if it leads by more than 1.6e-4 in log10 weight (ten
+// times the worst-case quantisation error of 33 terms); otherwise - and whenever 10**x could under/overflow,
+// or a term did not fit the fixed-point range - the site is re-evaluated exactly, in the reference's order,
+// from the float64 tables (gretel.py:166-174 semantics, first max wins a tie).
+// History: h[t] byte b = 32 * symbol chosen 4t+b+1 sites back (byte granular so one PRMT yields a row offset).
+//
+// PARALLEL IN TIME.  The greedy walk is a chain over sites, but a site only sees the L symbols before it.  So the
+// region is cut into blocks that are walked CONCURRENTLY (one CTA each): block b starts `warm` sites early from a
+// guessed history (the per-site majority allele) and is SPECULATIVE; k_walk_fix then goes through the blocks in
+// order and accepts a block iff the L symbols it chose right before its first site equal the final path there -
+// from that point on its choices are exactly what the sequential walk would have made.  A block that fails the
+// test (or ran into a site without a candidate) is walked again from the final path.  The result is always the
+// sequential greedy walk's; only the time differs (all blocks accepted: N/B + warm sites instead of N).
+template <int NIT>
+__global__ void __launch_bounds__(32)
+k_walk_q(const int32_t *__restrict__ termsq, const int32_t *__restrict__ logmq, const double *__restrict__ terms,
+         const double *__restrict__ logm, int N, int L, int C, int blk_len, int warm, const uint8_t *__restrict__ guess,
+         uint8_t *spec, int spec_stride, int *__restrict__ spec_ok, uint8_t *path,
+         int *__restrict__ flagsd) {
+    extern __shared__ __align__(128) unsigned char smraw[];
+    __shared__ __align__(8) unsigned long long bars[3];
+    const int lane = threadIdx.x;
+    if (flagsd[1]) return;
+    const bool force_exact = flagsd[2] != 0;
+    if (lane == 0) {
+        for (int b = 0; b < 3; ++b) mbar_init(smem_u32(&bars[b]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    uint32_t bar_uses = 0;
+    const int b = blockIdx.x;
+    const int start = 1 + b * blk_len;
+    if (start > N) return;
+    const int end = min(N, start + blk_len - 1);
+    if (b == 0) {
+        if (lane == 0) path[0] = HX_SYM_GAP;
+        __syncwarp();
+        const int hole = walk_q_range<NIT>(termsq, logmq, terms, logm, L, C, 1, end, path, path + 1, force_exact, smraw,
+                                           bars, bar_uses);
+        if (hole && lane == 0) { flagsd[0] = hole; flagsd[1] = 1; }
+        if (!hole && lane == 0 && end == N) flagsd[0] = 0;
+        return;
+    }
+    const int s0 = max(1, start - warm);
+    uint8_t *out = spec + (size_t)b * spec_stride;          // out[snp - s0]
+    const int hole = walk_q_range<NIT>(termsq, logmq, terms, logm, L, C, s0, end, guess, out, force_exact, smraw, bars,
+                                       bar_uses);
+    if (lane == 0) spec_ok[b] = hole ? 0 : 1;
+}
+
+// Accepts or redoes the speculative blocks, in order (one warp; see k_walk_q).
+template <int NIT>
+__global__ void __launch_bounds__(32)
+k_walk_fix(const int32_t *__restrict__ termsq, const int32_t *__restrict__ logmq, const double *__restrict__ terms,
+           const double *__restrict__ logm, int N, int L, int C, int blk_len, int warm, int n_blocks,
+           const uint8_t *__restrict__ spec, int spec_stride, const int *__restrict__ spec_ok, uint8_t *path,
+           int *__restrict__ flagsd) {
+    extern __shared__ __align__(128) unsigned char smraw[];
+    __shared__ __align__(8) unsigned long long bars[3];
+    const int lane = threadIdx.x;
+    if (flagsd[1]) return;
+    const bool force_exact = flagsd[2] != 0;
+    if (lane == 0) {
+        for (int b = 0; b < 3; ++b) mbar_init(smem_u32(&bars[b]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    uint32_t bar_uses = 0;
+    int redone = 0;
+    for (int b = 1; b < n_blocks; ++b) {
+        const int start = 1 + b * blk_len;
+        if (start > N) break;
+        const int end = min(N, start + blk_len - 1);
+        const int s0 = max(1, start - warm);
+        const uint8_t *sp = spec + (size_t)b * spec_stride;  // sp[snp - s0]
+        // the block is the sequential walk's continuation iff it agrees with the final path on the L sites before it
+        // (a block that started at site 1 had the true history all along)
+        bool ok = spec_ok[b] != 0;
+        if (ok && s0 > 1) {
+            const int need = min(L, start - 1);
+            ok = start - need >= s0;                         // the warm-up must cover the whole lookback
+            bool same = true;
+            for (int i = lane; i < need && ok; i += 32) same &= sp[start - 1 - i - s0] == path[start - 1 - i];
+            ok = ok && __all_sync(0xffffffffu, same);
+        }
+        if (ok) {
+            for (int snp = start + lane; snp <= end; snp += 32) path[snp] = sp[snp - s0];
+            __syncwarp();
+            __threadfence_block();
+        } else {
+            ++redone;
+            __syncwarp();
+            __threadfence();                                 // path[] written above by this warp is read as history
+            const int hole = walk_q_range<NIT>(termsq, logmq, terms, logm, L, C, start, end, path, path + start,
+                                               force_exact, smraw, bars, bar_uses);
+            if (hole) {
+                if (lane == 0) { flagsd[0] = hole; flagsd[1] = 1; }
+                return;
+            }
+            __syncwarp();
+            __threadfence_block();
+        }
+    }
+    if (lane == 0) { flagsd[0] = 0; flagsd[3] += redone; }
 }
 
 // Wide-lookback walk (L*448 B per site does not fit the staged pipeline, e.g. ONT L ~ 300):
@@ -786,7 +907,24 @@ int launch_generate(hx_matrix *cur, hx_matrix *orig, int L, int flags, uint8_t *
     k_walk_terms<<<(unsigned)((tthreads + 255) / 256), 256, 0, cur->stream>>>(cur->band, cur->vseen, N, cur->W, Lw,
                                                                               flags, cur->d_terms, termsq, Lq,
                                                                               cur->d_flags + 2);
-    k_walk_logm<<<(N + 1 + 127) / 128, 128, 0, cur->stream>>>(cur->scnt, N, flags, logm, logmq);
+    // parallel-in-time walk (k_walk_q): blocks of sites walked concurrently from a guessed history, then verified
+    int n_blocks = 1, blk_len = N > 0 ? N : 1, warm = 0;
+    static const int blocks_env = getenv("HX_WALK_BLOCKS") ? atoi(getenv("HX_WALK_BLOCKS")) : 0;   // 1 = sequential
+    if (use_q && N >= 1024 && blocks_env != 1) {
+        warm = 4 * L > 64 ? 4 * L : 64;
+        const int want = blocks_env > 1 ? blocks_env : 32;
+        blk_len = (N + want - 1) / want;
+        if (blk_len < 2 * warm) blk_len = 2 * warm;
+        n_blocks = (N + blk_len - 1) / blk_len;
+    }
+    const int spec_stride = blk_len + warm;
+    rc = ensure_buf((void **)&cur->d_spec, &cur->cap_spec, (int64_t)n_blocks * spec_stride + (int64_t)N + 2 + 4 * (int64_t)n_blocks + 64,
+                    cur->stream);
+    if (rc) return rc;
+    uint8_t *spec = cur->d_spec;
+    uint8_t *guess = spec + (size_t)n_blocks * spec_stride;
+    int *spec_ok = reinterpret_cast<int *>(reinterpret_cast<uintptr_t>(guess + (size_t)N + 2 + 15) & ~(uintptr_t)15);
+    k_walk_logm<<<(N + 1 + 127) / 128, 128, 0, cur->stream>>>(cur->scnt, N, flags, logm, logmq, guess);
     // sites per staged chunk: three chunks (terms + log-marginals) must fit in shared memory
     const int64_t site_bytes = (int64_t)Lw * 448 + 64;
     int C = (int)((200 * 1024) / (3 * site_bytes));
@@ -799,8 +937,14 @@ int launch_generate(hx_matrix *cur, hx_matrix *orig, int L, int flags, uint8_t *
 #define HX_WALK_Q(NIT)                                                                                              \
     case NIT:                                                                                                       \
         HX_CUDA(cudaFuncSetAttribute(k_walk_q<NIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qsmem));      \
-        k_walk_q<NIT><<<1, 32, qsmem, cur->stream>>>(termsq, logmq, cur->d_terms, logm, N, L, Cq, d_path,           \
-                                                     cur->d_flags);                                                 \
+        k_walk_q<NIT><<<n_blocks, 32, qsmem, cur->stream>>>(termsq, logmq, cur->d_terms, logm, N, L, Cq, blk_len, warm,  \
+                                                            guess, spec, spec_stride, spec_ok, d_path, cur->d_flags);  \
+        if (n_blocks > 1) {                                                                                         \
+            HX_CUDA(cudaFuncSetAttribute(k_walk_fix<NIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qsmem)); \
+            k_walk_fix<NIT><<<1, 32, qsmem, cur->stream>>>(termsq, logmq, cur->d_terms, logm, N, L, Cq, blk_len, warm, \
+                                                           n_blocks, spec, spec_stride, spec_ok, d_path, cur->d_flags); \
+            cur->launches++;                                                                                        \
+        }                                                                                                           \
         break;
         switch (nit) {
             HX_WALK_Q(0) HX_WALK_Q(1) HX_WALK_Q(2) HX_WALK_Q(3) HX_WALK_Q(4) HX_WALK_Q(5) HX_WALK_Q(6) HX_WALK_Q(7)
@@ -838,6 +982,15 @@ int launch_generate(hx_matrix *cur, hx_matrix *orig, int L, int flags, uint8_t *
 }
 
 }  // namespace
+
+// how many speculative walk blocks had to be walked again so far (diagnostics; tools/ and tests)
+extern "C" int hx_debug_walk_redone(hx_matrix *h, int *n) {
+    if (!h || !n) return HX_E_ARG;
+    if (cudaSetDevice(h->device) != cudaSuccess) return HX_E_CUDA;
+    if (cudaMemcpyAsync(n, h->d_flags + 3, sizeof(int), cudaMemcpyDeviceToHost, h->stream) != cudaSuccess) return HX_E_CUDA;
+    if (cudaStreamSynchronize(h->stream) != cudaSuccess) return HX_E_CUDA;
+    return HX_OK;
+}
 
 int hx_ensure_counts(hx_matrix *h) {
     if (!h->counts_dirty) return HX_OK;
