@@ -521,12 +521,40 @@ __device__ __forceinline__ int walk_q_range(const int32_t *__restrict__ termsq, 
 // from that point on its choices are exactly what the sequential walk would have made.  A block that fails the
 // test (or ran into a site without a candidate) is walked again from the final path.  The result is always the
 // sequential greedy walk's; only the time differs (all blocks accepted: N/B + warm sites instead of N).
+constexpr int HX_WALK_CAND = 6;      // speculative starts per block: the majority-allele guess + 5 earlier haplotypes
+
+// Which earlier haplotypes a block starts from: the most recent ones whose L symbols before the block differ from
+// each other (many of the haplotypes found so far coincide around any one block).  One warp per block.
+__global__ void __launch_bounds__(32)
+k_walk_pick(const uint8_t *__restrict__ paths0, int it, int N, int L, int blk_len, int *__restrict__ cand_idx) {
+    const int b = blockIdx.x, lane = threadIdx.x;
+    const int start = 1 + b * blk_len;
+    int chosen[HX_WALK_CAND];
+    int n = 0;
+    if (b >= 1 && start <= N) {
+        const int need = min(L, start - 1);
+        for (int j = it - 1; j >= 0 && n < HX_WALK_CAND - 1; --j) {
+            const uint8_t *pj = paths0 + (size_t)j * ((size_t)N + 1);
+            bool fresh = true;
+            for (int q = 0; q < n && fresh; ++q) {
+                const uint8_t *pq = paths0 + (size_t)chosen[q] * ((size_t)N + 1);
+                bool same = true;
+                for (int i = lane; i < need; i += 32) same &= pj[start - 1 - i] == pq[start - 1 - i];
+                if (__all_sync(0xffffffffu, same)) fresh = false;
+            }
+            if (fresh) chosen[n++] = j;
+        }
+    }
+    if (lane == 0)
+        for (int c = 1; c < HX_WALK_CAND; ++c) cand_idx[b * HX_WALK_CAND + c] = c - 1 < n ? chosen[c - 1] : -1;
+}
+
 template <int NIT>
 __global__ void __launch_bounds__(32)
 k_walk_q(const int32_t *__restrict__ termsq, const int32_t *__restrict__ logmq, const double *__restrict__ terms,
          const double *__restrict__ logm, int N, int L, int C, int blk_len, int warm, const uint8_t *__restrict__ guess,
-         uint8_t *spec, int spec_stride, int *__restrict__ spec_ok, uint8_t *path,
-         int *__restrict__ flagsd) {
+         const uint8_t *paths0, const int *__restrict__ cand_idx, uint8_t *spec, int spec_stride, int *__restrict__ spec_ok,
+         uint8_t *path, int *__restrict__ flagsd) {
     extern __shared__ __align__(128) unsigned char smraw[];
     __shared__ __align__(8) unsigned long long bars[3];
     const int lane = threadIdx.x;
@@ -538,11 +566,8 @@ k_walk_q(const int32_t *__restrict__ termsq, const int32_t *__restrict__ logmq, 
     }
     __syncwarp();
     uint32_t bar_uses = 0;
-    const int b = blockIdx.x;
-    const int start = 1 + b * blk_len;
-    if (start > N) return;
-    const int end = min(N, start + blk_len - 1);
-    if (b == 0) {
+    if (blockIdx.x == 0) {                                  // block 0 of the region: the walk proper
+        const int end = min(N, blk_len);
         if (lane == 0) path[0] = HX_SYM_GAP;
         __syncwarp();
         const int hole = walk_q_range<NIT>(termsq, logmq, terms, logm, L, C, 1, end, path, path + 1, force_exact, smraw,
@@ -551,11 +576,26 @@ k_walk_q(const int32_t *__restrict__ termsq, const int32_t *__restrict__ logmq, 
         if (!hole && lane == 0 && end == N) flagsd[0] = 0;
         return;
     }
+    // speculative walks: CTA 1 + (b-1)*CAND + c = block b >= 1 from candidate history c
+    const int b = 1 + ((int)blockIdx.x - 1) / HX_WALK_CAND, c = ((int)blockIdx.x - 1) % HX_WALK_CAND;
+    const int start = 1 + b * blk_len;
+    if (start > N) return;
+    const int end = min(N, start + blk_len - 1);
     const int s0 = max(1, start - warm);
-    uint8_t *out = spec + (size_t)b * spec_stride;          // out[snp - s0]
-    const int hole = walk_q_range<NIT>(termsq, logmq, terms, logm, L, C, s0, end, guess, out, force_exact, smraw, bars,
-                                       bar_uses);
-    if (lane == 0) spec_ok[b] = hole ? 0 : 1;
+    uint8_t *out = spec + ((size_t)b * HX_WALK_CAND + c) * spec_stride;     // out[snp - s0]
+    int hole;
+    if (c == 0) {
+        // from the majority alleles, `warm` sites early so that the walk's own choices fill the lookback window
+        hole = walk_q_range<NIT>(termsq, logmq, terms, logm, L, C, s0, end, guess, out, force_exact, smraw, bars, bar_uses);
+    } else {
+        const int j = cand_idx[b * HX_WALK_CAND + c];
+        if (j < 0) { if (lane == 0) spec_ok[b * HX_WALK_CAND + c] = 0; return; }
+        // from an earlier haplotype's choices right before the block (the walk often retraces a strain it has found)
+        const uint8_t *cand = paths0 + (size_t)j * ((size_t)N + 1);
+        hole = walk_q_range<NIT>(termsq, logmq, terms, logm, L, C, start, end, cand, out + (start - s0), force_exact, smraw,
+                                 bars, bar_uses);
+    }
+    if (lane == 0) spec_ok[b * HX_WALK_CAND + c] = hole ? 0 : 1;
 }
 
 // Accepts or redoes the speculative blocks, in order (one warp; see k_walk_q).
@@ -563,8 +603,8 @@ template <int NIT>
 __global__ void __launch_bounds__(32)
 k_walk_fix(const int32_t *__restrict__ termsq, const int32_t *__restrict__ logmq, const double *__restrict__ terms,
            const double *__restrict__ logm, int N, int L, int C, int blk_len, int warm, int n_blocks,
-           const uint8_t *__restrict__ spec, int spec_stride, const int *__restrict__ spec_ok, uint8_t *path,
-           int *__restrict__ flagsd) {
+           const uint8_t *paths0, const int *__restrict__ cand_idx, const uint8_t *__restrict__ spec, int spec_stride,
+           const int *__restrict__ spec_ok, uint8_t *path, int *__restrict__ flagsd) {
     extern __shared__ __align__(128) unsigned char smraw[];
     __shared__ __align__(8) unsigned long long bars[3];
     const int lane = threadIdx.x;
@@ -576,39 +616,70 @@ k_walk_fix(const int32_t *__restrict__ termsq, const int32_t *__restrict__ logmq
     }
     __syncwarp();
     uint32_t bar_uses = 0;
-    int redone = 0;
+    int redone = 0;                                          // sites walked again
     for (int b = 1; b < n_blocks; ++b) {
         const int start = 1 + b * blk_len;
         if (start > N) break;
         const int end = min(N, start + blk_len - 1);
         const int s0 = max(1, start - warm);
-        const uint8_t *sp = spec + (size_t)b * spec_stride;  // sp[snp - s0]
-        // the block is the sequential walk's continuation iff it agrees with the final path on the L sites before it
-        // (a block that started at site 1 had the true history all along)
-        bool ok = spec_ok[b] != 0;
-        if (ok && s0 > 1) {
-            const int need = min(L, start - 1);
-            ok = start - need >= s0;                         // the warm-up must cover the whole lookback
+        // A speculative walk of the block is the sequential walk's continuation iff the history it assumed agrees with
+        // the final path on the L sites before the block (a site only sees L symbols back).
+        const int need = min(L, start - 1);
+        int hit = -1;
+        for (int c = 0; c < HX_WALK_CAND && hit < 0; ++c) {
+            if (!spec_ok[b * HX_WALK_CAND + c]) continue;
+            const uint8_t *sp = spec + ((size_t)b * HX_WALK_CAND + c) * spec_stride;
             bool same = true;
-            for (int i = lane; i < need && ok; i += 32) same &= sp[start - 1 - i - s0] == path[start - 1 - i];
-            ok = ok && __all_sync(0xffffffffu, same);
+            if (c == 0) {
+                if (s0 > 1) {                               // (a walk that started at site 1 had the true history)
+                    if (start - need < s0) continue;        // the warm-up must cover the whole lookback
+                    for (int i = lane; i < need; i += 32) same &= sp[start - 1 - i - s0] == path[start - 1 - i];
+                }
+            } else {
+                const uint8_t *cand = paths0 + (size_t)cand_idx[b * HX_WALK_CAND + c] * ((size_t)N + 1);
+                for (int i = lane; i < need; i += 32) same &= cand[start - 1 - i] == path[start - 1 - i];
+            }
+            if (__all_sync(0xffffffffu, same)) hit = c;
         }
-        if (ok) {
+        if (hit >= 0) {
+            const uint8_t *sp = spec + ((size_t)b * HX_WALK_CAND + hit) * spec_stride;
             for (int snp = start + lane; snp <= end; snp += 32) path[snp] = sp[snp - s0];
             __syncwarp();
             __threadfence_block();
-        } else {
-            ++redone;
+            continue;
+        }
+        // No candidate started from the right history: walk the block from the final path - but only until it falls
+        // in step with one of the speculative walks (agreement on L consecutive sites is agreement for good).
+        const int SUB = L > 48 ? L : 48;
+        for (int sub = start; sub <= end; sub += SUB) {
+            const int e = min(end, sub + SUB - 1);
             __syncwarp();
-            __threadfence();                                 // path[] written above by this warp is read as history
-            const int hole = walk_q_range<NIT>(termsq, logmq, terms, logm, L, C, start, end, path, path + start,
-                                               force_exact, smraw, bars, bar_uses);
+            __threadfence();                                 // path[] written by this warp is read as history
+            const int hole = walk_q_range<NIT>(termsq, logmq, terms, logm, L, C, sub, e, path, path + sub, force_exact,
+                                               smraw, bars, bar_uses);
             if (hole) {
                 if (lane == 0) { flagsd[0] = hole; flagsd[1] = 1; }
                 return;
             }
+            redone += e - sub + 1;
             __syncwarp();
             __threadfence_block();
+            if (e == end || e - L + 1 < start) continue;
+            int join = -1;
+            for (int c = 0; c < HX_WALK_CAND && join < 0; ++c) {
+                if (!spec_ok[b * HX_WALK_CAND + c]) continue;
+                const uint8_t *sp = spec + ((size_t)b * HX_WALK_CAND + c) * spec_stride;
+                bool same = true;
+                for (int i = lane; i < L; i += 32) same &= path[e - i] == sp[e - i - s0];
+                if (__all_sync(0xffffffffu, same)) join = c;
+            }
+            if (join >= 0) {
+                const uint8_t *sp = spec + ((size_t)b * HX_WALK_CAND + join) * spec_stride;
+                for (int snp = e + 1 + lane; snp <= end; snp += 32) path[snp] = sp[snp - s0];
+                __syncwarp();
+                __threadfence_block();
+                break;
+            }
         }
     }
     if (lane == 0) { flagsd[0] = 0; flagsd[3] += redone; }
@@ -881,7 +952,7 @@ int join_sums(hx_matrix *cur) {
 }
 
 int launch_generate(hx_matrix *cur, hx_matrix *orig, int L, int flags, uint8_t *d_path,
-                    double *d_stats, double min_remove, int it = 0) {
+                    double *d_stats, double min_remove, int it = 0, int n_prev = 0) {
     int rc = hx_ensure_counts(cur);
     if (rc) return rc;
     rc = hx_ensure_counts(orig);
@@ -912,19 +983,25 @@ int launch_generate(hx_matrix *cur, hx_matrix *orig, int L, int flags, uint8_t *
     static const int blocks_env = getenv("HX_WALK_BLOCKS") ? atoi(getenv("HX_WALK_BLOCKS")) : 0;   // 1 = sequential
     if (use_q && N >= 1024 && blocks_env != 1) {
         warm = 4 * L > 64 ? 4 * L : 64;
-        const int want = blocks_env > 1 ? blocks_env : 32;
+        const int want = blocks_env > 1 ? blocks_env : 24;      // 1 + 23 x HX_WALK_CAND CTAs of one warp: one wave on 148 SMs
         blk_len = (N + want - 1) / want;
         if (blk_len < 2 * warm) blk_len = 2 * warm;
         n_blocks = (N + blk_len - 1) / blk_len;
     }
     const int spec_stride = blk_len + warm;
-    rc = ensure_buf((void **)&cur->d_spec, &cur->cap_spec, (int64_t)n_blocks * spec_stride + (int64_t)N + 2 + 4 * (int64_t)n_blocks + 64,
+    rc = ensure_buf((void **)&cur->d_spec, &cur->cap_spec, (int64_t)n_blocks * HX_WALK_CAND * spec_stride + (int64_t)N + 2 + 8 * (int64_t)n_blocks * HX_WALK_CAND + 64,
                     cur->stream);
     if (rc) return rc;
     uint8_t *spec = cur->d_spec;
-    uint8_t *guess = spec + (size_t)n_blocks * spec_stride;
+    uint8_t *guess = spec + (size_t)n_blocks * HX_WALK_CAND * spec_stride;
+    const uint8_t *paths0 = d_path - (size_t)n_prev * ((size_t)N + 1);              // the haplotypes found so far (hx_recover)
     int *spec_ok = reinterpret_cast<int *>(reinterpret_cast<uintptr_t>(guess + (size_t)N + 2 + 15) & ~(uintptr_t)15);
+    int *cand_idx = spec_ok + (size_t)n_blocks * HX_WALK_CAND;
     k_walk_logm<<<(N + 1 + 127) / 128, 128, 0, cur->stream>>>(cur->scnt, N, flags, logm, logmq, guess);
+    if (n_blocks > 1) {
+        k_walk_pick<<<n_blocks, 32, 0, cur->stream>>>(paths0, n_prev, N, L, blk_len, cand_idx);
+        cur->launches++;
+    }
     // sites per staged chunk: three chunks (terms + log-marginals) must fit in shared memory
     const int64_t site_bytes = (int64_t)Lw * 448 + 64;
     int C = (int)((200 * 1024) / (3 * site_bytes));
@@ -937,12 +1014,14 @@ int launch_generate(hx_matrix *cur, hx_matrix *orig, int L, int flags, uint8_t *
 #define HX_WALK_Q(NIT)                                                                                              \
     case NIT:                                                                                                       \
         HX_CUDA(cudaFuncSetAttribute(k_walk_q<NIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qsmem));      \
-        k_walk_q<NIT><<<n_blocks, 32, qsmem, cur->stream>>>(termsq, logmq, cur->d_terms, logm, N, L, Cq, blk_len, warm,  \
-                                                            guess, spec, spec_stride, spec_ok, d_path, cur->d_flags);  \
+        k_walk_q<NIT><<<1 + (n_blocks - 1) * HX_WALK_CAND, 32, qsmem, cur->stream>>>(                                  \
+            termsq, logmq, cur->d_terms, logm, N, L, Cq, blk_len, warm, guess, paths0, cand_idx, spec, spec_stride,    \
+            spec_ok, d_path, cur->d_flags);                                                                         \
         if (n_blocks > 1) {                                                                                         \
             HX_CUDA(cudaFuncSetAttribute(k_walk_fix<NIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qsmem)); \
             k_walk_fix<NIT><<<1, 32, qsmem, cur->stream>>>(termsq, logmq, cur->d_terms, logm, N, L, Cq, blk_len, warm, \
-                                                           n_blocks, spec, spec_stride, spec_ok, d_path, cur->d_flags); \
+                                                           n_blocks, paths0, cand_idx, spec, spec_stride, spec_ok,     \
+                                                           d_path, cur->d_flags);                                       \
             cur->launches++;                                                                                        \
         }                                                                                                           \
         break;
@@ -1131,7 +1210,7 @@ int hx_recover(hx_matrix *cur, hx_matrix *orig, int32_t L, int flags, int32_t ma
     for (int it = 0; it < max_paths; ++it) {
         uint8_t *dp = cur->d_path + (size_t)it * (N + 1);
         double *ds = cur->d_stats + (size_t)it * 8;
-        rc = launch_generate(cur, orig, L, flags, dp, ds, min_remove, it);
+        rc = launch_generate(cur, orig, L, flags, dp, ds, min_remove, it, it);
         if (rc) return rc;
         rc = launch_reweight(cur, dp, ds + 3, 0.0, ds + 4);
         if (rc) return rc;
