@@ -136,6 +136,7 @@ void free_all(hx_matrix *h) {
     if (!h) return;
     cudaSetDevice(h->device);
     hx_lr_free(h);
+    hx_l2_free(h);
     hx_wire_free(h);
     if (h->d_peer_tbl) cudaFree(h->d_peer_tbl);
     if (h->band) cudaFreeAsync(h->band, h->stream);
@@ -376,7 +377,7 @@ int hx_ensure_counts_buffer(hx_matrix *h) {
 extern "C" {
 
 int hx_set_ingest_kernel(hx_matrix *h, int which) {
-    HX_CHECK_ARG(h && which >= 0 && which <= 6);
+    HX_CHECK_ARG(h && which >= 0 && which <= 7);
     h->ingest_kernel = which;
     return HX_OK;
 }

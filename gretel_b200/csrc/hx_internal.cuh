@@ -90,6 +90,7 @@ struct hx_matrix {
     int ingest_kernel;
     int ingest_sms;                  // SMs the persistent ingestion kernels may use (0 = all)
     void *lr_scratch;                // long-read ingestion scratch (ingest_long.cu)
+    void *l2_scratch;                // long-read tensor-core ingestion scratch (ingest_lumma.cu)
     cudaEvent_t ev0, ev1;
     cudaEvent_t host_ev;             // orders the chunked host->device copies of hx_ingest_host
     bool ev_rec;                     // ev0/ev1 have been recorded at least once
@@ -166,5 +167,10 @@ int hx_ingest_host_pipelined(hx_matrix *h, const int32_t *rank, const int64_t *o
 int hx_launch_ingest_long(hx_matrix *h, const int32_t *d_rank, const int64_t *d_off,
                           const uint8_t *d_codes, int64_t n_reads, const int *sorted_flag);
 void hx_lr_free(hx_matrix *h);
+// ingest_lumma.cu
+int hx_launch_ingest_lumma(hx_matrix *h, const int32_t *d_rank, const int64_t *d_off, const uint8_t *d_codes,
+                           int64_t n_reads, const int *go);
+int64_t hx_lumma_scratch_bytes(const hx_matrix *h, int64_t n_reads);
+void hx_l2_free(hx_matrix *h);
 // recover.cu
 int hx_ensure_counts(hx_matrix *h);

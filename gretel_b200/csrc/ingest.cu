@@ -783,9 +783,16 @@ static int launch_ingest(hx_matrix *h, const int32_t *d_rank, const int64_t *d_o
                           (h->ingest_kernel == 6 || (h->ingest_kernel == 0 && n_reads >= 64 * ((int64_t)h->N + 1)));
     const bool fused = h->peer_world > 1;
     const bool use_long = !use_bs && (h->ingest_kernel == 3 || (h->ingest_kernel == 0 && kmax >= 2));
+    // long-read tensor-core kernel (ingest_lumma.cu): default for wide reads unless its one-hot scratch would be huge
+    const bool use_lumma = kmax >= 2 && (h->ingest_kernel == 7 ||
+                                         (h->ingest_kernel == 0 && !use_bs &&
+                                          hx_lumma_scratch_bytes(h, n_reads) <= ((int64_t)24 << 30)));
 
     HX_CUDA(cudaEventRecord(h->ev0, h->stream));
-    if (use_long) {
+    if (use_lumma) {
+        int rc = hx_launch_ingest_lumma(h, d_rank, d_off, d_codes, n_reads, presorted ? ok : nullptr);
+        if (rc) return rc;
+    } else if (use_long) {
         if (!presorted) {
             HX_CUDA(hx_fill_async(h->d_flags + 4, 1, sizeof(int), h->stream));     // non-zero = sorted
             k_prepass<<<(unsigned)((n_reads + 255) / 256), 256, 0, h->stream>>>(d_rank, n_reads, h->N, h->d_flags + 4,

@@ -1,0 +1,527 @@
+// K1 for long reads on the 5th-generation tensor cores (ONT-like, BASELINE configs[3]; any read wider than the
+// bit-sliced / short-read tensor-core kernels take).  Same pair-expansion semantics as gretel/util.py:226-286.
+//
+// A read is a one-hot row x over the columns (site p, symbol a in A C G T N - _ and a spare): x[8p + a] = 1.  The
+// counts it adds to every site pair (pi < pj) and symbol pair (a, b) are the entries of x^T x, so the whole band is
+// C = X^T X restricted to 1 <= pj - pi <= W: an int8 GEMM with int32 accumulation (tcgen05.mma kind::i8, exact).
+// Sites are cut into blocks of 16 (128 columns = the M / N of one MMA); the K of an MMA is a CHUNK of 32 reads.
+//
+//   k_l2_keys      per read: validate, key = (first block sb, blocks spanned), histogram of the keys
+//   k_l2_pad       per first block: pad its reads up to a multiple of 32 -> chunks never mix first blocks
+//   k_scan_*       exclusive scan of the padded histogram = where each key's reads go
+//   k_l2_scatter   counting sort: perm[] = read indices ordered by (sb, span) (order inside a key is free: the
+//                  counts are integer sums), so the 32 reads of a chunk start in the same block and end close together
+//   k_l2_onehot    warp per chunk, lane = read: writes the chunk's one-hot operand slabs, one 4 KB slab per site
+//                  block it touches, laid out exactly as the MN-major UMMA operand (core matrix = 16 columns x 8
+//                  reads), so a slab is one 4 KB bulk copy away from the tensor core.  Sentinels, totals here.
+//   k_l2_tiles     persistent CTAs over tiles (I = one block of 16 first sites, q = a pair of blocks of second sites):
+//                  a producer warp finds the chunks that touch both (per first block the chunks are sorted by their
+//                  last block: one binary search each) and streams their slabs through an 8-stage TMA/mbarrier ring;
+//                  one thread issues two M=128, N=128, K=32 MMAs per chunk into a double-buffered TMEM accumulator;
+//                  8 epilogue warps read the finished accumulator (tcgen05.ld), turn it through shared memory
+//                  into the band's cell order and add it to the band with coalesced read-modify-writes.  Every band
+//                  cell has exactly one writer: no atomics.
+// Rank-sortedness is not needed (the counting sort orders the reads itself).
+#include <limits.h>
+
+#include "hx_internal.cuh"
+#include "ingest_common.cuh"
+#include "scan.cuh"
+
+namespace {
+
+constexpr int L2_STAGES = 8;
+constexpr int L2_EP_WARPS = 8;
+constexpr int L2_THREADS = (2 + L2_EP_WARPS) * 32;
+constexpr uint32_t L2_SLAB = 4096;                 // one chunk x one block: 32 reads x 128 one-hot bytes
+constexpr uint32_t L2_STAGE_BYTES = 3 * L2_SLAB;   // A (first sites), B0, B1 (second sites)
+constexpr int L2_STG_WORDS = 4 * 196;              // epilogue staging per warp: 4 second sites x 4 cells x 49 counters
+
+struct L2Geom {
+    int N, W, NB, SP, nq;
+    __host__ __device__ static L2Geom make(int N, int W) {
+        L2Geom g;
+        g.N = N; g.W = W;
+        g.NB = (N >> 4) + 1;                        // sites 1..N live in blocks 0..N>>4
+        g.SP = W / 16 + 2;                          // a read of k <= W+1 SNPs spans at most W/16 + 2 blocks
+        g.nq = (g.SP + 1) / 2 + 1;                  // pairs of second-site blocks per first-site block
+        return g;
+    }
+    __host__ __device__ int64_t n_bins() const { return (int64_t)NB * SP; }
+};
+
+// ---- sort keys ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_l2_keys(const int32_t *__restrict__ rank, const int64_t *__restrict__ off, int64_t n_reads, L2Geom g,
+          int32_t *__restrict__ keys, int32_t *__restrict__ hist, int *__restrict__ err, const int *__restrict__ go) {
+    if (go && !*go) return;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_reads) return;
+    const int64_t k = off[i + 1] - off[i];
+    const int r = rank[i];
+    int key = -1;
+    if (k >= 2) {                                                                    // util.py:230
+        if (r < 0 || (int64_t)r + k > g.N || k - 1 > g.W) atomicOr(err, 1);
+        else {
+            const int sb = (r + 1) >> 4, eb = (r + (int)k) >> 4;
+            key = sb * g.SP + (eb - sb);
+            atomicAdd(&hist[key], 1);
+        }
+    }
+    keys[i] = key;
+}
+
+// the last key of every first block absorbs the padding that makes the block's read count a multiple of 32
+__global__ void k_l2_pad(int32_t *__restrict__ hist, L2Geom g, const int *__restrict__ go) {
+    if (go && !*go) return;
+    const int sb = blockIdx.x * blockDim.x + threadIdx.x;
+    if (sb >= g.NB) return;
+    int32_t *h = hist + (int64_t)sb * g.SP;
+    int s = 0;
+    for (int j = 0; j < g.SP; ++j) s += h[j];
+    h[g.SP - 1] += (32 - (s & 31)) & 31;
+}
+
+__global__ void __launch_bounds__(256)
+k_l2_scatter(const int32_t *__restrict__ keys, int64_t n_reads, const int32_t *__restrict__ bstart,
+             int32_t *__restrict__ cursor, int32_t *__restrict__ perm, const int *__restrict__ go) {
+    if (go && !*go) return;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_reads) return;
+    const int key = keys[i];
+    if (key < 0) return;
+    perm[bstart[key] + atomicAdd(&cursor[key], 1)] = (int32_t)i;
+}
+
+// ---- one-hot operand slabs ----------------------------------------------------------------------------------
+// Slab of (chunk c, block sb+j) at onehot + (c*SP + j) * 4096; inside: [8 reads][16 columns] core matrices of 128 B,
+// the 8 column groups of a block 128 B apart, the 4 groups of 8 reads 1024 B apart.
+__global__ void __launch_bounds__(256)
+k_l2_onehot(const int32_t *__restrict__ rank, const int64_t *__restrict__ off, const uint8_t *__restrict__ codes,
+            const int32_t *__restrict__ perm, const int32_t *__restrict__ bstart, L2Geom g,
+            uint8_t *__restrict__ onehot, int32_t *__restrict__ chunk_eb, const HxCnt cnt,
+            unsigned long long *__restrict__ totals, int *__restrict__ err, const int *__restrict__ go) {
+    if (go && !*go) return;
+    const int lane = threadIdx.x & 31;
+    const int64_t n_chunks = bstart[g.n_bins()] >> 5;
+    const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    unsigned long long t_slices = 0, t_cov = 0, t_sent = 0;
+    if (c < n_chunks) {
+        const int idx = perm[c * 32 + lane];
+        int r = 0, k = 0;
+        int64_t o = 0;
+        if (idx >= 0) {
+            o = off[idx];
+            k = (int)(off[idx + 1] - o);
+            r = rank[idx];
+        }
+        const uint8_t *__restrict__ cd = codes + o;
+        const int sb = __reduce_min_sync(0xffffffffu, idx >= 0 ? (r + 1) >> 4 : INT_MAX);
+        const int eb = __reduce_max_sync(0xffffffffu, idx >= 0 ? (r + k) >> 4 : 0);
+        if (lane == 0) chunk_eb[c] = eb;
+        t_slices += idx >= 0;
+        uint8_t *slab = onehot + ((size_t)c * g.SP) * L2_SLAB + (size_t)(lane >> 3) * 1024 + (size_t)(lane & 7) * 16;
+        for (int b = sb; b <= eb; ++b, slab += L2_SLAB) {
+            const int u0 = 16 * b - (r + 1);                       // position in my read of the block's first site
+#pragma unroll
+            for (int ch = 0; ch < 8; ++ch) {
+                uint32_t w[4] = {0, 0, 0, 0};
+#pragma unroll
+                for (int s = 0; s < 2; ++s) {
+                    const int u = u0 + 2 * ch + s;
+                    if (u >= 0 && u < k) {
+                        const unsigned a = cd[u];
+                        if (a > 6) { atomicOr(err, 2); continue; }
+                        t_cov += (a < 4 || a == HX_SYM_DEL);
+                        if (a < 4) w[2 * s] = 1u << (8 * a);
+                        else w[2 * s + 1] = 1u << (8 * (a - 4));
+                    }
+                }
+                *reinterpret_cast<uint4 *>(slab + ch * 128) = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+        }
+        if (k >= 2) {
+            // start sentinel (util.py:262-266) / end sentinel (:271-275); the start rule wins
+            const unsigned a0 = cd[0];
+            if (r == 0 && sym_valid_from(a0)) {
+                atomicAdd(cnt.cell(g.W, 0, 1) + HX_SYM_GAP * HX_NSYM + a0, 1u);
+                t_sent++;
+            }
+            if (r + k == g.N && !(k == 2 && r == 0)) {
+                const unsigned ap = cd[k - 2], bl = cd[k - 1];
+                if (sym_valid_from(ap) && bl <= 6) {
+                    atomicAdd(cnt.cell(g.W, g.N, g.N + 1) + bl * HX_NSYM + HX_SYM_GAP, 1u);
+                    t_sent++;
+                }
+            }
+        }
+    }
+    flush_totals(t_slices, 0, t_cov, t_sent, totals);
+}
+
+// ---- tensor-core tiles -----------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t l2_desc(uint32_t saddr) {      // MN-major, no swizzle: LBO = 1024 (next 8 reads),
+    uint64_t d = 0;                                                //                       SBO = 128 (next 16 columns)
+    d |= (uint64_t)((saddr >> 4) & 0x3fffu);
+    d |= (uint64_t)((1024u >> 4) & 0x3fffu) << 16;
+    d |= (uint64_t)((128u >> 4) & 0x3fffu) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
+// kind::i8, unsigned 8-bit A and B (both MN-major), int32 accumulators, M = 128, N = 128
+constexpr uint32_t L2_IDESC = (2u << 4) | (1u << 15) | (1u << 16) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+
+__device__ __forceinline__ void l2_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(L2_IDESC), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void l2_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void l2_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void l2_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void l2_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void l2_bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void l2_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// stage meta = (I, q, flags): flags 1 = B0 present, 2 = B1 present, 4 = last chunk of the tile, 8 = exit
+
+template <bool FUSED>
+__global__ void __launch_bounds__(L2_THREADS, 1)
+k_l2_tiles(const uint8_t *__restrict__ onehot, const int32_t *__restrict__ bstart, const int32_t *__restrict__ chunk_eb,
+           L2Geom g, const HxCnt cnt_in, unsigned long long *__restrict__ totals, unsigned *__restrict__ tile_counter,
+           const int *__restrict__ go) {
+    extern __shared__ __align__(1024) uint8_t l2_smem[];
+    __shared__ __align__(8) unsigned long long s_full[L2_STAGES], s_empty[L2_STAGES], s_acc_full[2], s_acc_empty[2];
+    __shared__ volatile int s_meta[L2_STAGES][4];
+    __shared__ volatile int s_tile[2][4];                      // (I, q, halves present, exit) of the tile in each accumulator
+    __shared__ uint32_t s_tmem;
+    if (go && !*go) return;
+    HxCnt cnt = cnt_in;
+    if (!FUSED) { cnt.world = 1; cnt.rows_per = 1; cnt.peer = nullptr; }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t stage0 = ws_smem_u32(l2_smem);
+    uint32_t *const staging = reinterpret_cast<uint32_t *>(l2_smem + (size_t)L2_STAGES * L2_STAGE_BYTES);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < L2_STAGES; ++s) {
+            ws_mbar_init(ws_smem_u32(&s_full[s]), 1);
+            ws_mbar_init(ws_smem_u32(&s_empty[s]), 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            ws_mbar_init(ws_smem_u32(&s_acc_full[s]), 1);
+            ws_mbar_init(ws_smem_u32(&s_acc_empty[s]), L2_EP_WARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(ws_smem_u32(&s_tmem)),
+                     "r"(512u)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    l2_fence_before();
+    __syncthreads();
+    l2_fence_after();
+    const uint32_t tmem_base = s_tmem;
+    const int SP = g.SP;
+    unsigned long long crumbs = 0;
+
+    if (warp == 0) {
+        // ============================== producer ======================================
+        const int64_t n_tiles = (int64_t)g.NB * g.nq;
+        unsigned stage = 0, ph = 0;                      // ring position / phase of the empty barriers
+        // the chunk waiting to be sent (so that the tile's last chunk can be marked)
+        int p_c = -1, p_sb = 0, p_eb = 0, p_I = 0, p_q = 0;
+        auto emit = [&](int last) {
+            if (lane == 0) {
+                ws_mbar_wait(ws_smem_u32(&s_empty[stage]), ph ^ 1);
+                const int b0 = 2 * p_q >= p_I, b1 = p_eb >= 2 * p_q + 1;
+                s_meta[stage][0] = p_I; s_meta[stage][1] = p_q; s_meta[stage][2] = b0 | (b1 << 1) | (last << 2);
+                const uint32_t bar = ws_smem_u32(&s_full[stage]);
+                const uint32_t dst = stage0 + stage * L2_STAGE_BYTES;
+                const uint8_t *src = onehot + ((size_t)p_c * SP) * L2_SLAB;
+                l2_expect_tx(bar, L2_SLAB * (uint32_t)(1 + b0 + b1));
+                l2_bulk_g2s(dst, src + (size_t)(p_I - p_sb) * L2_SLAB, L2_SLAB, bar);
+                if (b0) l2_bulk_g2s(dst + L2_SLAB, src + (size_t)(2 * p_q - p_sb) * L2_SLAB, L2_SLAB, bar);
+                if (b1) l2_bulk_g2s(dst + 2 * L2_SLAB, src + (size_t)(2 * p_q + 1 - p_sb) * L2_SLAB, L2_SLAB, bar);
+            }
+            if (++stage == L2_STAGES) { stage = 0; ph ^= 1; }
+        };
+        for (;;) {
+            unsigned t = 0;
+            if (lane == 0) t = atomicAdd(tile_counter, 1u);
+            t = __shfl_sync(0xffffffffu, t, 0);
+            if ((int64_t)t >= n_tiles) break;
+            const int I = (int)(t / (unsigned)g.nq), q = (I >> 1) + (int)(t % (unsigned)g.nq);
+            const int jmax = min(I + SP - 1, g.NB - 1);
+            if (2 * q > jmax) continue;
+            const int jlo = max(2 * q, I);
+            // first blocks whose reads can reach jlo: sb >= jlo - (SP-1); they must start at or before I
+            const int sb_lo = max(0, jlo - SP + 1);
+            for (int sb0 = sb_lo; sb0 <= I; sb0 += 32) {
+                const int sb = sb0 + lane;
+                int first = 0, end = 0;
+                if (sb <= I) {
+                    int a = bstart[(int64_t)sb * SP] >> 5;
+                    end = bstart[(int64_t)(sb + 1) * SP] >> 5;
+                    int b = end;
+                    while (a < b) {                                  // chunks of a first block are sorted by their last block
+                        const int m = (a + b) >> 1;
+                        if (chunk_eb[m] >= jlo) b = m; else a = m + 1;
+                    }
+                    first = a;
+                }
+                unsigned hits = __ballot_sync(0xffffffffu, first < end);
+                while (hits) {
+                    const int src = __ffs(hits) - 1;
+                    hits &= hits - 1;
+                    const int c0 = __shfl_sync(0xffffffffu, first, src), c1 = __shfl_sync(0xffffffffu, end, src);
+                    for (int c = c0; c < c1; ++c) {
+                        if (p_c >= 0) emit(0);
+                        p_c = c; p_sb = sb0 + src; p_eb = chunk_eb[c]; p_I = I; p_q = q;
+                    }
+                }
+            }
+            if (p_c >= 0) { emit(1); p_c = -1; }
+        }
+        if (lane == 0) {                                             // tell the MMA thread to stop
+            ws_mbar_wait(ws_smem_u32(&s_empty[stage]), ph ^ 1);
+            s_meta[stage][2] = 8;
+            ws_mbar_arrive(ws_smem_u32(&s_full[stage]));
+        }
+    } else if (warp == 1) {
+        // ============================== MMA issue ======================================
+        if (lane == 0) {
+            unsigned stage = 0, ph = 0, acc = 0, acc_ph[2] = {0, 0};
+            bool new_tile = true;
+            int has = 0;
+            for (;;) {
+                ws_mbar_wait(ws_smem_u32(&s_full[stage]), ph);
+                const int m_I = s_meta[stage][0], m_q = s_meta[stage][1], m_flags = s_meta[stage][2];
+                if (m_flags & 8) {
+                    ws_mbar_wait(ws_smem_u32(&s_acc_empty[acc]), acc_ph[acc] ^ 1);
+                    s_tile[acc][3] = 1;
+                    ws_mbar_arrive(ws_smem_u32(&s_acc_full[acc]));
+                    break;
+                }
+                if (new_tile) {
+                    ws_mbar_wait(ws_smem_u32(&s_acc_empty[acc]), acc_ph[acc] ^ 1);
+                    new_tile = false;
+                    has = 0;
+                }
+                l2_fence_after();
+                const uint32_t sa = stage0 + stage * L2_STAGE_BYTES;
+                const uint32_t d = tmem_base + acc * 256u;
+                if (m_flags & 1) { l2_mma(d, l2_desc(sa), l2_desc(sa + L2_SLAB), has & 1); has |= 1; }
+                if (m_flags & 2) { l2_mma(d + 128u, l2_desc(sa), l2_desc(sa + 2 * L2_SLAB), (has >> 1) & 1); has |= 2; }
+                l2_commit(ws_smem_u32(&s_empty[stage]));
+                if (m_flags & 4) {
+                    s_tile[acc][0] = m_I; s_tile[acc][1] = m_q; s_tile[acc][2] = has; s_tile[acc][3] = 0;
+                    asm volatile("fence.acq_rel.cta;" ::: "memory");
+                    l2_commit(ws_smem_u32(&s_acc_full[acc]));
+                    acc_ph[acc] ^= 1;
+                    acc ^= 1;
+                    new_tile = true;
+                }
+                if (++stage == L2_STAGES) { stage = 0; ph ^= 1; }
+            }
+        }
+    } else {
+        // ============================== epilogue ======================================
+        const int ew = warp - 2, qd = warp & 3, hsel = ew >> 2;
+        uint32_t *const stg = staging + (size_t)ew * L2_STG_WORDS;
+        const int t1l = lane >> 3, a = lane & 7;
+        const bool row_ok = a != HX_SYM_N && a != HX_SYM_GAP && a != 7;        // util.py:258: N and _ never come first
+        const int my_stg = (3 - t1l) * 49 + a * 7;
+        const int64_t W = g.W;
+        unsigned acc = 0, acc_ph[2] = {0, 0};
+        for (;;) {
+            ws_mbar_wait_sleep(ws_smem_u32(&s_acc_full[acc]), acc_ph[acc]);
+            acc_ph[acc] ^= 1;
+            l2_fence_after();
+            if (s_tile[acc][3]) break;
+            const int I = s_tile[acc][0], q = s_tile[acc][1], has = s_tile[acc][2];
+            const int pi = 16 * I + 4 * qd + t1l;
+            for (int gq = hsel; gq < 8; gq += 2) {
+                const int half = gq >> 2;
+                if (!((has >> half) & 1)) continue;
+                uint32_t v[32];
+                l2_ld32(tmem_base + acc * 256u + (uint32_t)gq * 32u + ((uint32_t)(qd * 32) << 16), v);
+                const int pj0 = 16 * (2 * q + half) + (gq & 3) * 4;
+                if (a != 7) {
+#pragma unroll
+                    for (int t2l = 0; t2l < 4; ++t2l) {
+                        const bool ok = row_ok && pj0 + t2l > pi;
+#pragma unroll
+                        for (int b = 0; b < 7; ++b) stg[t2l * 196 + my_stg + b] = ok ? v[t2l * 8 + b] : 0u;
+                    }
+                }
+                __syncwarp();
+                // cells (pi, pj) of my quarter's four first sites are contiguous in band row pj: staging word i of
+                // second site t2l lives at band word gbase + i
+                uint32_t x[28];
+#pragma unroll
+                for (int t2l = 0; t2l < 4; ++t2l)
+#pragma unroll
+                    for (int k = 0; k < 7; ++k) {
+                        const int i = k * 32 + lane;
+                        x[t2l * 7 + k] = i < 196 ? stg[t2l * 196 + i] : 0u;
+                    }
+                __syncwarp();
+                if (!FUSED) {
+                    uint32_t old[28];
+#pragma unroll
+                    for (int t2l = 0; t2l < 4; ++t2l) {
+                        const int64_t pj = pj0 + t2l;
+                        uint32_t *gb = cnt.local + (pj * W + pj - 16 * I - 4 * qd - 4) * HX_CELL + lane;
+#pragma unroll
+                        for (int k = 0; k < 7; ++k)
+                            if (x[t2l * 7 + k]) old[t2l * 7 + k] = gb[k * 32];
+                    }
+#pragma unroll
+                    for (int t2l = 0; t2l < 4; ++t2l) {
+                        const int64_t pj = pj0 + t2l;
+                        uint32_t *gb = cnt.local + (pj * W + pj - 16 * I - 4 * qd - 4) * HX_CELL + lane;
+#pragma unroll
+                        for (int k = 0; k < 7; ++k)
+                            if (x[t2l * 7 + k]) {
+                                gb[k * 32] = old[t2l * 7 + k] + x[t2l * 7 + k];
+                                crumbs += x[t2l * 7 + k];
+                            }
+                    }
+                } else {
+#pragma unroll
+                    for (int t2l = 0; t2l < 4; ++t2l) {
+                        const int64_t pj = pj0 + t2l;
+                        uint32_t *base = cnt.peer[pj / cnt.rows_per];
+                        uint32_t *gb = base + (pj * W + pj - 16 * I - 4 * qd - 4) * HX_CELL + lane;
+#pragma unroll
+                        for (int k = 0; k < 7; ++k)
+                            if (x[t2l * 7 + k]) {
+                                atomicAdd(gb + k * 32, x[t2l * 7 + k]);
+                                crumbs += x[t2l * 7 + k];
+                            }
+                    }
+                }
+            }
+            l2_fence_before();
+            __syncwarp();
+            if (lane == 0) ws_mbar_arrive(ws_smem_u32(&s_acc_empty[acc]));
+            acc ^= 1;
+        }
+    }
+    l2_fence_before();
+    flush_totals(0, crumbs, 0, 0, totals);                            // barriers inside
+    if (warp == 0) {
+        l2_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+template <typename T>
+int l2_grow(T **p, int64_t *cap, int64_t need, cudaStream_t st) {
+    if (*cap >= need) return HX_OK;
+    if (*p) cudaFreeAsync(*p, st);
+    *p = nullptr;
+    *cap = 0;
+    HX_CUDA(cudaMallocAsync((void **)p, sizeof(T) * (size_t)need, st));
+    *cap = need;
+    return HX_OK;
+}
+
+}  // namespace
+
+// Scratch owned by the matrix for this path (freed in hx_destroy through hx_l2_free).
+struct hx_l2_scratch {
+    int32_t *keys = nullptr, *hist = nullptr, *bstart = nullptr, *perm = nullptr, *chunk_eb = nullptr, *part = nullptr;
+    uint8_t *onehot = nullptr;
+    int64_t cap_keys = 0, cap_hist = 0, cap_bstart = 0, cap_perm = 0, cap_ceb = 0, cap_part = 0, cap_onehot = 0;
+};
+
+void hx_l2_free(hx_matrix *h) {
+    hx_l2_scratch *s = (hx_l2_scratch *)h->l2_scratch;
+    if (!s) return;
+    void *ptrs[] = {s->keys, s->hist, s->bstart, s->perm, s->chunk_eb, s->part, s->onehot};
+    for (void *p : ptrs)
+        if (p) cudaFreeAsync(p, h->stream);
+    delete s;
+    h->l2_scratch = nullptr;
+}
+
+// bytes of one-hot operand scratch the path would need (the caller falls back to the tile kernels above a limit)
+int64_t hx_lumma_scratch_bytes(const hx_matrix *h, int64_t n_reads) {
+    const L2Geom g = L2Geom::make(h->N, h->W);
+    const int64_t max_chunks = (n_reads + 31) / 32 + (n_reads < g.NB ? n_reads : g.NB);
+    return max_chunks * g.SP * (int64_t)L2_SLAB;
+}
+
+// go: optional device flag; the kernels do nothing when it is zero (a wire-format chunk that failed its checks)
+int hx_launch_ingest_lumma(hx_matrix *h, const int32_t *d_rank, const int64_t *d_off, const uint8_t *d_codes,
+                           int64_t n_reads, const int *go) {
+    if (!h->l2_scratch) h->l2_scratch = new hx_l2_scratch();
+    hx_l2_scratch *s = (hx_l2_scratch *)h->l2_scratch;
+    cudaStream_t st = h->stream;
+    const L2Geom g = L2Geom::make(h->N, h->W);
+    const int64_t nbins = g.n_bins();
+    const int64_t max_chunks = (n_reads + 31) / 32 + (n_reads < g.NB ? n_reads : g.NB);
+    HX_CHECK_ARG(n_reads < ((int64_t)1 << 30) && nbins < ((int64_t)1 << 30));
+    constexpr int ITEMS = 16;
+    const int64_t nscan = nbins + 1;
+    const int64_t nblk = (nscan + 256 * ITEMS - 1) / (256 * ITEMS);
+    int rc;
+    if ((rc = l2_grow(&s->keys, &s->cap_keys, n_reads, st))) return rc;
+    if ((rc = l2_grow(&s->hist, &s->cap_hist, 2 * nscan + 4, st))) return rc;        // histogram | cursors | tile counter
+    if ((rc = l2_grow(&s->bstart, &s->cap_bstart, nscan, st))) return rc;
+    if ((rc = l2_grow(&s->perm, &s->cap_perm, max_chunks * 32, st))) return rc;
+    if ((rc = l2_grow(&s->chunk_eb, &s->cap_ceb, max_chunks, st))) return rc;
+    if ((rc = l2_grow(&s->part, &s->cap_part, nblk, st))) return rc;
+    if ((rc = l2_grow(&s->onehot, &s->cap_onehot, max_chunks * g.SP * (int64_t)L2_SLAB, st))) return rc;
+    int32_t *cursor = s->hist + nscan;
+    unsigned *tile_counter = reinterpret_cast<unsigned *>(s->hist + 2 * nscan);
+
+    HX_CUDA(hx_fill_async(s->hist, 0, sizeof(int32_t) * (size_t)(2 * nscan + 4), st));
+    HX_CUDA(hx_fill_async(s->perm, 0xff, sizeof(int32_t) * (size_t)(max_chunks * 32), st));
+    const unsigned rgrid = (unsigned)((n_reads + 255) / 256);
+    k_l2_keys<<<rgrid, 256, 0, st>>>(d_rank, d_off, n_reads, g, s->keys, s->hist, h->d_err, go);
+    k_l2_pad<<<(unsigned)((g.NB + 255) / 256), 256, 0, st>>>(s->hist, g, go);
+    k_scan_partials<int32_t, 0, ITEMS><<<(unsigned)nblk, 256, 0, st>>>(s->hist, nscan, s->part);
+    k_scan_spine<int32_t, 0><<<1, 32, 0, st>>>(s->part, nblk, nullptr);
+    k_scan_apply<int32_t, 0, ITEMS, true><<<(unsigned)nblk, 256, 0, st>>>(s->hist, nscan, s->part, s->bstart);
+    k_l2_scatter<<<rgrid, 256, 0, st>>>(s->keys, n_reads, s->bstart, cursor, s->perm, go);
+    k_l2_onehot<<<(unsigned)((max_chunks * 32 + 255) / 256), 256, 0, st>>>(d_rank, d_off, d_codes, s->perm, s->bstart, g,
+                                                                           s->onehot, s->chunk_eb, hx_cnt_ref(h),
+                                                                           h->d_totals, h->d_err, go);
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+    if (h->ingest_sms > 0 && h->ingest_sms < sms) sms = h->ingest_sms;
+    const size_t smem = (size_t)L2_STAGES * L2_STAGE_BYTES + (size_t)L2_EP_WARPS * L2_STG_WORDS * 4 + 1024;
+    const bool fused = h->peer_world > 1;
+    auto kern = fused ? k_l2_tiles<true> : k_l2_tiles<false>;
+    HX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<sms, L2_THREADS, smem, st>>>(s->onehot, s->bstart, s->chunk_eb, g, hx_cnt_ref(h), h->d_totals, tile_counter, go);
+    h->launches += 10;
+    HX_CUDA(cudaGetLastError());
+    return HX_OK;
+}

@@ -97,7 +97,9 @@ int hx_ingest_device(hx_matrix *h, const int32_t *d_rank, const int64_t *d_off,
  * 3 = bit-plane transpose + owner-computes tiles (rank-sorted long reads),
  * 4 / 5 = force the barrier-phased / the warp-specialised variant of kernel 2 (2 picks by read width),
  * 6 = tensor-core kernel (int8 tcgen05.mma over one-hot allele rows; rank-sorted reads of <= 32 SNPs; what
- * auto picks for such reads). */
+ * auto picks for such reads),
+ * 7 = long-read tensor-core kernel (counting sort of the reads by first/last site block, one-hot operand slabs,
+ * int8 tcgen05.mma per 16 x 32-site tile; any read width, any order; what auto picks for reads wider than 52 SNPs). */
 int hx_set_ingest_kernel(hx_matrix *h, int which);
 /* Limit the persistent ingestion kernels to n_sms SMs (0 = all of them): leaves room for a collective that runs
  * beside the pair expansion of the next batch (bench.py --overlap-steps). */

@@ -45,7 +45,7 @@ def test_reference_golden_through_gpu(golden_dir):
         assert h.L == 3
 
 
-@pytest.mark.parametrize("kernel", [1, 2, 3, 4, 5, 6])
+@pytest.mark.parametrize("kernel", [1, 2, 3, 4, 5, 6, 7])
 @pytest.mark.parametrize("seed", range(8))
 def test_random_packed_bit_exact(c_oracle, seed, kernel):
     rng = np.random.default_rng(500 + seed)
@@ -60,7 +60,7 @@ def test_random_packed_bit_exact(c_oracle, seed, kernel):
     assert np.array_equal(band, ref.astype(np.float32))
 
 
-@pytest.mark.parametrize("kernel", [1, 2, 3, 4, 5, 6])
+@pytest.mark.parametrize("kernel", [1, 2, 3, 4, 5, 6, 7])
 def test_edge_cases(c_oracle, kernel):
     # empty input, reads with k<2, N=2 (start rule beats end rule), reads ending on the last SNP
     cases = []
@@ -91,7 +91,7 @@ def test_bad_reads_raise():
 
 
 @pytest.mark.parametrize("name,n_reads", [("hiv", 200_000), ("metagenome", 300_000), ("ont", 600)])
-@pytest.mark.parametrize("kernel", [0, 1, 3, 4, 5, 6])
+@pytest.mark.parametrize("kernel", [0, 1, 3, 4, 5, 6, 7])
 def test_workloads_bit_exact(c_oracle, name, n_reads, kernel):
     """Config 2 at full size, configs 3/4 at sizes the C oracle finishes in seconds."""
     w = synth.scaled(synth.WORKLOADS[name], n_reads)
@@ -359,7 +359,7 @@ def test_dense_wire_format_rejects_bad_input():
 
 @pytest.mark.parametrize("shape", [(600, 40, 300_000, 150), (600, 100, 120_000, 200), (3000, 300, 400_000, 150)],
                          ids=["7k-reads-per-rank", "wide-reads-deep", "1k-reads-per-rank"])
-@pytest.mark.parametrize("kernel", [0, 4, 5, 3, 6])
+@pytest.mark.parametrize("kernel", [0, 4, 5, 3, 6, 7])
 def test_deep_coverage_runs_bit_exact(c_oracle, shape, kernel):
     """Runs of thousands of reads per rank (several 1024-read batches per run, several CTAs per
     run) - the regime of the full-size configs - at a size the C oracle checks in a second."""
@@ -391,7 +391,7 @@ def test_adversarial_shapes(c_oracle):
     cases.append((ranks, off, rng.integers(0, 5, size=off[-1]).astype(np.uint8), 2000, 9))
     for rank, off, codes, N, W in cases:
         ref, rt = c_oracle.ingest(rank, off, codes, N, W)
-        for kernel in (0, 1, 3, 4, 5, 6):
+        for kernel in (0, 1, 3, 4, 5, 6, 7):
             band, totals = _gpu_band(rank, off, codes, N, W, kernel)
             assert totals == tuple(int(x) for x in rt), (N, kernel)
             assert np.array_equal(band, ref.astype(np.float32)), (N, kernel)
