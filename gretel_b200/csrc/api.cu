@@ -372,6 +372,7 @@ int hx_ensure_counts_buffer(hx_matrix *h) {
     h->cnt_elems = h->band_elems;
     HX_CUDA(cudaMallocAsync((void **)&h->cnt, sizeof(uint32_t) * (size_t)h->cnt_elems, h->stream));
     HX_CUDA(hx_fill_async(h->cnt, 0, sizeof(uint32_t) * (size_t)h->cnt_elems, h->stream));
+    h->cnt_fresh = true;
     return HX_OK;
 }
 extern "C" {
@@ -557,6 +558,7 @@ int hx_counts_buffer(hx_matrix *h, void **d_counts, int64_t *n_u32, void **d_tot
     int rc = hx_ensure_counts_buffer(h);
     if (rc) return rc;
     *d_counts = h->cnt;
+    h->cnt_fresh = false;                 // the caller may write through the pointer (until the next hx_reset_counts)
     *n_u32 = h->cnt_elems;
     *d_totals = h->d_totals;
     *n_i64 = 4;
@@ -594,6 +596,7 @@ int hx_counts_unpack(hx_matrix *h, int32_t *overflowed) {
     const int64_t n_pairs = h->band_elems / HX_CELL;
     const int64_t flag_at = (n_pairs * HX_PACK_WORDS + 3) & ~(int64_t)3;
     const int64_t n_w = n_pairs * HX_PACK_WORDS;
+    h->cnt_fresh = false;
     k_unpack_counts<<<(unsigned)((n_w + 255) / 256), 256, 0, h->stream>>>(h->d_pack, n_pairs, h->cnt, flag_at);
     h->launches++;
     HX_CUDA(cudaGetLastError());
@@ -613,6 +616,7 @@ int hx_counts_ipc_export(hx_matrix *h, int32_t world, void *handle_out) {
     h->cnt_elems = rows_per * world * h->W * HX_CELL;          // padded so that every rank owns rows_per rows
     HX_CUDA(cudaMalloc((void **)&h->cnt, sizeof(uint32_t) * (size_t)h->cnt_elems));   // IPC needs a plain allocation
     h->cnt_ipc = true;
+    h->cnt_fresh = false;
     HX_CUDA(hx_fill_async(h->cnt, 0, sizeof(uint32_t) * (size_t)h->cnt_elems, h->stream));
     HX_CUDA(cudaStreamSynchronize(h->stream));
     cudaIpcMemHandle_t hd;
@@ -665,6 +669,7 @@ int hx_reset_counts(hx_matrix *h) {
         k_reset_counts<<<grid, 256, 0, h->stream>>>(reinterpret_cast<uint4 *>(h->cnt), sizeof(uint32_t) * (size_t)h->cnt_elems,
                                                     h->d_totals, h->d_err);
         HX_CUDA(cudaGetLastError());
+        h->cnt_fresh = true;
     } else {
         HX_CUDA(hx_fill_async(h->d_totals, 0, 8 * sizeof(unsigned long long), h->stream));
         HX_CUDA(hx_fill_async(h->d_err, 0, sizeof(int), h->stream));

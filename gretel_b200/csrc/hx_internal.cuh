@@ -46,6 +46,7 @@ struct hx_matrix {
     bool own_stream;
     float *band;                     // float32 working matrix (what the Hansel surface reads)
     uint32_t *cnt;                   // integer counts being ingested (lazily allocated)
+    bool cnt_fresh;                  // cnt is still all zero (nothing ingested / received since it was cleared)
     bool cnt_ipc;                    // cnt is a plain cudaMalloc allocation shared through CUDA IPC
     int64_t cnt_elems;               // allocated uint32 elements (>= band_elems; padded for the fused exchange)
     uint32_t *peer_host[HX_MAX_PEERS];   // fused exchange: every rank's cnt (own entry = local pointer)

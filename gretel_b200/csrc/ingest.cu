@@ -888,6 +888,7 @@ static int launch_ingest(hx_matrix *h, const int32_t *d_rank, const int64_t *d_o
             h->launches++;
         }
     }
+    h->cnt_fresh = false;
     HX_CUDA(cudaGetLastError());
     HX_CUDA(cudaEventRecord(h->ev1, h->stream));
     h->ev_rec = true;

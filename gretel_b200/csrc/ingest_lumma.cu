@@ -16,9 +16,11 @@
 //                  reads), so a slab is one 4 KB bulk copy away from the tensor core.  Sentinels, totals here.
 //   k_l2_tiles     persistent CTAs over tiles (I = one block of 16 first sites, q = a pair of blocks of second sites):
 //                  a producer warp finds the chunks that touch both (per first block the chunks are sorted by their
-//                  last block: one binary search each) and streams their slabs through an 8-stage TMA/mbarrier ring;
+//                  last block: the sort's own offsets say where the reaching chunks start) and streams their slabs
+//                  (runs of up to 4 chunks of a first block are contiguous: three bulk copies per run) through a
+//                  3-stage TMA/mbarrier ring;
 //                  one thread issues two M=128, N=128, K=32 MMAs per chunk into a double-buffered TMEM accumulator;
-//                  8 epilogue warps read the finished accumulator (tcgen05.ld), turn it through shared memory
+//                  16 epilogue warps read the finished accumulator (tcgen05.ld), turn it through shared memory
 //                  into the band's cell order and add it to the band with coalesced read-modify-writes.  Every band
 //                  cell has exactly one writer: no atomics.
 // Rank-sortedness is not needed (the counting sort orders the reads itself).
@@ -30,11 +32,12 @@
 
 namespace {
 
-constexpr int L2_STAGES = 8;
-constexpr int L2_EP_WARPS = 8;
+constexpr int L2_G = 4;                             // chunks (of one first block) per pipeline stage
+constexpr int L2_STAGES = 3;
+constexpr int L2_EP_WARPS = 16;
 constexpr int L2_THREADS = (2 + L2_EP_WARPS) * 32;
 constexpr uint32_t L2_SLAB = 4096;                 // one chunk x one block: 32 reads x 128 one-hot bytes
-constexpr uint32_t L2_STAGE_BYTES = 3 * L2_SLAB;   // A (first sites), B0, B1 (second sites)
+constexpr uint32_t L2_STAGE_BYTES = 3 * L2_G * L2_SLAB;   // A (first sites), B0, B1 (second sites), L2_G chunks each
 constexpr int L2_STG_WORDS = 4 * 196;              // epilogue staging per warp: 4 second sites x 4 cells x 49 counters
 
 struct L2Geom {
@@ -47,7 +50,8 @@ struct L2Geom {
         g.nq = (g.SP + 1) / 2 + 1;                  // pairs of second-site blocks per first-site block
         return g;
     }
-    __host__ __device__ int64_t n_bins() const { return (int64_t)NB * SP; }
+    __host__ __device__ int SPB() const { return SP + 1; }      // bins per first block: padding, then spans 0..SP-1
+    __host__ __device__ int64_t n_bins() const { return (int64_t)NB * (SP + 1); }
 };
 
 // ---- sort keys ------------------------------------------------------------------------------------------------
@@ -64,22 +68,23 @@ k_l2_keys(const int32_t *__restrict__ rank, const int64_t *__restrict__ off, int
         if (r < 0 || (int64_t)r + k > g.N || k - 1 > g.W) atomicOr(err, 1);
         else {
             const int sb = (r + 1) >> 4, eb = (r + (int)k) >> 4;
-            key = sb * g.SP + (eb - sb);
+            key = sb * g.SPB() + 1 + (eb - sb);
             atomicAdd(&hist[key], 1);
         }
     }
     keys[i] = key;
 }
 
-// the last key of every first block absorbs the padding that makes the block's read count a multiple of 32
+// bin 0 of every first block = the padding (in front of its shortest reads) that makes the block's read count a
+// multiple of 32: bstart[sb*SPB + 1 + s] >> 5 is then exactly the first chunk holding a read that spans > s blocks
 __global__ void k_l2_pad(int32_t *__restrict__ hist, L2Geom g, const int *__restrict__ go) {
     if (go && !*go) return;
     const int sb = blockIdx.x * blockDim.x + threadIdx.x;
     if (sb >= g.NB) return;
-    int32_t *h = hist + (int64_t)sb * g.SP;
+    int32_t *h = hist + (int64_t)sb * g.SPB();
     int s = 0;
-    for (int j = 0; j < g.SP; ++j) s += h[j];
-    h[g.SP - 1] += (32 - (s & 31)) & 31;
+    for (int j = 1; j <= g.SP; ++j) s += h[j];
+    h[0] = (32 - (s & 31)) & 31;
 }
 
 __global__ void __launch_bounds__(256)
@@ -94,7 +99,8 @@ k_l2_scatter(const int32_t *__restrict__ keys, int64_t n_reads, const int32_t *_
 }
 
 // ---- one-hot operand slabs ----------------------------------------------------------------------------------
-// Slab of (chunk c, block sb+j) at onehot + (c*SP + j) * 4096; inside: [8 reads][16 columns] core matrices of 128 B,
+// Slab of (chunk c of first block sb, block sb+j) at onehot + (cs*SP + j*nch + (c-cs)) * 4096 with cs / nch = first
+// chunk / number of chunks of sb; inside: [8 reads][16 columns] core matrices of 128 B,
 // the 8 column groups of a block 128 B apart, the 4 groups of 8 reads 1024 B apart.
 __global__ void __launch_bounds__(256)
 k_l2_onehot(const int32_t *__restrict__ rank, const int64_t *__restrict__ off, const uint8_t *__restrict__ codes,
@@ -120,8 +126,10 @@ k_l2_onehot(const int32_t *__restrict__ rank, const int64_t *__restrict__ off, c
         const int eb = __reduce_max_sync(0xffffffffu, idx >= 0 ? (r + k) >> 4 : 0);
         if (lane == 0) chunk_eb[c] = eb;
         t_slices += idx >= 0;
-        uint8_t *slab = onehot + ((size_t)c * g.SP) * L2_SLAB + (size_t)(lane >> 3) * 1024 + (size_t)(lane & 7) * 16;
-        for (int b = sb; b <= eb; ++b, slab += L2_SLAB) {
+        // the slabs of a first block's chunks are stored block-major: a run of its chunks x one site block is contiguous
+        const int64_t cs = bstart[(int64_t)sb * g.SPB()] >> 5, nch = (bstart[(int64_t)(sb + 1) * g.SPB()] >> 5) - cs;
+        uint8_t *slab = onehot + ((size_t)cs * g.SP + (size_t)(c - cs)) * L2_SLAB + (size_t)(lane >> 3) * 1024 + (size_t)(lane & 7) * 16;
+        for (int b = sb; b <= eb; ++b, slab += (size_t)nch * L2_SLAB) {
             const int u0 = 16 * b - (r + 1);                       // position in my read of the block's first site
 #pragma unroll
             for (int ch = 0; ch < 8; ++ch) {
@@ -207,7 +215,7 @@ __device__ __forceinline__ void l2_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 
 // stage meta = (I, q, flags): flags 1 = B0 present, 2 = B1 present, 4 = last chunk of the tile, 8 = exit
 
-template <bool FUSED>
+template <bool FUSED, bool FRESH>
 __global__ void __launch_bounds__(L2_THREADS, 1)
 k_l2_tiles(const uint8_t *__restrict__ onehot, const int32_t *__restrict__ bstart, const int32_t *__restrict__ chunk_eb,
            L2Geom g, const HxCnt cnt_in, unsigned long long *__restrict__ totals, unsigned *__restrict__ tile_counter,
@@ -251,21 +259,24 @@ k_l2_tiles(const uint8_t *__restrict__ onehot, const int32_t *__restrict__ bstar
     if (warp == 0) {
         // ============================== producer ======================================
         const int64_t n_tiles = (int64_t)g.NB * g.nq;
+        const int SPB = g.SPB();
         unsigned stage = 0, ph = 0;                      // ring position / phase of the empty barriers
-        // the chunk waiting to be sent (so that the tile's last chunk can be marked)
-        int p_c = -1, p_sb = 0, p_eb = 0, p_I = 0, p_q = 0;
+        // the piece (a run of up to L2_G chunks of one first block) waiting to be sent, so that the tile's last one can be marked
+        int p_c = -1, p_n = 0, p_sb = 0, p_cs = 0, p_nch = 0, p_b1 = 0, p_I = 0, p_q = 0;
         auto emit = [&](int last) {
+            const int b0 = 2 * p_q >= p_I, b1 = p_b1;
+            const uint32_t bar = ws_smem_u32(&s_full[stage]);
+            const uint32_t bytes = L2_SLAB * (uint32_t)p_n;
             if (lane == 0) {
                 ws_mbar_wait(ws_smem_u32(&s_empty[stage]), ph ^ 1);
-                const int b0 = 2 * p_q >= p_I, b1 = p_eb >= 2 * p_q + 1;
-                s_meta[stage][0] = p_I; s_meta[stage][1] = p_q; s_meta[stage][2] = b0 | (b1 << 1) | (last << 2);
-                const uint32_t bar = ws_smem_u32(&s_full[stage]);
-                const uint32_t dst = stage0 + stage * L2_STAGE_BYTES;
-                const uint8_t *src = onehot + ((size_t)p_c * SP) * L2_SLAB;
-                l2_expect_tx(bar, L2_SLAB * (uint32_t)(1 + b0 + b1));
-                l2_bulk_g2s(dst, src + (size_t)(p_I - p_sb) * L2_SLAB, L2_SLAB, bar);
-                if (b0) l2_bulk_g2s(dst + L2_SLAB, src + (size_t)(2 * p_q - p_sb) * L2_SLAB, L2_SLAB, bar);
-                if (b1) l2_bulk_g2s(dst + 2 * L2_SLAB, src + (size_t)(2 * p_q + 1 - p_sb) * L2_SLAB, L2_SLAB, bar);
+                s_meta[stage][0] = p_I; s_meta[stage][1] = p_q; s_meta[stage][2] = b0 | (b1 << 1) | (last << 2) | (p_n << 8);
+                l2_expect_tx(bar, bytes * (uint32_t)(1 + b0 + b1));
+            }
+            __syncwarp();
+            if (lane < 3 && (lane == 0 || (lane == 1 ? b0 : b1))) {    // lane 0: A, lane 1: B0, lane 2: B1
+                const int blk = lane == 0 ? p_I : 2 * p_q + lane - 1;
+                l2_bulk_g2s(stage0 + stage * L2_STAGE_BYTES + (uint32_t)lane * (L2_G * L2_SLAB),
+                            onehot + ((size_t)p_cs * SP + (size_t)(blk - p_sb) * p_nch + (size_t)(p_c - p_cs)) * L2_SLAB, bytes, bar);
             }
             if (++stage == L2_STAGES) { stage = 0; ph ^= 1; }
         };
@@ -282,25 +293,29 @@ k_l2_tiles(const uint8_t *__restrict__ onehot, const int32_t *__restrict__ bstar
             const int sb_lo = max(0, jlo - SP + 1);
             for (int sb0 = sb_lo; sb0 <= I; sb0 += 32) {
                 const int sb = sb0 + lane;
-                int first = 0, end = 0;
+                int first = 0, end = 0, cb1 = 0, cs = 0;
                 if (sb <= I) {
-                    int a = bstart[(int64_t)sb * SP] >> 5;
-                    end = bstart[(int64_t)(sb + 1) * SP] >> 5;
-                    int b = end;
-                    while (a < b) {                                  // chunks of a first block are sorted by their last block
-                        const int m = (a + b) >> 1;
-                        if (chunk_eb[m] >= jlo) b = m; else a = m + 1;
-                    }
-                    first = a;
+                    // the reads of a first block are sorted by the blocks they span: those reaching block j are a suffix
+                    const int32_t *__restrict__ bs = bstart + (int64_t)sb * SPB;
+                    const int d1 = 2 * q + 1 - sb;
+                    cs = bs[0] >> 5;
+                    first = bs[1 + jlo - sb] >> 5;
+                    end = bs[SPB] >> 5;
+                    cb1 = d1 < SP ? max(bs[1 + d1] >> 5, first) : end;       // chunks from cb1 on reach block 2q+1
                 }
                 unsigned hits = __ballot_sync(0xffffffffu, first < end);
                 while (hits) {
                     const int src = __ffs(hits) - 1;
                     hits &= hits - 1;
                     const int c0 = __shfl_sync(0xffffffffu, first, src), c1 = __shfl_sync(0xffffffffu, end, src);
-                    for (int c = c0; c < c1; ++c) {
+                    const int cb = __shfl_sync(0xffffffffu, cb1, src), ws = __shfl_sync(0xffffffffu, cs, src);
+                    for (int c = c0; c < c1;) {
+                        // pieces do not straddle cb: the slabs of block 2q+1 only exist from chunk cb on
+                        const int lim = c < cb ? cb : c1;
+                        const int n = min(L2_G, lim - c);
                         if (p_c >= 0) emit(0);
-                        p_c = c; p_sb = sb0 + src; p_eb = chunk_eb[c]; p_I = I; p_q = q;
+                        p_c = c; p_n = n; p_sb = sb0 + src; p_cs = ws; p_nch = c1 - ws; p_b1 = c >= cb; p_I = I; p_q = q;
+                        c += n;
                     }
                 }
             }
@@ -334,8 +349,13 @@ k_l2_tiles(const uint8_t *__restrict__ onehot, const int32_t *__restrict__ bstar
                 l2_fence_after();
                 const uint32_t sa = stage0 + stage * L2_STAGE_BYTES;
                 const uint32_t d = tmem_base + acc * 256u;
-                if (m_flags & 1) { l2_mma(d, l2_desc(sa), l2_desc(sa + L2_SLAB), has & 1); has |= 1; }
-                if (m_flags & 2) { l2_mma(d + 128u, l2_desc(sa), l2_desc(sa + 2 * L2_SLAB), (has >> 1) & 1); has |= 2; }
+                const uint64_t da = l2_desc(sa), db0 = l2_desc(sa + L2_G * L2_SLAB), db1 = l2_desc(sa + 2 * L2_G * L2_SLAB);
+                const int n = m_flags >> 8;
+                for (int i = 0; i < n; ++i) {                       // the next chunk's slab is 4096 B = 256 descriptor units on
+                    const uint64_t o = (uint64_t)(i * (int)(L2_SLAB >> 4));
+                    if (m_flags & 1) { l2_mma(d, da + o, db0 + o, has & 1); has |= 1; }
+                    if (m_flags & 2) { l2_mma(d + 128u, da + o, db1 + o, (has >> 1) & 1); has |= 2; }
+                }
                 l2_commit(ws_smem_u32(&s_empty[stage]));
                 if (m_flags & 4) {
                     s_tile[acc][0] = m_I; s_tile[acc][1] = m_q; s_tile[acc][2] = has; s_tile[acc][3] = 0;
@@ -364,7 +384,7 @@ k_l2_tiles(const uint8_t *__restrict__ onehot, const int32_t *__restrict__ bstar
             if (s_tile[acc][3]) break;
             const int I = s_tile[acc][0], q = s_tile[acc][1], has = s_tile[acc][2];
             const int pi = 16 * I + 4 * qd + t1l;
-            for (int gq = hsel; gq < 8; gq += 2) {
+            for (int gq = hsel; gq < 8; gq += L2_EP_WARPS / 4) {
                 const int half = gq >> 2;
                 if (!((has >> half) & 1)) continue;
                 uint32_t v[32];
@@ -390,7 +410,24 @@ k_l2_tiles(const uint8_t *__restrict__ onehot, const int32_t *__restrict__ bstar
                         x[t2l * 7 + k] = i < 196 ? stg[t2l * 196 + i] : 0u;
                     }
                 __syncwarp();
-                if (!FUSED) {
+                if (!FUSED && FRESH) {
+                    // the band is still all zero (first ingestion into this matrix): plain stores, no loads.  Where the
+                    // warp's four cells lie inside the band every word is written, zeros too (whole sectors: nothing
+                    // for L2 to fetch); the sentinel cells (pi = 0, pj = N+1) are never touched.
+                    const int pi_lo = 16 * I + 4 * qd;
+#pragma unroll
+                    for (int t2l = 0; t2l < 4; ++t2l) {
+                        const int64_t pj = pj0 + t2l;
+                        const bool full = pi_lo >= 1 && pj <= g.N && pj - (pi_lo + 3) >= 1 && pj - pi_lo <= W;
+                        uint32_t *gb = cnt.local + (pj * W + pj - 16 * I - 4 * qd - 4) * HX_CELL + lane;
+#pragma unroll
+                        for (int k = 0; k < 7; ++k) {
+                            const uint32_t xv = x[t2l * 7 + k];
+                            if (xv || (full && k * 32 + lane < 196)) gb[k * 32] = xv;
+                            crumbs += xv;
+                        }
+                    }
+                } else if (!FUSED) {
                     uint32_t old[28];
 #pragma unroll
                     for (int t2l = 0; t2l < 4; ++t2l) {
@@ -518,7 +555,8 @@ int hx_launch_ingest_lumma(hx_matrix *h, const int32_t *d_rank, const int64_t *d
     if (h->ingest_sms > 0 && h->ingest_sms < sms) sms = h->ingest_sms;
     const size_t smem = (size_t)L2_STAGES * L2_STAGE_BYTES + (size_t)L2_EP_WARPS * L2_STG_WORDS * 4 + 1024;
     const bool fused = h->peer_world > 1;
-    auto kern = fused ? k_l2_tiles<true> : k_l2_tiles<false>;
+    const bool fresh = !fused && h->cnt_fresh;
+    auto kern = fused ? k_l2_tiles<true, false> : (fresh ? k_l2_tiles<false, true> : k_l2_tiles<false, false>);
     HX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<sms, L2_THREADS, smem, st>>>(s->onehot, s->bstart, s->chunk_eb, g, hx_cnt_ref(h), h->d_totals, tile_counter, go);
     h->launches += 10;

@@ -107,7 +107,9 @@ int hx_set_ingest_sms(hx_matrix *h, int n_sms);
 int hx_ingest_totals(hx_matrix *h, int64_t totals[4]);               /* synchronises */
 /* Partial-matrix exchange across GPUs (the reference's fork-shared matrix,
  * util.py:303-326): device pointer + length of the uint32 counts and of the int64
- * totals, for an integer sum-allreduce by the caller (NCCL). */
+ * totals, for an integer sum-allreduce by the caller (NCCL).  A caller that writes through the pointer
+ * BEFORE an ingestion (rather than summing after it) must fetch it again after every hx_reset_counts: a
+ * freshly cleared matrix lets the long-read kernel store instead of read-modify-write. */
 int hx_counts_buffer(hx_matrix *h, void **d_counts, int64_t *n_u32, void **d_totals, int64_t *n_i64);
 /* The same exchange with half the bytes: hx_counts_pack() copies the pending counts into a packed device
  * buffer (49 x uint16 per site pair in 25 words; the last 4 words are an overflow flag), the caller
