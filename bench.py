@@ -137,6 +137,31 @@ def workload_config(args, k_mean=None, n_reads=None):
 
 
 # ----------------------------------------------------------------------------------- reference arm
+def lumma_floor(rank, off, kernel_ms):
+    """Tensor-core floor of the long-read kernel (ingest_lumma.cu): the reads sorted by (first 16-site block, blocks
+    spanned) and cut into chunks of 32 per first block exactly as k_l2_scatter / k_l2_onehot do; a chunk spanning n
+    blocks takes n(n+1)/2 MMAs of M=128, N=128, K=32 (int8, 64 cycles each at the 8192 MAC/clk/SM peak)."""
+    k = np.diff(off)
+    ok = k >= 2
+    r, k = rank[ok].astype(np.int64), k[ok]
+    if not len(r):
+        return None
+    sb, eb = (r + 1) >> 4, (r + k) >> 4
+    order = np.lexsort((eb, sb))
+    sb, eb = sb[order], eb[order]
+    first = np.concatenate([[0], np.flatnonzero(np.diff(sb)) + 1])                 # start of every first block's reads
+    within = np.arange(len(sb)) - np.repeat(first, np.diff(np.concatenate([first, [len(sb)]])))
+    chunk_start = np.flatnonzero(within % 32 == 0)
+    n = np.maximum.reduceat(eb, chunk_start) - sb[chunk_start] + 1
+    mma = float((n * (n + 1) // 2).sum())
+    floor_ms = mma * 64 / 148 / 1.965e6
+    return {"mma_per_launch": mma, "cycles_per_mma": 64, "floor_ms": floor_ms, "frac": floor_ms / kernel_ms,
+            "chunks": int(len(chunk_start)), "operand_slabs": int(n.sum()),
+            "note": "one M=128,N=128,K=32 int8 MMA per (chunk of 32 reads, 16 first sites, 16 second sites) at the 8192 "
+                    "MAC/clk/SM peak; measured in the kernel: ~140 cycles per MMA, because an MMA of this shape reads "
+                    "8 KB of operands from shared memory (the whole 128 B/clk) while TMA refills 6 KB per MMA"}
+
+
 def popc_floor(rank, off, kernel_ms):
     """The compute floor of the bit-sliced kernel: 16 POPC per (site pair x group of 32 same-rank reads), issued
     by whole warps over the t2-major pair prefix, on the quarter-rate XU pipe (15.5 lanes/clk/SM measured,
@@ -561,8 +586,9 @@ def run_ours(args):
     s8d_bytes = local_obs * b_obs(k_mean)
     s8d_achieved = s8d_bytes / (kms * 1e-3) / 1e9
     umma = args.kernel in (0, 6) and d["max_k"] <= 32 and R >= 64 * (N + 1)
+    lumma = args.kernel == 7 or (args.kernel == 0 and d["max_k"] > 52)
     groups = float(np.ceil(np.bincount(d["rank"]) / 32.0).sum()) if R else 0.0
-    roofline = {"bound": "hbm", "kernel": "ingestion (pair expansion): " + ("k1_umma (int8 tcgen05.mma)" if umma else "k1_bitsliced / tiles"),
+    roofline = {"bound": "hbm", "kernel": "ingestion (pair expansion): " + ("k1_umma (int8 tcgen05.mma)" if umma else "k_l2_tiles (int8 tcgen05.mma over one-hot slabs, long reads)" if lumma else "k1_bitsliced / tiles"),
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_src, "kernel_ms": kms,
                 "algorithmic_bytes_per_launch": compulsory,
@@ -576,7 +602,8 @@ def run_ours(args):
                                       "this exceed 1 - reported for continuity, not as a bound"},
                 "tensor_floor": ({"mma_per_launch": groups, "cycles_per_mma": 64, "floor_ms": groups * 64 / 148 / 1.965e6,
                                   "frac": (groups * 64 / 148 / 1.965e6) / kms,
-                                  "note": "one M=128,N<=128,K=32 int8 MMA per 32 reads at the 8192 MAC/clk/SM peak"} if umma else None),
+                                  "note": "one M=128,N<=128,K=32 int8 MMA per 32 reads at the 8192 MAC/clk/SM peak"} if umma
+                                 else lumma_floor(d["rank"], d["off"], kms) if lumma else None),
                 "pipe_floor": (popc_floor(d["rank"], d["off"], kms) if (d["max_k"] <= 52 and not umma) else None)}
 
     # ---- CPU baseline: the reference's per-pair Python loop on a bounded sample, all cores
@@ -747,7 +774,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="metagenome", choices=sorted(synth.WORKLOADS))
     ap.add_argument("--reads", type=int, default=0, help="reads per GPU (default: the workload's full size)")
-    ap.add_argument("--kernel", type=int, default=0, help="ingestion kernel: 0 auto, 1 generic, 2 bit-sliced")
+    ap.add_argument("--kernel", type=int, default=0, help="ingestion kernel: 0 auto, 1 generic, 2 bit-sliced, 3 long-read bit-plane tiles, 6 tensor-core (short reads), 7 tensor-core (long reads)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="N>1: weak = every GPU ingests its own full-size read set of the same region (default, what the "
                          "driver's scaling run uses); strong = ONE read set cut into contiguous chunks, seam-only exchange")

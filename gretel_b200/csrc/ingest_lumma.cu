@@ -40,6 +40,15 @@ constexpr uint32_t L2_SLAB = 4096;                 // one chunk x one block: 32 
 constexpr uint32_t L2_STAGE_BYTES = 3 * L2_G * L2_SLAB;   // A (first sites), B0, B1 (second sites), L2_G chunks each
 constexpr int L2_STG_WORDS = 4 * 196;              // epilogue staging per warp: 4 second sites x 4 cells x 49 counters
 
+#ifdef L2_PROFILE
+__device__ unsigned long long l2_prof[16];
+#define L2_T(var) const long long var = clock64()
+#define L2_ACC(slot, expr) l2_pacc[slot] += (unsigned long long)(expr)
+#else
+#define L2_T(var)
+#define L2_ACC(slot, expr)
+#endif
+
 struct L2Geom {
     int N, W, NB, SP, nq;
     __host__ __device__ static L2Geom make(int N, int W) {
@@ -222,7 +231,8 @@ k_l2_tiles(const uint8_t *__restrict__ onehot, const int32_t *__restrict__ bstar
            const int *__restrict__ go) {
     extern __shared__ __align__(1024) uint8_t l2_smem[];
     __shared__ __align__(8) unsigned long long s_full[L2_STAGES], s_empty[L2_STAGES], s_acc_full[2], s_acc_empty[2];
-    __shared__ volatile int s_meta[L2_STAGES][4];
+    __shared__ __align__(8) int s_meta[L2_STAGES][2];
+    __shared__ int4 s_runs[64];                       // producer: the runs of chunks of the tile being sent
     __shared__ volatile int s_tile[2][4];                      // (I, q, halves present, exit) of the tile in each accumulator
     __shared__ uint32_t s_tmem;
     if (go && !*go) return;
@@ -255,6 +265,10 @@ k_l2_tiles(const uint8_t *__restrict__ onehot, const int32_t *__restrict__ bstar
     const uint32_t tmem_base = s_tmem;
     const int SP = g.SP;
     unsigned long long crumbs = 0;
+#ifdef L2_PROFILE
+    unsigned long long l2_pacc[4] = {0, 0, 0, 0};
+    const long long l2_t0 = clock64();
+#endif
 
     if (warp == 0) {
         // ============================== producer ======================================
@@ -262,25 +276,32 @@ k_l2_tiles(const uint8_t *__restrict__ onehot, const int32_t *__restrict__ bstar
         const int SPB = g.SPB();
         unsigned stage = 0, ph = 0;                      // ring position / phase of the empty barriers
         // the piece (a run of up to L2_G chunks of one first block) waiting to be sent, so that the tile's last one can be marked
-        int p_c = -1, p_n = 0, p_sb = 0, p_cs = 0, p_nch = 0, p_b1 = 0, p_I = 0, p_q = 0;
+        int p_slab = -1, p_n = 0, p_nch = 0, p_b1 = 0, p_I = 0, p_q = 0;
         auto emit = [&](int last) {
             const int b0 = 2 * p_q >= p_I, b1 = p_b1;
             const uint32_t bar = ws_smem_u32(&s_full[stage]);
             const uint32_t bytes = L2_SLAB * (uint32_t)p_n;
             if (lane == 0) {
+                L2_T(w0);
                 ws_mbar_wait(ws_smem_u32(&s_empty[stage]), ph ^ 1);
-                s_meta[stage][0] = p_I; s_meta[stage][1] = p_q; s_meta[stage][2] = b0 | (b1 << 1) | (last << 2) | (p_n << 8);
+                L2_T(w1);
+                L2_ACC(0, w1 - w0); L2_ACC(1, 1);
+                asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(ws_smem_u32(&s_meta[stage][0])), "r"(p_I),
+                             "r"(p_q | (p_n << 20) | ((b0 | (b1 << 1) | (last << 2)) << 24))
+                             : "memory");
                 l2_expect_tx(bar, bytes * (uint32_t)(1 + b0 + b1));
             }
             __syncwarp();
             if (lane < 3 && (lane == 0 || (lane == 1 ? b0 : b1))) {    // lane 0: A, lane 1: B0, lane 2: B1
-                const int blk = lane == 0 ? p_I : 2 * p_q + lane - 1;
+                const int slab = p_slab + (lane ? (2 * p_q - p_I + lane - 1) * p_nch : 0);
                 l2_bulk_g2s(stage0 + stage * L2_STAGE_BYTES + (uint32_t)lane * (L2_G * L2_SLAB),
-                            onehot + ((size_t)p_cs * SP + (size_t)(blk - p_sb) * p_nch + (size_t)(p_c - p_cs)) * L2_SLAB, bytes, bar);
+                            onehot + (size_t)slab * L2_SLAB, bytes, bar);
             }
             if (++stage == L2_STAGES) { stage = 0; ph ^= 1; }
         };
+        const unsigned lt = (1u << lane) - 1u;
         for (;;) {
+            L2_T(s0);
             unsigned t = 0;
             if (lane == 0) t = atomicAdd(tile_counter, 1u);
             t = __shfl_sync(0xffffffffu, t, 0);
@@ -303,60 +324,89 @@ k_l2_tiles(const uint8_t *__restrict__ onehot, const int32_t *__restrict__ bstar
                     end = bs[SPB] >> 5;
                     cb1 = d1 < SP ? max(bs[1 + d1] >> 5, first) : end;       // chunks from cb1 on reach block 2q+1
                 }
-                unsigned hits = __ballot_sync(0xffffffffu, first < end);
-                while (hits) {
-                    const int src = __ffs(hits) - 1;
-                    hits &= hits - 1;
-                    const int c0 = __shfl_sync(0xffffffffu, first, src), c1 = __shfl_sync(0xffffffffu, end, src);
-                    const int cb = __shfl_sync(0xffffffffu, cb1, src), ws = __shfl_sync(0xffffffffu, cs, src);
-                    for (int c = c0; c < c1;) {
-                        // pieces do not straddle cb: the slabs of block 2q+1 only exist from chunk cb on
-                        const int lim = c < cb ? cb : c1;
-                        const int n = min(L2_G, lim - c);
-                        if (p_c >= 0) emit(0);
-                        p_c = c; p_n = n; p_sb = sb0 + src; p_cs = ws; p_nch = c1 - ws; p_b1 = c >= cb; p_I = I; p_q = q;
-                        c += n;
+                // every first block gives up to two runs of chunks: [first, cb1) without and [cb1, end) with block 2q+1
+                // (the slabs of block 2q+1 only exist from chunk cb1 on); the runs go to shared memory in lane order
+                const int nch = end - cs;
+                const int slab0 = cs * SP + (I - sb) * nch - cs;           // + chunk index = slab of (chunk, block I)
+                const unsigned mA = __ballot_sync(0xffffffffu, first < cb1), mB = __ballot_sync(0xffffffffu, cb1 < end);
+                int at = __popc(mA & lt) + __popc(mB & lt);
+                if (first < cb1) s_runs[at++] = make_int4(slab0 + first, nch, cb1 - first, 0);
+                if (cb1 < end) s_runs[at] = make_int4(slab0 + cb1, nch, end - cb1, 1);
+                const int n_runs = __popc(mA) + __popc(mB);
+                __syncwarp();
+                L2_T(s1);
+                if (sb0 == sb_lo) { L2_ACC(2, s1 - s0); L2_ACC(3, 1); }
+                for (int j = 0; j < n_runs; ++j) {
+                    const int4 run = s_runs[j];
+                    for (int o = 0; o < run.z; o += L2_G) {
+                        if (p_slab >= 0) emit(0);
+                        p_slab = run.x + o; p_nch = run.y; p_n = min(L2_G, run.z - o); p_b1 = run.w; p_I = I; p_q = q;
                     }
                 }
+                __syncwarp();
             }
-            if (p_c >= 0) { emit(1); p_c = -1; }
+            if (p_slab >= 0) { emit(1); p_slab = -1; }
         }
+#ifdef L2_PROFILE
+        if (lane == 0) { for (int i = 0; i < 4; ++i) atomicAdd(&l2_prof[i], l2_pacc[i]); atomicAdd(&l2_prof[12], (unsigned long long)(clock64() - l2_t0)); }
+#endif
         if (lane == 0) {                                             // tell the MMA thread to stop
             ws_mbar_wait(ws_smem_u32(&s_empty[stage]), ph ^ 1);
-            s_meta[stage][2] = 8;
+            asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(ws_smem_u32(&s_meta[stage][0])), "r"(0), "r"(8 << 24) : "memory");
             ws_mbar_arrive(ws_smem_u32(&s_full[stage]));
         }
     } else if (warp == 1) {
         // ============================== MMA issue ======================================
         if (lane == 0) {
             unsigned stage = 0, ph = 0, acc = 0, acc_ph[2] = {0, 0};
+#ifdef L2_PROFILE
+            unsigned long long l2_extra[3] = {0, 0, 0};
+#endif
             bool new_tile = true;
             int has = 0;
             for (;;) {
+                L2_T(m0);
                 ws_mbar_wait(ws_smem_u32(&s_full[stage]), ph);
-                const int m_I = s_meta[stage][0], m_q = s_meta[stage][1], m_flags = s_meta[stage][2];
+                L2_T(m1);
+                L2_ACC(0, m1 - m0); L2_ACC(1, 1);
+                int m_I, m_w;
+                asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(m_I), "=r"(m_w) : "r"(ws_smem_u32(&s_meta[stage][0])) : "memory");
+                const int m_q = m_w & 0xfffff, m_flags = m_w >> 24, n = (m_w >> 20) & 15;
                 if (m_flags & 8) {
+#ifdef L2_PROFILE
+                    for (int i = 0; i < 4; ++i) atomicAdd(&l2_prof[4 + i], l2_pacc[i]);
+                    for (int i = 0; i < 3; ++i) atomicAdd(&l2_prof[13 + i], l2_extra[i]);
+#endif
                     ws_mbar_wait(ws_smem_u32(&s_acc_empty[acc]), acc_ph[acc] ^ 1);
                     s_tile[acc][3] = 1;
                     ws_mbar_arrive(ws_smem_u32(&s_acc_full[acc]));
                     break;
                 }
                 if (new_tile) {
+                    L2_T(m2);
                     ws_mbar_wait(ws_smem_u32(&s_acc_empty[acc]), acc_ph[acc] ^ 1);
+                    L2_T(m3);
+                    L2_ACC(2, m3 - m2); L2_ACC(3, 1);
                     new_tile = false;
                     has = 0;
                 }
+                L2_T(m4);
                 l2_fence_after();
                 const uint32_t sa = stage0 + stage * L2_STAGE_BYTES;
                 const uint32_t d = tmem_base + acc * 256u;
                 const uint64_t da = l2_desc(sa), db0 = l2_desc(sa + L2_G * L2_SLAB), db1 = l2_desc(sa + 2 * L2_G * L2_SLAB);
-                const int n = m_flags >> 8;
+                L2_T(m5);
                 for (int i = 0; i < n; ++i) {                       // the next chunk's slab is 4096 B = 256 descriptor units on
                     const uint64_t o = (uint64_t)(i * (int)(L2_SLAB >> 4));
                     if (m_flags & 1) { l2_mma(d, da + o, db0 + o, has & 1); has |= 1; }
                     if (m_flags & 2) { l2_mma(d + 128u, da + o, db1 + o, (has >> 1) & 1); has |= 2; }
                 }
+                L2_T(m6);
                 l2_commit(ws_smem_u32(&s_empty[stage]));
+                L2_T(m7);
+#ifdef L2_PROFILE
+                l2_extra[0] += m5 - m4; l2_extra[1] += m6 - m5; l2_extra[2] += m7 - m6;
+#endif
                 if (m_flags & 4) {
                     s_tile[acc][0] = m_I; s_tile[acc][1] = m_q; s_tile[acc][2] = has; s_tile[acc][3] = 0;
                     asm volatile("fence.acq_rel.cta;" ::: "memory");
@@ -378,10 +428,18 @@ k_l2_tiles(const uint8_t *__restrict__ onehot, const int32_t *__restrict__ bstar
         const int64_t W = g.W;
         unsigned acc = 0, acc_ph[2] = {0, 0};
         for (;;) {
+            L2_T(e0);
             ws_mbar_wait_sleep(ws_smem_u32(&s_acc_full[acc]), acc_ph[acc]);
+            L2_T(e1);
+            L2_ACC(0, e1 - e0); L2_ACC(1, 1);
             acc_ph[acc] ^= 1;
             l2_fence_after();
-            if (s_tile[acc][3]) break;
+            if (s_tile[acc][3]) {
+#ifdef L2_PROFILE
+                if (threadIdx.x == 64) for (int i = 0; i < 4; ++i) atomicAdd(&l2_prof[8 + i], l2_pacc[i]);
+#endif
+                break;
+            }
             const int I = s_tile[acc][0], q = s_tile[acc][1], has = s_tile[acc][2];
             const int pi = 16 * I + 4 * qd + t1l;
             for (int gq = hsel; gq < 8; gq += L2_EP_WARPS / 4) {
@@ -489,6 +547,17 @@ int l2_grow(T **p, int64_t *cap, int64_t need, cudaStream_t st) {
 }
 
 }  // namespace
+
+#ifdef L2_PROFILE
+extern "C" int hx_debug_l2_prof(unsigned long long *out, int reset) {
+    if (cudaMemcpyFromSymbol(out, l2_prof, sizeof(unsigned long long) * 16) != cudaSuccess) return -1;
+    if (reset) {
+        unsigned long long z[16] = {0};
+        cudaMemcpyToSymbol(l2_prof, z, sizeof(z));
+    }
+    return 0;
+}
+#endif
 
 // Scratch owned by the matrix for this path (freed in hx_destroy through hx_l2_free).
 struct hx_l2_scratch {

@@ -477,17 +477,34 @@ def test_config5_recovery_sweep_parity(c_oracle, L):
     orig.close()
 
 
-def test_config4_full_size_bit_exact(c_oracle):
-    """BASELINE.json configs[3] at FULL size (100k ONT-like reads, ~300 SNPs/read, 4.7 G observations) through the
-    cp.async-staged tile kernel, bit for bit against the C oracle."""
-    d = synth.generate(synth.WORKLOADS["ont"])
-    N, W = d["n_snps"], d["max_k"] - 1
+_CONFIG4 = {}
+
+
+@pytest.mark.parametrize("kernel", [0, 3], ids=["auto-tensor-core", "bit-plane-tiles"])
+def test_config4_full_size_bit_exact(c_oracle, kernel):
+    """BASELINE.json configs[3] at FULL size (100k ONT-like reads, ~300 SNPs/read, 4.7 G observations), bit for bit
+    against the C oracle: through the long-read tensor-core kernel (what auto picks) - into a cleared matrix (plain
+    stores) and again on top of it (read-modify-write) - and through the cp.async-staged bit-plane tile kernel."""
+    from gretel_b200.hansel import Hansel, REF_SYMBOLS, REF_UNSYMBOLS
+    if not _CONFIG4:
+        d = synth.generate(synth.WORKLOADS["ont"])
+        N, W = d["n_snps"], d["max_k"] - 1
+        ref, rt = c_oracle.ingest(d["rank"], d["off"], d["codes"], N, W)
+        _CONFIG4.update(d=d, N=N, W=W, ref=ref.astype(np.float32), rt=tuple(int(x) for x in rt))
+    d, N, W, ref, rt = (_CONFIG4[k] for k in ("d", "N", "W", "ref", "rt"))
     assert len(d["rank"]) >= 6 * N                      # dense enough for the staged tiles
-    band, totals = _gpu_band(d["rank"], d["off"], d["codes"], N, W, 0)
-    ref, rt = c_oracle.ingest(d["rank"], d["off"], d["codes"], N, W)
-    assert totals == tuple(int(x) for x in rt)
+    h = Hansel.init_matrix(REF_SYMBOLS, REF_UNSYMBOLS, N, band_w=W)
+    h.set_ingest_kernel(kernel)
+    totals = h.ingest_packed(d["rank"], d["off"], d["codes"])
+    assert totals == rt
     assert totals[1] > 4_000_000_000
-    assert np.array_equal(band, ref.astype(np.float32))
+    if kernel == 0:
+        totals2 = h.ingest_packed(d["rank"], d["off"], d["codes"])
+        assert totals2 == tuple(2 * x for x in rt)
+        ref = ref * 2
+    band = h.band()
+    h.close()
+    assert np.array_equal(band, ref)
 
 
 @pytest.mark.parametrize("seed", range(4))

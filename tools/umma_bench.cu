@@ -85,6 +85,9 @@ int main() {
         {"f8  K-major  N=128 (lbo128 sbo256) ", 1, 128, 0, 128, 256, 1},
         {"f8  K-major  N=80  (lbo128 sbo256) ", 1, 80, 0, 128, 256, 1},
         {"i8  MN-major N=16  lbo1024 same A,B", 0, 16, 1, 1024, 128, 1},
+        {"i8  MN-major N=256 lbo2048 A != B  ", 0, 256, 1, 2048, 128, 0},
+        {"i8  K-major  N=128 A != B          ", 0, 128, 0, 128, 256, 0},
+        {"i8  K-major  N=256 A != B          ", 0, 256, 0, 128, 256, 0},
         {"f8  MN-major N=16  lbo1024 same A,B", 1, 16, 1, 1024, 128, 1},
     };
     for (auto &c : cfgs) {
