@@ -424,16 +424,22 @@ int hx_ingest_host(hx_matrix *h, const int32_t *rank, const int64_t *off, const 
                    int64_t n_reads, int64_t totals[4]) {
     HX_CHECK_ARG(h && totals && n_reads >= 0);
     HX_CUDA(cudaSetDevice(h->device));
-    // Large inputs.  HX_HOST_PIPELINE=dense: re-encode into the dense wire format on the host threads, pipelined
-    // with the copies and the pair expansion - wins when the host has cores to spare (one pass over 27 B/read at
-    // ~10 ns per read and thread against 4.9 ms of PCIe for 10M reads).  Default: the packed arrays as they are, in
-    // a few chunks so that the copy of chunk i+1 overlaps the expansion of chunk i (measured on the 16-core GPU
-    // box: 5.4 ms vs 11.9 ms for 10M reads).
+    // Large inputs travel in chunks so that the copy of chunk i+1 overlaps the expansion of chunk i.  Default
+    // ("slim"): the allele bytes are copied as they are, straight from the caller's memory, while a few host threads
+    // turn the chunk's int32 ranks and int64 offsets (12 of the 27 bytes per read of a 150 bp metagenome) into uint8
+    // rank deltas and SNP counts (2 bytes per read); the device rebuilds rank / offsets with one scan.
+    // HX_HOST_PIPELINE=dense: the alleles are re-encoded too (2 bits each) - fewer bytes, but one pass over every
+    // allele on the host (measured on the 16-core GPU box: 11.9 ms per 10M reads against 5.3 ms as they are);
+    // HX_HOST_PIPELINE=packed: the three arrays as they are in 4 chunks; =off: one copy, one launch.
     const char *pipe_env = getenv("HX_HOST_PIPELINE");
-    if (n_reads >= 200000 && rank && off && codes && pipe_env && !strcmp(pipe_env, "dense")) {
-        const int rc = hx_ingest_host_pipelined(h, rank, off, codes, n_reads);
+    const bool want_dense = pipe_env && !strcmp(pipe_env, "dense");
+    const bool want_slim = !pipe_env || !strcmp(pipe_env, "slim");       // default
+    if (n_reads >= 200000 && rank && off && codes && (want_dense || want_slim)) {
+        int64_t done = 0;
+        const int rc = hx_ingest_host_pipelined(h, rank, off, codes, n_reads, !want_dense, &done);
         if (rc == HX_OK) return hx_ingest_totals(h, totals);
-        if (rc != HX_E_STATE) return rc;            // HX_E_STATE: not sorted by rank -> the packed arrays as they are
+        if (rc != HX_E_STATE) return rc;            // HX_E_STATE: not sorted by rank from read `done` on -> the rest of
+        rank += done; off += done; n_reads -= done; //               the packed arrays as they are (counts just add up)
     }
     if (n_reads > 0) {
         HX_CHECK_ARG(rank && off && codes);

@@ -815,16 +815,64 @@ static inline int64_t al16(int64_t x) { return (x + 15) & ~(int64_t)15; }
 
 static inline uint64_t ld64(const uint8_t *p) { uint64_t v; memcpy(&v, p, 8); return v; }
 
+// A small persistent pool: the per-chunk encoding passes last a few hundred microseconds, which is what creating
+// sixteen threads costs.  One job at a time (callers serialise on the mutex); the workers are detached and sleep on
+// a condition variable between jobs.
+#include <condition_variable>
+#include <functional>
+#include <mutex>
+namespace {
+struct HxPool {
+    std::mutex call_mu, mu;
+    std::condition_variable cv_go, cv_done;
+    std::function<void(int)> job;
+    int n_workers = 0, want = 0, pending = 0;
+    uint64_t gen = 0;
+    void worker(int id) {
+        uint64_t seen = 0;
+        for (;;) {
+            std::unique_lock<std::mutex> lk(mu);
+            cv_go.wait(lk, [&] { return gen != seen; });
+            seen = gen;
+            if (id >= want) continue;
+            std::function<void(int)> f = job;
+            lk.unlock();
+            f(id);
+            lk.lock();
+            if (--pending == 0) cv_done.notify_one();
+        }
+    }
+    void run(int nt, const std::function<void(int)> &f) {
+        std::lock_guard<std::mutex> call(call_mu);
+        if (nt <= 1) { f(0); return; }
+        {
+            std::unique_lock<std::mutex> lk(mu);
+            while (n_workers < nt - 1) {
+                const int id = ++n_workers;                       // worker ids 1..: id 0 is the caller
+                std::thread([this, id] { worker(id); }).detach();
+            }
+            job = f;
+            want = nt;
+            pending = nt - 1;
+            ++gen;
+        }
+        cv_go.notify_all();
+        f(0);
+        std::unique_lock<std::mutex> lk(mu);
+        cv_done.wait(lk, [&] { return pending == 0; });
+    }
+};
+HxPool *hx_pool() { static HxPool *p = new HxPool(); return p; }   // leaked on purpose: workers outlive static destructors
+}  // namespace
+
 template <class F>
 static void run_threads(int nt, F f) {
-    std::vector<std::thread> th;
-    for (int t = 1; t < nt; ++t) th.emplace_back(f, t);
-    f(0);
-    for (auto &x : th) x.join();
+    hx_pool()->run(nt, std::function<void(int)>(f));
 }
 
-int hx_dense_begin(const int64_t *off, int64_t n_reads, int n_threads, int64_t kmax_hint, HxDensePlan *pl) {
+int hx_dense_begin(const int64_t *off, int64_t n_reads, int n_threads, int64_t kmax_hint, HxDensePlan *pl, bool slim) {
     HxDensePlan &P = *pl;
+    P.slim = slim;
     P.c0 = n_reads ? off[0] : 0;
     P.n_codes = n_reads ? off[n_reads] - P.c0 : 0;
     P.n_reads = n_reads;
@@ -846,7 +894,7 @@ int hx_dense_begin(const int64_t *off, int64_t n_reads, int n_threads, int64_t k
     }
     if (km > 65535) { hx_set_error("hx_dense_encode: a read covers more than 65535 SNPs"); return HX_E_ARG; }
     P.klen_bytes = km < 256 ? 1 : 2;
-    const int64_t n_words = (P.n_codes + 15) / 16;
+    const int64_t n_words = slim ? 0 : (P.n_codes + 15) / 16;
     P.o_klen = al16(n_reads);
     P.o_codes2 = P.o_klen + al16(n_reads * P.klen_bytes);
     P.o_exc = P.o_codes2 + al16(n_words * 4);
@@ -872,6 +920,51 @@ int hx_dense_pack(const int32_t *rank, const int64_t *off, const uint8_t *codes,
         std::vector<int32_t> &ed = P.esc_delta[t];
         exc.clear(); ei.clear(); ed.clear();
         int bd = 0;
+        if (P.slim) {
+            // branch-free (vectorisable) pass; the rare escapes (a gap of >= 255 sites, the chunk's first read) are
+            // collected in a second look at the blocks that hold one
+            constexpr int64_t BLK = 4096;
+            for (int64_t r0 = a; r0 < b; r0 += BLK) {
+                const int64_t r1 = std::min(b, r0 + BLK);
+                int64_t neg = 0, kbad = 0, esc = 0;
+                int64_t r = r0;
+                if (r == 0) {
+                    const int64_t d = rank[0], k = off[1] - off[0];
+                    neg |= d; kbad |= (k < 0) | (k > klim); esc |= d >= 255;
+                    blob[0] = (uint8_t)std::min<int64_t>(std::max<int64_t>(d, 0), 255);
+                    if (kb == 1) blob[P.o_klen] = (uint8_t)k; else ((uint16_t *)(blob + P.o_klen))[0] = (uint16_t)k;
+                    r = 1;
+                }
+                if (kb == 1) {
+                    uint8_t *kl = blob + P.o_klen;
+                    for (; r < r1; ++r) {
+                        const int32_t d = rank[r] - rank[r - 1];
+                        const int64_t k = off[r + 1] - off[r];
+                        neg |= d; kbad |= (k < 0) | (k > 255); esc |= d >= 255;
+                        blob[r] = (uint8_t)(d > 255 ? 255 : d);
+                        kl[r] = (uint8_t)k;
+                    }
+                } else {
+                    uint16_t *kl = (uint16_t *)(blob + P.o_klen);
+                    for (; r < r1; ++r) {
+                        const int32_t d = rank[r] - rank[r - 1];
+                        const int64_t k = off[r + 1] - off[r];
+                        neg |= d; kbad |= (k < 0) | (k > 65535); esc |= d >= 255;
+                        blob[r] = (uint8_t)(d > 255 ? 255 : d);
+                        kl[r] = (uint16_t)k;
+                    }
+                }
+                if (neg < 0) bd = 1;
+                if (kbad) bd = 2;
+                if (esc)
+                    for (int64_t q = r0; q < r1; ++q) {
+                        const int64_t d = (int64_t)rank[q] - (q ? (int64_t)rank[q - 1] : 0);
+                        if (d >= 255) { ei.push_back(q); ed.push_back((int32_t)d); }
+                    }
+            }
+            bad[(size_t)t] = bd;
+            return;
+        }
         for (int64_t r = a; r < b; ++r) {
             const int64_t d = (int64_t)rank[r] - (r ? (int64_t)rank[r - 1] : 0), k = off[r + 1] - off[r];
             if (d < 0) bd = 1;

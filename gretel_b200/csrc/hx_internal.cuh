@@ -163,7 +163,8 @@ int hx_ensure_counts_buffer(hx_matrix *h);
 // wire.cu
 void hx_wire_free(hx_matrix *h);
 void hx_wire_trace_dump();
-int hx_ingest_host_pipelined(hx_matrix *h, const int32_t *rank, const int64_t *off, const uint8_t *codes, int64_t n_reads);
+int hx_ingest_host_pipelined(hx_matrix *h, const int32_t *rank, const int64_t *off, const uint8_t *codes, int64_t n_reads,
+                             bool slim, int64_t *done_reads);
 // ingest_long.cu
 int hx_launch_ingest_long(hx_matrix *h, const int32_t *d_rank, const int64_t *d_off,
                           const uint8_t *d_codes, int64_t n_reads, const int *sorted_flag);

@@ -291,16 +291,18 @@ void hx_wire_free(hx_matrix *h) {
     h->decode_stream = nullptr;
 }
 
-extern "C" int hx_ingest_host_dense(hx_matrix *h, const uint8_t *rank_delta, const int64_t *esc_idx,
-                                    const int32_t *esc_delta, int64_t n_esc, const void *klen, int32_t klen_bytes,
-                                    const uint8_t *codes2, const uint32_t *exc_pos, int64_t n_exc, int64_t n_reads,
-                                    int64_t n_codes, int64_t totals[4]) {
+// raw_codes != NULL: the "slim" variant - the allele bytes are copied as they are (from the caller's memory, before
+// the small encoded sections), codes2 / exc_pos are unused
+static int ingest_dense_impl(hx_matrix *h, const uint8_t *rank_delta, const int64_t *esc_idx,
+                             const int32_t *esc_delta, int64_t n_esc, const void *klen, int32_t klen_bytes,
+                             const uint8_t *codes2, const uint32_t *exc_pos, int64_t n_exc, int64_t n_reads,
+                             int64_t n_codes, int64_t totals[4], const uint8_t *raw_codes) {
     HX_CHECK_ARG(h && n_reads >= 0 && n_codes >= 0 && n_esc >= 0 && n_exc >= 0);
     HX_CHECK_ARG(klen_bytes == 1 || klen_bytes == 2);
     HX_CHECK_ARG(n_codes < ((int64_t)1 << 32));
     HX_CUDA(cudaSetDevice(h->device));
     if (n_reads > 0) {
-        HX_CHECK_ARG(rank_delta && klen && (codes2 || n_codes == 0) && (exc_pos || n_exc == 0));
+        HX_CHECK_ARG(rank_delta && klen && (codes2 || raw_codes || n_codes == 0) && (exc_pos || n_exc == 0));
         HX_CHECK_ARG(n_esc == 0 || (esc_idx && esc_delta));
         cudaStream_t st = h->stream;
         if (!h->copy_stream) HX_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
@@ -309,8 +311,9 @@ extern "C" int hx_ingest_host_dense(hx_matrix *h, const uint8_t *rank_delta, con
         hx_wire_set &w = h->wire[h->wire_next];
         h->wire_next = (h->wire_next + 1) % HX_WIRE_SETS;
         const int64_t n_words = (n_codes + 15) / 16;        // 32-bit words of 2-bit alleles
+        const int64_t n_words_sent = raw_codes ? 0 : n_words;
         const int64_t o_rd = 0, o_kl = o_rd + al16(n_reads), o_c2 = o_kl + al16(n_reads * klen_bytes);
-        const int64_t o_ex = o_c2 + al16(n_words * 4), o_ei = o_ex + al16(n_exc * 4), o_ed = o_ei + al16(n_esc * 8);
+        const int64_t o_ex = o_c2 + al16(n_words_sent * 4), o_ei = o_ex + al16(n_exc * 4), o_ed = o_ei + al16(n_esc * 8);
         const int64_t raw_bytes = o_ed + al16(n_esc * 4) + 16;
         const int64_t nblk = (n_reads + 1 + WB - 1) / WB;
         // `consumed` was recorded after the previous use of a staging set: the copy stream may overwrite the set
@@ -342,11 +345,12 @@ extern "C" int hx_ingest_host_dense(hx_matrix *h, const uint8_t *rank_delta, con
         uint8_t *raw = static_cast<uint8_t *>(w.raw);
         // util.dense_packed lays the arrays out in one host buffer exactly like the staging set: one copy
         const uint8_t *hb = rank_delta;
-        const bool blob = (const uint8_t *)klen == hb + o_kl && (n_codes == 0 || codes2 == hb + o_c2) &&
+        if (raw_codes && n_codes) HX_CUDA(cudaMemcpyAsync(w.codes, raw_codes, (size_t)n_codes, cudaMemcpyHostToDevice, cs));
+        const bool blob = (const uint8_t *)klen == hb + o_kl && (n_codes == 0 || raw_codes || codes2 == hb + o_c2) &&
                           (n_exc == 0 || (const uint8_t *)exc_pos == hb + o_ex) &&
                           (n_esc == 0 || ((const uint8_t *)esc_idx == hb + o_ei && (const uint8_t *)esc_delta == hb + o_ed));
         if (blob) {
-            const int64_t used = n_esc ? o_ed + n_esc * 4 : (n_exc ? o_ex + n_exc * 4 : (n_codes ? o_c2 + (n_codes + 3) / 4
+            const int64_t used = n_esc ? o_ed + n_esc * 4 : (n_exc ? o_ex + n_exc * 4 : (n_codes && !raw_codes ? o_c2 + (n_codes + 3) / 4
                                                                                         : o_kl + n_reads * klen_bytes));
             HX_CUDA(cudaMemcpyAsync(raw, hb, (size_t)used, cudaMemcpyHostToDevice, cs));
         } else {
@@ -356,7 +360,7 @@ extern "C" int hx_ingest_host_dense(hx_matrix *h, const uint8_t *rank_delta, con
             HX_CUDA(cudaMemcpyAsync(raw + o_ei, esc_idx, (size_t)(n_esc * 8), cudaMemcpyHostToDevice, cs));
             HX_CUDA(cudaMemcpyAsync(raw + o_ed, esc_delta, (size_t)(n_esc * 4), cudaMemcpyHostToDevice, cs));
         }
-        if (n_codes) HX_CUDA(cudaMemcpyAsync(raw + o_c2, codes2, (size_t)((n_codes + 3) / 4), cudaMemcpyHostToDevice, cs));
+        if (n_codes && !raw_codes) HX_CUDA(cudaMemcpyAsync(raw + o_c2, codes2, (size_t)((n_codes + 3) / 4), cudaMemcpyHostToDevice, cs));
         if (n_exc) HX_CUDA(cudaMemcpyAsync(raw + o_ex, exc_pos, (size_t)(n_exc * 4), cudaMemcpyHostToDevice, cs));
         }
         trace_mark(1, cs);
@@ -380,7 +384,7 @@ extern "C" int hx_ingest_host_dense(hx_matrix *h, const uint8_t *rank_delta, con
                                                             w.rank, w.off, h->N, w.run_end);
         }
         h->launches += 3;
-        if (n_words) {
+        if (n_words_sent) {
             k_unpack_2bit<<<(unsigned)((n_words + 255) / 256), 256, 0, ds>>>(reinterpret_cast<const uint32_t *>(raw + o_c2),
                                                                             n_words, reinterpret_cast<uint4 *>(w.codes));
             h->launches++;
@@ -406,20 +410,31 @@ extern "C" int hx_ingest_host_dense(hx_matrix *h, const uint8_t *rank_delta, con
     return totals ? hx_ingest_totals(h, totals) : HX_OK;
 }
 
+extern "C" int hx_ingest_host_dense(hx_matrix *h, const uint8_t *rank_delta, const int64_t *esc_idx,
+                                    const int32_t *esc_delta, int64_t n_esc, const void *klen, int32_t klen_bytes,
+                                    const uint8_t *codes2, const uint32_t *exc_pos, int64_t n_exc, int64_t n_reads,
+                                    int64_t n_codes, int64_t totals[4]) {
+    return ingest_dense_impl(h, rank_delta, esc_idx, esc_delta, n_esc, klen, klen_bytes, codes2, exc_pos, n_exc, n_reads,
+                             n_codes, totals, nullptr);
+}
+
 
 // ---- host arrays -> matrix, pipelined -------------------------------------------------------------------------
 // hx_ingest_host for large rank-sorted inputs: the packed arrays are cut into a few chunks at read boundaries;
 // each chunk is encoded into the dense wire format by the host threads straight into one of two pinned buffers
 // and enqueued with hx_ingest_host_dense(totals = NULL), so the encoding of chunk i+1 runs while chunk i is
 // copied, decoded and pair-expanded.  HX_E_STATE = the reads are not sorted by rank (the caller ships them as
-// they are); nothing has been enqueued in that case.
-int hx_ingest_host_pipelined(hx_matrix *h, const int32_t *rank, const int64_t *off, const uint8_t *codes, int64_t n_reads) {
+// they are) from read *done_reads on; the reads before it have been enqueued.
+int hx_ingest_host_pipelined(hx_matrix *h, const int32_t *rank, const int64_t *off, const uint8_t *codes, int64_t n_reads,
+                             bool slim, int64_t *done_reads) {
+    *done_reads = 0;
     int nt = 0;
     if (const char *e = getenv("HX_HOST_THREADS")) nt = atoi(e);
     if (nt <= 0) nt = (int)std::min(32u, std::max(1u, std::thread::hardware_concurrency()));
     const int64_t n_codes = off[n_reads] - off[0];
     constexpr int64_t CHUNK_CODES = (int64_t)32 << 20;
-    int n_chunks = (int)std::max<int64_t>(3, (n_codes + CHUNK_CODES - 1) / CHUNK_CODES);
+    int n_chunks = (int)std::max<int64_t>(slim ? 6 : 3, (n_codes + CHUNK_CODES - 1) / CHUNK_CODES);
+    if (slim && nt > 8) nt = 8;                       // a few hundred microseconds of work per chunk
     if ((int64_t)n_chunks > n_reads) n_chunks = (int)n_reads;
     int64_t a = 0;
     static thread_local HxDensePlan plan;             // keeps its list buffers between chunks and calls
@@ -431,7 +446,7 @@ int hx_ingest_host_pipelined(hx_matrix *h, const int32_t *rank, const int64_t *o
             if (b <= a) continue;
         }
         HxDensePlan &P = plan;
-        int rc = hx_dense_begin(off + a, b - a, nt, (int64_t)h->W + 1, &P);
+        int rc = hx_dense_begin(off + a, b - a, nt, (int64_t)h->W + 1, &P, slim);
         if (rc) return rc;
         const int slot = c & 1;
         if (h->pin_busy[slot]) { HX_CUDA(cudaEventSynchronize(h->pin_ev[slot])); h->pin_busy[slot] = false; }
@@ -450,23 +465,20 @@ int hx_ingest_host_pipelined(hx_matrix *h, const int32_t *rank, const int64_t *o
         if (rc) return rc;
         if (!h->pin_ev[slot]) HX_CUDA(cudaEventCreateWithFlags(&h->pin_ev[slot], cudaEventDisableTiming));
         rc = hx_dense_pack(rank + a, off + a, codes, &P, h->pin[slot]);
-        if (rc == HX_E_STATE && c > 0) {           // sorted so far, not here: chunks already went out
-            hx_set_error("hx_ingest_host: reads stop being sorted by rank inside the input");
-            return HX_E_ARG;
-        }
-        if (rc) return rc;
+        if (rc) return rc;                         // HX_E_STATE: not sorted from here on; *done_reads went out already
         rc = ensure_pin(P.bytes, P.head_bytes);
         if (rc) return rc;
         uint8_t *blob = h->pin[slot];
         hx_dense_finish(&P, blob);
-        rc = hx_ingest_host_dense(h, blob, reinterpret_cast<const int64_t *>(blob + P.o_esc_idx),
-                                  reinterpret_cast<const int32_t *>(blob + P.o_esc_delta), P.n_esc, blob + P.o_klen,
-                                  P.klen_bytes, blob + P.o_codes2, reinterpret_cast<const uint32_t *>(blob + P.o_exc), P.n_exc,
-                                  b - a, P.n_codes, nullptr);
+        rc = ingest_dense_impl(h, blob, reinterpret_cast<const int64_t *>(blob + P.o_esc_idx),
+                               reinterpret_cast<const int32_t *>(blob + P.o_esc_delta), P.n_esc, blob + P.o_klen,
+                               P.klen_bytes, blob + P.o_codes2, reinterpret_cast<const uint32_t *>(blob + P.o_exc), P.n_exc,
+                               b - a, P.n_codes, nullptr, slim ? codes + off[a] : nullptr);
         if (rc) return rc;
         HX_CUDA(cudaEventRecord(h->pin_ev[slot], h->copy_stream));      // the slot is free again once its copy is done
         h->pin_busy[slot] = true;
         a = b;
+        *done_reads = a;
     }
     return HX_OK;
 }

@@ -292,9 +292,9 @@ def test_packed_exchange_format_single_gpu(c_oracle):
 
 
 def test_load_from_packed_host_paths_agree(monkeypatch):
-    """util.load_from_packed from host arrays: the chunked copy of the packed arrays (default), the host-side dense
-    encoder pipelined in C (HX_HOST_PIPELINE=dense), the Python-driven dense chunks and one plain copy all give
-    the same matrix."""
+    """util.load_from_packed from host arrays: allele bytes as they are + encoded ranks / SNP counts (default, "slim"),
+    the host-side dense encoder pipelined in C (HX_HOST_PIPELINE=dense), the packed arrays in chunks (=packed), the
+    Python-driven dense chunks and one plain copy (=off) all give the same matrix."""
     from gretel_b200 import util
     d = synth.generate(synth.scaled(synth.WORKLOADS["metagenome"], 250_000))
     N, W = d["n_snps"], d["max_k"] - 1
@@ -303,12 +303,14 @@ def test_load_from_packed_host_paths_agree(monkeypatch):
     ref = a.band()
     monkeypatch.setenv("HX_HOST_PIPELINE", "dense")
     b = util.load_from_packed(d["rank"], d["off"], d["codes"], N, band_w=W)
-    assert b.launch_count() > a.launch_count()              # the decode kernels ran
     monkeypatch.setenv("HX_HOST_PIPELINE", "off")
     c = util.load_from_packed(d["rank"], d["off"], d["codes"], N, band_w=W)
+    assert b.launch_count() > c.launch_count() and a.launch_count() > c.launch_count()    # the decode kernels ran
+    monkeypatch.setenv("HX_HOST_PIPELINE", "packed")
+    f = util.load_from_packed(d["rank"], d["off"], d["codes"], N, band_w=W)
     monkeypatch.delenv("HX_HOST_PIPELINE")
     e = util.load_from_packed(d["rank"], d["off"], d["codes"], N, band_w=W, wire="dense")
-    for x in (b, c, e):
+    for x in (b, c, e, f):
         assert (a.n_slices, a.n_crumbs, a.L) == (x.n_slices, x.n_crumbs, x.L)
         assert np.array_equal(ref, x.band())
     # unsorted input cannot be dense-encoded: the library notices and ships it as it is
@@ -316,10 +318,20 @@ def test_load_from_packed_host_paths_agree(monkeypatch):
     k = np.diff(d["off"])
     off2 = np.concatenate([[0], np.cumsum(k[perm])]).astype(np.int64)
     idx = np.repeat(d["off"][:-1][perm], k[perm]) + (np.arange(int(off2[-1])) - np.repeat(off2[:-1], k[perm]))
-    monkeypatch.setenv("HX_HOST_PIPELINE", "dense")
-    u = util.load_from_packed(d["rank"][perm], off2, d["codes"][idx], N, band_w=W)
-    assert (a.n_slices, a.n_crumbs, a.L) == (u.n_slices, u.n_crumbs, u.L)
-    assert np.array_equal(ref, u.band())
+    for mode in ("dense", "slim"):
+        monkeypatch.setenv("HX_HOST_PIPELINE", mode)
+        u = util.load_from_packed(d["rank"][perm], off2, d["codes"][idx], N, band_w=W)
+        assert (a.n_slices, a.n_crumbs, a.L) == (u.n_slices, u.n_crumbs, u.L)
+        assert np.array_equal(ref, u.band())
+    # sorted at first, shuffled from the middle on: the chunks that were sorted go out encoded, the rest as it is
+    half = len(perm) // 2
+    perm2 = np.concatenate([np.arange(half), half + np.random.default_rng(1).permutation(len(perm) - half)])
+    off3 = np.concatenate([[0], np.cumsum(k[perm2])]).astype(np.int64)
+    idx3 = np.repeat(d["off"][:-1][perm2], k[perm2]) + (np.arange(int(off3[-1])) - np.repeat(off3[:-1], k[perm2]))
+    monkeypatch.delenv("HX_HOST_PIPELINE")
+    v = util.load_from_packed(d["rank"][perm2], off3, d["codes"][idx3], N, band_w=W)
+    assert (a.n_slices, a.n_crumbs, a.L) == (v.n_slices, v.n_crumbs, v.L)
+    assert np.array_equal(ref, v.band())
 
 
 def test_dense_wire_format_rejects_bad_input():
