@@ -62,6 +62,7 @@ SIGNATURES = {
     "hx_bam_contig_length": (_int, [C.c_char_p, C.c_char_p, C.POINTER(_i32)]),
     "hx_probe_expected_rows": (_int, [_p, _p, _p, _p, _i64, _p]),
     "hx_counts_row_sums": (_int, [_p, _p]),
+    "hx_device_math": (_int, [_i32, _int, _p, _p, _i64]),
     "hx_band_to_host": (_int, [_p, _p]),
     "hx_band_from_host": (_int, [_p, _p]),
     "hx_to_dense": (_int, [_p, _p]),

@@ -9,12 +9,13 @@
 //
 // All probability arithmetic is float64 on float32-stored cells, in the same
 // operation order as oracle/hansel_oracle.c, compiled with -fmad=false so that +,-,*,/
-// round exactly like the CPU; only log10/pow may differ from glibc by an ulp.
+// round exactly like the CPU; log10 and 10**x are evaluated exactly as glibc does (glibc_math.cuh).
 #include <limits.h>
 #include <stdlib.h>
 #include <math.h>
 
 #include "hx_internal.cuh"
+#include "glibc_math.cuh"
 
 namespace {
 
@@ -56,7 +57,7 @@ __device__ __forceinline__ double edge_weight_lane(const float *__restrict__ ban
     const bool cand = lane < HX_NSYM && c > 0 && !(skip_unsym && (s == HX_SYM_N || s == HX_SYM_GAP));
     double ws = 0.0;
     if (cand) {
-        double lw = log10(c / total);
+        double lw = hx_gl_log10(c / total);
         const int lmax = L < snp ? L : snp;
         const int v_to = vseen[snp];
         for (int l = 1; l <= lmax; ++l) {
@@ -71,9 +72,9 @@ __device__ __forceinline__ double edge_weight_lane(const float *__restrict__ ban
             }
             const int v = (flags & HX_F_VSITE_TO) ? v_to : vseen[pf];
             const double den = (double)v + sup;
-            if (den != 0) lw += log10((1.0 + obs) / den);
+            if (den != 0) lw += hx_gl_log10((1.0 + obs) / den);
         }
-        ws = pow(10.0, lw);
+        ws = hx_gl_pow10(lw);
     }
     *cand_mask = __ballot_sync(0xffffffffu, cand);
     return ws;
@@ -160,7 +161,7 @@ __global__ void k_walk_terms(const float *__restrict__ band, const int32_t *__re
     bool unsafe = false;
 #pragma unroll
     for (int a = 0; a < HX_NSYM; ++a) {
-        const double t = den != 0 ? log10((1.0 + obs[a]) / den) : 0.0;
+        const double t = den != 0 ? hx_gl_log10((1.0 + obs[a]) / den) : 0.0;
         out[a * 8] = t;
         if (outq) {
             unsafe |= !(fabs(t) < 15.0);
@@ -183,7 +184,7 @@ __global__ void k_walk_logm(const double *__restrict__ scnt, int N, int flags, d
         const double c = scnt[(int64_t)snp * 8 + s];
         const bool cand = c > 0 && !(skip_unsym && (s == HX_SYM_N || s == HX_SYM_GAP));
         if (cand && snp > 0 && c > gbest) { gbest = c; gsym = s; }
-        const double lm = cand ? log10(c / total) : 0.0;
+        const double lm = cand ? hx_gl_log10(c / total) : 0.0;
         logm[(int64_t)snp * 8 + s] = lm;
         if (logmq) logmq[(int64_t)snp * 8 + s] = cand ? __double2int_rn(lm * HX_QSCALE) : HX_QSUNK;
         if (cand) mask |= 1u << s;
@@ -302,7 +303,7 @@ k_walk_tables(const double *__restrict__ terms, const double *__restrict__ logm,
             double tail = 0.0;                           // lookback beyond the band: cells are zero
             for (int l = lt + 1; l <= lmax; ++l) {
                 const int v = (flags & HX_F_VSITE_TO) ? vseen[snp] : vseen[snp - l];
-                if (v != 0) tail += log10(1.0 / (double)v);
+                if (v != 0) tail += hx_gl_log10(1.0 / (double)v);
             }
             const double lwf = (p0 + p1) + tail + v1;
             // best log-weight over the 7 candidate lanes (butterfly), then who is within 1e-6 of it
@@ -326,9 +327,9 @@ k_walk_tables(const double *__restrict__ terms, const double *__restrict__ logm,
                 }
                 for (int l = lt + 1; l <= lmax; ++l) {
                     const int v = (flags & HX_F_VSITE_TO) ? vseen[snp] : vseen[snp - l];
-                    if (v != 0) lw += log10(1.0 / (double)v);
+                    if (v != 0) lw += hx_gl_log10(1.0 / (double)v);
                 }
-                const double ws = cand ? pow(10.0, lw) : 0.0;
+                const double ws = cand ? hx_gl_pow10(lw) : 0.0;
                 double wn, tw;
                 next = normalise_and_pick(ws, cmask, &wn, &tw);
             }
@@ -473,7 +474,7 @@ __device__ __forceinline__ int walk_q_range(const int32_t *__restrict__ termsq, 
                             lw += base[((l - 1) * HX_NSYM + al) * 8];
                         }
                     }
-                    const double ws = cand ? pow(10.0, lw) : 0.0;
+                    const double ws = cand ? hx_gl_pow10(lw) : 0.0;
                     double wn, tw;
                     next = normalise_and_pick(ws, cmask, &wn, &tw);
                 }
@@ -713,7 +714,7 @@ k_walk_wide(const double *__restrict__ terms, const double *__restrict__ logm,
                 p += base[((l - 1) * HX_NSYM + ring[(snp - l) & (HX_RING - 1)]) * 8];
             for (int l = lt + 1 + lane; l <= lmax; l += 32) {       // beyond the band: cells are zero
                 const int v = (flags & HX_F_VSITE_TO) ? vseen[snp] : vseen[snp - l];
-                if (v != 0) p += log10(1.0 / (double)v);
+                if (v != 0) p += hx_gl_log10(1.0 / (double)v);
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
@@ -745,10 +746,10 @@ k_walk_wide(const double *__restrict__ terms, const double *__restrict__ logm,
                         lw += base[((l - 1) * HX_NSYM + ring[(snp - l) & (HX_RING - 1)]) * 8];
                     for (int l = lt + 1; l <= lmax; ++l) {
                         const int v = (flags & HX_F_VSITE_TO) ? vseen[snp] : vseen[snp - l];
-                        if (v != 0) lw += log10(1.0 / (double)v);
+                        if (v != 0) lw += hx_gl_log10(1.0 / (double)v);
                     }
                 }
-                const double ws = lcand ? pow(10.0, lw) : 0.0;
+                const double ws = lcand ? hx_gl_pow10(lw) : 0.0;
                 double wn, tw;
                 next = normalise_and_pick(ws, cmask, &wn, &tw);
             }
@@ -777,8 +778,8 @@ __global__ void k_path_stats(const double *__restrict__ scnt_cur, const double *
     const double to = scnt_orig[(int64_t)snp * 8 + 7];
     const double mo = to == 0 ? 0.0 : scnt_orig[(int64_t)snp * 8 + s] / to;
     const int64_t stride = (int64_t)N + 2;
-    site[snp] = log10(m);
-    site[stride + snp] = log10(mo);
+    site[snp] = hx_gl_log10(m);
+    site[stride + snp] = hx_gl_log10(mo);
     site[2 * stride + snp] = m;
 }
 
@@ -1255,3 +1256,30 @@ int hx_reweight_matrix(hx_matrix *h, double ratio) {
 }
 
 }  // extern "C"
+
+// ---- diagnostic: the device's log10 / 10**x on host arrays (hanselx.h) ---------------------------------------------
+namespace {
+__global__ void k_device_math(const double *__restrict__ x, double *__restrict__ y, int64_t n, int which) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = which ? hx_gl_pow10(x[i]) : hx_gl_log10(x[i]);
+}
+}  // namespace
+
+extern "C" int hx_device_math(int32_t device, int which, const double *x, double *y, int64_t n) {
+    HX_CHECK_ARG(x && y && n >= 0 && (which == 0 || which == 1));
+    if (n == 0) return HX_OK;
+    HX_CUDA(cudaSetDevice(device));
+    double *dx = nullptr, *dy = nullptr;
+    HX_CUDA(cudaMalloc((void **)&dx, sizeof(double) * (size_t)n));
+    if (cudaMalloc((void **)&dy, sizeof(double) * (size_t)n) != cudaSuccess) { cudaFree(dx); hx_set_error("hx_device_math: out of memory"); return HX_E_NOMEM; }
+    cudaError_t e = cudaMemcpy(dx, x, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        k_device_math<<<(unsigned)((n + 255) / 256), 256>>>(dx, dy, n, which);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(y, dy, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost);
+    cudaFree(dx);
+    cudaFree(dy);
+    if (e != cudaSuccess) { hx_set_error("hx_device_math: %s", cudaGetErrorString(e)); return HX_E_CUDA; }
+    return HX_OK;
+}

@@ -225,6 +225,12 @@ int hx_probe_expected_rows(hx_matrix *h, const int32_t *d_rank, const int64_t *d
 /* Row sums of the pending integer counts (after any cross-GPU exchange): d_rows[N+2] (device, uint64). */
 int hx_counts_row_sums(hx_matrix *h, uint64_t *d_rows);
 
+/* ---- the recovery kernels' log10 / 10**x (diagnostic; tests) ------------------------ */
+/* y[i] = log10(x[i]) (which = 0) or 10**x[i] (which = 1) evaluated ON THE DEVICE by the routines the recovery kernels
+ * use: a transcription of glibc's log10() / pow() (what math.log10 and float ** reach at gretel/gretel.py:166-187),
+ * bit-identical to the host's libm on this image.  x, y: host arrays of n doubles. */
+int hx_device_math(int32_t device, int which, const double *x, double *y, int64_t n);
+
 /* ---- bulk matrix I/O (tests, --dumpmatrix gretel/cmd.py:81-82) ------------------- */
 int hx_band_to_host(hx_matrix *h, float *out /* (N+2)*W*49 */);
 int hx_band_from_host(hx_matrix *h, const float *in);
