@@ -25,6 +25,8 @@
 //                  cell has exactly one writer: no atomics.
 // Rank-sortedness is not needed (the counting sort orders the reads itself).
 #include <limits.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "hx_internal.cuh"
 #include "ingest_common.cuh"
@@ -33,20 +35,19 @@
 namespace {
 
 constexpr int L2_G = 4;                             // chunks (of one first block) per pipeline stage
-constexpr int L2_STAGES = 3;
-constexpr int L2_EP_WARPS = 16;
-constexpr int L2_THREADS = (2 + L2_EP_WARPS) * 32;
+constexpr int L2_STAGES = 4;
+constexpr int L2_EP_WARPS = 8;
+constexpr int L2_PW = L2_STAGES;                        // producer warps: one per ring stage
+constexpr int L2_THREADS = (L2_PW + 1 + L2_EP_WARPS) * 32;
+constexpr int L2P_STAGES = 5;
+constexpr int L2P_PW = L2P_STAGES;                      // the CTA-pair variant: its producer warps
+constexpr int L2P_THREADS = (L2P_PW + 1 + L2_EP_WARPS) * 32;
 constexpr uint32_t L2_SLAB = 4096;                 // one chunk x one block: 32 reads x 128 one-hot bytes
 constexpr uint32_t L2_STAGE_BYTES = 3 * L2_G * L2_SLAB;   // A (first sites), B0, B1 (second sites), L2_G chunks each
 constexpr int L2_STG_WORDS = 4 * 196;              // epilogue staging per warp: 4 second sites x 4 cells x 49 counters
 
 #ifdef L2_PROFILE
 __device__ unsigned long long l2_prof[16];
-#define L2_T(var) const long long var = clock64()
-#define L2_ACC(slot, expr) l2_pacc[slot] += (unsigned long long)(expr)
-#else
-#define L2_T(var)
-#define L2_ACC(slot, expr)
 #endif
 
 struct L2Geom {
@@ -222,18 +223,110 @@ __device__ __forceinline__ void l2_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// One finished accumulator (128 TMEM lanes = 16 first sites x 8 symbols of block I; 256 columns = 32 second sites x 8
+// symbols of blocks 2q, 2q+1) -> the band.  Called by every epilogue warp: quarter qd of the lanes (first sites 4qd..4qd+3),
+// every (L2_EP_WARPS/4)-th group of four second sites starting at hsel.
+template <bool FUSED, bool FRESH>
+__device__ __forceinline__ void l2_epilogue_tile(uint32_t tmem_acc, int I, int q, int has, uint32_t *stg, int lane, int qd,
+                                                 int hsel, const HxCnt &cnt, const L2Geom &g, unsigned long long &crumbs) {
+    const int t1l = lane >> 3, a = lane & 7;
+    const bool row_ok = a != HX_SYM_N && a != HX_SYM_GAP && a != 7;        // util.py:258: N and _ never come first
+    const int my_stg = (3 - t1l) * 49 + a * 7;
+    const int64_t W = g.W;
+    const int pi = 16 * I + 4 * qd + t1l;
+    for (int gq = hsel; gq < 8; gq += L2_EP_WARPS / 4) {
+        const int half = gq >> 2;
+        if (!((has >> half) & 1)) continue;
+        uint32_t v[32];
+        l2_ld32(tmem_acc + (uint32_t)gq * 32u + ((uint32_t)(qd * 32) << 16), v);
+        const int pj0 = 16 * (2 * q + half) + (gq & 3) * 4;
+        if (a != 7) {
+#pragma unroll
+            for (int t2l = 0; t2l < 4; ++t2l) {
+                const bool ok = row_ok && pj0 + t2l > pi;
+#pragma unroll
+                for (int b = 0; b < 7; ++b) stg[t2l * 196 + my_stg + b] = ok ? v[t2l * 8 + b] : 0u;
+            }
+        }
+        __syncwarp();
+        // cells (pi, pj) of my quarter's four first sites are contiguous in band row pj: staging word i of
+        // second site t2l lives at band word gbase + i
+        uint32_t x[28];
+#pragma unroll
+        for (int t2l = 0; t2l < 4; ++t2l)
+#pragma unroll
+            for (int k = 0; k < 7; ++k) {
+                const int i = k * 32 + lane;
+                x[t2l * 7 + k] = i < 196 ? stg[t2l * 196 + i] : 0u;
+            }
+        __syncwarp();
+        if (!FUSED && FRESH) {
+            // the band is still all zero (first ingestion into this matrix): plain stores, no loads.  Where the
+            // warp's four cells lie inside the band every word is written, zeros too (whole sectors: nothing
+            // for L2 to fetch); the sentinel cells (pi = 0, pj = N+1) are never touched.
+            const int pi_lo = 16 * I + 4 * qd;
+#pragma unroll
+            for (int t2l = 0; t2l < 4; ++t2l) {
+                const int64_t pj = pj0 + t2l;
+                const bool full = pi_lo >= 1 && pj <= g.N && pj - (pi_lo + 3) >= 1 && pj - pi_lo <= W;
+                uint32_t *gb = cnt.local + (pj * W + pj - 16 * I - 4 * qd - 4) * HX_CELL + lane;
+#pragma unroll
+                for (int k = 0; k < 7; ++k) {
+                    const uint32_t xv = x[t2l * 7 + k];
+                    if (xv || (full && k * 32 + lane < 196)) gb[k * 32] = xv;
+                    crumbs += xv;
+                }
+            }
+        } else if (!FUSED) {
+            uint32_t old[28];
+#pragma unroll
+            for (int t2l = 0; t2l < 4; ++t2l) {
+                const int64_t pj = pj0 + t2l;
+                uint32_t *gb = cnt.local + (pj * W + pj - 16 * I - 4 * qd - 4) * HX_CELL + lane;
+#pragma unroll
+                for (int k = 0; k < 7; ++k)
+                    if (x[t2l * 7 + k]) old[t2l * 7 + k] = gb[k * 32];
+            }
+#pragma unroll
+            for (int t2l = 0; t2l < 4; ++t2l) {
+                const int64_t pj = pj0 + t2l;
+                uint32_t *gb = cnt.local + (pj * W + pj - 16 * I - 4 * qd - 4) * HX_CELL + lane;
+#pragma unroll
+                for (int k = 0; k < 7; ++k)
+                    if (x[t2l * 7 + k]) {
+                        gb[k * 32] = old[t2l * 7 + k] + x[t2l * 7 + k];
+                        crumbs += x[t2l * 7 + k];
+                    }
+            }
+        } else {
+#pragma unroll
+            for (int t2l = 0; t2l < 4; ++t2l) {
+                const int64_t pj = pj0 + t2l;
+                uint32_t *base = cnt.peer[pj / cnt.rows_per];
+                uint32_t *gb = base + (pj * W + pj - 16 * I - 4 * qd - 4) * HX_CELL + lane;
+#pragma unroll
+                for (int k = 0; k < 7; ++k)
+                    if (x[t2l * 7 + k]) {
+                        atomicAdd(gb + k * 32, x[t2l * 7 + k]);
+                        crumbs += x[t2l * 7 + k];
+                    }
+            }
+        }
+    }
+}
+
 // stage meta = (I, q, flags): flags 1 = B0 present, 2 = B1 present, 4 = last chunk of the tile, 8 = exit
 
 template <bool FUSED, bool FRESH>
 __global__ void __launch_bounds__(L2_THREADS, 1)
-k_l2_tiles(const uint8_t *__restrict__ onehot, const int32_t *__restrict__ bstart, const int32_t *__restrict__ chunk_eb,
-           L2Geom g, const HxCnt cnt_in, unsigned long long *__restrict__ totals, unsigned *__restrict__ tile_counter,
-           const int *__restrict__ go) {
+k_l2_tiles(const uint8_t *__restrict__ onehot, const int32_t *__restrict__ bstart, L2Geom g, const HxCnt cnt_in,
+           unsigned long long *__restrict__ totals, const int *__restrict__ go) {
     extern __shared__ __align__(1024) uint8_t l2_smem[];
     __shared__ __align__(8) unsigned long long s_full[L2_STAGES], s_empty[L2_STAGES], s_acc_full[2], s_acc_empty[2];
     __shared__ __align__(8) int s_meta[L2_STAGES][2];
-    __shared__ int4 s_runs[64];                       // producer: the runs of chunks of the tile being sent
-    __shared__ volatile int s_tile[2][4];                      // (I, q, halves present, exit) of the tile in each accumulator
+    __shared__ int4 s_runs[L2_STAGES][64];            // per producer warp: the runs of chunks of the tile being sent
+    __shared__ int2 s_pend[L2_STAGES][L2_G];
+    __shared__ volatile int s_tile[2][4];             // (I, q, halves present, exit) of the tile in each accumulator
     __shared__ uint32_t s_tmem;
     if (go && !*go) return;
     HxCnt cnt = cnt_in;
@@ -265,48 +358,66 @@ k_l2_tiles(const uint8_t *__restrict__ onehot, const int32_t *__restrict__ bstar
     const uint32_t tmem_base = s_tmem;
     const int SP = g.SP;
     unsigned long long crumbs = 0;
-#ifdef L2_PROFILE
-    unsigned long long l2_pacc[4] = {0, 0, 0, 0};
-    const long long l2_t0 = clock64();
-#endif
 
-    if (warp == 0) {
-        // ============================== producer ======================================
+    if (warp < L2_PW) {
+        // ============================== producers ======================================
+        // A lone warp needs several hundred cycles per stage (barrier wait, meta, three bulk copies), more than the
+        // MMAs of the stage take, so there is one producer warp per ring stage: every warp walks the same static tile
+        // list and derives the same sequence of pieces (runs of up to L2_G chunks of one first block); warp w sends the
+        // pieces k = w (mod L2_PW), always into stage w.
         const int64_t n_tiles = (int64_t)g.NB * g.nq;
         const int SPB = g.SPB();
-        unsigned stage = 0, ph = 0;                      // ring position / phase of the empty barriers
-        // the piece (a run of up to L2_G chunks of one first block) waiting to be sent, so that the tile's last one can be marked
-        int p_slab = -1, p_n = 0, p_nch = 0, p_b1 = 0, p_I = 0, p_q = 0;
+        const uint32_t bar_full = ws_smem_u32(&s_full[warp]), bar_empty = ws_smem_u32(&s_empty[warp]);
+        const uint32_t dst0 = stage0 + (uint32_t)warp * L2_STAGE_BYTES;
+        int4 *const runs = s_runs[warp];
+        int2 *const pend = s_pend[warp];                 // the stage being collected: up to L2_G chunks (slab of block I, nch | b1)
+        unsigned ph = 0, turn = 0;                       // phase of my stage; whose stage comes next
+        int n_pend = 0, p_I = 0, p_q = 0;
+        // a stage = up to L2_G chunks of the tile, whatever first block they belong to: one 4 KB bulk copy per chunk
+        // and operand (lane = 3 * slot + operand)
         auto emit = [&](int last) {
-            const int b0 = 2 * p_q >= p_I, b1 = p_b1;
-            const uint32_t bar = ws_smem_u32(&s_full[stage]);
-            const uint32_t bytes = L2_SLAB * (uint32_t)p_n;
-            if (lane == 0) {
-                L2_T(w0);
-                ws_mbar_wait(ws_smem_u32(&s_empty[stage]), ph ^ 1);
-                L2_T(w1);
-                L2_ACC(0, w1 - w0); L2_ACC(1, 1);
-                asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(ws_smem_u32(&s_meta[stage][0])), "r"(p_I),
-                             "r"(p_q | (p_n << 20) | ((b0 | (b1 << 1) | (last << 2)) << 24))
-                             : "memory");
-                l2_expect_tx(bar, bytes * (uint32_t)(1 + b0 + b1));
+            if (turn == (unsigned)warp) {
+                const int b0 = 2 * p_q >= p_I;
+                __syncwarp();
+                const int slot = lane / 3, op = lane - 3 * slot;
+                int2 c = make_int2(0, 0);
+                if (slot < n_pend) c = pend[slot];
+                const int b1 = (unsigned)c.y >> 31, nch = c.y & 0x7fffffff;
+                const bool mine = slot < n_pend && (op == 0 || (op == 1 ? b0 : b1));
+                const unsigned b1mask = __ballot_sync(0xffffffffu, slot < n_pend && op == 2 && b1);   // bit 3*slot+2
+                const unsigned n_copies = __popc(__ballot_sync(0xffffffffu, mine));
+                if (lane == 0) {
+                    ws_mbar_wait(bar_empty, ph ^ 1);
+                    // meta: I | q, chunks, B0 present, last, per-chunk "B1 present"
+                    unsigned b1bits = 0;
+#pragma unroll
+                    for (int i = 0; i < L2_G; ++i) b1bits |= ((b1mask >> (3 * i + 2)) & 1u) << i;
+                    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(ws_smem_u32(&s_meta[warp][0])), "r"(p_I),
+                                 "r"(p_q | (n_pend << 20) | ((b0 | (last << 2)) << 24) | (b1bits << 28))
+                                 : "memory");
+#ifdef L2_NOCOPY
+                    l2_expect_tx(bar_full, 0);
+#else
+                    l2_expect_tx(bar_full, L2_SLAB * n_copies);
+#endif
+                }
+                __syncwarp();
+#ifdef L2_NOCOPY
+                if (false) {
+#else
+                if (mine) {
+#endif
+                    const int slab = c.x + (op ? (2 * p_q - p_I + op - 1) * nch : 0);
+                    l2_bulk_g2s(dst0 + (uint32_t)(op * L2_G + slot) * L2_SLAB, onehot + (size_t)slab * L2_SLAB, L2_SLAB, bar_full);
+                }
+                ph ^= 1;
             }
-            __syncwarp();
-            if (lane < 3 && (lane == 0 || (lane == 1 ? b0 : b1))) {    // lane 0: A, lane 1: B0, lane 2: B1
-                const int slab = p_slab + (lane ? (2 * p_q - p_I + lane - 1) * p_nch : 0);
-                l2_bulk_g2s(stage0 + stage * L2_STAGE_BYTES + (uint32_t)lane * (L2_G * L2_SLAB),
-                            onehot + (size_t)slab * L2_SLAB, bytes, bar);
-            }
-            if (++stage == L2_STAGES) { stage = 0; ph ^= 1; }
+            if (++turn == L2_PW) turn = 0;
+            n_pend = 0;
         };
         const unsigned lt = (1u << lane) - 1u;
-        for (;;) {
-            L2_T(s0);
-            unsigned t = 0;
-            if (lane == 0) t = atomicAdd(tile_counter, 1u);
-            t = __shfl_sync(0xffffffffu, t, 0);
-            if ((int64_t)t >= n_tiles) break;
-            const int I = (int)(t / (unsigned)g.nq), q = (I >> 1) + (int)(t % (unsigned)g.nq);
+        for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            const int I = (int)(t / g.nq), q = (I >> 1) + (int)(t % g.nq);
             const int jmax = min(I + SP - 1, g.NB - 1);
             if (2 * q > jmax) continue;
             const int jlo = max(2 * q, I);
@@ -330,52 +441,53 @@ k_l2_tiles(const uint8_t *__restrict__ onehot, const int32_t *__restrict__ bstar
                 const int slab0 = cs * SP + (I - sb) * nch - cs;           // + chunk index = slab of (chunk, block I)
                 const unsigned mA = __ballot_sync(0xffffffffu, first < cb1), mB = __ballot_sync(0xffffffffu, cb1 < end);
                 int at = __popc(mA & lt) + __popc(mB & lt);
-                if (first < cb1) s_runs[at++] = make_int4(slab0 + first, nch, cb1 - first, 0);
-                if (cb1 < end) s_runs[at] = make_int4(slab0 + cb1, nch, end - cb1, 1);
+                if (first < cb1) runs[at++] = make_int4(slab0 + first, nch, cb1 - first, 0);
+                if (cb1 < end) runs[at] = make_int4(slab0 + cb1, nch, end - cb1, 1);
                 const int n_runs = __popc(mA) + __popc(mB);
                 __syncwarp();
-                L2_T(s1);
-                if (sb0 == sb_lo) { L2_ACC(2, s1 - s0); L2_ACC(3, 1); }
                 for (int j = 0; j < n_runs; ++j) {
-                    const int4 run = s_runs[j];
-                    for (int o = 0; o < run.z; o += L2_G) {
-                        if (p_slab >= 0) emit(0);
-                        p_slab = run.x + o; p_nch = run.y; p_n = min(L2_G, run.z - o); p_b1 = run.w; p_I = I; p_q = q;
+                    const int4 run = runs[j];
+                    for (int o = 0; o < run.z; ++o) {
+                        if (n_pend == L2_G) emit(0);
+                        if (turn == (unsigned)warp && lane == 0) pend[n_pend] = make_int2(run.x + o, run.y | (run.w << 31));
+                        ++n_pend; p_I = I; p_q = q;
                     }
                 }
                 __syncwarp();
             }
-            if (p_slab >= 0) { emit(1); p_slab = -1; }
+            if (n_pend) emit(1);
         }
-#ifdef L2_PROFILE
-        if (lane == 0) { for (int i = 0; i < 4; ++i) atomicAdd(&l2_prof[i], l2_pacc[i]); atomicAdd(&l2_prof[12], (unsigned long long)(clock64() - l2_t0)); }
-#endif
-        if (lane == 0) {                                             // tell the MMA thread to stop
-            ws_mbar_wait(ws_smem_u32(&s_empty[stage]), ph ^ 1);
-            asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(ws_smem_u32(&s_meta[stage][0])), "r"(0), "r"(8 << 24) : "memory");
-            ws_mbar_arrive(ws_smem_u32(&s_full[stage]));
+        if (turn == (unsigned)warp && lane == 0) {                   // the warp whose turn it is tells the MMA thread to stop
+            ws_mbar_wait(bar_empty, ph ^ 1);
+            asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(ws_smem_u32(&s_meta[warp][0])), "r"(0), "r"(8 << 24) : "memory");
+            ws_mbar_arrive(bar_full);
         }
-    } else if (warp == 1) {
+    } else if (warp == L2_PW) {
         // ============================== MMA issue ======================================
         if (lane == 0) {
             unsigned stage = 0, ph = 0, acc = 0, acc_ph[2] = {0, 0};
-#ifdef L2_PROFILE
-            unsigned long long l2_extra[3] = {0, 0, 0};
-#endif
             bool new_tile = true;
             int has = 0;
+#ifdef L2_PROFILE
+            unsigned long long pw = 0, pi_ = 0, pa = 0, pn = 0, pm = 0;
+            const long long t_begin = clock64();
+#endif
             for (;;) {
-                L2_T(m0);
+#ifdef L2_PROFILE
+                const long long c0 = clock64();
+#endif
                 ws_mbar_wait(ws_smem_u32(&s_full[stage]), ph);
-                L2_T(m1);
-                L2_ACC(0, m1 - m0); L2_ACC(1, 1);
+#ifdef L2_PROFILE
+                const long long c1 = clock64(); pw += c1 - c0; pn++;
+#endif
                 int m_I, m_w;
                 asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(m_I), "=r"(m_w) : "r"(ws_smem_u32(&s_meta[stage][0])) : "memory");
-                const int m_q = m_w & 0xfffff, m_flags = m_w >> 24, n = (m_w >> 20) & 15;
+                const int m_q = m_w & 0xfffff, m_flags = (m_w >> 24) & 15, n = (m_w >> 20) & 15;
+                const unsigned m_b1 = (unsigned)m_w >> 28;
                 if (m_flags & 8) {
 #ifdef L2_PROFILE
-                    for (int i = 0; i < 4; ++i) atomicAdd(&l2_prof[4 + i], l2_pacc[i]);
-                    for (int i = 0; i < 3; ++i) atomicAdd(&l2_prof[13 + i], l2_extra[i]);
+                    atomicAdd(&l2_prof[0], pw); atomicAdd(&l2_prof[1], pi_); atomicAdd(&l2_prof[2], pa); atomicAdd(&l2_prof[3], pn); atomicAdd(&l2_prof[4], pm);
+                    atomicAdd(&l2_prof[5], (unsigned long long)(clock64() - t_begin));
 #endif
                     ws_mbar_wait(ws_smem_u32(&s_acc_empty[acc]), acc_ph[acc] ^ 1);
                     s_tile[acc][3] = 1;
@@ -383,30 +495,32 @@ k_l2_tiles(const uint8_t *__restrict__ onehot, const int32_t *__restrict__ bstar
                     break;
                 }
                 if (new_tile) {
-                    L2_T(m2);
+#ifdef L2_PROFILE
+                    const long long c2 = clock64();
+#endif
                     ws_mbar_wait(ws_smem_u32(&s_acc_empty[acc]), acc_ph[acc] ^ 1);
-                    L2_T(m3);
-                    L2_ACC(2, m3 - m2); L2_ACC(3, 1);
+#ifdef L2_PROFILE
+                    pa += clock64() - c2;
+#endif
                     new_tile = false;
                     has = 0;
                 }
-                L2_T(m4);
+#ifdef L2_PROFILE
+                const long long c3 = clock64();
+#endif
                 l2_fence_after();
                 const uint32_t sa = stage0 + stage * L2_STAGE_BYTES;
                 const uint32_t d = tmem_base + acc * 256u;
                 const uint64_t da = l2_desc(sa), db0 = l2_desc(sa + L2_G * L2_SLAB), db1 = l2_desc(sa + 2 * L2_G * L2_SLAB);
-                L2_T(m5);
                 for (int i = 0; i < n; ++i) {                       // the next chunk's slab is 4096 B = 256 descriptor units on
                     const uint64_t o = (uint64_t)(i * (int)(L2_SLAB >> 4));
                     if (m_flags & 1) { l2_mma(d, da + o, db0 + o, has & 1); has |= 1; }
-                    if (m_flags & 2) { l2_mma(d + 128u, da + o, db1 + o, (has >> 1) & 1); has |= 2; }
+                    if ((m_b1 >> i) & 1) { l2_mma(d + 128u, da + o, db1 + o, (has >> 1) & 1); has |= 2; }
                 }
-                L2_T(m6);
-                l2_commit(ws_smem_u32(&s_empty[stage]));
-                L2_T(m7);
 #ifdef L2_PROFILE
-                l2_extra[0] += m5 - m4; l2_extra[1] += m6 - m5; l2_extra[2] += m7 - m6;
+                pi_ += clock64() - c3; pm += n * ((m_flags & 1) != 0) + __popc(m_b1);
 #endif
+                l2_commit(ws_smem_u32(&s_empty[stage]));
                 if (m_flags & 4) {
                     s_tile[acc][0] = m_I; s_tile[acc][1] = m_q; s_tile[acc][2] = has; s_tile[acc][3] = 0;
                     asm volatile("fence.acq_rel.cta;" ::: "memory");
@@ -420,107 +534,16 @@ k_l2_tiles(const uint8_t *__restrict__ onehot, const int32_t *__restrict__ bstar
         }
     } else {
         // ============================== epilogue ======================================
-        const int ew = warp - 2, qd = warp & 3, hsel = ew >> 2;
+        const int ew = warp - (L2_PW + 1), qd = warp & 3, hsel = ew >> 2;
         uint32_t *const stg = staging + (size_t)ew * L2_STG_WORDS;
-        const int t1l = lane >> 3, a = lane & 7;
-        const bool row_ok = a != HX_SYM_N && a != HX_SYM_GAP && a != 7;        // util.py:258: N and _ never come first
-        const int my_stg = (3 - t1l) * 49 + a * 7;
-        const int64_t W = g.W;
         unsigned acc = 0, acc_ph[2] = {0, 0};
         for (;;) {
-            L2_T(e0);
             ws_mbar_wait_sleep(ws_smem_u32(&s_acc_full[acc]), acc_ph[acc]);
-            L2_T(e1);
-            L2_ACC(0, e1 - e0); L2_ACC(1, 1);
             acc_ph[acc] ^= 1;
             l2_fence_after();
-            if (s_tile[acc][3]) {
-#ifdef L2_PROFILE
-                if (threadIdx.x == 64) for (int i = 0; i < 4; ++i) atomicAdd(&l2_prof[8 + i], l2_pacc[i]);
-#endif
-                break;
-            }
+            if (s_tile[acc][3]) break;
             const int I = s_tile[acc][0], q = s_tile[acc][1], has = s_tile[acc][2];
-            const int pi = 16 * I + 4 * qd + t1l;
-            for (int gq = hsel; gq < 8; gq += L2_EP_WARPS / 4) {
-                const int half = gq >> 2;
-                if (!((has >> half) & 1)) continue;
-                uint32_t v[32];
-                l2_ld32(tmem_base + acc * 256u + (uint32_t)gq * 32u + ((uint32_t)(qd * 32) << 16), v);
-                const int pj0 = 16 * (2 * q + half) + (gq & 3) * 4;
-                if (a != 7) {
-#pragma unroll
-                    for (int t2l = 0; t2l < 4; ++t2l) {
-                        const bool ok = row_ok && pj0 + t2l > pi;
-#pragma unroll
-                        for (int b = 0; b < 7; ++b) stg[t2l * 196 + my_stg + b] = ok ? v[t2l * 8 + b] : 0u;
-                    }
-                }
-                __syncwarp();
-                // cells (pi, pj) of my quarter's four first sites are contiguous in band row pj: staging word i of
-                // second site t2l lives at band word gbase + i
-                uint32_t x[28];
-#pragma unroll
-                for (int t2l = 0; t2l < 4; ++t2l)
-#pragma unroll
-                    for (int k = 0; k < 7; ++k) {
-                        const int i = k * 32 + lane;
-                        x[t2l * 7 + k] = i < 196 ? stg[t2l * 196 + i] : 0u;
-                    }
-                __syncwarp();
-                if (!FUSED && FRESH) {
-                    // the band is still all zero (first ingestion into this matrix): plain stores, no loads.  Where the
-                    // warp's four cells lie inside the band every word is written, zeros too (whole sectors: nothing
-                    // for L2 to fetch); the sentinel cells (pi = 0, pj = N+1) are never touched.
-                    const int pi_lo = 16 * I + 4 * qd;
-#pragma unroll
-                    for (int t2l = 0; t2l < 4; ++t2l) {
-                        const int64_t pj = pj0 + t2l;
-                        const bool full = pi_lo >= 1 && pj <= g.N && pj - (pi_lo + 3) >= 1 && pj - pi_lo <= W;
-                        uint32_t *gb = cnt.local + (pj * W + pj - 16 * I - 4 * qd - 4) * HX_CELL + lane;
-#pragma unroll
-                        for (int k = 0; k < 7; ++k) {
-                            const uint32_t xv = x[t2l * 7 + k];
-                            if (xv || (full && k * 32 + lane < 196)) gb[k * 32] = xv;
-                            crumbs += xv;
-                        }
-                    }
-                } else if (!FUSED) {
-                    uint32_t old[28];
-#pragma unroll
-                    for (int t2l = 0; t2l < 4; ++t2l) {
-                        const int64_t pj = pj0 + t2l;
-                        uint32_t *gb = cnt.local + (pj * W + pj - 16 * I - 4 * qd - 4) * HX_CELL + lane;
-#pragma unroll
-                        for (int k = 0; k < 7; ++k)
-                            if (x[t2l * 7 + k]) old[t2l * 7 + k] = gb[k * 32];
-                    }
-#pragma unroll
-                    for (int t2l = 0; t2l < 4; ++t2l) {
-                        const int64_t pj = pj0 + t2l;
-                        uint32_t *gb = cnt.local + (pj * W + pj - 16 * I - 4 * qd - 4) * HX_CELL + lane;
-#pragma unroll
-                        for (int k = 0; k < 7; ++k)
-                            if (x[t2l * 7 + k]) {
-                                gb[k * 32] = old[t2l * 7 + k] + x[t2l * 7 + k];
-                                crumbs += x[t2l * 7 + k];
-                            }
-                    }
-                } else {
-#pragma unroll
-                    for (int t2l = 0; t2l < 4; ++t2l) {
-                        const int64_t pj = pj0 + t2l;
-                        uint32_t *base = cnt.peer[pj / cnt.rows_per];
-                        uint32_t *gb = base + (pj * W + pj - 16 * I - 4 * qd - 4) * HX_CELL + lane;
-#pragma unroll
-                        for (int k = 0; k < 7; ++k)
-                            if (x[t2l * 7 + k]) {
-                                atomicAdd(gb + k * 32, x[t2l * 7 + k]);
-                                crumbs += x[t2l * 7 + k];
-                            }
-                    }
-                }
-            }
+            l2_epilogue_tile<FUSED, FRESH>(tmem_base + acc * 256u, I, q, has, stg, lane, qd, hsel, cnt, g, crumbs);
             l2_fence_before();
             __syncwarp();
             if (lane == 0) ws_mbar_arrive(ws_smem_u32(&s_acc_empty[acc]));
@@ -532,6 +555,340 @@ k_l2_tiles(const uint8_t *__restrict__ onehot, const int32_t *__restrict__ bstar
     if (warp == 0) {
         l2_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// ---- the same tiles on CTA pairs (cta_group::2) ---------------------------------------------------------------
+// An M=N=128, K=32 int8 MMA reads 8 KB of operands from shared memory in its 64 cycles - all of the 128 B/clk there
+// is - so in k_l2_tiles every byte TMA refills comes out of the MMA rate (measured: ~140 cycles per MMA).  Two CTAs of a
+// cluster (the two SMs of a TPC) run ONE M=256, N=256 MMA per chunk instead: CTA r holds the A rows of first-site block
+// 2Ip+r and the B columns of second-site block 2q+r, the hardware shares the halves, and each SM's shared memory sees
+// 4 KB of fills + 4 KB of operand reads per 128x128x32 of work instead of 6 + 8.
+//   * both CTAs walk the same static tile list (tile = pair of first blocks x pair of second blocks) and derive the
+//     same runs of chunks from the sort offsets; each loads its own two slabs per chunk (a zero slab where the chunk
+//     has none for that block) and signals its own `full` barrier;
+//   * warp 1 of the second CTA forwards `full` to the leader (remote mbarrier arrive); the leader's MMA thread waits for
+//     both, issues, and tcgen05.commit-multicasts `empty` (stage reusable) and `acc_full` (tile done) to both CTAs;
+//   * each CTA's epilogue warps drain their own 128 TMEM lanes exactly as in k_l2_tiles and release the accumulator
+//     on a local barrier and on the leader's pair barrier.
+constexpr int L2P_G = 4;
+constexpr uint32_t L2P_STAGE_BYTES = 2 * L2P_G * L2_SLAB;        // A slabs, B slabs
+constexpr uint32_t L2P_IDESC = (2u << 4) | (1u << 15) | (1u << 16) | ((256u >> 3) << 17) | ((256u >> 4) << 24);
+
+__device__ __forceinline__ uint32_t l2_mapa(uint32_t addr, uint32_t cta) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta));
+    return r;
+}
+__device__ __forceinline__ void l2_remote_arrive(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void l2_wait_cluster(uint32_t bar, uint32_t parity) {
+    for (;;) {
+        uint32_t done;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (done) break;
+    }
+}
+__device__ __forceinline__ void l2_mma2(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(L2P_IDESC), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void l2_commit2(uint32_t bar) {       // arrives on the barrier at this offset in BOTH CTAs
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
+__device__ __forceinline__ void l2_cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+template <bool FRESH>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(L2P_THREADS, 1)
+k_l2_tiles2(const uint8_t *__restrict__ onehot, const uint8_t *__restrict__ zero_slabs, const int32_t *__restrict__ bstart,
+            L2Geom g, const HxCnt cnt_in, unsigned long long *__restrict__ totals, const int *__restrict__ go) {
+    extern __shared__ __align__(1024) uint8_t l2_smem[];
+    __shared__ __align__(8) unsigned long long s_full[L2P_STAGES], s_empty[L2P_STAGES], s_peer_full[L2P_STAGES];
+    __shared__ __align__(8) unsigned long long s_acc_full[2], s_acc_empty_local[2], s_acc_empty_pair[2], s_tile_ready[2];
+    __shared__ __align__(8) int s_meta[L2P_STAGES][2];
+    __shared__ int4 s_runs[L2P_STAGES][128];
+    __shared__ int4 s_pend[L2P_STAGES][L2P_G];
+    __shared__ volatile int s_tile[2][4];
+    __shared__ uint32_t s_tmem;
+    if (go && !*go) return;                              // (uniform over the cluster)
+    HxCnt cnt = cnt_in;
+    cnt.world = 1; cnt.rows_per = 1; cnt.peer = nullptr;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t rank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+    const uint32_t stage0 = ws_smem_u32(l2_smem);
+    uint32_t *const staging = reinterpret_cast<uint32_t *>(l2_smem + (size_t)L2P_STAGES * L2P_STAGE_BYTES);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < L2P_STAGES; ++s) {
+            ws_mbar_init(ws_smem_u32(&s_full[s]), 1);
+            ws_mbar_init(ws_smem_u32(&s_empty[s]), 1);
+            ws_mbar_init(ws_smem_u32(&s_peer_full[s]), 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            ws_mbar_init(ws_smem_u32(&s_acc_full[s]), 1);
+            ws_mbar_init(ws_smem_u32(&s_acc_empty_local[s]), L2_EP_WARPS);
+            ws_mbar_init(ws_smem_u32(&s_acc_empty_pair[s]), 2 * L2_EP_WARPS);
+            ws_mbar_init(ws_smem_u32(&s_tile_ready[s]), 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(ws_smem_u32(&s_tmem)),
+                     "r"(512u)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    l2_fence_before();
+    __syncthreads();
+    l2_cluster_sync();                                    // the partner's barriers exist before anything arrives on them
+    l2_fence_after();
+    const uint32_t tmem_base = s_tmem;
+    const int SP = g.SP;
+    unsigned long long crumbs = 0;
+
+    if (warp < L2P_PW) {
+        // ============================== producers (both CTAs, identical tile and chunk lists) ===================
+        // one warp per ring stage, as in k_l2_tiles; a stage = up to L2P_G chunks, two 4 KB bulk copies per chunk here
+        // (lane = 2 * slot + operand: my A block, my B block; a zero slab where the chunk has none for that block)
+        const int nq = g.nq;
+        const int64_t n_tiles = (int64_t)((g.NB + 1) >> 1) * nq;
+        const int SPB = g.SPB();
+        const uint32_t bar_full = ws_smem_u32(&s_full[warp]), bar_empty = ws_smem_u32(&s_empty[warp]);
+        const uint32_t dst0 = stage0 + (uint32_t)warp * L2P_STAGE_BYTES;
+        int4 *const runs = s_runs[warp];
+        int4 *const pend = s_pend[warp];                 // chunk: slab of its first block, nch, first block, reaches 2q+1
+        const uint32_t peer_full_at_leader = l2_mapa(ws_smem_u32(&s_peer_full[warp]), 0);
+        unsigned ph = 0, gturn = 0;                      // phase of my stage; (stages sent so far by all warps) mod L2P_PW
+        int n_pend = 0, p_Ip = 0, p_q = 0;
+        auto emit = [&](int last) {                      // called by the stage's owner only
+            {
+                __syncwarp();
+                const int slot = lane >> 1, op = lane & 1;
+                const bool mine = slot < n_pend;
+                if (lane == 0) {
+                    l2_wait_cluster(bar_empty, ph ^ 1);
+                    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(ws_smem_u32(&s_meta[warp][0])), "r"(p_Ip),
+                                 "r"(p_q | (n_pend << 20) | (last << 24))
+                                 : "memory");
+                    l2_expect_tx(bar_full, 2 * L2_SLAB * (uint32_t)n_pend);
+                }
+                __syncwarp();
+                if (mine) {
+                    const int4 c = pend[slot];                       // x, nch, sb, b1
+                    const int blk = op == 0 ? 2 * p_Ip + (int)rank : 2 * p_q + (int)rank;
+                    // does this chunk have a slab for blk?  (its first block is at or before it and it reaches it)
+                    bool have = c.z <= blk;
+                    if (rank == 1) have = have && (op == 0 ? (p_q > p_Ip || c.w) : (c.w != 0));
+                    const uint8_t *src = have ? onehot + ((size_t)c.x + (size_t)(blk - c.z) * c.y) * L2_SLAB : zero_slabs;
+                    l2_bulk_g2s(dst0 + (uint32_t)(op * L2P_G + slot) * L2_SLAB, src, L2_SLAB, bar_full);
+                }
+                // the second CTA tells the leader when its half of the stage has landed: each producer warp forwards its
+                // own stage (a remote arrive costs its issuer several hundred cycles - one forwarding thread for all
+                // stages paced the whole pipeline)
+                if (rank == 1 && lane == 0) {
+                    l2_wait_cluster(bar_full, ph);
+                    l2_remote_arrive(peer_full_at_leader);
+                }
+                ph ^= 1;
+            }
+        };
+        const unsigned lt = (1u << lane) - 1u;
+        for (int64_t t = pair; t < n_tiles; t += n_pairs) {
+            const int Ip = (int)(t / nq), q = Ip + (int)(t % nq);
+            const int I0 = 2 * Ip, I1 = min(I0 + 1, g.NB - 1);
+            const int jmax = min(I1 + SP - 1, g.NB - 1);
+            if (2 * q > jmax) continue;
+            const int jlo = 2 * q;                                  // q >= Ip: the second blocks start at or after I0
+            const int sb_lo = max(0, jlo - SP + 1);
+            // the tile's runs of chunks (two per first block, SP <= 64 first blocks: at most 128), in shared memory
+            int n_runs = 0;
+            for (int sb0 = sb_lo; sb0 <= I1; sb0 += 32) {
+                const int sb = sb0 + lane;
+                int first = 0, end = 0, cb1 = 0, cs = 0;
+                if (sb <= I1) {
+                    const int32_t *__restrict__ bs = bstart + (int64_t)sb * SPB;
+                    const int d1 = 2 * q + 1 - sb;
+                    cs = bs[0] >> 5;
+                    first = bs[1 + max(jlo - sb, 0)] >> 5;
+                    end = bs[SPB] >> 5;
+                    cb1 = d1 <= 0 ? first : (d1 < SP ? max(bs[1 + d1] >> 5, first) : end);
+                }
+                const int nch = end - cs;
+                const int x0 = cs * SP - cs;                        // + chunk index = slab of (chunk, block sb)
+                const unsigned mA = __ballot_sync(0xffffffffu, first < cb1), mB = __ballot_sync(0xffffffffu, cb1 < end);
+                int at = n_runs + __popc(mA & lt) + __popc(mB & lt);
+                if (first < cb1) runs[at++] = make_int4(x0 + first, nch, cb1 - first, sb << 1);
+                if (cb1 < end) runs[at] = make_int4(x0 + cb1, nch, end - cb1, (sb << 1) | 1);
+                n_runs += __popc(mA) + __popc(mB);
+            }
+            __syncwarp();
+            // chunk c of the tile = chunk (c - start[r]) of run r: lane j keeps runs 4j .. 4j+3 and their starts
+            int4 my[4];
+            int st[5];
+            st[0] = 0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                my[i] = 4 * lane + i < n_runs ? runs[4 * lane + i] : make_int4(0, 0, 0, 0);
+                st[i + 1] = st[i] + my[i].z;
+            }
+            int incl = st[4];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            const int base = incl - st[4];
+            const int T = __shfl_sync(0xffffffffu, incl, 31);
+            const int n_st = (T + L2P_G - 1) / L2P_G;
+            __syncwarp();
+            // my stages of this tile: the global stage counter decides whose turn it is
+            for (int k = (int)((unsigned)(warp + L2P_PW - (int)gturn) % L2P_PW); k < n_st; k += L2P_PW) {
+                const int n_slots = min(L2P_G, T - k * L2P_G);
+#pragma unroll
+                for (int sl = 0; sl < L2P_G; ++sl) {
+                    const int c = k * L2P_G + sl - base;             // position among my runs' chunks
+                    if (sl < n_slots && c >= 0 && c < st[4]) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            if (c >= st[i] && c < st[i + 1])
+                                pend[sl] = make_int4(my[i].x + (c - st[i]), my[i].y, my[i].w >> 1, my[i].w & 1);
+                    }
+                }
+                n_pend = n_slots; p_Ip = Ip; p_q = q;
+                emit(k == n_st - 1);
+            }
+            gturn = (gturn + (unsigned)n_st) % L2P_PW;
+        }
+        if (gturn == (unsigned)warp && lane == 0) {                  // the warp whose turn it is tells warp L2P_PW to stop
+            l2_wait_cluster(bar_empty, ph ^ 1);
+            asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(ws_smem_u32(&s_meta[warp][0])), "r"(0), "r"(8 << 24) : "memory");
+            ws_mbar_arrive(bar_full);
+        }
+    } else if (warp == L2P_PW) {
+        // ============================== MMA issue (leader) / forwarding (second CTA) ===========================
+        if (lane == 0) {
+            unsigned stage = 0, ph = 0, acc = 0, acc_ph[2] = {0, 0};
+            bool new_tile = true, first = true;
+            const uint32_t acc_empty = ws_smem_u32(rank == 0 ? &s_acc_empty_pair[0] : &s_acc_empty_local[0]);
+#ifdef L2_PROFILE
+            unsigned long long pw = 0, pp = 0, pi_ = 0, pa = 0, pn = 0, pm = 0;
+            const long long t_begin = clock64();
+#endif
+            for (;;) {
+#ifdef L2_PROFILE
+                const long long c0 = clock64();
+#endif
+                l2_wait_cluster(ws_smem_u32(&s_full[stage]), ph);
+#ifdef L2_PROFILE
+                pw += clock64() - c0; pn++;
+#endif
+                int m_Ip, m_w;
+                asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(m_Ip), "=r"(m_w) : "r"(ws_smem_u32(&s_meta[stage][0])) : "memory");
+                const int m_q = m_w & 0xfffff, m_flags = m_w >> 24, n = (m_w >> 20) & 15;
+                if (m_flags & 8) {
+#ifdef L2_PROFILE
+                    if (rank == 0) { atomicAdd(&l2_prof[0], pw); atomicAdd(&l2_prof[1], pi_); atomicAdd(&l2_prof[2], pa); atomicAdd(&l2_prof[3], pn); atomicAdd(&l2_prof[4], pm);
+                    atomicAdd(&l2_prof[5], (unsigned long long)(clock64() - t_begin)); atomicAdd(&l2_prof[6], pp); }
+#endif
+                    l2_wait_cluster(acc_empty + 8u * acc, acc_ph[acc] ^ 1);
+                    s_tile[acc][3] = 1;
+                    ws_mbar_arrive(ws_smem_u32(&s_tile_ready[acc]));
+                    ws_mbar_arrive(ws_smem_u32(&s_acc_full[acc]));
+                    break;
+                }
+                if (new_tile) {
+#ifdef L2_PROFILE
+                    const long long c2 = clock64();
+#endif
+                    l2_wait_cluster(acc_empty + 8u * acc, acc_ph[acc] ^ 1);
+#ifdef L2_PROFILE
+                    pa += clock64() - c2;
+#endif
+                    new_tile = false;
+                    first = true;
+                }
+                if (m_flags & 1) {                                   // the tile's last stage: say which tile it was
+                    s_tile[acc][0] = 2 * m_Ip + (int)rank; s_tile[acc][1] = m_q; s_tile[acc][2] = 3; s_tile[acc][3] = 0;
+                    ws_mbar_arrive(ws_smem_u32(&s_tile_ready[acc]));
+                }
+                if (rank == 0) {
+#ifdef L2_PROFILE
+                    const long long c3 = clock64();
+#endif
+                    l2_wait_cluster(ws_smem_u32(&s_peer_full[stage]), ph);
+#ifdef L2_PROFILE
+                    const long long c4 = clock64(); pp += c4 - c3;
+#endif
+                    l2_fence_after();
+                    const uint32_t sa = stage0 + stage * L2P_STAGE_BYTES;
+                    const uint32_t d = tmem_base + acc * 256u;
+                    const uint64_t da = l2_desc(sa), db = l2_desc(sa + L2P_G * L2_SLAB);
+                    for (int i = 0; i < n; ++i) {
+                        const uint64_t o = (uint64_t)(i * (int)(L2_SLAB >> 4));
+                        l2_mma2(d, da + o, db + o, first ? 0u : 1u);
+                        first = false;
+                    }
+#ifdef L2_PROFILE
+                    pi_ += clock64() - c4; pm += n;
+#endif
+                    l2_commit2(ws_smem_u32(&s_empty[stage]));
+                    if (m_flags & 1) l2_commit2(ws_smem_u32(&s_acc_full[acc]));
+                }
+                if (m_flags & 1) {
+                    acc_ph[acc] ^= 1;
+                    acc ^= 1;
+                    new_tile = true;
+                }
+                if (++stage == L2P_STAGES) { stage = 0; ph ^= 1; }
+            }
+        }
+    } else {
+        // ============================== epilogue (each CTA drains its own 128 TMEM lanes) ======================
+        const int ew = warp - (L2P_PW + 1), qd = warp & 3, hsel = ew >> 2;
+        uint32_t *const stg = staging + (size_t)ew * L2_STG_WORDS;
+        const uint32_t pair_bar0 = l2_mapa(ws_smem_u32(&s_acc_empty_pair[0]), 0);
+        unsigned acc = 0, acc_ph[2] = {0, 0};
+        for (;;) {
+            l2_wait_cluster(ws_smem_u32(&s_acc_full[acc]), acc_ph[acc]);
+            l2_wait_cluster(ws_smem_u32(&s_tile_ready[acc]), acc_ph[acc]);      // (warp L2P_PW has said which tile it is)
+            acc_ph[acc] ^= 1;
+            l2_fence_after();
+            if (s_tile[acc][3]) break;
+            const int I = s_tile[acc][0], q = s_tile[acc][1];
+            if (I < g.NB)
+                l2_epilogue_tile<false, FRESH>(tmem_base + acc * 256u, I, q, 3, stg, lane, qd, hsel, cnt, g, crumbs);
+            l2_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                ws_mbar_arrive(ws_smem_u32(&s_acc_empty_local[acc]));
+                l2_remote_arrive(pair_bar0 + 8u * acc);
+            }
+            acc ^= 1;
+        }
+    }
+    l2_fence_before();
+    flush_totals(0, crumbs, 0, 0, totals);                            // barriers inside
+    l2_cluster_sync();                                                // nothing of the partner is still on its way here
+    if (warp == 0) {
+        l2_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
 }
 
@@ -603,9 +960,9 @@ int hx_launch_ingest_lumma(hx_matrix *h, const int32_t *d_rank, const int64_t *d
     if ((rc = l2_grow(&s->perm, &s->cap_perm, max_chunks * 32, st))) return rc;
     if ((rc = l2_grow(&s->chunk_eb, &s->cap_ceb, max_chunks, st))) return rc;
     if ((rc = l2_grow(&s->part, &s->cap_part, nblk, st))) return rc;
-    if ((rc = l2_grow(&s->onehot, &s->cap_onehot, max_chunks * g.SP * (int64_t)L2_SLAB, st))) return rc;
+    const int64_t onehot_bytes = max_chunks * g.SP * (int64_t)L2_SLAB;
+    if ((rc = l2_grow(&s->onehot, &s->cap_onehot, onehot_bytes + L2P_G * (int64_t)L2_SLAB, st))) return rc;   // + zero slabs
     int32_t *cursor = s->hist + nscan;
-    unsigned *tile_counter = reinterpret_cast<unsigned *>(s->hist + 2 * nscan);
 
     HX_CUDA(hx_fill_async(s->hist, 0, sizeof(int32_t) * (size_t)(2 * nscan + 4), st));
     HX_CUDA(hx_fill_async(s->perm, 0xff, sizeof(int32_t) * (size_t)(max_chunks * 32), st));
@@ -622,12 +979,24 @@ int hx_launch_ingest_lumma(hx_matrix *h, const int32_t *d_rank, const int64_t *d
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
     if (h->ingest_sms > 0 && h->ingest_sms < sms) sms = h->ingest_sms;
-    const size_t smem = (size_t)L2_STAGES * L2_STAGE_BYTES + (size_t)L2_EP_WARPS * L2_STG_WORDS * 4 + 1024;
     const bool fused = h->peer_world > 1;
     const bool fresh = !fused && h->cnt_fresh;
-    auto kern = fused ? k_l2_tiles<true, false> : (fresh ? k_l2_tiles<false, true> : k_l2_tiles<false, false>);
-    HX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<sms, L2_THREADS, smem, st>>>(s->onehot, s->bstart, s->chunk_eb, g, hx_cnt_ref(h), h->d_totals, tile_counter, go);
+    static const bool pairs_on = getenv("HX_LUMMA_PAIRS") && !strcmp(getenv("HX_LUMMA_PAIRS"), "1");
+    if (!fused && sms >= 2 && pairs_on && g.SP <= 62) {
+        // CTA pairs (cta_group::2): one cluster of two per TPC
+        uint8_t *zero_slabs = s->onehot + onehot_bytes;
+        HX_CUDA(hx_fill_async(zero_slabs, 0, L2P_G * (size_t)L2_SLAB, st));
+        const size_t smem = (size_t)L2P_STAGES * L2P_STAGE_BYTES + (size_t)L2_EP_WARPS * L2_STG_WORDS * 4 + 1024;
+        auto kern = fresh ? k_l2_tiles2<true> : k_l2_tiles2<false>;
+        HX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<sms & ~1, L2P_THREADS, smem, st>>>(s->onehot, zero_slabs, s->bstart, g, hx_cnt_ref(h), h->d_totals, go);
+        h->launches++;
+    } else {
+        const size_t smem = (size_t)L2_STAGES * L2_STAGE_BYTES + (size_t)L2_EP_WARPS * L2_STG_WORDS * 4 + 1024;
+        auto kern = fused ? k_l2_tiles<true, false> : (fresh ? k_l2_tiles<false, true> : k_l2_tiles<false, false>);
+        HX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<sms, L2_THREADS, smem, st>>>(s->onehot, s->bstart, g, hx_cnt_ref(h), h->d_totals, go);
+    }
     h->launches += 10;
     HX_CUDA(cudaGetLastError());
     return HX_OK;
