@@ -870,6 +870,74 @@ static void run_threads(int nt, F f) {
     hx_pool()->run(nt, std::function<void(int)>(f));
 }
 
+#if defined(__x86_64__)
+#include <immintrin.h>
+// 0 = 64-bit words, 1 = SSE4.1 (16 alleles per step), 2 = AVX2 (32 per step): what the CPU supports, capped by
+// HX_DENSE_SIMD=0|1|2 (the tests run every level the machine has against each other)
+static int dense_simd_level() {
+    int have = __builtin_cpu_supports("avx2") ? 2 : (__builtin_cpu_supports("sse4.1") && __builtin_cpu_supports("ssse3")) ? 1 : 0;
+    if (const char *e = getenv("HX_DENSE_SIMD")) have = std::min(have, std::max(0, atoi(e)));
+    return have;
+}
+// alleles >= 4 (N, -, _) among the bytes flagged in m are listed as exceptions (inside [xlo, xhi) only: the caller's own reads)
+static inline void dense_note_mask(uint32_t m, int64_t i, int64_t xlo, int64_t xhi, std::vector<uint32_t> &exc) {
+    while (m) {
+        const int64_t j = i + __builtin_ctz(m);
+        if (j >= xlo && j < xhi) exc.push_back((uint32_t)j);
+        m &= m - 1;
+    }
+}
+// 32 alleles -> 8 bytes per step (allele j of a byte at bits 2j, as the 64-bit loop of hx_dense_pack); a code > 6 sets
+// `any`.  Returns where it stopped.
+__attribute__((target("avx2"))) static int64_t dense_pack_avx2(const uint8_t *codes, uint8_t *c2, int64_t i, int64_t hi,
+                                                                int64_t xlo, int64_t xhi, std::vector<uint32_t> &exc,
+                                                                uint64_t &any) {
+    const __m256i three = _mm256_set1_epi8(3), six = _mm256_set1_epi8(6);
+    const __m256i w14 = _mm256_set1_epi16(0x0401), w116 = _mm256_set1_epi32(0x00100001);
+    for (; i + 32 <= hi; i += 32) {
+        const __m256i v = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(codes + i));
+        const uint32_t sign = (uint32_t)_mm256_movemask_epi8(v);                              // codes >= 128
+        const uint32_t m = (uint32_t)_mm256_movemask_epi8(_mm256_cmpgt_epi8(v, three)) | sign;      // codes >= 4
+        if (m) {
+            if (sign | (uint32_t)_mm256_movemask_epi8(_mm256_cmpgt_epi8(v, six))) any = 1;
+            dense_note_mask(m, i, xlo, xhi, exc);
+        }
+        const __m256i a = _mm256_and_si256(v, three);
+        const __m256i t = _mm256_madd_epi16(_mm256_maddubs_epi16(a, w14), w116);     // a byte of four alleles per 32-bit lane
+        const __m256i p16 = _mm256_packus_epi32(t, t);
+        const __m256i p8 = _mm256_packus_epi16(p16, p16);
+        const uint32_t lo4 = (uint32_t)_mm256_extract_epi32(p8, 0), hi4 = (uint32_t)_mm256_extract_epi32(p8, 4);
+        const uint64_t out = (uint64_t)lo4 | ((uint64_t)hi4 << 32);
+        memcpy(c2 + (i >> 2), &out, 8);
+    }
+    return i;
+}
+// the same, 2 x 16 alleles per step
+__attribute__((target("sse4.1,ssse3"))) static int64_t dense_pack_sse41(const uint8_t *codes, uint8_t *c2, int64_t i, int64_t hi,
+                                                                        int64_t xlo, int64_t xhi, std::vector<uint32_t> &exc,
+                                                                        uint64_t &any) {
+    const __m128i three = _mm_set1_epi8(3), six = _mm_set1_epi8(6);
+    const __m128i w14 = _mm_set1_epi16(0x0401), w116 = _mm_set1_epi32(0x00100001);
+    for (; i + 32 <= hi; i += 32) {
+        const __m128i v0 = _mm_loadu_si128(reinterpret_cast<const __m128i *>(codes + i));
+        const __m128i v1 = _mm_loadu_si128(reinterpret_cast<const __m128i *>(codes + i + 16));
+        const uint32_t sign = (uint32_t)_mm_movemask_epi8(v0) | ((uint32_t)_mm_movemask_epi8(v1) << 16);
+        const uint32_t m = (uint32_t)_mm_movemask_epi8(_mm_cmpgt_epi8(v0, three)) |
+                           ((uint32_t)_mm_movemask_epi8(_mm_cmpgt_epi8(v1, three)) << 16) | sign;
+        if (m) {
+            if (sign | (uint32_t)_mm_movemask_epi8(_mm_or_si128(_mm_cmpgt_epi8(v0, six), _mm_cmpgt_epi8(v1, six)))) any = 1;
+            dense_note_mask(m, i, xlo, xhi, exc);
+        }
+        const __m128i t0 = _mm_madd_epi16(_mm_maddubs_epi16(_mm_and_si128(v0, three), w14), w116);
+        const __m128i t1 = _mm_madd_epi16(_mm_maddubs_epi16(_mm_and_si128(v1, three), w14), w116);
+        const __m128i p16 = _mm_packus_epi32(t0, t1);
+        const __m128i p8 = _mm_packus_epi16(p16, p16);
+        _mm_storel_epi64(reinterpret_cast<__m128i *>(c2 + (i >> 2)), p8);
+    }
+    return i;
+}
+#endif
+
 int hx_dense_begin(const int64_t *off, int64_t n_reads, int n_threads, int64_t kmax_hint, HxDensePlan *pl, bool slim) {
     HxDensePlan &P = *pl;
     P.slim = slim;
@@ -913,6 +981,9 @@ int hx_dense_pack(const int32_t *rank, const int64_t *off, const uint8_t *codes,
     const int64_t klim = kb == 1 ? 255 : 65535;
     uint8_t *c2 = blob + P.o_codes2;
     std::vector<int> bad((size_t)nt, 0);
+#if defined(__x86_64__)
+    const int simd = P.slim ? 0 : dense_simd_level();
+#endif
     run_threads(nt, [&](int t) {
         const int64_t a = n_reads * t / nt, b = n_reads * (t + 1) / nt;
         std::vector<uint32_t> &exc = P.exc[t];
@@ -920,9 +991,9 @@ int hx_dense_pack(const int32_t *rank, const int64_t *off, const uint8_t *codes,
         std::vector<int32_t> &ed = P.esc_delta[t];
         exc.clear(); ei.clear(); ed.clear();
         int bd = 0;
-        if (P.slim) {
-            // branch-free (vectorisable) pass; the rare escapes (a gap of >= 255 sites, the chunk's first read) are
-            // collected in a second look at the blocks that hold one
+        {
+            // ranks and SNP counts: a branch-free (vectorisable) pass; the rare escapes (a gap of >= 255 sites, the
+            // chunk's first read) are collected in a second look at the blocks that hold one
             constexpr int64_t BLK = 4096;
             for (int64_t r0 = a; r0 < b; r0 += BLK) {
                 const int64_t r1 = std::min(b, r0 + BLK);
@@ -962,18 +1033,8 @@ int hx_dense_pack(const int32_t *rank, const int64_t *off, const uint8_t *codes,
                         if (d >= 255) { ei.push_back(q); ed.push_back((int32_t)d); }
                     }
             }
-            bad[(size_t)t] = bd;
-            return;
         }
-        for (int64_t r = a; r < b; ++r) {
-            const int64_t d = (int64_t)rank[r] - (r ? (int64_t)rank[r - 1] : 0), k = off[r + 1] - off[r];
-            if (d < 0) bd = 1;
-            if (k < 0 || k > klim) bd = 2;
-            blob[r] = (uint8_t)std::min<int64_t>(d, 255);
-            if (d >= 255) { ei.push_back(r); ed.push_back((int32_t)d); }
-            if (kb == 1) blob[P.o_klen + r] = (uint8_t)k; else ((uint16_t *)(blob + P.o_klen))[r] = (uint16_t)k;
-        }
-        if (b <= a || bd) { bad[(size_t)t] = bd; return; }
+        if (P.slim || b <= a || bd) { bad[(size_t)t] = bd; return; }
         // This thread lists the exceptions of its reads' alleles [xlo, xhi) and writes the output bytes of the
         // alleles [lo, hi): the same range rounded so that every output byte has exactly one writer.
         const int64_t xlo = off[a] - c0, xhi = off[b] - c0;
@@ -992,6 +1053,10 @@ int hx_dense_pack(const int32_t *rank, const int64_t *off, const uint8_t *codes,
         // head: the alleles of this thread's reads before its first output byte belong to the previous writer
         for (int64_t i = xlo; i < std::min(lo, xhi); ++i) { const uint8_t c = codes[c0 + i]; if (c > 6) any = 1; if (c >= 4) exc.push_back((uint32_t)i); }
         int64_t i = lo;
+#if defined(__x86_64__)
+        if (simd == 2) i = dense_pack_avx2(codes + c0, c2, i, hi, xlo, xhi, exc, any);
+        else if (simd == 1) i = dense_pack_sse41(codes + c0, c2, i, hi, xlo, xhi, exc, any);
+#endif
         for (; i + 8 <= hi; i += 8) {              // 8 alleles -> 16 bits (code & 3: N, -, _ store code - 4)
             const uint64_t x = ld64(codes + c0 + i);
             any |= (x & 0xf8f8f8f8f8f8f8f8ull) | (x & (x >> 1) & (x >> 2) & 0x0101010101010101ull);   // a code > 6

@@ -1,4 +1,6 @@
 """Host-side encoders of the wire formats (no GPU): decoding them with numpy gives the packed reads back."""
+import os
+
 import numpy as np
 import pytest
 
@@ -91,3 +93,36 @@ def test_dense_encoders_agree_on_random_shapes():
         assert np.array_equal(a.blob, b.blob), trial
         r2, o2, c2 = _decode_dense(a)
         assert np.array_equal(r2, rank) and np.array_equal(o2, off) and np.array_equal(c2, codes), trial
+
+
+def _simd_levels_agree():
+    rng = np.random.default_rng(77)
+    rank, off, codes = synth.random_packed(rng, 5000, 150_000, 30, p_special=0.02)
+    codes[rng.integers(0, len(codes), 50)] = 6
+    blobs = []
+    for level in ("0", "1", "2"):          # 64-bit words, SSE4.1, AVX2 (a level the CPU lacks falls back to the one below)
+        os.environ["HX_DENSE_SIMD"] = level
+        try:
+            blobs.append(util.dense_packed_native(rank, off, codes, n_threads=3).blob.copy())
+            h = len(rank) // 3                # a chunk starting at an allele offset that is not a multiple of 32
+            blobs.append(util.dense_packed_native(rank[h:], off[h:], codes, n_threads=2).blob.copy())
+            bad = codes.copy()
+            bad[len(bad) // 2 + 5] = 9         # an invalid allele must be caught at every level
+            with pytest.raises(ValueError):
+                util.dense_packed_native(rank, off, bad, n_threads=3)
+        finally:
+            del os.environ["HX_DENSE_SIMD"]
+    assert np.array_equal(blobs[0], util.dense_packed(rank, off, codes).blob)
+    for i in (2, 4):
+        assert np.array_equal(blobs[i], blobs[0]) and np.array_equal(blobs[i + 1], blobs[1])
+
+
+def test_dense_encoder_simd_levels_agree():
+    """The SSE4.1 / AVX2 allele packers write the same bytes as the 64-bit loop and the numpy encoder."""
+    _simd_levels_agree()
+
+
+@pytest.mark.gpu
+def test_dense_encoder_simd_levels_agree_on_the_gpu_box():
+    """The same on the GPU box's host CPU (it may have AVX2 where the build container does not)."""
+    _simd_levels_agree()
