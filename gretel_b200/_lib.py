@@ -60,6 +60,7 @@ SIGNATURES = {
     "hx_count_coverage": (_int, [C.c_char_p, C.c_char_p, _i32, _i32, _int, _p]),
     "hx_count_coverage_gpu": (_int, [C.c_char_p, C.c_char_p, _i32, _i32, _int, _i32, _p]),
     "hx_bam_contig_length": (_int, [C.c_char_p, C.c_char_p, C.POINTER(_i32)]),
+    "hx_inflate_raw": (_int, [_p, _i64, _i64, _p, _i64, _i32]),
     "hx_probe_expected_rows": (_int, [_p, _p, _p, _p, _i64, _p]),
     "hx_counts_row_sums": (_int, [_p, _p]),
     "hx_device_math": (_int, [_i32, _int, _p, _p, _i64]),

@@ -36,6 +36,7 @@
 #include <cuda_runtime.h>
 
 #include "hanselx.h"
+#include "hx_inflate.h"
 
 void hx_set_error(const char *fmt, ...);
 int hx_launch_coverage(const int32_t *d_seg_start, const int64_t *d_seg_nib, const int32_t *d_seg_len,
@@ -48,8 +49,8 @@ inline uint16_t rd16(const uint8_t *p) { return (uint16_t)(p[0] | (p[1] << 8)); 
 inline uint32_t rd32(const uint8_t *p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
 inline int32_t rdi32(const uint8_t *p) { return (int32_t)rd32(p); }
 
-bool inflate_block(const uint8_t *src, size_t n, uint8_t *dst, size_t m) {
-    if (m == 0) return true;
+// zlib's inflate: the verdict on whatever the fast decoder declines
+bool inflate_block_zlib(const uint8_t *src, size_t n, uint8_t *dst, size_t m) {
     z_stream z;
     memset(&z, 0, sizeof(z));
     if (inflateInit2(&z, -15) != Z_OK) return false;
@@ -60,6 +61,15 @@ bool inflate_block(const uint8_t *src, size_t n, uint8_t *dst, size_t m) {
     const int rc = inflate(&z, Z_FINISH);
     inflateEnd(&z);
     return rc == Z_STREAM_END && z.avail_out == 0;
+}
+
+// one BGZF block: src[0..n) is the raw DEFLATE payload, followed in the file by the frame's 8-byte trailer (CRC32,
+// ISIZE) - which is what lets the decoder refill with whole 8-byte loads up to the payload's last byte
+bool inflate_block(const uint8_t *src, size_t n, uint8_t *dst, size_t m) {
+    if (m == 0) return true;
+    static const bool use_zlib = getenv("HX_INFLATE") && !strcmp(getenv("HX_INFLATE"), "zlib");
+    if (!use_zlib && hxz::inflate_raw(src, n, n + 8, dst, m)) return true;
+    return inflate_block_zlib(src, n, dst, m);
 }
 
 struct Out {
@@ -790,6 +800,14 @@ int hx_count_coverage_gpu(const char *bam_path, const char *contig, int32_t star
     cudaStreamDestroy(st);
 #undef COV_CUDA
     return rc;
+}
+
+int hx_inflate_raw(const uint8_t *src, int64_t n, int64_t n_readable, uint8_t *dst, int64_t m, int32_t use_zlib) {
+    if (!src || !dst || n < 0 || m < 0 || n_readable < n) { hx_set_error("hx_inflate_raw: bad arguments"); return HX_E_ARG; }
+    const bool ok = use_zlib ? (m == 0 || inflate_block_zlib(src, (size_t)n, dst, (size_t)m))
+                             : hxz::inflate_raw(src, (size_t)n, (size_t)n_readable, dst, (size_t)m);
+    if (!ok) { hx_set_error("hx_inflate_raw: not a DEFLATE stream of %lld bytes inflating to %lld", (long long)n, (long long)m); return HX_E_ARG; }
+    return HX_OK;
 }
 
 int hx_bam_contig_length(const char *bam_path, const char *contig, int32_t *length) {

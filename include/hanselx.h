@@ -215,6 +215,11 @@ int hx_count_coverage(const char *bam_path, const char *contig, int32_t start0, 
 int hx_count_coverage_gpu(const char *bam_path, const char *contig, int32_t start0, int32_t end0, int n_threads,
                           int32_t device, uint32_t *out);
 int hx_bam_contig_length(const char *bam_path, const char *contig, int32_t *length);
+/* The packer's own raw-DEFLATE decoder (csrc/hx_inflate.h; what pysam/htslib's bgzf reader does with zlib under
+ * gretel/util.py:137), exposed for the differential tests against zlib: src[0..n) inflates to exactly m bytes into dst;
+ * n_readable >= n bytes of src may be read (a BGZF payload is followed by its 8-byte trailer).  use_zlib != 0 runs
+ * zlib's inflate on the same buffers instead.  HX_OK or HX_E_ARG. */
+int hx_inflate_raw(const uint8_t *src, int64_t n, int64_t n_readable, uint8_t *dst, int64_t m, int32_t use_zlib);
 
 /* ---- parity probe (bench.py parity_probe, multi-GPU tests) ------------------------ */
 /* An independent recount of gretel/util.py:254-281: adds into d_rows[N+2] (device, uint64) the number of
