@@ -9,6 +9,8 @@
 #include <mutex>
 #include <vector>
 
+#include <atomic>
+
 #include "hx_internal.cuh"
 #include "scan.cuh"
 
@@ -407,7 +409,9 @@ int hx_ingest_totals(hx_matrix *h, int64_t totals[4]) {
     int *he = (int *)(hp + 8);
     HX_CUDA(cudaMemcpyAsync(hp, h->d_totals, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
     HX_CUDA(cudaMemcpyAsync(he, h->d_err, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    if (h->prepass_ran) HX_CUDA(cudaMemcpyAsync(he + 1, h->d_flags + 4, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     HX_CUDA(cudaStreamSynchronize(h->stream));
+    if (h->prepass_ran && he[1] == 0) hx_note_unsorted();
     hx_wire_trace_dump();
     if (h->ev_rec) cudaEventElapsedTime(&h->last_ms[0], h->ev0, h->ev1);
     for (int i = 0; i < 4; ++i) totals[i] = (int64_t)hp[i];
@@ -439,6 +443,7 @@ int hx_ingest_host(hx_matrix *h, const int32_t *rank, const int64_t *off, const 
         const int rc = hx_ingest_host_pipelined(h, rank, off, codes, n_reads, !want_dense, &done);
         if (rc == HX_OK) return hx_ingest_totals(h, totals);
         if (rc != HX_E_STATE) return rc;            // HX_E_STATE: not sorted by rank from read `done` on -> the rest of
+        hx_note_unsorted();
         rank += done; off += done; n_reads -= done; //               the packed arrays as they are (counts just add up)
     }
     if (n_reads > 0) {

@@ -95,6 +95,7 @@ struct hx_matrix {
     cudaEvent_t ev0, ev1;
     cudaEvent_t host_ev;             // orders the chunked host->device copies of hx_ingest_host
     bool ev_rec;                     // ev0/ev1 have been recorded at least once
+    bool prepass_ran;                // d_flags[4] holds the sortedness verdict of the last ingestion launch
     float last_ms[3];
     int64_t launches;
 };
@@ -163,6 +164,11 @@ int hx_ensure_counts_buffer(hx_matrix *h);
 // wire.cu
 void hx_wire_free(hx_matrix *h);
 void hx_wire_trace_dump();
+// set once an ingestion of this process met reads that were not sorted by rank (hx_ingest_totals reads the pre-pass
+// verdict back; hx_ingest_host knows from its own pass): later short-read launches queue the counting-sort tensor-core
+// kernel (ingest_lumma.cu) as their unsorted-input fallback instead of one RED per pair
+bool hx_unsorted_seen();
+void hx_note_unsorted();
 int hx_ingest_host_pipelined(hx_matrix *h, const int32_t *rank, const int64_t *off, const uint8_t *codes, int64_t n_reads,
                              bool slim, int64_t *done_reads);
 // ingest_long.cu

@@ -18,6 +18,8 @@
 //                  shared-memory tile (ring of band rows); a row is flushed to HBM with
 //                  REDs once no later read of the CTA can touch it.  Rare alleles
 //                  (N, -, _), sentinels and totals are handled per read on the side.
+#include <atomic>
+
 #include "hx_internal.cuh"
 #include "ingest_common.cuh"
 
@@ -742,6 +744,14 @@ k1_bitsliced_ws(const int32_t *__restrict__ rank, const int64_t *__restrict__ of
 
 }  // namespace
 
+static std::atomic<bool> g_unsorted_seen{false};
+bool hx_unsorted_seen() { return g_unsorted_seen.load(std::memory_order_relaxed); }
+void hx_note_unsorted() { g_unsorted_seen.store(true, std::memory_order_relaxed); }
+
+__global__ void k_flag_not(const int *__restrict__ in, int *__restrict__ out) {
+    if (threadIdx.x == 0) *out = !*in;
+}
+
 static int launch_ingest(hx_matrix *h, const int32_t *d_rank, const int64_t *d_off, const uint8_t *d_codes,
                          int64_t n_reads, int64_t *run_end, const int *ok);
 
@@ -788,6 +798,12 @@ static int launch_ingest(hx_matrix *h, const int32_t *d_rank, const int64_t *d_o
                                          (h->ingest_kernel == 0 && !use_bs &&
                                           hx_lumma_scratch_bytes(h, n_reads) <= ((int64_t)24 << 30)));
 
+    // unsorted short reads: once this process has met some, the counting-sort tensor-core kernel is queued as the
+    // fallback (it runs only if the pre-pass says "not sorted"); before that, and when its scratch would be huge, one
+    // RED per pair (k1_pairs_red)
+    const bool lumma_fallback = !presorted && use_bs && !use_lumma && h->ingest_kernel == 0 && hx_unsorted_seen() &&
+                                hx_lumma_scratch_bytes(h, n_reads) <= ((int64_t)24 << 30);
+    h->prepass_ran = !presorted && !use_lumma && (use_long || use_bs);
     HX_CUDA(cudaEventRecord(h->ev0, h->stream));
     if (use_lumma) {
         int rc = hx_launch_ingest_lumma(h, d_rank, d_off, d_codes, n_reads, presorted ? ok : nullptr);
@@ -882,7 +898,12 @@ static int launch_ingest(hx_matrix *h, const int32_t *d_rank, const int64_t *d_o
         }
         h->launches++;
         // fallback for unsorted input: runs only when the flag says the bit-sliced kernel declined
-        if (!presorted) {
+        if (lumma_fallback) {
+            k_flag_not<<<1, 32, 0, h->stream>>>(h->d_flags + 4, h->d_flags + 5);
+            h->launches++;
+            int rc = hx_launch_ingest_lumma(h, d_rank, d_off, d_codes, n_reads, h->d_flags + 5);
+            if (rc) return rc;
+        } else if (!presorted) {
             k1_pairs_red<GBLOCK><<<ggrid, GBLOCK, 0, h->stream>>>(d_rank, d_off, d_codes, n_reads, h->N, h->W,
                                                                   hx_cnt_ref(h), h->d_totals, h->d_err, sorted_flag, 0);
             h->launches++;

@@ -565,3 +565,34 @@ def test_tensor_core_kernel_deep_single_rank(c_oracle):
     assert totals == tuple(int(x) for x in rt)
     assert ref.max() > 60_000
     assert np.array_equal(band, ref.astype(np.float32))
+
+
+def test_unsorted_short_reads_take_the_counting_sort_kernel(c_oracle, monkeypatch):
+    """Short reads that are not sorted by rank: the first such ingestion of a process falls back to one RED per pair;
+    the library remembers, and from then on queues the counting-sort tensor-core kernel as the fallback.  Both give the
+    oracle's counts; sorted input afterwards still goes through the sorted-run kernels (with the fallback idle)."""
+    from gretel_b200.hansel import Hansel, REF_SYMBOLS, REF_UNSYMBOLS
+    monkeypatch.setenv("HX_HOST_PIPELINE", "off")          # one launch per ingest_packed: kernel_ms covers all of it
+    rng = np.random.default_rng(99)
+    N, R, mk = 3000, 400_000, 24
+    rank, off, codes = synth.random_packed(rng, N, R, mk, p_special=0.05, sort=False)
+    W = mk - 1
+    ref, rt = c_oracle.ingest(rank, off, codes, N, W)
+    ms = []
+    for _ in range(3):
+        h = Hansel.init_matrix(REF_SYMBOLS, REF_UNSYMBOLS, N, band_w=W)
+        totals = h.ingest_packed(rank, off, codes)
+        ms.append(h.kernel_ms("ingest"))
+        assert totals == tuple(int(x) for x in rt)
+        assert np.array_equal(h.band(), ref.astype(np.float32))
+        h.ingest_packed(rank, off, codes)                  # on top of existing counts
+        assert np.array_equal(h.band(), 2 * ref.astype(np.float32))
+        h.close()
+    print("unsorted short reads: %.3f ms (first), %.3f ms, %.3f ms" % tuple(ms))
+    order = np.argsort(rank, kind="stable")
+    k = np.diff(off)
+    off_s = np.concatenate([[0], np.cumsum(k[order])]).astype(np.int64)
+    idx = np.repeat(off[:-1][order], k[order]) + (np.arange(int(off_s[-1])) - np.repeat(off_s[:-1], k[order]))
+    band, totals = _gpu_band(rank[order], off_s, codes[idx], N, W)
+    assert totals == tuple(int(x) for x in rt)
+    assert np.array_equal(band, ref.astype(np.float32))
