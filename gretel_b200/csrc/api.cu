@@ -162,6 +162,7 @@ void free_all(hx_matrix *h) {
     if (h->d_flags) cudaFreeAsync(h->d_flags, h->stream);
     if (h->d_run_end) cudaFreeAsync(h->d_run_end, h->stream);
     if (h->d_run_list) cudaFreeAsync(h->d_run_list, h->stream);
+    if (h->d_jobs) cudaFreeAsync(h->d_jobs, h->stream);
     if (h->d_misc) cudaFreeAsync(h->d_misc, h->stream);
     if (h->d_pack) cudaFreeAsync(h->d_pack, h->stream);
     if (h->stream) cudaStreamSynchronize(h->stream);

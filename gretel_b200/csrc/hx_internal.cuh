@@ -84,6 +84,8 @@ struct hx_matrix {
     int *d_flags;                    // [0] hole site / abort flag, [1..] misc
     int64_t *d_run_end;              // (N+1) end (exclusive) of the run of reads with each rank
     int64_t *d_run_list;             // compact run list for the tensor-core kernel: ranks (int32), stops (int64), count
+    void *d_jobs;                    // per-CTA job tables of the tensor-core kernel (ingest_umma.cu)
+    int64_t cap_jobs;
     double *d_misc;                  // small outputs (weights etc.)
     uint32_t *d_pack;                // packed counts for the cross-GPU exchange (api.cu)
     int64_t cap_pack;

@@ -19,6 +19,8 @@
 //
 // Reads holding N, - or _, the sentinels and the totals are handled per read by the expander warps exactly as
 // in the bit-sliced kernels (ingest_common.cuh).
+#include <algorithm>
+
 #include "hx_internal.cuh"
 #include "ingest_common.cuh"
 
@@ -30,6 +32,7 @@ namespace {
 constexpr int UM_RD_WARPS = 8;               // readout warps: two per TMEM lane quarter (warp id % 4)
 constexpr int UM_EXP_WARPS = UM_EXP_WARPS_N; // expander warps 8..
 constexpr int UM_THREADS = (UM_RD_WARPS + UM_EXP_WARPS) * 32;
+constexpr int UM_JB = 256;                  // runs per batch of the job-table build
 constexpr int UM_NACC = 4;                   // accumulator stages (runs in flight)
 constexpr int UM_TMEM_COLS = 128 * UM_NACC;  // 128 int32 columns each
 constexpr uint32_t UM_ACC_COUNT = 1u << 19;  // arrivals that complete an accumulator stage (see the readout warps)
@@ -243,7 +246,8 @@ __global__ void __launch_bounds__(UM_THREADS, 1)
 k1_umma(const int32_t *__restrict__ rank, const int64_t *__restrict__ off, const uint8_t *__restrict__ codes,
         int64_t n_reads, int N, int W, int kmax, const HxCnt cnt_in, unsigned long long *__restrict__ totals,
         int *__restrict__ err, const int *__restrict__ sorted_flag, const int32_t *__restrict__ run_rank,
-        const int64_t *__restrict__ run_stop, const int *__restrict__ n_runs_ptr) {
+        const int64_t *__restrict__ run_stop, const int *__restrict__ n_runs_ptr, int4 *__restrict__ jobs_all,
+        int jobs_cap) {
     extern __shared__ __align__(1024) uint8_t um_smem[];
     UM_T(k_begin);
     HxCnt cnt = cnt_in;                              // single-GPU build: the peer path folds away
@@ -253,6 +257,8 @@ k1_umma(const int32_t *__restrict__ rank, const int64_t *__restrict__ off, const
     __shared__ int s_runkg[UM_NACC];                       // widest read of the run accumulating in each stage
     __shared__ unsigned s_runs_read;                 // runs read out of TMEM (and their stage zeroed again)
     __shared__ uint32_t s_tmem;
+    __shared__ int s_jb_off[UM_JB + 1], s_jb_start[UM_JB], s_jb_n[UM_JB], s_jb_r[UM_JB], s_jb_warp[UM_JB / 32];
+    __shared__ int s_njobs;
     if (!*sorted_flag) return;                       // the generic fallback launch takes over
 
     constexpr int ROWB = 16 * CH;                    // bytes of one read's operand row
@@ -310,6 +316,73 @@ k1_umma(const int32_t *__restrict__ rank, const int64_t *__restrict__ off, const
 
     UmWalk wk;
     wk.init(run_rank, run_stop, *n_runs_ptr, lo, hi);
+
+    // ---- the CTA's job table.  A job = one group of up to 32 reads of one run = the K of one MMA, as
+    // (first read - lo, reads | run length << 8 on a run's first job, rank, run index).  The runs of the slice are taken
+    // UM_JB at a time: a block scan of their group counts gives every run its place, then all threads write the jobs.
+    // The expander warps read their jobs from the table instead of each walking the run list.
+    int4 *const myjobs = jobs_all + (size_t)blockIdx.x * jobs_cap;
+    {
+        const int n_runs_all = *n_runs_ptr;
+        const int j0 = wk.j;                                   // first run that ends behind lo
+        int job_base = 0;
+        for (int jb = j0; jb < n_runs_all; jb += UM_JB) {
+            int ng = 0;
+            if (threadIdx.x < UM_JB) {
+                const int j = jb + (int)threadIdx.x;
+                int64_t s0 = hi;
+                if (j < n_runs_all) {
+                    const int64_t prev = j > 0 ? run_stop[j - 1] : 0;
+                    s0 = prev > lo ? prev : lo;
+                }
+                if (s0 < hi) {
+                    const int64_t stop = run_stop[j];
+                    const int64_t e0 = stop < hi ? stop : hi;
+                    ng = (int)((e0 - s0 + 31) >> 5);
+                    s_jb_start[threadIdx.x] = (int)(s0 - lo);
+                    s_jb_n[threadIdx.x] = (int)(e0 - s0);
+                    s_jb_r[threadIdx.x] = run_rank[j];
+                }
+                int incl = ng;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += v;
+                }
+                if (lane == 31) s_jb_warp[warp] = incl;
+                s_jb_off[threadIdx.x + 1] = incl;              // inclusive within the warp for now
+            }
+            __syncthreads();
+            if (threadIdx.x < UM_JB) {
+                int before = 0;
+                for (int w2 = 0; w2 < warp; ++w2) before += s_jb_warp[w2];
+                const int incl = s_jb_off[threadIdx.x + 1] + before;
+                __syncwarp();
+                s_jb_off[threadIdx.x + 1] = incl;
+                if (threadIdx.x == 0) s_jb_off[0] = 0;
+            }
+            __syncthreads();
+            const int batch_jobs = s_jb_off[UM_JB];
+            for (int q = threadIdx.x; q < batch_jobs; q += blockDim.x) {
+                int a = 0, b = UM_JB - 1;                      // the run whose jobs hold q: last t with off[t] <= q and off[t+1] > q
+                while (a < b) {
+                    const int m = (a + b) >> 1;
+                    if (s_jb_off[m + 1] > q) b = m; else a = m + 1;
+                }
+                const int g = q - s_jb_off[a];
+                const int n_run = s_jb_n[a];
+                const int nj = min(32, n_run - 32 * g);
+                myjobs[job_base + q] = make_int4(s_jb_start[a] + 32 * g, nj | (g == 0 ? (min(n_run, 2048) << 8) : 0), s_jb_r[a],
+                                                 jb - j0 + a);
+            }
+            job_base += batch_jobs;
+            const bool more = s_jb_off[UM_JB] > s_jb_off[UM_JB - 1];     // the batch's last run was inside the slice
+            __syncthreads();
+            if (!more) break;
+        }
+        if (threadIdx.x == 0) s_njobs = job_base;
+        __syncthreads();
+    }
     UM_T(k_roles);
 
     if (warp >= UM_RD_WARPS) {
@@ -329,54 +402,46 @@ k1_umma(const int32_t *__restrict__ rank, const int64_t *__restrict__ off, const
 #define UM_PF_READS 2048
 #endif
         constexpr int64_t PF_READS = UM_PF_READS;               // L2 prefetch distance in reads
-        int gmod = 0;                                            // groups dealt so far, modulo the expander count
         unsigned njobs = 0;
-        int jg = 0, cur_ng = 0;
-        struct Job { int64_t start; int n, r, g; unsigned ri; bool valid; };
-        auto next_job = [&]() -> Job {
-            for (;;) {
-                if (jg < cur_ng) {
-                    Job j{wk.start, (int)wk.n, wk.r, jg, wk.ri, true};
-                    jg += UM_EXP_WARPS;
-                    return j;
-                }
-                if (!wk.next_run()) return Job{0, 0, 0, 0, 0, false};
-                cur_ng = (int)((wk.n + 31) >> 5);
-                jg = e - gmod;
-                if (jg < 0) jg += UM_EXP_WARPS;
-                gmod = (int)((unsigned)(gmod + cur_ng) % (unsigned)UM_EXP_WARPS);
-                if (lane == 0 && (int)(wk.ri % UM_EXP_WARPS) == e) {
-                    // the packed reads are streamed from HBM exactly once: request the offsets and (extrapolated
-                    // from this run's byte range) the codes of the reads PF_READS further on
-                    const int64_t pf0 = wk.start + PF_READS;
-                    if (pf0 < hi) {
-                        const int64_t np = min(min(wk.n, (int64_t)2048), hi - pf0);
-                        bs_prefetch_l2(off + pf0, (uint32_t)((np + 1) * 8));
-                        const int64_t o_lo = off[wk.start], o_hi = off[wk.start + wk.n];
-                        const int64_t per_read16 = ((o_hi - o_lo) << 4) / wk.n;
-                        bs_prefetch_l2(codes + o_lo + ((PF_READS * per_read16) >> 4), (uint32_t)(((np * per_read16) >> 4) + 64));
-                    }
-                }
-            }
+        const int n_jobs = s_njobs;
+        // job = (first read - lo, reads | run length << 8 on a run's first job, rank, run index); y = 0: no job left
+        auto get_job = [&](int idx) -> int4 {
+            int4 j = make_int4(0, 0, 0, 0);
+            if (idx < n_jobs) j = myjobs[idx];
+            return j;
         };
-        auto load_off = [&](const Job &j, int64_t &o, int64_t &o1) {
-            const int idx = j.g * 32 + lane;
+        auto load_off = [&](const int4 &j, int64_t &o, int64_t &o1) {
             o = 0; o1 = 0;
-            if (j.valid && idx < j.n) { const int64_t *p = off + j.start + idx; o = p[0]; o1 = p[1]; }
+            if (lane < (j.y & 0xff)) { const int64_t *p = off + lo + j.x + lane; o = p[0]; o1 = p[1]; }
         };
         const uint32_t runs_addr = ws_smem_u32(&s_runs_read);
-        Job cur = next_job();
+        int ji = e;
+        int4 cur = get_job(ji);
         int64_t o, o1;
         load_off(cur, o, o1);
-        while (cur.valid) {
+        while (cur.y) {
             UM_T(tA);
-#ifndef UM_NO_LOOKAHEAD
-            const Job nxt = next_job();
+            ji += UM_EXP_WARPS;
+            const int4 nxt = get_job(ji);
             int64_t on, o1n;
             load_off(nxt, on, o1n);                             // in flight while this job is expanded
-#endif
-            const int r = cur.r;
-            const int s = cur.ri % UM_NACC;
+            if (lane == 0 && (cur.y >> 8)) {
+                // a run's first job: the packed reads are streamed from HBM exactly once: request the offsets and
+                // (extrapolated from this job's byte range) the codes of the reads PF_READS further on
+                const int64_t start = lo + cur.x, n_run = cur.y >> 8;
+                const int64_t pf0 = start + PF_READS;
+                if (pf0 < hi) {
+                    const int64_t np = min(n_run, hi - pf0);
+                    bs_prefetch_l2(off + pf0, (uint32_t)((np + 1) * 8));
+                    const int nj = cur.y & 0xff;
+                    const int64_t o_lo = o, o_hi = off[start + nj];
+                    const int64_t per_read16 = ((o_hi - o_lo) << 4) / nj;
+                    bs_prefetch_l2(codes + o_lo + ((PF_READS * per_read16) >> 4), (uint32_t)(((np * per_read16) >> 4) + 64));
+                }
+            }
+            const int r = cur.z;
+            const unsigned cur_ri = (unsigned)cur.w;
+            const int s = cur_ri % UM_NACC;
             // SNPs on my read: 0 for a lane past the run's end or a read with fewer than two; a read that leaves
             // [0, N] or is wider than the band is an error (the same test as the other kernels)
             const uint64_t kd = (uint64_t)(o1 - o);
@@ -396,8 +461,8 @@ k1_umma(const int32_t *__restrict__ rank, const int64_t *__restrict__ off, const
             UM_T(tD);
             // the run's accumulator stage: run ri-NACC must have been read out (and the stage zeroed) before anything
             // of run ri is added; the previous MMA of this warp must have read the slot before it is rewritten
-            if (cur.ri >= (unsigned)UM_NACC) {
-                const unsigned need = cur.ri - UM_NACC + 1;
+            if (cur_ri >= (unsigned)UM_NACC) {
+                const unsigned need = cur_ri - UM_NACC + 1;
                 while (um_ld_acquire(runs_addr) < need) __nanosleep(200);
             }
             ws_mbar_wait(slot_bar, (njobs & 1) ^ 1);
@@ -447,12 +512,7 @@ k1_umma(const int32_t *__restrict__ rank, const int64_t *__restrict__ off, const
             }
             UM_T(tH);
             UM_ACC(0, tC - tA); UM_ACC(1, tD - tC); UM_ACC(2, tE - tD); UM_ACC(3, tG - tE); UM_ACC(4, tH - tG); UM_ACC(5, 1);
-#ifndef UM_NO_LOOKAHEAD
             cur = nxt; o = on; o1 = o1n;
-#else
-            cur = next_job();
-            load_off(cur, o, o1);
-#endif
         }
 #ifdef UM_PROFILE
         if (lane == 0) for (int i = 0; i < 6; ++i) atomicAdd(&um_prof[i], prof_acc[i]);
@@ -627,13 +687,25 @@ int hx_launch_ingest_umma(hx_matrix *h, const int32_t *d_rank, const int64_t *d_
     int *n_runs = reinterpret_cast<int *>(run_stop + (size_t)h->N + 2);
     k_run_list<<<1, 1024, 0, h->stream>>>(run_end, h->N, run_rank, run_stop, n_runs);
     h->launches++;
+    // per-CTA job tables: a slice of `per` reads holds at most per/32 full groups plus one partial group per run
+    const int64_t per = (n_reads + grid - 1) / grid;
+    const int64_t jobs_cap = per / 32 + std::min<int64_t>((int64_t)h->N + 2, per) + 2;
+    HX_CHECK_ARG(jobs_cap < ((int64_t)1 << 31) && per < ((int64_t)1 << 31));
+    const int64_t jobs_bytes = jobs_cap * grid * (int64_t)sizeof(int4);
+    if (jobs_bytes > h->cap_jobs) {
+        if (h->d_jobs) cudaFreeAsync(h->d_jobs, h->stream);
+        h->d_jobs = nullptr; h->cap_jobs = 0;
+        HX_CUDA(cudaMallocAsync(&h->d_jobs, (size_t)(jobs_bytes + jobs_bytes / 8), h->stream));
+        h->cap_jobs = jobs_bytes + jobs_bytes / 8;
+    }
 #define HX_UM_LAUNCH(CH_)                                                                                       \
     do {                                                                                                        \
         auto kern = fused ? k1_umma<CH_, true> : k1_umma<CH_, false>;                                           \
         HX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));            \
         kern<<<(unsigned)grid, UM_THREADS, smem, h->stream>>>(d_rank, d_off, d_codes, n_reads, h->N, h->W, kmax, \
                                                               hx_cnt_ref(h), h->d_totals, h->d_err, sorted_flag, \
-                                                              run_rank, run_stop, n_runs);                      \
+                                                              run_rank, run_stop, n_runs,                       \
+                                                              reinterpret_cast<int4 *>(h->d_jobs), (int)jobs_cap); \
     } while (0)
     if (kmax <= 16) HX_UM_LAUNCH(4);
     else HX_UM_LAUNCH(8);
