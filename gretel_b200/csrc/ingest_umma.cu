@@ -558,7 +558,7 @@ k1_umma(const int32_t *__restrict__ rank, const int64_t *__restrict__ off, const
         auto word_off = [](int w) { return (w >> 4) * HX_CELL + ((w & 15) >> 2) * HX_NSYM + (w & 3); };
         const int goff0 = word_off(threadIdx.x), goff1 = word_off(threadIdx.x + npt);
         static_assert(UM_RD_WARPS * 32 * 2 >= 31 * 16, "two tile words per readout thread cover a band row");
-        int64_t flushed_upto = (int64_t)rank[lo] + 1;
+        int64_t flushed_upto = (int64_t)max(rank[lo], 0) + 1;  // (a negative rank is an error the pre-pass has flagged)
         while (wk.next_run()) {
             const int r = wk.r;
             const unsigned ri = wk.ri;
@@ -566,10 +566,13 @@ k1_umma(const int32_t *__restrict__ rank, const int64_t *__restrict__ off, const
             UM_T(r0);
             // (the tile adds of the previous run are complete: barrier at the end of the loop body)
             if ((int64_t)r + 1 > flushed_upto) {
+                // the rows flushed below and the rows this run adds to (r+2 .. r+kmax) share a ring slot only if the
+                // ranks jumped: rows of the ring are kmax+1 apart
+                const bool slots_reused = (int64_t)r - flushed_upto >= 2;
                 const int64_t lastrow = min((int64_t)r + 1, flushed_upto + rows - 2);
                 // rows pj <= r+1 can no longer be touched by this CTA
                 unsigned long long sum = 0;
-                int row = (int)((flushed_upto + 1) % rows);
+                int row = (int)((unsigned)(flushed_upto + 1) % (unsigned)rows);
                 for (int64_t pj = flushed_upto + 1; pj <= lastrow; ++pj) {
                     uint32_t *base = tile32 + (size_t)row * per_row;
                     uint32_t *grow = cnt.cell(W, pj - 1, pj);        // cell d = 1 of band row pj; cell d is 49*(d-1) further
@@ -585,9 +588,9 @@ k1_umma(const int32_t *__restrict__ rank, const int64_t *__restrict__ off, const
                 }
                 t_crumbs += sum;
                 flushed_upto = (int64_t)r + 1;
-                ws_pair_barrier(npt);            // retired ring slots may be reused by this run's tile add
+                if (slots_reused) ws_pair_barrier(npt);   // retired ring slots are reused by this run's tile add
             }
-            const int rbase = (int)(((int64_t)r + 1) % rows);
+            const int rbase = (int)((unsigned)(r + 1) % (unsigned)rows);
             UM_T(r1);
             // the stage is complete after UM_ACC_COUNT arrivals: one per group (the expanders' commits) plus the rest here
             if (threadIdx.x == 0) {
@@ -596,7 +599,7 @@ k1_umma(const int32_t *__restrict__ rank, const int64_t *__restrict__ off, const
                              "r"(UM_ACC_COUNT - ng)
                              : "memory");
             }
-            ws_mbar_wait_sleep(ws_smem_u32(&s_acc_full[s]), (ri / UM_NACC) & 1);
+            ws_mbar_wait(ws_smem_u32(&s_acc_full[s]), (ri / UM_NACC) & 1);
             um_fence_after();
             UM_T(r2);
             const int kg = *reinterpret_cast<volatile int *>(&s_runkg[s]);
