@@ -319,7 +319,7 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device; there is no CPU fallback")
     torch.cuda.set_device(local_rank)
     dist = None
-    overlap = world > 1 and args.overlap_steps and args.exchange == "allreduce" and args.scaling == "weak" and args.segments <= 1
+    overlap = world > 1 and args.overlap_steps and args.exchange in ("allreduce", "auto") and args.scaling == "weak" and args.segments <= 1
     if world > 1:
         import torch.distributed as dist
         if overlap:
@@ -401,7 +401,7 @@ def run_ours(args):
     pipe = None
     fused = None
     seam = None
-    if strong and args.exchange in ("allreduce", "seam"):
+    if strong and args.exchange in ("auto", "allreduce", "seam"):
         seam = gdist.SeamExchange(h, int(d["rank"][-1]) if R else -1)
     if world > 1 and args.exchange == "fused":
         fused = gdist.FusedExchange(h)
@@ -442,7 +442,14 @@ def run_ours(args):
         h2 = Hansel.init_matrix(REF_SYMBOLS, REF_UNSYMBOLS, N, band_w=W, device=local_rank)
         h2.set_ingest_kernel(args.kernel)
         h2.counts_buffer()
-        ov = gdist.OverlappedAllreduce([h, h2], free_sms=args.comm_sms)
+        # "auto": the same NCCL integer all-reduce over counts packed two to a word when one job's counts leave room
+        # (largest count on any rank x world x 2 <= 65535; decided once, on a first complete job)
+        packed_ok = False
+        if args.exchange == "auto" and world >= 4:          # (2 GPUs: the plain all-reduce is short enough; measured slower packed)
+            h.reset_counts()
+            h.ingest_device(t_rank.data_ptr(), t_off.data_ptr(), t_codes.data_ptr(), R)
+            packed_ok = gdist.OverlappedAllreduce.packing_is_safe(h)
+        ov = gdist.OverlappedAllreduce([h, h2], free_sms=args.comm_sms, packed=packed_ok)
         stream = ov.main
 
     def ov_ingest(hh):
@@ -481,6 +488,18 @@ def run_ours(args):
         sampler.region(False)
         launches = h.launch_count() + h2.launch_count() - launches0
         total_ms = float(ev[0][0].elapsed_time(ev[0][1]))
+        # parity of the overlapped path itself: the matrix of the last job against the independent per-row recount
+        last = ov.hs[(ov.i - 1) & 1]
+        o_exp = torch.zeros(N + 2, dtype=torch.int64, device=dev)
+        o_got = torch.zeros(N + 2, dtype=torch.int64, device=dev)
+        torch.cuda.synchronize()
+        last.probe_expected_rows(t_rank.data_ptr(), t_off.data_ptr(), t_codes.data_ptr(), R, o_exp.data_ptr())
+        last.counts_row_sums(o_got.data_ptr())
+        last.sync()
+        dist.all_reduce(o_exp, op=dist.ReduceOp.SUM)
+        o_ok = torch.tensor([int(torch.equal(o_exp, o_got))], device=dev)
+        dist.all_reduce(o_ok, op=dist.ReduceOp.MIN)
+        overlap_probe_ok = bool(o_ok.item())
         # the same K steps one after the other (the all-reduce fully exposed), for comparison
         barrier()
         with torch.cuda.stream(stream):
@@ -539,6 +558,8 @@ def run_ours(args):
     pok = torch.tensor([int(rows_ok and sum_ok)], device=dev)
     if world > 1:
         dist.all_reduce(pok, op=dist.ReduceOp.MIN)
+    if ov is not None:
+        pok = torch.tensor([int(bool(pok.item()) and overlap_probe_ok)], device=dev)
     parity_probe = {"ok": bool(pok.item()), "rows_equal": rows_ok, "sum_equals_crumbs_plus_sentinels": sum_ok,
                     "rows": N + 2, "band_sum": int(rows_got.sum().item()), "n_crumbs": int(pt[1]),
                     "sentinel_increments": int(pt[3]), "ranks_checked": world if (args.exchange != "reduce" and seam is None) else 1,
@@ -805,7 +826,8 @@ def run_ours(args):
             "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
             "config": dict(workload_config(args, k_mean, R), **({"reads_total": int(args.reads or w.n_reads),
                                                                  "reads_per_gpu": "one read set cut into %d contiguous chunks balanced by pair count" % world} if strong else {})),
-            "step_overlap": ({"on": True, "comm_sms": args.comm_sms,
+            "step_overlap": ({"on": True, "comm_sms": args.comm_sms, "packed_uint16_lanes": bool(ov.packed),
+                              "parity_probe_ok": overlap_probe_ok,
                               "what": "the all-reduce of step i runs on a second stream beside the pair expansion of step i+1 "
                                       "(two matrices take turns; the ingestion kernel leaves comm_sms SMs to NCCL)",
                               "value_without_overlap": n_obs_global * args.steps / (serial_ms * 1e-3),
@@ -850,7 +872,7 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="N>1: weak = every GPU ingests its own full-size read set of the same region (default, what the "
                          "driver's scaling run uses); strong = ONE read set cut into contiguous chunks, seam-only exchange")
-    ap.add_argument("--exchange", default="allreduce", choices=["allreduce", "packed", "reduce", "fused", "seam"],
+    ap.add_argument("--exchange", default="auto", choices=["auto", "allreduce", "packed", "reduce", "fused", "seam"],
                     help="N>1: NCCL all-reduce of the partial matrices (default, as north_star names it); the same "
                          "all-reduce over counts packed into uint16 lanes (half the bytes); reduce onto "
                          "rank 0 only (recovery runs there); or counts added straight into the owning GPU over "

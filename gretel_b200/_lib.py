@@ -30,6 +30,9 @@ SIGNATURES = {
     "hx_ingest_host": (_int, [_p, _p, _p, _p, _i64, _p]),
     "hx_counts_pack": (_int, [_p, _i32, _pp, C.POINTER(_i64)]),
     "hx_counts_unpack": (_int, [_p, C.POINTER(_i32)]),
+    "hx_counts_unpack_async": (_int, [_p, _p]),
+    "hx_counts_pack_overflowed": (_int, [_p, C.POINTER(_i32)]),
+    "hx_counts_max": (_int, [_p, C.POINTER(C.c_uint32)]),
     "hx_ingest_host_compact": (_int, [_p, _p, _p, _p, _i64, _i64, _p]),
     "hx_dense_encode": (_int, [_p, _p, _p, _i64, _int, _p]),
     "hx_dense_free": (None, [_p]),

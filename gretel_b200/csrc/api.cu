@@ -619,6 +619,56 @@ int hx_counts_unpack(hx_matrix *h, int32_t *overflowed) {
     return HX_OK;
 }
 
+int hx_counts_unpack_async(hx_matrix *h, void *stream) {
+    HX_CHECK_ARG(h && h->d_pack && h->cnt);
+    HX_CUDA(cudaSetDevice(h->device));
+    const int64_t n_pairs = h->band_elems / HX_CELL;
+    const int64_t flag_at = (n_pairs * HX_PACK_WORDS + 3) & ~(int64_t)3;
+    const int64_t n_w = n_pairs * HX_PACK_WORDS;
+    h->cnt_fresh = false;
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    k_unpack_counts<<<(unsigned)((n_w + 255) / 256), 256, 0, st>>>(h->d_pack, n_pairs, h->cnt, flag_at);
+    h->launches++;
+    HX_CUDA(cudaGetLastError());
+    return HX_OK;
+}
+
+int hx_counts_pack_overflowed(hx_matrix *h, int32_t *overflowed) {
+    HX_CHECK_ARG(h && overflowed && h->d_pack);
+    HX_CUDA(cudaSetDevice(h->device));
+    const int64_t n_pairs = h->band_elems / HX_CELL;
+    const int64_t flag_at = (n_pairs * HX_PACK_WORDS + 3) & ~(int64_t)3;
+    uint32_t *hp = (uint32_t *)h->h_pinned + 40;
+    HX_CUDA(cudaMemcpyAsync(hp, h->d_pack + flag_at, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    HX_CUDA(cudaStreamSynchronize(h->stream));
+    *overflowed = *hp != 0;
+    return HX_OK;
+}
+
+__global__ void k_counts_max(const uint32_t *__restrict__ cnt, int64_t n, uint32_t *__restrict__ out) {
+    uint32_t m = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) m = max(m, cnt[i]);
+    m = __reduce_max_sync(0xffffffffu, m);
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
+}
+
+int hx_counts_max(hx_matrix *h, uint32_t *max_count) {
+    HX_CHECK_ARG(h && max_count);
+    HX_CUDA(cudaSetDevice(h->device));
+    int rc = hx_ensure_counts_buffer(h);
+    if (rc) return rc;
+    uint32_t *d_out = reinterpret_cast<uint32_t *>(h->d_flags + 6);
+    HX_CUDA(hx_fill_async(d_out, 0, sizeof(uint32_t), h->stream));
+    k_counts_max<<<592, 256, 0, h->stream>>>(h->cnt, h->cnt_elems, d_out);
+    h->launches++;
+    HX_CUDA(cudaGetLastError());
+    uint32_t *hp = (uint32_t *)h->h_pinned + 41;
+    HX_CUDA(cudaMemcpyAsync(hp, d_out, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    HX_CUDA(cudaStreamSynchronize(h->stream));
+    *max_count = *hp;
+    return HX_OK;
+}
+
 int hx_counts_ipc_export(hx_matrix *h, int32_t world, void *handle_out) {
     HX_CHECK_ARG(h && handle_out && world >= 1 && world <= HX_MAX_PEERS);
     HX_CUDA(cudaSetDevice(h->device));

@@ -101,10 +101,17 @@ class OverlappedAllreduce:
     collective changes.  The ingestion kernels are persistent (one CTA per SM), so a few SMs are left to NCCL
     (``free_sms``)."""
 
-    def __init__(self, hansels, group=None, free_sms=8):
+    def __init__(self, hansels, group=None, free_sms=8, packed=False):
+        """``packed``: the counts travel as uint16 lanes packed into uint32 words (hx_counts_pack: 25 words instead of
+        49 per cell); pack and write-back are kernels on the compute / communication stream, nothing waits for the
+        host.  Safe while every count * world <= 65535 (``packing_is_safe``); the pack kernel flags anything larger,
+        the flag is summed with the data, the write-back then leaves the partials alone and ``drain`` raises."""
         import torch
         import torch.distributed as dist
         self.hs, self.group, self.dist, self.torch = list(hansels), group, dist, torch
+        self.packed = bool(packed)
+        self.world = dist.get_world_size(group)
+        self.pbufs = [None, None]
         assert len(self.hs) == 2
         dev = torch.device("cuda", self.hs[0].device)
         self.dev = dev
@@ -131,12 +138,19 @@ class OverlappedAllreduce:
         if self.used[b]:
             self.main.wait_event(self.reduced[b])            # the matrix's previous job has been summed and consumed
         ingest(h)
+        counts, totals = self.bufs[b]
+        if self.packed:
+            pptr, pn = h.counts_pack(self.world)               # on the compute stream, behind the expansion
+            if self.pbufs[b] is None or self.pbufs[b][0] != (pptr, pn):
+                self.pbufs[b] = ((pptr, pn), self.torch.as_tensor(_DevBuf(pptr, pn, "<i4"), device=self.dev))
+            counts = self.pbufs[b][1]
         self.ingested[b].record(self.main)
         self.comm.wait_event(self.ingested[b])
-        counts, totals = self.bufs[b]
         with self.torch.cuda.stream(self.comm):
             self.dist.all_reduce(counts, op=self.dist.ReduceOp.SUM, group=self.group)
             self.dist.all_reduce(totals, op=self.dist.ReduceOp.SUM, group=self.group)
+            if self.packed:
+                h.counts_unpack_async(self.comm.cuda_stream)   # sums back into the counts, still off the compute stream
             self.reduced[b].record(self.comm)
         self.used[b] = True
         self.i += 1
@@ -147,6 +161,22 @@ class OverlappedAllreduce:
         for b in range(2):
             if self.used[b]:
                 self.main.wait_event(self.reduced[b])
+        if self.packed:
+            for b in range(2):
+                if self.used[b] and self.hs[b].counts_pack_overflowed():
+                    raise RuntimeError("packed exchange: a count exceeded 65535 / world on some rank; the sums of the "
+                                       "jobs since the last drain are partial - use packed=False")
+
+    @staticmethod
+    def packing_is_safe(hansel, group=None, headroom=2):
+        """True on every rank iff the largest pending count on any rank, times world (times ``headroom`` for jobs that
+        are not identical to this one), fits a uint16 lane.  Synchronises; call it once, on a representative job."""
+        import torch
+        import torch.distributed as dist
+        world = dist.get_world_size(group)
+        m = torch.tensor([hansel.counts_max()], dtype=torch.int64, device=torch.device("cuda", hansel.device))
+        dist.all_reduce(m, op=dist.ReduceOp.MAX, group=group)
+        return int(m.item()) * world * headroom <= 65535
 
 
 class SeamExchange:

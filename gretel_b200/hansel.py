@@ -205,6 +205,24 @@ class Hansel:
         self._touch()
         return o.value == 0
 
+    def counts_unpack_async(self, stream=None):
+        """Enqueue the write-back of the all-reduced packed sums on ``stream`` (a raw cudaStream_t; default: the
+        matrix's own); no synchronisation - see counts_pack_overflowed."""
+        _lib.check(self._lib.hx_counts_unpack_async(self._h, C.c_void_p(stream or 0)))
+        self._touch()
+
+    def counts_pack_overflowed(self):
+        """True if a lane of the last packed exchange overflowed on some rank (its counts were left as partials)."""
+        o = C.c_int32()
+        _lib.check(self._lib.hx_counts_pack_overflowed(self._h, C.byref(o)))
+        return o.value != 0
+
+    def counts_max(self):
+        """Largest pending count on this GPU (synchronises)."""
+        m = C.c_uint32()
+        _lib.check(self._lib.hx_counts_max(self._h, C.byref(m)))
+        return int(m.value)
+
     def ingest_device(self, d_rank_ptr, d_off_ptr, d_codes_ptr, n_reads):
         """Asynchronous ingestion of packed reads already resident on this GPU (raw device pointers)."""
         _lib.check(self._lib.hx_ingest_device(self._h, d_rank_ptr, d_off_ptr, d_codes_ptr, int(n_reads)))

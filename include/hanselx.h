@@ -118,6 +118,13 @@ int hx_counts_buffer(hx_matrix *h, void **d_counts, int64_t *n_u32, void **d_tot
  * untouched and the caller must fall back to hx_counts_buffer().  hx_counts_unpack synchronises. */
 int hx_counts_pack(hx_matrix *h, int32_t world, void **d_packed, int64_t *n_u32);
 int hx_counts_unpack(hx_matrix *h, int32_t *overflowed);
+/* For exchanges that run behind the next ingestion (no host synchronisation per job): hx_counts_unpack_async launches
+ * the write-back on `stream` (a cudaStream_t; NULL = the matrix's stream) and returns; hx_counts_pack_overflowed reads
+ * the all-reduced overflow flag of the last packed exchange (synchronises).  hx_counts_max = the largest pending
+ * count on this GPU (synchronises): packing is safe while max * world <= 65535. */
+int hx_counts_unpack_async(hx_matrix *h, void *stream);
+int hx_counts_pack_overflowed(hx_matrix *h, int32_t *overflowed);
+int hx_counts_max(hx_matrix *h, uint32_t *max_count);
 /* Fused exchange (one process per GPU, NVLink peer memory): band rows are dealt out to the ranks in
  * contiguous blocks of ceil((N+2)/world); after export + import every ingestion kernel adds its counts
  * straight into the GPU that owns the row, so when all ranks' kernels are done each rank holds the final

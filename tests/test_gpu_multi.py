@@ -65,6 +65,30 @@ def _worker(rank, world, port, segments, out):
         elif segments == -2:                                # packed exchange (uint16 lanes)
             h.ingest_device(t_rank.data_ptr(), t_off.data_ptr(), t_codes.data_ptr(), hi - lo)
             assert gdist.allreduce_counts_packed(h)
+        elif segments == -3:                                # packed exchange behind the next job's expansion
+            hb = Hansel.init_matrix(REF_SYMBOLS, REF_UNSYMBOLS, N, band_w=W, device=rank)
+            hb.counts_buffer()
+
+            def job(hh):
+                hh.reset_counts()
+                hh.ingest_device(t_rank.data_ptr(), t_off.data_ptr(), t_codes.data_ptr(), hi - lo)
+
+            job(h)                                           # a representative job decides whether packing is safe
+            assert gdist.OverlappedAllreduce.packing_is_safe(h)
+            ov = gdist.OverlappedAllreduce([hb, h], free_sms=16, packed=True)
+            for _ in range(4):                               # the jobs alternate between hb and h: the last one lands in h
+                ov.step(job)
+            ov.drain()
+            # a count that cannot travel in a uint16 lane is flagged (the flag is summed with the data), not truncated
+            with torch.cuda.stream(ov.main):
+                job(hb)
+                cptr, cn, _t, _tn = hb.counts_buffer()
+                if rank == 1:
+                    torch.as_tensor(gdist._DevBuf(cptr, cn, "<i4"), device=dev)[7] = 50000
+                pptr, pn = hb.counts_pack(world)
+                dist.all_reduce(torch.as_tensor(gdist._DevBuf(pptr, pn, "<i4"), device=dev), op=dist.ReduceOp.SUM)
+            assert hb.counts_pack_overflowed()
+            hb.close()
         elif segments > 1:
             pipe = gdist.PipelinedIngest(h, d["rank"][lo:hi], hi - lo, segments=segments)
             h.reset_counts()
@@ -90,7 +114,7 @@ def _worker(rank, world, port, segments, out):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("segments", [1, 4, 40, 50, -1, -2])
+@pytest.mark.parametrize("segments", [1, 4, 40, 50, -1, -2, -3])
 def test_two_gpu_sharded_ingest(tmp_path, c_oracle, segments):
     import torch
     import torch.multiprocessing as mp
