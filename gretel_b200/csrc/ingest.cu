@@ -298,9 +298,8 @@ k1_bitsliced(const int32_t *__restrict__ rank, const int64_t *__restrict__ off,
     __shared__ int s_claim[3];                       // next group to transpose (same rotation): warps claim work
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    const int64_t per = (n_reads + gridDim.x - 1) / gridDim.x;
-    const int64_t lo = (int64_t)blockIdx.x * per;
-    const int64_t hi = lo + per < n_reads ? lo + per : n_reads;
+    int64_t lo, hi;                                  // equal shares of the work, not of the read count
+    hx_weighted_slice(rank, off, n_reads, HX_SLICE_READ_W, HX_SLICE_RANK_W, lo, hi);
     if (lo >= hi) return;
 
     for (size_t w = threadIdx.x; w < (size_t)rows * cells * 4; w += blockDim.x) tile[w] = make_uint4(0, 0, 0, 0);
@@ -525,9 +524,8 @@ k1_bitsliced_ws(const int32_t *__restrict__ rank, const int64_t *__restrict__ of
     const int bw = nwarps - pw;                      // builder warps
     const bool is_pair = warp < pw;
     const int npt = pw * 32;                         // threads that own site pairs
-    const int64_t per = (n_reads + gridDim.x - 1) / gridDim.x;
-    const int64_t lo = (int64_t)blockIdx.x * per;
-    const int64_t hi = lo + per < n_reads ? lo + per : n_reads;
+    int64_t lo, hi;                                  // equal shares of the work, not of the read count
+    hx_weighted_slice(rank, off, n_reads, HX_SLICE_READ_W, HX_SLICE_RANK_W, lo, hi);
     if (lo >= hi) return;
 
     for (size_t w = threadIdx.x; w < (size_t)rows * cells * 4; w += blockDim.x) tile[w] = make_uint4(0, 0, 0, 0);

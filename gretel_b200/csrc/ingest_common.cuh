@@ -82,6 +82,45 @@ __device__ __forceinline__ void bs_prefetch_l2(const void *p, uint32_t bytes) {
 }
 
 
+// The CTA's slice [lo, hi) of rank-sorted reads: equal shares of the weight
+//   f(i) = alleles before read i + HX_SLICE_READ_W * i + HX_SLICE_RANK_W * (rank[i] - rank[0])
+// - the per-allele, per-read and per-run costs of the sorted-run kernels - not of the read count: SNP density varies
+// along a region and with it the alleles per read and the runs per read (BASELINE configs[2]: the densest of 148
+// equal-count slices holds 1.34x the mean).  Slice c starts at the first i with f(i) >= total * c / grid; warps 0 and 1
+// find the two ends with a 32-ary search over off[] / rank[].  Every thread of the CTA must call it (one barrier).
+constexpr int HX_SLICE_READ_W = 16, HX_SLICE_RANK_W = 8192;      // swept on the B200 with k1_umma on configs[2]
+__device__ __forceinline__ void hx_weighted_slice(const int32_t *__restrict__ rank, const int64_t *__restrict__ off,
+                                                  int64_t n_reads, int read_w, int rank_w, int64_t &lo, int64_t &hi) {
+    __shared__ long long s_lohi[2];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (warp < 2) {
+        const int64_t base = off[0];
+        const int64_t rbase = rank[0];
+        const int64_t total = off[n_reads] - base + (int64_t)read_w * n_reads + (int64_t)rank_w * (rank[n_reads - 1] - rbase);
+        const int c = (int)blockIdx.x + warp;
+        const int64_t G = (int64_t)gridDim.x;
+        const int64_t target = c >= (int)gridDim.x ? total : (total / G) * c + ((total % G) * c) / G;
+        int64_t a = 0, b = n_reads;                      // the answer lies in [a, b]: f(n_reads) = total >= target
+        while (a < b) {
+            const int64_t span = b - a;
+            const int64_t p = a + (span * (lane + 1)) / 33;               // 32 probes inside [a, b)
+            const bool ge = off[p] - base + (int64_t)read_w * p + (int64_t)rank_w * (rank[p] - rbase) >= target;
+            const unsigned m = __ballot_sync(0xffffffffu, ge);
+            if (m == 0) {
+                a = __shfl_sync(0xffffffffu, p, 31) + 1;
+            } else {
+                const int first = __ffs(m) - 1;
+                b = __shfl_sync(0xffffffffu, p, first);
+                if (first > 0) a = __shfl_sync(0xffffffffu, p, first - 1) + 1;
+            }
+        }
+        if (lane == 0) s_lohi[warp] = a;
+    }
+    __syncthreads();
+    lo = s_lohi[0];
+    hi = s_lohi[1];
+}
+
 __device__ __forceinline__ uint32_t ws_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void ws_mbar_init(uint32_t bar, int count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));

@@ -268,36 +268,8 @@ k1_umma(const int32_t *__restrict__ rank, const int64_t *__restrict__ off, const
     constexpr uint32_t SLOTB = 32u * ROWB;           // one group: 32 reads = the K of one MMA
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // The CTA's slice of the reads [lo, hi): equal shares of the weight f(i) = alleles before read i + read_w * i +
-    // rank_w * (rank[i] - rank[0]), not of the read count - SNP density varies along the region, and with it the alleles per read and the runs per
-    // read (config 3: the densest of 148 equal-count slices holds 1.34x the mean).  Slice c starts at the first i
-    // with f(i) >= total * c / grid; warps 0 and 1 find the two ends with a 32-ary search over off[].
-    __shared__ long long s_lohi[2];
-    if (warp < 2) {
-        const int64_t base = off[0];
-        const int64_t rbase = rank[0];
-        const int64_t total = off[n_reads] - base + (int64_t)read_w * n_reads + (int64_t)rank_w * (rank[n_reads - 1] - rbase);
-        const int c = (int)blockIdx.x + warp;
-        const int64_t G = (int64_t)gridDim.x;
-        const int64_t target = c >= (int)gridDim.x ? total : (total / G) * c + ((total % G) * c) / G;
-        int64_t a = 0, b = n_reads;                      // the answer lies in [a, b]: f(n_reads) = total >= target
-        while (a < b) {
-            const int64_t span = b - a;
-            const int64_t p = a + (span * (lane + 1)) / 33;               // 32 probes inside [a, b)
-            const bool ge = off[p] - base + (int64_t)read_w * p + (int64_t)rank_w * (rank[p] - rbase) >= target;
-            const unsigned m = __ballot_sync(0xffffffffu, ge);
-            if (m == 0) {
-                a = __shfl_sync(0xffffffffu, p, 31) + 1;
-            } else {
-                const int first = __ffs(m) - 1;
-                b = __shfl_sync(0xffffffffu, p, first);
-                if (first > 0) a = __shfl_sync(0xffffffffu, p, first - 1) + 1;
-            }
-        }
-        if (lane == 0) s_lohi[warp] = a;
-    }
-    __syncthreads();
-    const int64_t lo = s_lohi[0], hi = s_lohi[1];
+    int64_t lo, hi;                                  // equal shares of the work, not of the read count
+    hx_weighted_slice(rank, off, n_reads, read_w, rank_w, lo, hi);
     if (lo >= hi) return;
 
     const int rows = kmax + 1, cells = kmax - 1;
@@ -723,8 +695,8 @@ int hx_launch_ingest_umma(hx_matrix *h, const int32_t *d_rank, const int64_t *d_
     // per-run costs of the kernel (config 3, tuned on the B200: 16 / 8192 gives 0.330 ms per step, equal read counts
     // 0.373); a read carries at most kmax alleles, so a slice holds at most (kmax + read_w) / read_w times its even
     // share of the reads (plus the rank term's share)
-    static const int read_w = [] { const char *e = getenv("HX_UM_READ_W"); const int v = e ? atoi(e) : 16; return v < 1 ? 1 : v; }();
-    static const int rank_w = [] { const char *e = getenv("HX_UM_RANK_W"); const int v = e ? atoi(e) : 8192; return v < 0 ? 0 : v; }();
+    static const int read_w = [] { const char *e = getenv("HX_UM_READ_W"); const int v = e ? atoi(e) : HX_SLICE_READ_W; return v < 1 ? 1 : v; }();
+    static const int rank_w = [] { const char *e = getenv("HX_UM_RANK_W"); const int v = e ? atoi(e) : HX_SLICE_RANK_W; return v < 0 ? 0 : v; }();
     // per-CTA job tables: a slice of `per` reads holds at most per/32 full groups plus one partial group per run
     const int64_t per = (((n_reads + grid - 1) / grid + 1) * (kmax + read_w) + ((int64_t)rank_w * (h->N + 2) + grid - 1) / grid) / read_w + 2;
     const int64_t jobs_cap = per / 32 + std::min<int64_t>((int64_t)h->N + 2, per) + 2;
