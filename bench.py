@@ -685,6 +685,18 @@ def run_ours(args):
                                  else lumma_floor(d["rank"], d["off"], kms) if lumma else None),
                 "pipe_floor": (popc_floor(d["rank"], d["off"], kms) if (d["max_k"] <= 52 and not umma) else None)}
 
+    # which of the floors is the tightest (the largest fraction = the resource closest to binding)
+    cands = [("hbm (compulsory traffic)", roofline["frac"])]
+    if roofline["tensor_floor"]:
+        cands.append(("tensor (MMA count at the 64-cycle int8 peak)", roofline["tensor_floor"]["frac"]))
+    if roofline["pipe_floor"]:
+        cands.append(("xu pipe (POPC count)", roofline["pipe_floor"]["frac"]))
+    best = max(cands, key=lambda c: c[1])
+    roofline["tightest_bound"] = {"name": best[0], "frac": best[1],
+                                  "note": "none of the floors binds: the short-read kernel is limited by instruction issue and the "
+                                          "per-run hand-over between its expander and readout warps, the long-read kernel by "
+                                          "shared-memory bandwidth under the MMAs (DESIGN.md section 4, profiles/r2_ingest_*.md)"}
+
     # ---- CPU baseline: the reference's per-pair Python loop on a bounded sample, all cores
     if args.no_cpu_baseline:
         args.recovery_cpu_baseline = False
