@@ -34,6 +34,9 @@ namespace {
 constexpr int UM_RD_WARPS = 8;               // readout warps: two per TMEM lane quarter (warp id % 4)
 constexpr int UM_EXP_WARPS = UM_EXP_WARPS_N; // expander warps 8..
 constexpr int UM_THREADS = (UM_RD_WARPS + UM_EXP_WARPS) * 32;
+#ifndef UM_GATE_NS
+#define UM_GATE_NS 200
+#endif
 constexpr int UM_JB = 256;                  // runs per batch of the job-table build
 constexpr int UM_NACC = 4;                   // accumulator stages (runs in flight)
 constexpr int UM_TMEM_COLS = 128 * UM_NACC;  // 128 int32 columns each
@@ -464,7 +467,7 @@ k1_umma(const int32_t *__restrict__ rank, const int64_t *__restrict__ off, const
             // of run ri is added; the previous MMA of this warp must have read the slot before it is rewritten
             if (cur_ri >= (unsigned)UM_NACC) {
                 const unsigned need = cur_ri - UM_NACC + 1;
-                while (um_ld_acquire(runs_addr) < need) __nanosleep(200);
+                while (um_ld_acquire(runs_addr) < need) __nanosleep(UM_GATE_NS);
             }
             ws_mbar_wait(slot_bar, (njobs & 1) ^ 1);
             um_fence_after();
