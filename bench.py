@@ -599,7 +599,7 @@ def run_ours(args):
         return hh
 
     def time_e2e(fmt, steps):
-        for _ in range(2):
+        for _ in range(6):                    # untimed: thread pool, pinned staging and parked handles warm (fresh box)
             e2e_step(fmt).close()
         barrier()
         t0 = time.perf_counter()
