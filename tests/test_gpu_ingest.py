@@ -596,3 +596,51 @@ def test_unsorted_short_reads_take_the_counting_sort_kernel(c_oracle, monkeypatc
     band, totals = _gpu_band(rank[order], off_s, codes[idx], N, W)
     assert totals == tuple(int(x) for x in rt)
     assert np.array_equal(band, ref.astype(np.float32))
+
+
+def _packed_from(rank, k, rng, p_special=0.02):
+    order = np.argsort(rank, kind="stable")
+    rank, k = rank[order].astype(np.int32), k[order]
+    off = np.concatenate([[0], np.cumsum(k)]).astype(np.int64)
+    codes = rng.integers(0, 4, size=int(off[-1])).astype(np.uint8)
+    sp = rng.random(len(codes)) < p_special
+    codes[sp] = rng.integers(4, 7, size=int(sp.sum())).astype(np.uint8)
+    return rank, off, codes
+
+
+@pytest.mark.parametrize("shape", ["one_run", "many_runs_per_cta", "mostly_narrow_reads", "rank_jumps", "dense_then_sparse"])
+@pytest.mark.parametrize("kernel", [6, 2, 5])
+def test_slices_and_job_tables_on_skewed_shapes(c_oracle, shape, kernel):
+    """The sorted-run kernels cut the reads into CTA slices of equal WEIGHT (alleles, reads, ranks) with a search over
+    off[] / rank[], and the tensor-core kernel builds per-CTA job tables from the run list in batches of 256 runs:
+    shapes that put the cuts inside one giant run, that give a CTA more than 256 runs, whose weight is almost all
+    per-read or per-rank, and whose density changes abruptly."""
+    rng = np.random.default_rng({"one_run": 1, "many_runs_per_cta": 2, "mostly_narrow_reads": 3, "rank_jumps": 4, "dense_then_sparse": 5}[shape])
+    if shape == "one_run":
+        N, R = 40, 300_000
+        rank = np.full(R, 5)
+        k = rng.integers(2, 21, size=R)
+    elif shape == "many_runs_per_cta":
+        N, R = 300_000, 150_000                  # ~118k populated ranks over 148 CTAs: ~800 runs each, 4 batches of 256
+        rank = rng.integers(0, N - 8, size=R)
+        k = rng.integers(2, 9, size=R)
+    elif shape == "mostly_narrow_reads":
+        N, R = 2000, 250_000
+        rank = rng.integers(0, N - 12, size=R)
+        k = np.where(rng.random(R) < 0.9, rng.integers(0, 2, size=R), rng.integers(2, 13, size=R))
+    elif shape == "rank_jumps":
+        N, R = 50_000, 120_000
+        rank = rng.choice(np.arange(0, N - 32, 977), size=R)      # 52 populated ranks, 977 apart
+        k = rng.integers(2, 31, size=R)
+    else:
+        N, R = 6000, 200_000
+        dense = rng.random(R) < 0.8
+        rank = np.where(dense, rng.integers(0, 300, size=R), rng.integers(300, N - 30, size=R))
+        k = np.where(dense, rng.integers(20, 31, size=R), rng.integers(2, 6, size=R))
+    k = np.minimum(k, N - rank)
+    rank, off, codes = _packed_from(rank, k, rng)
+    W = int(max(1, k.max() - 1))
+    ref, rt = c_oracle.ingest(rank, off, codes, N, W)
+    band, totals = _gpu_band(rank, off, codes, N, W, kernel)
+    assert totals == tuple(int(x) for x in rt)
+    assert np.array_equal(band, ref.astype(np.float32))
