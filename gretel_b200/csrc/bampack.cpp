@@ -397,15 +397,65 @@ struct BamStream {
             q = (size_t)used;
         }
         const uint8_t *d = ubuf.get();
-        while (q + 4 <= ulen) {
-            const int32_t bs = rdi32(d + q);
-            if (bs < 32) { hx_set_error("%s: corrupt alignment record (block_size %d)", path.c_str(), bs); return HX_E_ARG; }
-            if (q + 4 + (size_t)bs > ulen) break;
-            // the chain of block_size fields is serial and every step is a cache miss: fetch where the chain will
-            // be in 16 records if they are about this long
-            __builtin_prefetch(d + std::min(ulen - 1, q + 16 * (4 + (size_t)bs)));
-            recs.push_back({q + 4, (uint32_t)bs});
-            q += 4 + (size_t)bs;
+        // The chain of block_size fields is serial and every step is a cache miss (20 ns per record).  htslib never
+        // splits a record between BGZF blocks unless it is larger than a block (bam_write1 flushes first), so in
+        // practice a block starts a record: the threads walk the chain speculatively from block starts, one
+        // stretch of blocks each, and the serial pass below only checks that the real chain arrives exactly where
+        // a stretch started - if it does not (records cut by block ends), it walks that stretch itself.
+        struct Stretch { size_t start, end, exit; bool ok; std::vector<RecRef> recs; };
+        std::vector<Stretch> st;
+        {
+            const int nt = (int)std::min<size_t>((size_t)n_threads, blocks.size() / 8);
+            for (int t = 1; t < nt; ++t) {                     // (the stretch of thread 0 is walked by the serial pass)
+                const size_t b0 = blocks.size() * (size_t)t / (size_t)nt, b1 = blocks.size() * (size_t)(t + 1) / (size_t)nt;
+                const size_t s0 = base + blocks[b0].uoff, s1 = b1 < blocks.size() ? base + blocks[b1].uoff : ulen;
+                if (s0 < s1 && s0 >= q) st.push_back({s0, s1, s0, false, {}});
+            }
+            auto walk = [&](Stretch &x) {
+                size_t p = x.start;
+                x.recs.reserve((x.end - x.start) / 200 + 16);
+                bool ok = true;
+                while (p < x.end) {
+                    if (p + 4 > ulen) break;
+                    const int32_t bs = rdi32(d + p);
+                    if (bs < 32) { ok = false; break; }
+                    if (p + 4 + (size_t)bs > ulen) break;          // the wave's last, partial record
+                    __builtin_prefetch(d + std::min(ulen - 1, p + 16 * (4 + (size_t)bs)));
+                    x.recs.push_back({p + 4, (uint32_t)bs});
+                    p += 4 + (size_t)bs;
+                }
+                x.exit = p;
+                x.ok = ok;
+            };
+            std::vector<std::thread> th;
+            for (size_t i = 1; i < st.size(); ++i) th.emplace_back(walk, std::ref(st[i]));
+            if (!st.empty()) walk(st[0]);
+            for (auto &t : th) t.join();
+        }
+        size_t si = 0;
+        bool at_end = false;
+        while (!at_end && q + 4 <= ulen) {
+            while (si < st.size() && st[si].start < q) ++si;       // stretches the chain has already passed
+            if (si < st.size() && st[si].start == q) {
+                if (st[si].ok) {
+                    recs.insert(recs.end(), st[si].recs.begin(), st[si].recs.end());
+                    at_end = st[si].exit + 4 > ulen || st[si].exit < st[si].end;   // stopped at the wave's partial record
+                    q = st[si].exit;
+                    ++si;
+                    continue;
+                }
+                ++si;                                  // it met a block_size < 32: the walk below says what is wrong
+            }
+            const size_t stop = si < st.size() ? st[si].start : ulen;     // walk up to the next stretch
+            while (q < stop && q + 4 <= ulen) {
+                const int32_t bs = rdi32(d + q);
+                if (bs < 32) { hx_set_error("%s: corrupt alignment record (block_size %d)", path.c_str(), bs); return HX_E_ARG; }
+                if (q + 4 + (size_t)bs > ulen) { at_end = true; break; }
+                __builtin_prefetch(d + std::min(ulen - 1, q + 16 * (4 + (size_t)bs)));
+                recs.push_back({q + 4, (uint32_t)bs});
+                q += 4 + (size_t)bs;
+            }
+            if (q >= ulen || q + 4 > ulen) break;
         }
         carry.assign(d + q, d + ulen);
         if (eof && !carry.empty()) { hx_set_error("%s: truncated BAM (partial record at EOF)", path.c_str()); return HX_E_ARG; }

@@ -207,14 +207,15 @@ def write_bam(path, d, w, contig="ctg", threads=8, level=1):
     text = "@HD\tVN:1.0\tSO:coordinate\n@SQ\tSN:%s\tLN:%d\n" % (contig, G)
     head = (b"BAM\x01" + struct.pack("<i", len(text)) + text.encode() + struct.pack("<i", 1)
             + struct.pack("<i", len(contig) + 1) + contig.encode() + b"\x00" + struct.pack("<i", G))
-    payload = head + buf[order].tobytes()
+    body = buf[order].tobytes()
     def bgzf(chunk):
         co = zlib.compressobj(level, zlib.DEFLATED, -15)
         comp = co.compress(chunk) + co.flush()
         return (b"\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff\x06\x00BC\x02\x00" + struct.pack("<H", len(comp) + 25)
                 + comp + struct.pack("<II", zlib.crc32(chunk) & 0xffffffff, len(chunk)))
-    blk = 65280
-    chunks = [payload[i:i + blk] for i in range(0, len(payload), blk)]
+    # as htslib writes it: the header in a block of its own, and a block ends rather than cut a record
+    blk = (65280 // rec) * rec
+    chunks = [head] + [body[i:i + blk] for i in range(0, len(body), blk)]
     with ThreadPoolExecutor(max_workers=max(1, threads)) as ex, open(path, "wb") as fh:
         for b in ex.map(bgzf, chunks, chunksize=64):
             fh.write(b)

@@ -154,3 +154,35 @@ def test_snpper_gpu_histogram(tmp_path, golden_dir):
     buf = io.StringIO()
     snpper.main(["--bam", os.path.join(golden_dir, "ref_test.bam"), "--contig", "hoot"], out=buf)
     assert [int(l.split("\t")[1]) for l in buf.getvalue().strip().split("\n")[1:]] == [1, 2, 10]
+
+
+@pytest.mark.parametrize("layout", ["aligned", "cut_anywhere", "tiny_blocks"])
+def test_record_scan_over_many_blocks(tmp_path, layout):
+    """The packer finds the records of a wave with a speculative parallel walk from BGZF block starts (htslib ends a
+    block rather than cut a record) and falls back to the serial chain where the real chain does not arrive at a block
+    start.  Files of hundreds of blocks in both layouts, 1 and 8 threads: identical packed reads, equal to the
+    Python packer's on a sample window."""
+    rng = np.random.default_rng(7)
+    G, n = 60_000, 40_000
+    starts = np.sort(rng.integers(0, G - 150, size=n))
+    bases = np.array(list("ACGT"))
+    seqs = bases[rng.integers(0, 4, size=(n, 150))]
+    reads = [(0, int(s0), 0, "r%d" % i, [("M", 100), ("D", 2), ("M", 50)] if i % 7 == 0 else [("M", 150)], "".join(seqs[i]))
+             for i, s0 in enumerate(starts)]
+    path = str(tmp_path / "big.bam")
+    write_bam(path, [("ctg", G)], reads, block={"aligned": 30000, "cut_anywhere": 30011, "tiny_blocks": 700}[layout],
+              align=layout != "cut_anywhere")
+    snps = np.sort(rng.choice(np.arange(1, G + 1), size=4000, replace=False))
+    vh = {"N": len(snps), "snp_rev": {i: int(p) for i, p in enumerate(snps)}}
+    one = bamio.pack_bam_native(path, "ctg", 1, G, vh, n_threads=1)
+    many = bamio.pack_bam_native(path, "ctg", 1, G, vh, n_threads=8)
+    for a, b in zip(one, many):
+        assert np.array_equal(a, b)
+    assert len(one[0]) > 30_000
+    lo, hi = 20_000, 22_000                                  # the slow Python packer on a window of the same file
+    sel = [int(p) for p in snps if lo <= p <= hi]
+    vw = {"N": len(sel), "snp_rev": {i: p for i, p in enumerate(sel)}}
+    exp = bamio.pack_bam(path, "ctg", lo, hi, vw)
+    got = bamio.pack_bam_native(path, "ctg", lo, hi, vw, n_threads=8)
+    for a, b in zip(exp, got):
+        assert np.array_equal(a, b)

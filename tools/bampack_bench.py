@@ -14,7 +14,7 @@ seqs = bases[rng.integers(0, 4, size=(n, 150))]
 t = time.time()
 reads = [(0, int(s), 0, "r%d" % i, [("M", 150)], "".join(seqs[i])) for i, s in enumerate(starts)]
 path = os.path.join(tempfile.mkdtemp(), "big.bam")
-write_bam(path, [("ctg", G)], reads, block=60000)
+write_bam(path, [("ctg", G)], reads, block=60000, align=os.environ.get("BAM_ALIGN", "0") == "1")
 print("wrote %d reads, %.1f MB BAM in %.1fs" % (n, os.path.getsize(path) / 1e6, time.time() - t))
 snps = np.sort(rng.choice(np.arange(1, G + 1), size=10_000, replace=False))
 vh = {"N": len(snps), "snp_rev": {i: int(p) for i, p in enumerate(snps)}}
