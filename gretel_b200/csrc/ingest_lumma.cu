@@ -11,18 +11,19 @@
 //   k_scan_*       exclusive scan of the padded histogram = where each key's reads go
 //   k_l2_scatter   counting sort: perm[] = read indices ordered by (sb, span) (order inside a key is free: the
 //                  counts are integer sums), so the 32 reads of a chunk start in the same block and end close together
-//   k_l2_onehot    warp per chunk, lane = read: writes the chunk's one-hot operand slabs, one 4 KB slab per site
-//                  block it touches, laid out exactly as the MN-major UMMA operand (core matrix = 16 columns x 8
-//                  reads), so a slab is one 4 KB bulk copy away from the tensor core.  Sentinels, totals here.
+//   k_l2_onehot    warp per chunk: the chunk's last block, sentinels, totals
+//   k_l2_slabs     warp per (chunk, site block it touches), lane = read: writes the one-hot operand slab, 4 KB, laid out
+//                  exactly as the MN-major UMMA operand (core matrix = 16 columns x 8 reads), so a slab is one 4 KB
+//                  bulk copy away from the tensor core
 //   k_l2_tiles     persistent CTAs over tiles (I = one block of 16 first sites, q = a pair of blocks of second sites):
-//                  a producer warp finds the chunks that touch both (per first block the chunks are sorted by their
-//                  last block: the sort's own offsets say where the reaching chunks start) and streams their slabs
-//                  (runs of up to 4 chunks of a first block are contiguous: three bulk copies per run) through a
-//                  3-stage TMA/mbarrier ring;
+//                  four producer warps (one per stage of the TMA/mbarrier ring) find the chunks that touch both (per
+//                  first block the chunks are sorted by their last block: the sort's own offsets say where the
+//                  reaching chunks start) and stream their slabs, up to 4 chunks per stage;
 //                  one thread issues two M=128, N=128, K=32 MMAs per chunk into a double-buffered TMEM accumulator;
-//                  16 epilogue warps read the finished accumulator (tcgen05.ld), turn it through shared memory
-//                  into the band's cell order and add it to the band with coalesced read-modify-writes.  Every band
-//                  cell has exactly one writer: no atomics.
+//                  8 epilogue warps read the finished accumulator (tcgen05.ld), turn it through shared memory
+//                  into the band's cell order and add it to the band with coalesced read-modify-writes (plain stores
+//                  into a freshly cleared matrix).  Every band cell has exactly one writer: no atomics.
+//   k_l2_tiles2    the same over CTA pairs (cta_group::2, M = 256 across two SMs); opt-in, HX_LUMMA_PAIRS=1
 // Rank-sortedness is not needed (the counting sort orders the reads itself).
 #include <limits.h>
 #include <stdlib.h>
