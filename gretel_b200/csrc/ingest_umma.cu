@@ -7,15 +7,19 @@
 // rank contributes C = X^T X with X = [reads x columns] in {0,1}.  That is an int8 GEMM with int32 accumulation
 // (tcgen05.mma kind::i8: exact by construction), M = N = columns (<= 128), K = reads:
 //
-//   expander warps   lane = read: load its allele bytes, turn four sites at a time into four one-hot words
-//                    (1 << 8*code; N, -, _ and positions past the read's end give 0) and store them with one
-//                    16-byte shared-memory store.  The row of a read IS the MN-major UMMA operand layout
-//                    (core matrix = 16 columns x 8 reads), so there is no transpose anywhere.
-//   MMA thread       one tcgen05.mma (M=128, N=16*ceil(k/4), K=32) per 32 reads, A and B descriptors pointing at
-//                    the same shared-memory tile; accumulators in TMEM (two stages of 128 columns), released
-//                    to the readout warps with tcgen05.commit at the end of a run.
-//   readout warps    tcgen05.ld the upper triangle of C, add it into the CTA's sliding shared-memory tile of
-//                    band rows (as k1_bitsliced does), flush retired rows to HBM with integer reductions.
+//   slices           a CTA takes an equal share of the WEIGHT of the rank-sorted reads (alleles, reads, ranks:
+//                    hx_weighted_slice), builds the table of its jobs (one job = up to 32 reads of one run = the K of
+//                    one MMA) with a block scan over the runs of its slice, then splits into
+//   expander warps   (24) job e, e+24, ...; lane = read: load its allele bytes, turn four sites at a time into four
+//                    one-hot words (1 << 8*code; N, -, _ and positions past the read's end give 0) and store them
+//                    with one 16-byte shared-memory store into the warp's own operand slot.  The row of a read IS the
+//                    MN-major UMMA operand layout (core matrix = 16 columns x 8 reads), so there is no transpose
+//                    anywhere.  Lane 0 issues the tcgen05.mma (M=128, N=16*ceil(k/4), K=32; A and B descriptors point
+//                    at the same slot) into the run's accumulator stage in TMEM (four stages of 128 columns) and
+//                    commits it to the slot's mbarrier and to the stage's completion barrier.
+//   readout warps    (8) one run at a time: wait for the stage, tcgen05.ld the upper triangle of C, add it into the
+//                    CTA's sliding shared-memory tile of band rows (as k1_bitsliced does), zero the stage, flush
+//                    retired rows to HBM with integer reductions.
 //
 // Reads holding N, - or _, the sentinels and the totals are handled per read by the expander warps exactly as
 // in the bit-sliced kernels (ingest_common.cuh).
