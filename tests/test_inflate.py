@@ -117,3 +117,92 @@ def test_reference_fixture_blocks():
         p += bsize
         n += 1
     assert n >= 2
+
+
+class _Bits:
+    def __init__(self):
+        self.acc, self.n, self.out = 0, 0, bytearray()
+
+    def put(self, v, nbits):                   # LSB first
+        self.acc |= v << self.n
+        self.n += nbits
+        while self.n >= 8:
+            self.out.append(self.acc & 255)
+            self.acc >>= 8
+            self.n -= 8
+
+    def code(self, c, nbits):                  # a Huffman code: most significant bit first
+        self.put(int(format(c, "0%db" % nbits)[::-1], 2), nbits)
+
+    def done(self):
+        if self.n:
+            self.out.append(self.acc & 255)
+        return bytes(self.out)
+
+
+def _canonical(lens):
+    codes, code = {}, 0
+    for ln in range(1, 16):
+        for s in sorted(k for k, v in lens.items() if v == ln):
+            codes[s] = (code, ln)
+            code += 1
+        code <<= 1
+    return codes
+
+
+_LBASE = [3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258]
+_LEXTRA = [0] * 8 + [1] * 4 + [2] * 4 + [3] * 4 + [4] * 4 + [5] * 4 + [0]
+_DBASE = [1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145,
+          8193, 12289, 16385, 24577]
+_DEXTRA = [0, 0, 0, 0] + [i // 2 for i in range(2, 28)]
+
+
+def test_hand_built_block_with_15_bit_codes():
+    """A dynamic block written by hand whose literal/length AND distance codes are maximally skewed (lengths 1, 2, ...,
+    14, 15, 15): every code longer than the primary tables (11 / 8 bits) goes through a second-level table.  zlib must
+    accept the stream (it is a valid, complete code) and both decoders must agree byte for byte."""
+    rng = np.random.default_rng(5)
+    lit_syms = [ord(c) for c in "etaoinshrdlu"] + [256, 257, 264, 285]            # 12 literals, EOB, three length codes
+    for trial in range(6):
+        order = list(rng.permutation(16))
+        ll = {lit_syms[order[i]]: min(i + 1, 15) for i in range(16)}               # lengths 1..15, 15: a complete code
+        dorder = list(rng.permutation(16))
+        dl = {int(dorder[i]) * 29 // 15: min(i + 1, 15) for i in range(16)}         # 16 distinct distance codes in 0..29
+        assert len(dl) == 16
+        lc, dc = _canonical(ll), _canonical(dl)
+        w = _Bits()
+        w.put(1, 1); w.put(2, 2)                                                    # BFINAL, dynamic
+        hlit, hdist = max(ll) + 1, max(dl) + 1
+        w.put(hlit - 257, 5); w.put(hdist - 1, 5); w.put(19 - 4, 4)
+        cl_order = [16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15]
+        for s in cl_order:                                                          # code-length code: 0..15 at 4 bits each
+            w.put(4 if s < 16 else 0, 3)
+        for s in range(hlit):
+            w.code(ll.get(s, 0), 4)
+        for s in range(hdist):
+            w.code(dl.get(s, 0), 4)
+        # symbols: literals with every code length, matches with every length / distance code that is legal here
+        out = bytearray()
+        lits = [s for s in ll if s < 256]
+        for step in range(4000):
+            if step % 3 == 2 and len(out) > 0:
+                lsym = int(rng.choice([257, 264, 285]))
+                dsym = int(rng.choice([d for d in dl if _DBASE[d] <= len(out)] or [-1]))
+                if dsym >= 0:
+                    length = _LBASE[lsym - 257] + int(rng.integers(0, 1 << _LEXTRA[lsym - 257]))
+                    dist = min(len(out), _DBASE[dsym] + int(rng.integers(0, 1 << _DEXTRA[dsym])))
+                    dist = max(dist, _DBASE[dsym])
+                    w.code(*lc[lsym]); w.put(length - _LBASE[lsym - 257], _LEXTRA[lsym - 257])
+                    w.code(*dc[dsym]); w.put(dist - _DBASE[dsym], _DEXTRA[dsym])
+                    for _ in range(length):
+                        out.append(out[-dist])
+                    continue
+            s = int(rng.choice(lits))
+            w.code(*lc[s])
+            out.append(s)
+        w.code(*lc[256])
+        stream = w.done()
+        assert zlib.decompress(stream, -15) == bytes(out)                           # the encoder above is right
+        for slack in (8, 0):
+            rc, got = _inflate(stream, len(out), slack)
+            assert rc == 0 and got == bytes(out), (trial, slack)
