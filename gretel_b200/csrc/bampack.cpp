@@ -366,18 +366,58 @@ struct BamStream {
         if (!carry.empty()) memcpy(ubuf.get(), carry.data(), carry.size());
         const size_t base = carry.size();
         ulen = need;
+        // The records of the wave are found by following the chain of block_size fields - serial, one cache miss per
+        // record (20 ns).  htslib never splits a record between BGZF blocks unless it is larger than a block
+        // (bam_write1 flushes first), so in practice a block starts a record: the thread that has just inflated a
+        // group of consecutive blocks walks the chain through them speculatively from the group's first byte while
+        // they are still in its cache; the serial pass further down only checks that the real chain arrives exactly
+        // where a group started - where it does not (records cut by block ends), it walks that stretch itself.
+        struct Stretch { size_t start, end, exit; bool ok, wave_end; std::vector<RecRef> recs; };
+        std::vector<Stretch> st;
         {
+            const uint8_t *d = ubuf.get();
+            const size_t gb = std::min<size_t>(16, std::max<size_t>(1, blocks.size() / (4 * (size_t)n_threads)));
+            const size_t n_groups = (blocks.size() + gb - 1) / gb;
+            st.resize(n_groups);
+            for (size_t g = 0; g < n_groups; ++g) {
+                const size_t b1 = (g + 1) * gb;
+                st[g].start = base + blocks[g * gb].uoff;
+                st[g].end = b1 < blocks.size() ? base + blocks[b1].uoff : ulen;
+                st[g].exit = st[g].start;
+                st[g].ok = false;
+                st[g].wave_end = false;
+            }
+            auto walk = [&](Stretch &x) {
+                size_t p = x.start;
+                x.recs.reserve((x.end - x.start) / 200 + 16);
+                bool good = true;
+                // only bytes of this group are read (the next group may still be inflating): a block_size field cut
+                // by the group's end is left to the serial pass
+                while (p + 4 <= x.end) {
+                    const int32_t bs = rdi32(d + p);
+                    if (bs < 32) { good = false; break; }
+                    if (p + 4 + (size_t)bs > ulen) { x.wave_end = true; break; }   // the wave's last, partial record
+                    x.recs.push_back({p + 4, (uint32_t)bs});
+                    p += 4 + (size_t)bs;
+                }
+                x.exit = p;
+                x.ok = good;
+            };
             std::atomic<size_t> next(0);
             std::atomic<bool> ok(true);
             auto work = [&]() {
                 for (;;) {
-                    const size_t b = next.fetch_add(1);
-                    if (b >= blocks.size()) break;
-                    if (!inflate_block(cbase + blocks[b].coff, blocks[b].csize, ubuf.get() + base + blocks[b].uoff, blocks[b].usize))
-                        ok = false;
+                    const size_t g = next.fetch_add(1);
+                    if (g >= n_groups) break;
+                    bool fine = true;
+                    for (size_t b = g * gb; b < std::min(blocks.size(), (g + 1) * gb); ++b)
+                        if (!inflate_block(cbase + blocks[b].coff, blocks[b].csize, ubuf.get() + base + blocks[b].uoff, blocks[b].usize))
+                            fine = false;
+                    if (!fine) ok = false;
+                    else if (n_groups > 1) walk(st[g]);
                 }
             };
-            const int nt = (int)std::min<size_t>((size_t)n_threads, std::max<size_t>(1, blocks.size() / 4));
+            const int nt = (int)std::min<size_t>((size_t)n_threads, std::max<size_t>(1, n_groups));
             std::vector<std::thread> th;
             for (int t = 1; t < nt; ++t) th.emplace_back(work);
             work();
@@ -397,41 +437,6 @@ struct BamStream {
             q = (size_t)used;
         }
         const uint8_t *d = ubuf.get();
-        // The chain of block_size fields is serial and every step is a cache miss (20 ns per record).  htslib never
-        // splits a record between BGZF blocks unless it is larger than a block (bam_write1 flushes first), so in
-        // practice a block starts a record: the threads walk the chain speculatively from block starts, one
-        // stretch of blocks each, and the serial pass below only checks that the real chain arrives exactly where
-        // a stretch started - if it does not (records cut by block ends), it walks that stretch itself.
-        struct Stretch { size_t start, end, exit; bool ok; std::vector<RecRef> recs; };
-        std::vector<Stretch> st;
-        {
-            const int nt = (int)std::min<size_t>((size_t)n_threads, blocks.size() / 8);
-            for (int t = 1; t < nt; ++t) {                     // (the stretch of thread 0 is walked by the serial pass)
-                const size_t b0 = blocks.size() * (size_t)t / (size_t)nt, b1 = blocks.size() * (size_t)(t + 1) / (size_t)nt;
-                const size_t s0 = base + blocks[b0].uoff, s1 = b1 < blocks.size() ? base + blocks[b1].uoff : ulen;
-                if (s0 < s1 && s0 >= q) st.push_back({s0, s1, s0, false, {}});
-            }
-            auto walk = [&](Stretch &x) {
-                size_t p = x.start;
-                x.recs.reserve((x.end - x.start) / 200 + 16);
-                bool ok = true;
-                while (p < x.end) {
-                    if (p + 4 > ulen) break;
-                    const int32_t bs = rdi32(d + p);
-                    if (bs < 32) { ok = false; break; }
-                    if (p + 4 + (size_t)bs > ulen) break;          // the wave's last, partial record
-                    __builtin_prefetch(d + std::min(ulen - 1, p + 16 * (4 + (size_t)bs)));
-                    x.recs.push_back({p + 4, (uint32_t)bs});
-                    p += 4 + (size_t)bs;
-                }
-                x.exit = p;
-                x.ok = ok;
-            };
-            std::vector<std::thread> th;
-            for (size_t i = 1; i < st.size(); ++i) th.emplace_back(walk, std::ref(st[i]));
-            if (!st.empty()) walk(st[0]);
-            for (auto &t : th) t.join();
-        }
         size_t si = 0;
         bool at_end = false;
         while (!at_end && q + 4 <= ulen) {
@@ -439,7 +444,7 @@ struct BamStream {
             if (si < st.size() && st[si].start == q) {
                 if (st[si].ok) {
                     recs.insert(recs.end(), st[si].recs.begin(), st[si].recs.end());
-                    at_end = st[si].exit + 4 > ulen || st[si].exit < st[si].end;   // stopped at the wave's partial record
+                    at_end = st[si].wave_end || st[si].exit + 4 > ulen;            // stopped at the wave's partial record
                     q = st[si].exit;
                     ++si;
                     continue;
