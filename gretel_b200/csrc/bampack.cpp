@@ -521,7 +521,13 @@ int hx_pack_bam_ex(const char *bam_path, const char *contig, int32_t start_pos, 
     // two waves take turns: while this thread filters and walks wave i, a helper reads, inflates and indexes wave i+1
     // (the serial parts of either side - the record scan, the depth cap - hide behind the other side's parallel work)
     Wave wv[2];
-    constexpr size_t PACK_WAVE = (size_t)16 << 20;
+    // compressed bytes per wave: small enough that the first wave's inflate and the last wave's walk - the two ends of
+    // the pipeline that nothing hides - stay short (HX_PACK_WAVE_MB overrides, for measurements)
+    static const size_t PACK_WAVE = [] {
+        const char *e = getenv("HX_PACK_WAVE_MB");
+        const long mb = e ? atol(e) : 16;
+        return (size_t)(mb < 1 ? 1 : mb > 256 ? 256 : mb) << 20;
+    }();
     std::future<int> next = std::async(std::launch::async, [&]() { return bs.next_wave(wv[0], PACK_WAVE); });
     for (int wi = 0;; ++wi) {
         rc = next.get();
