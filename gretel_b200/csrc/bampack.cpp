@@ -607,12 +607,18 @@ int hx_pack_bam_ex(const char *bam_path, const char *contig, int32_t start_pos, 
             std::vector<Out> &outs = waves.back();
             auto work = [&](int t) {
                 std::vector<uint8_t> tmp;
+                Out mine;                             // (the Out objects of neighbouring threads share cache lines, and
+                                                      //  every push_back writes the vector's end pointer)
                 const size_t a = nrec * (size_t)t / (size_t)nt, b = nrec * (size_t)(t + 1) / (size_t)nt;
+                mine.rank.reserve((b - a) / 2 + 16);
+                mine.klen.reserve((b - a) / 2 + 16);
+                mine.codes.reserve((b - a) * 8 + 64);
                 for (size_t i = a; i < b; ++i) {
                     if (depth_on && !admit[i]) continue;
                     pack_record(parse_rec(d + recs[i].off, recs[i].size), bs.target_tid, start_pos, end_pos, snp_pos,
-                                n_snps, stepper, outs[(size_t)t], tmp);
+                                n_snps, stepper, mine, tmp);
                 }
+                outs[(size_t)t] = std::move(mine);
             };
             std::vector<std::thread> th;
             for (int t = 1; t < nt; ++t) th.emplace_back(work, t);
